@@ -1,0 +1,263 @@
+/* sdtree.h -- C ABI of libsdtree.so: the SD-tree hot path of the Mitsuba 3
+ * "Practical Path Guiding" lab, as hand-written sm_100a CUDA kernels.
+ *
+ * This is the drop-in boundary.  The reference has no FFI (it is pure
+ * Python traced by Dr.Jit); the cut is the interface its integrator uses on its two
+ * KDTree objects (sdTree_prev / sdTree_current,
+ * /root/reference/src/path_guiding_integrator.py:68-69).  One sdt_handle owns that
+ * PAIR: an immutable "prev" tree that sample/pdf read, and the "current" statistics
+ * (same topology) that splat accumulates into, exactly as the reference uses them.
+ * Every entry point cites the reference method it replaces (paths relative to
+ * /root/reference).
+ *
+ * Conventions
+ *  - every function returns 0 (SDT_OK) or a negative sdt_status; the message is at
+ *    sdt_last_error(handle).  No exception crosses the boundary.
+ *  - one handle per GPU, not thread-safe.  All device work is enqueued on the
+ *    `stream` argument (a cudaStream_t; NULL = default stream) and is asynchronous
+ *    unless SDT_SYNC is given.
+ *  - query / record buffers belong to the caller.  They are DEVICE pointers unless
+ *    SDT_HOST_PTRS is given, in which case they are host pointers (pinned for speed)
+ *    and the library stages them through its own device buffers inside the call.
+ *  - vectors are strided component views (sdt_vec3 / sdt_vec2): Dr.Jit's SoA
+ *    Vector3f is {x,y,z,stride=1}; a C-contiguous (n,3) array is {p,p+1,p+2,stride=3}.
+ *  - no torch / Dr.Jit / Mitsuba type appears in any signature.
+ */
+#ifndef SDTREE_H
+#define SDTREE_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SDT_VERSION 1
+
+typedef struct sdt_tree_s* sdt_handle;
+typedef void* sdt_stream; /* cudaStream_t */
+
+typedef enum sdt_status {
+    SDT_OK = 0,
+    SDT_ERR_INVALID = -1,  /* bad argument */
+    SDT_ERR_CUDA = -2,     /* CUDA runtime error (message has the cudaError string) */
+    SDT_ERR_CAPACITY = -3, /* node arena too small for the requested tree */
+    SDT_ERR_LAYOUT = -4,   /* uploaded arrays are not a valid SD-tree */
+    SDT_ERR_NCCL = -5,     /* NCCL missing or failed */
+    SDT_ERR_STATE = -6     /* call not valid in the current state */
+} sdt_status;
+
+/* flags for the query / splat / refine entry points */
+#define SDT_HOST_PTRS 1u     /* buffers are host memory; H2D/D2H staging inside the call */
+#define SDT_SYNC 2u          /* cudaStreamSynchronize(stream) before returning */
+#define SDT_REFINE_NO_KD 4u   /* sdt_refine: skip the spatial split (KDTree.refine) */
+#define SDT_REFINE_NO_QUAD 8u /* sdt_refine: skip threshold + merge/split of the quadtrees */
+
+typedef struct sdt_vec3 { const float* x; const float* y; const float* z; int64_t stride; } sdt_vec3;
+typedef struct sdt_vec2 { const float* x; const float* y; int64_t stride; } sdt_vec2;
+typedef struct sdt_vec3_out { float* x; float* y; float* z; int64_t stride; } sdt_vec3_out;
+
+/* PathGuidingIntegrator.setup() arguments that reach the trees
+ * (src/path_guiding_integrator.py:77-105) plus arena sizes. */
+typedef struct sdt_config {
+    float bbox_min[3];
+    float bbox_max[3];
+    int32_t kd_max_depth;    /* KDTree.maxDepth            (sdTreeMaxDepth)   */
+    int32_t quad_max_depth;  /* QuadTree.maxDepth          (quadTreeMaxDepth, <= 32) */
+    int32_t store_nee;       /* QuadTree.isStoreNEERadiance                    */
+    int32_t device;          /* CUDA ordinal                                   */
+    uint32_t kd_capacity;    /* spatial-node arena (0 = 1<<21)                 */
+    uint32_t quad_capacity;  /* quadtree-node arena per buffer (0 = 1<<24)     */
+} sdt_config;
+
+typedef struct sdt_sizes {
+    uint32_t n_kd;       /* spatial nodes  (KDTreeNode.getWidth)   */
+    uint32_t n_quad;     /* quadtree nodes (QuadTreeNode.getWidth) */
+    uint32_t n_roots;    /* quadtrees      (len(rootNodeIndex))    */
+    uint32_t n_interior; /* non-leaf quadtree nodes                */
+    uint32_t n_levels;   /* quadtree levels in use                 */
+    uint32_t kd_leaves;
+    uint32_t error;      /* sticky device-side error flag (0 = none) */
+    uint32_t refine_count;
+} sdt_sizes;
+
+/* The reference's on-disk contract: the 23 arrays of KDTree.saveToFile
+ * (src/kdtree.py:539-602), host memory, dtypes float32 / uint32 / uint8(bool). */
+typedef struct sdt_arrays {
+    uint32_t n_kd, n_quad, n_roots;
+    float kd_max_leaf_size;
+    int32_t kd_max_depth;
+    int32_t quad_max_depth;
+    int32_t quad_store_nee;
+    float* kd_bbox_min;        /* n_kd*3 */
+    float* kd_bbox_max;        /* n_kd*3 */
+    uint32_t* kd_depth;        /* n_kd   */
+    float* kd_vert_count;      /* n_kd   */
+    uint8_t* kd_is_leaf;       /* n_kd   */
+    uint32_t* kd_quad_root;    /* n_kd   quadTreeRootIndex */
+    uint32_t* kd_child_left;   /* n_kd   */
+    uint32_t* kd_child_right;  /* n_kd   */
+    uint32_t* q_root_node;     /* n_roots rootNodeIndex */
+    float* q_bbox_min;         /* n_quad*2 */
+    float* q_bbox_max;         /* n_quad*2 */
+    uint32_t* q_depth;         /* n_quad */
+    float* q_irradiance;       /* n_quad */
+    uint8_t* q_is_leaf;        /* n_quad */
+    float* q_threshold;        /* n_quad refinementThreshold */
+    uint32_t* q_child[4];      /* n_quad child_1..4_index */
+} sdt_arrays;
+
+#define SDT_TREE_PREV 0    /* sdTree_prev   : what sample/pdf read   */
+#define SDT_TREE_CURRENT 1 /* sdTree_current: what splat writes into */
+
+/* ---- lifetime -------------------------------------------------------------- */
+/* KDTree() x2 + PathGuidingIntegrator.setup(): src/path_guiding_integrator.py:68-69,
+ * 98-105; KDTree.setup src/kdtree.py:133-138.  Starts as one spatial leaf that owns
+ * one single-node quadtree with threshold +inf (src/quadtree.py:350-362). */
+int sdt_create(const sdt_config* cfg, sdt_handle* out);
+int sdt_destroy(sdt_handle h);
+/* handle may be NULL: message of the last failed sdt_create in this thread */
+const char* sdt_last_error(sdt_handle h);
+
+/* ---- tree exchange in the reference schema --------------------------------- */
+/* loadSDTreeFromFile (src/path_guiding_integrator.py:597-608 -> KDTree.loadFromFile
+ * src/kdtree.py:156-170): prev <- arrays; current <- same topology, zero statistics.
+ * Quadtree nodes must have adjacent children; a non-canonical node order is
+ * re-labelled to the canonical layout of clearTreeUnusedNode (src/quadtree.py:844-851). */
+int sdt_upload(sdt_handle h, const sdt_arrays* host);
+/* Overwrite the statistics of `current` with frozen buffers (all nodes, interior
+ * included; same node numbering as the last upload / refine): q_irradiance[n_quad],
+ * kd_vert_count[n_kd].  Used to refine from identical stat buffers. */
+int sdt_upload_stats(sdt_handle h, const float* q_irradiance, const float* kd_vert_count);
+/* blocks until pending work on the handle's last stream is done */
+int sdt_get_sizes(sdt_handle h, sdt_sizes* out);
+/* saveSDTreeToFile (src/path_guiding_integrator.py:589-594 / src/kdtree.py:539-602).
+ * `out` arrays are caller-allocated with the sizes from sdt_get_sizes. */
+int sdt_download(sdt_handle h, int which, sdt_arrays* out);
+
+/* ---- queries on `prev` ------------------------------------------------------ */
+/* KDTree.getLeafNodeIndex (src/kdtree.py:435-470) + the masked quadTreeRootIndex
+ * gather of KDTree.sample/pdf (:482,:493).  active may be NULL (= all active). */
+int sdt_locate(sdt_handle h, const sdt_vec3* pos, const uint8_t* active, uint32_t n,
+               uint32_t* leaf, uint32_t* root, uint32_t flags, sdt_stream stream);
+
+/* KDTree.sample (src/kdtree.py:473-486): descent -> QuadTree.sampleQuadTree
+ * (src/quadtree.py:931-998) -> QuadTree.pdfQuadTree of the sampled direction
+ * (:1001-1101).  Uniforms: if `u` != NULL lane i uses u[i*u_stride + 3*level + k],
+ * k = 0,1,2 = (u_x, u_y, u_select), consumed as the reference consumes its sampler;
+ * else a counter-based generator keyed (seed, lane_offset + i, 3*level + k).
+ * dbg (optional, 4*n uint32): per lane {kd leaf, quadtree root id, quadtree node
+ * reached by the sample, quadtree node reached by the pdf}. */
+int sdt_sample(sdt_handle h, const sdt_vec3* pos, const uint8_t* active, uint32_t n,
+               const float* u, uint32_t u_stride, uint32_t seed, uint32_t lane_offset,
+               const sdt_vec3_out* dir, float* pdf, uint32_t* dbg,
+               uint32_t flags, sdt_stream stream);
+
+/* KDTree.pdf (src/kdtree.py:489-496).  dbg (optional, 3*n): {kd leaf, root id, node}. */
+int sdt_pdf(sdt_handle h, const sdt_vec3* pos, const sdt_vec3* dir, const uint8_t* active,
+            uint32_t n, float* pdf, uint32_t* dbg, uint32_t flags, sdt_stream stream);
+
+/* One bounce of the integrator's guided/BSDF choice in ONE pass over the wavefront
+ * (src/path_guiding_integrator.py:283-311): lanes with mode[i]==1 are sampled from
+ * the tree (:301), lanes with mode[i]==2 get the tree pdf of the BSDF-sampled
+ * direction `wo` (:307) and, when bsdf_pdf/bsdf_value are given, the fused one-sample
+ * mixture woPdf = f*bsdf_pdf + (1-f)*sdtree_pdf, weight = bsdf_value/woPdf (:310-311);
+ * mode 0 lanes are untouched.  Outputs: dir (mode 1), sdtree_pdf (mode 1,2), wo_pdf and
+ * weight (mode 2 when fused).  The reference runs two full descents for this. */
+typedef struct sdt_guided_args {
+    sdt_vec3 pos;
+    sdt_vec3 wo;               /* BSDF-sampled world direction (mode 2) */
+    const uint8_t* mode;
+    const float* u; uint32_t u_stride; uint32_t seed; uint32_t lane_offset;
+    const float* bsdf_pdf;     /* optional */
+    sdt_vec3 bsdf_value;       /* optional (x == NULL -> none) */
+    float bsdf_sampling_fraction;
+    sdt_vec3_out dir;          /* in: unused; out: sampled dir on mode 1 lanes */
+    float* sdtree_pdf;
+    float* wo_pdf;             /* optional */
+    sdt_vec3_out weight;       /* optional */
+} sdt_guided_args;
+int sdt_guided(sdt_handle h, const sdt_guided_args* a, uint32_t n, uint32_t flags, sdt_stream stream);
+
+/* mis_weight + NEE surface pdf (src/path_guiding_integrator.py:16-24, 241-253).
+ * iteration <= 1 -> surface_pdf_em = bsdf_pdf_em.  Outputs may be NULL. */
+int sdt_mis_nee(sdt_handle h, uint32_t n, const float* bsdf_pdf_em, const float* sdtree_pdf_em,
+                const float* pdf_with_delta, const float* pdf_without_delta, const float* ds_pdf,
+                const uint8_t* ds_delta, float bsdf_sampling_fraction, int32_t iteration,
+                float* surface_pdf_em, float* mis_em, uint32_t flags, sdt_stream stream);
+/* one-sample mixture (src/path_guiding_integrator.py:310-311) on lanes with do_mis != 0 */
+int sdt_mis_mixture(sdt_handle h, uint32_t n, const float* bsdf_pdf, const float* sdtree_pdf,
+                    const sdt_vec3* bsdf_value, const uint8_t* do_mis, float bsdf_sampling_fraction,
+                    float* wo_pdf, const sdt_vec3_out* weight, uint32_t flags, sdt_stream stream);
+
+/* ---- splat into `current` ---------------------------------------------------- */
+/* KDTree.addDataPropagate + QuadTree.addDataPropagate (src/kdtree.py:180-225,
+ * src/quadtree.py:389-464) on already-filtered records.  radiance_nee / direction_nee
+ * are read only when the tree was created with store_nee.  active may be NULL. */
+typedef struct sdt_records {
+    sdt_vec3 position;
+    sdt_vec2 direction;       /* canonical (phi/2pi, (cos theta + 1)/2) */
+    const float* radiance;
+    const float* wo_pdf;
+    sdt_vec3 radiance_nee;
+    sdt_vec2 direction_nee;
+    const uint8_t* active;
+} sdt_records;
+int sdt_splat_records(sdt_handle h, const sdt_records* rec, uint32_t n, uint32_t flags, sdt_stream stream);
+
+/* processPathData + scatterDataIntoSDTree + addDataPropagate in one pass
+ * (src/path_guiding_integrator.py:434-500): slot s belongs to ray s / max_depth;
+ * radiance = luminance(((Lfinal[ray]-throughputRadiance)/throughputBsdf)/bsdf) with the
+ * reference's NaN scrubbing; the reference's filter replaces its compaction. */
+typedef struct sdt_path_data {
+    uint32_t slots;           /* numRays * max_depth */
+    uint32_t max_depth;
+    sdt_vec3 l_final;         /* numRays */
+    sdt_vec3 throughput_radiance, throughput_bsdf, bsdf; /* slots */
+    sdt_vec3 position;
+    sdt_vec2 direction;
+    const float* wo_pdf;
+    sdt_vec3 radiance_nee;
+    sdt_vec2 direction_nee;
+    const uint8_t* active;
+    float* radiance_out;      /* optional: SurfaceInteractionRecord.radiance (slots) */
+} sdt_path_data;
+int sdt_splat_path_data(sdt_handle h, const sdt_path_data* pd, uint32_t flags, sdt_stream stream);
+
+/* ---- per-iteration refine ---------------------------------------------------- */
+/* KDTree.setRefinementThreshold (src/kdtree.py:327-330): maxLeafSize = 12000*sqrt(2^it) */
+int sdt_set_iteration_threshold(sdt_handle h, int32_t iteration);
+/* direct write of KDTree.maxLeafSize */
+int sdt_set_max_leaf_size(sdt_handle h, float max_leaf_size);
+/* refineAndPrepareSDTreeForNextIteration (src/path_guiding_integrator.py:566-586):
+ * KDTree.refine/split, setQuadTreeRefinementThreshold, refineAllQuadTree,
+ * cleanUnusedQuadTree, prev <- current, reset of current.  Entirely on the device,
+ * no host round-trip. */
+int sdt_refine(sdt_handle h, uint32_t flags, sdt_stream stream);
+/* resetTreeVertCount + resetAllQuadTreeIrradiance (src/kdtree.py:401-432,531-532) */
+int sdt_reset_stats(sdt_handle h, sdt_stream stream);
+
+/* ---- multi-GPU: replicated tree, one exchange per training iteration ---------- */
+/* libnccl.so.2 is dlopen'ed on first use.  id = 128-byte ncclUniqueId made by rank 0
+ * (sdt_comm_unique_id) and broadcast by the host program. */
+int sdt_comm_unique_id(void* id128);
+int sdt_comm_init(sdt_handle h, const void* id128, int32_t rank, int32_t nranks);
+/* ncclAllReduce(sum) over current's [quadtree energies | spatial leaf counts] */
+int sdt_allreduce(sdt_handle h, sdt_stream stream);
+/* device pointers + element counts of those two buffers (for callers that bring
+ * their own collective, e.g. torch.distributed) */
+int sdt_stat_buffers(sdt_handle h, float** q_energy, uint32_t* n_quad, float** kd_count, uint32_t* n_kd);
+
+/* ---- tuning / introspection --------------------------------------------------- */
+/* key: "query_block", "query_ctas_per_sm", "kd_smem_nodes", "splat_block",
+ * "splat_ctas_per_sm", "fuse_sample_pdf" */
+int sdt_set_tuning(sdt_handle h, const char* key, int64_t value);
+/* number of kernels this handle has launched since creation */
+uint64_t sdt_kernel_launches(sdt_handle h);
+/* L2-resident read bandwidth probe (GB/s): `bytes` working set read `passes` times */
+int sdt_measure_l2(sdt_handle h, uint64_t bytes, uint32_t passes, float* gbps, sdt_stream stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SDTREE_H */

@@ -1,0 +1,389 @@
+// Device layout, fp32 math and per-lane descent rules of the SD-tree hot path.
+// Everything here is per-lane logic (SDT_HD); the kernels that stage shared memory
+// and walk the wavefront are in sdtree.cu.  Reference citations are relative to
+// /root/reference.
+#pragma once
+
+#include "sdt_platform.h"
+#include "../../include/sdtree.h"
+
+#define SDT_MAX_LEVELS 34          // quadtree levels 0..33 (QuadTree.maxDepth <= 32)
+#define SDT_KD_MAX_DEPTH 40        // KDTree.maxDepth upper bound
+#define SDT_KD_LEAF_BIT 0x80000000u
+#define SDT_NONE 0xFFFFFFFFu
+
+// ---------------------------------------------------------------------------
+// Device layout
+// ---------------------------------------------------------------------------
+// Spatial binary tree: ONE 32-bit word per node (4 B per descent level):
+//   interior: child_base (left = base, right = base+1; the reference appends both
+//             children adjacently, src/kdtree.py:243-245)
+//   leaf    : SDT_KD_LEAF_BIT | quadTreeRootIndex
+// The split plane is never stored: children partition axis depth%3 at
+// (min+max)/2 (src/kdtree.py:268-304), so the running box reproduces the
+// reference's stored child boxes bit for bit.
+//
+// Directional quadtrees, canonical layout of clearTreeUnusedNode
+// (src/quadtree.py:695-828,844-851): node ids 0..R-1 are the roots (node id ==
+// root id), then level by level the four adjacent children of every non-leaf node.
+// Per NON-LEAF node one 32-byte record (= one L2 sector per descent level):
+struct __align__(32) QRec {
+    uint32_t child_base;     // canonical node id of child_1; children are base..base+3
+    uint32_t interior_base;  // record index of the first non-leaf child
+    uint32_t leafmask;       // bit c set: child c is a leaf (has no record)
+    float own;               // this node's stored energy (pdf denominator, :1056)
+    float e[4];              // the four children's stored energies (:969-972, :1057-1060)
+};
+
+// Device-resident description of the tree; kernels read sizes from here so that
+// refine needs no host round-trip.
+struct DevHeader {
+    uint32_t n_kd, n_quad, n_roots, n_interior, n_levels, kd_leaves, error, refine_count;
+    uint32_t root_of_node0;                 // quadTreeRootIndex[0] (out-of-box lanes, :224,:482)
+    uint32_t kd_max_depth, quad_max_depth, store_nee;
+    float bbox_min[3], bbox_max[3];         // spatial root box
+    float max_leaf_size;                    // KDTree.maxLeafSize as fp32
+    uint32_t pad1;
+    uint32_t level_off[SDT_MAX_LEVELS + 2];  // quadtree level l = nodes [level_off[l], level_off[l+1])
+    uint32_t level_cnt[SDT_MAX_LEVELS + 2];  // level_off[l+1] - level_off[l]
+    // ---- refine scratch ----
+    uint32_t kd_n_old;                      // spatial nodes before this refine
+    uint32_t kd_sel;                        // leaves selected in the current split round
+    uint32_t kd_round_new;                  // nodes appended in the current round (2 * kd_sel << (r-1))
+    uint32_t kd_round_base;                 // first node id appended in the current round
+    uint32_t kd_prev_round_base;            // ... in the previous round
+    uint32_t kd_round_root_base;            // first root id created in the current round
+    uint32_t kd_stop;                       // capacity exhausted: later rounds select nothing
+    uint32_t kd_cap, quad_cap;              // arena sizes
+    uint32_t lvl_n[2];                      // nodes of the quadtree level being built (ping-pong)
+    uint32_t lvl_trunc;                     // capacity exhausted: the level being built becomes all leaves
+    uint32_t n_roots_old, n_quad_old;
+    uint32_t pad2[2];
+};
+
+enum DevError : uint32_t {
+    DEV_OK = 0, DEV_ERR_KD_CAPACITY = 1, DEV_ERR_QUAD_CAPACITY = 2
+};
+
+// What the query kernels need (by value).
+struct TreeView {
+    const DevHeader* hdr;
+    const uint32_t* kd_word;
+    const uint32_t* root_iidx;  // per root id: record index of the root node or SDT_NONE
+    const QRec* rec;
+};
+
+// ---------------------------------------------------------------------------
+// fp32 math: every operation separately rounded (nvcc -fmad=false, IEEE div / sqrt;
+// g++ -ffp-contract=off for the host emulation).  Same operation order as
+// oracle/drjit_math.py, which restates Dr.Jit's CEPHES-based sincos / atan2
+// (third-party, absent from the reference).
+// ---------------------------------------------------------------------------
+#define SDT_PI 3.14159265358979323846f
+#define SDT_TWO_PI 6.28318530717958647692f
+#define SDT_HALF_PI 1.57079632679489661923f
+#define SDT_QUARTER_PI 0.78539816339744830962f
+#define SDT_INV_FOUR_PI 0.07957747154594766788f
+
+SDT_HD uint32_t sdt_f2u(float f) { uint32_t u; memcpy(&u, &f, 4); return u; }
+SDT_HD float sdt_u2f(uint32_t u) { float f; memcpy(&f, &u, 4); return f; }
+
+SDT_HD void sdt_sincos(float x, float& s, float& c) {
+    const float xa = fabsf(x);
+    uint32_t j = (uint32_t)(xa * 1.27323954473516f);
+    j = (j + 1u) & 0xFFFFFFFEu;
+    const float y = (float)j;
+    const float xr = ((xa - y * 0.78515625f) - y * 2.4187564849853515625e-4f) - y * 3.77489497744594108e-8f;
+    const float z = xr * xr;
+    const float ps = (((-1.9515295891e-4f * z + 8.3321608736e-3f) * z + -1.6666654611e-1f) * z) * xr + xr;
+    const float pc = ((((2.443315711809948e-5f * z + -1.388731625493765e-3f) * z + 4.166664568298827e-2f) * z) * z - 0.5f * z) + 1.0f;
+    const bool swap = (j & 2u) != 0u;
+    s = swap ? pc : ps;
+    c = swap ? ps : pc;
+    const bool neg_s = ((j & 4u) != 0u) != (x < 0.0f);
+    const bool neg_c = ((j + 2u) & 4u) != 0u;
+    s = neg_s ? -s : s;
+    c = neg_c ? -c : c;
+}
+
+SDT_HD float sdt_atan2(float y, float x) {
+    const float ax = fabsf(x), ay = fabsf(y);
+    const float mn = fminf(ax, ay), mx = fmaxf(ax, ay);
+    const float a = mn / mx;
+    const bool big = a > 0.4142135623730950f;
+    const float t = big ? (a - 1.0f) / (a + 1.0f) : a;
+    const float base = big ? SDT_QUARTER_PI : 0.0f;
+    const float z = t * t;
+    const float p = ((((8.05374449538e-2f * z + -1.38776856032e-1f) * z + 1.99777106478e-1f) * z + -3.33329491539e-1f) * z) * t + t;
+    float r = base + p;
+    r = (ay > ax) ? SDT_HALF_PI - r : r;
+    r = (x < 0.0f) ? SDT_PI - r : r;
+    r = (y < 0.0f) ? -r : r;
+    r = (mx == 0.0f) ? 0.0f : r;
+    return r;
+}
+
+// canonicalToDir, src/common.py:100-129
+SDT_HD void sdt_canonical_to_dir(float px, float py, float& dx, float& dy, float& dz) {
+    const float cos_theta = 2.0f * py - 1.0f;
+    const float sin_theta = sqrtf(1.0f - cos_theta * cos_theta);
+    const float phi = SDT_TWO_PI * px;
+    float sp, cp;
+    sdt_sincos(phi, sp, cp);
+    dx = sin_theta * cp;
+    dy = sin_theta * sp;
+    dz = cos_theta;
+}
+
+// dirToCanonical, src/common.py:132-158
+SDT_HD void sdt_dir_to_canonical(float dx, float dy, float dz, float& px, float& py) {
+    const float cos_theta = fminf(fmaxf(dz, -1.0f), 1.0f);
+    float phi = sdt_atan2(dy, dx);
+    while (phi < 0.0f) phi += SDT_TWO_PI;     // loop "rotate phi"
+    px = phi / SDT_TWO_PI;
+    py = (cos_theta + 1.0f) / 2.0f;
+    // isfinite on all three components, else (0,0)
+    const bool fin = (fabsf(dx) <= 3.402823466e38f) && (fabsf(dy) <= 3.402823466e38f) && (fabsf(dz) <= 3.402823466e38f);
+    if (!fin) { px = 0.0f; py = 0.0f; }
+}
+
+// mi.luminance(Color3f): Rec.709 weights (Mitsuba constant)
+SDT_HD float sdt_luminance(float r, float g, float b) {
+    return (r * 0.212671f + g * 0.715160f) + b * 0.072169f;
+}
+
+// counter-based uniform in [0,1): two murmur3 finaliser rounds (oracle: counter_uniform)
+SDT_HD uint32_t sdt_fmix(uint32_t h) {
+    h ^= h >> 16; h *= 0x85EBCA6Bu; h ^= h >> 13; h *= 0xC2B2AE35u; h ^= h >> 16;
+    return h;
+}
+SDT_HD float sdt_uniform(uint32_t seed, uint32_t lane, uint32_t idx) {
+    uint32_t h = sdt_fmix(seed + lane * 0x9E3779B1u);
+    h = sdt_fmix(h ^ (idx * 0x85EBCA77u + 0x165667B1u));
+    return (float)(h >> 8) * 5.9604644775390625e-08f;
+}
+
+// Uniform stream of one lane: explicit u[lane*stride + idx] (clamped like the oracle's
+// ExplicitSampler) or the counter generator.
+struct LaneRng {
+    const float* u; uint32_t u_stride; uint32_t seed; uint32_t lane_id; uint32_t lane_index;
+    SDT_HD float get(uint32_t idx) const {
+        if (u) {
+            const uint32_t c = idx < u_stride ? idx : u_stride - 1u;
+            return SDT_LDG(u + (size_t)lane_index * u_stride + c);
+        }
+        return sdt_uniform(seed, lane_id, idx);
+    }
+};
+
+SDT_HD float sdt_ld(const float* p, int64_t stride, uint32_t i) { return SDT_LDG(p + (int64_t)i * stride); }
+
+// ---- spatial descent: KDTree.getLeafNodeIndex, src/kdtree.py:435-470 --------
+// Returns the leaf node id (0 for lanes outside the root box, like the reference).
+// `kd` is the smem-staged prefix of kd_word (n_smem words), `kdg` the full array.
+struct KdResult { uint32_t leaf; uint32_t root; bool inbox; };
+
+SDT_HD KdResult sdt_kd_descend(const uint32_t* __restrict__ kd, uint32_t n_smem,
+                               const uint32_t* __restrict__ kdg, const DevHeader* __restrict__ hdr,
+                               float px, float py, float pz) {
+    KdResult r;
+    float lo0 = hdr->bbox_min[0], lo1 = hdr->bbox_min[1], lo2 = hdr->bbox_min[2];
+    float hi0 = hdr->bbox_max[0], hi1 = hdr->bbox_max[1], hi2 = hdr->bbox_max[2];
+    // BoundingBox3f.contains: inclusive; NaN fails every comparison
+    r.inbox = (px >= lo0) && (px <= hi0) && (py >= lo1) && (py <= hi1) && (pz >= lo2) && (pz <= hi2);
+    r.leaf = 0;
+    r.root = hdr->root_of_node0;
+    if (!r.inbox) return r;
+    uint32_t node = 0;
+    uint32_t w = n_smem ? kd[0] : SDT_LDG(kdg);
+    int axis = 0;
+    while (!(w & SDT_KD_LEAF_BIT)) {
+        // children: left [lo, mid], right [mid, hi] on `axis`; left is assigned first,
+        // right second, so the right child wins on the plane (:462-468)
+        bool right;
+        if (axis == 0) { const float mid = (lo0 + hi0) / 2.0f; right = px >= mid; if (right) lo0 = mid; else hi0 = mid; }
+        else if (axis == 1) { const float mid = (lo1 + hi1) / 2.0f; right = py >= mid; if (right) lo1 = mid; else hi1 = mid; }
+        else { const float mid = (lo2 + hi2) / 2.0f; right = pz >= mid; if (right) lo2 = mid; else hi2 = mid; }
+        node = w + (right ? 1u : 0u);
+        w = (node < n_smem) ? kd[node] : SDT_LDG(kdg + node);
+        axis = (axis == 2) ? 0 : axis + 1;
+    }
+    r.leaf = node;
+    r.root = w & ~SDT_KD_LEAF_BIT;
+    return r;
+}
+
+SDT_HD void sdt_load_rec(const QRec* __restrict__ rec, uint32_t i, QRec& out) {
+#if defined(__CUDA_ARCH__)
+    const float4* p = reinterpret_cast<const float4*>(rec + i);
+    const float4 a = __ldg(p), b = __ldg(p + 1);
+    out.child_base = __float_as_uint(a.x);
+    out.interior_base = __float_as_uint(a.y);
+    out.leafmask = __float_as_uint(a.z);
+    out.own = a.w;
+    out.e[0] = b.x; out.e[1] = b.y; out.e[2] = b.z; out.e[3] = b.w;
+#else
+    out = rec[i];
+#endif
+}
+
+SDT_HD uint32_t sdt_popc4(uint32_t v) {
+    v &= 0xFu;
+    return (v & 1u) + ((v >> 1) & 1u) + ((v >> 2) & 1u) + ((v >> 3) & 1u);
+}
+
+// quadrant c (0..3 = child_1..child_4) of [lo,hi], src/quadtree.py:153-175:
+// c1 = [mid,max], c2 = upper-left, c3 = [min,mid], c4 = lower-right
+SDT_HD void sdt_quadrant(int c, float& lox, float& loy, float& hix, float& hiy) {
+    const float mx = (lox + hix) / 2.0f, my = (loy + hiy) / 2.0f;
+    if (c == 0) { lox = mx; loy = my; }
+    else if (c == 1) { hix = mx; loy = my; }
+    else if (c == 2) { hix = mx; hiy = my; }
+    else { lox = mx; hiy = my; }
+}
+
+// record index of child c, or SDT_NONE when it is a leaf
+SDT_HD uint32_t sdt_child_rec(const QRec& r, int c) {
+    if ((r.leafmask >> c) & 1u) return SDT_NONE;
+    return r.interior_base + sdt_popc4((~r.leafmask) & ((1u << c) - 1u));
+}
+
+// child that the DESCENT follows for a point of the node box: the reference assigns
+// c1..c4 in turn, so the LAST matching (inclusive) child box wins
+// (src/quadtree.py:1095-1098 for pdf, :424-438 for splat)
+SDT_HD int sdt_descend_child(float x, float y, float mx, float my) {
+    return (y <= my) ? ((x >= mx) ? 3 : 2) : ((x <= mx) ? 1 : 0);
+}
+// child whose ENERGY enters the pdf: FIRST matching child box (src/quadtree.py:1063-1075)
+SDT_HD int sdt_energy_child(float x, float y, float mx, float my) {
+    return (y >= my) ? ((x >= mx) ? 0 : 1) : ((x <= mx) ? 2 : 3);
+}
+
+// QuadTree.pdfQuadTree, src/quadtree.py:1001-1101, from canonical position (x,y) in
+// [0,1]^2.  ri = record index of the root (SDT_NONE: single-leaf tree).
+SDT_HD float sdt_quad_pdf(const QRec* __restrict__ rec, uint32_t ri, uint32_t root_node,
+                          float x, float y, uint32_t& node_out) {
+    float pdf = 1.0f;
+    float lox = 0.0f, loy = 0.0f, hix = 1.0f, hiy = 1.0f;
+    uint32_t node = root_node;
+    for (int level = 0; level < SDT_MAX_LEVELS; ++level) {
+        if (ri == SDT_NONE) { pdf = pdf * SDT_INV_FOUR_PI; break; }     // :1030
+        QRec r;
+        sdt_load_rec(rec, ri, r);
+        const float mx = (lox + hix) / 2.0f, my = (loy + hiy) / 2.0f;
+        const int ce = sdt_energy_child(x, y, mx, my);
+        const int cd = sdt_descend_child(x, y, mx, my);
+        const float ratio = (4.0f * r.e[ce]) / r.own;                   // :1084
+        pdf = pdf * ratio;
+        if (pdf != pdf) { pdf = 0.0f; break; }                          // :1090-1092
+        node = r.child_base + cd;
+        sdt_quadrant(cd, lox, loy, hix, hiy);
+        ri = sdt_child_rec(r, cd);
+    }
+    node_out = node;
+    return pdf;
+}
+
+// QuadTree.sampleQuadTree, src/quadtree.py:931-998.  Consumes 3 uniforms per visited
+// node: (u_x, u_y) at index 3*level, 3*level+1 (used at the leaf only, :956-962) and
+// u_select at 3*level+2 (:980).  While descending it also accumulates the pdf of the
+// path, with exactly the operations of pdfQuadTree, so that KDTree.sample's second
+// descent (src/kdtree.py:483-484) can be skipped whenever the canonical->dir->canonical
+// round trip stays strictly inside the sampled leaf cell (then both descents take the
+// same path and every tie rule is moot).
+struct QSample {
+    float x, y;                 // canonical position
+    uint32_t node;              // leaf node reached
+    float pdf_path;             // product of 4*childE/nodeE along the path (0 if it went NaN)
+    bool pdf_dead;              // the product went NaN (-> pdf 0, :1090-1092)
+    bool stuck;                 // NaN child energies: no bin matched (oracle: stop at (0,0))
+    float lox, loy, hix, hiy;   // leaf cell
+};
+
+SDT_HD QSample sdt_quad_sample(const QRec* __restrict__ rec, uint32_t ri, uint32_t root_node, const LaneRng& rng) {
+    QSample q;
+    q.x = 0.0f; q.y = 0.0f; q.node = root_node; q.pdf_path = 1.0f; q.pdf_dead = false; q.stuck = false;
+    q.lox = 0.0f; q.loy = 0.0f; q.hix = 1.0f; q.hiy = 1.0f;
+    for (uint32_t level = 0; level < SDT_MAX_LEVELS; ++level) {
+        if (ri == SDT_NONE) {
+            const float ux = rng.get(3u * level), uy = rng.get(3u * level + 1u);
+            q.x = q.lox + ux * (q.hix - q.lox);                          // :960-962
+            q.y = q.loy + uy * (q.hiy - q.loy);
+            return q;
+        }
+        QRec r;
+        sdt_load_rec(rec, ri, r);
+        const float e1 = r.e[0];
+        const float e2 = r.e[1] + e1;                                    // :975-977
+        const float e3 = r.e[2] + e2;
+        const float e4 = r.e[3] + e3;
+        const float s = rng.get(3u * level + 2u) * e4;                   // :980
+        int c = -1;                                                      // :983-991, later bins override
+        if (s < e1) c = 0;
+        if (e1 <= s && s < e2) c = 1;
+        if (e2 <= s && s < e3) c = 2;
+        if (e3 <= s) c = 3;
+        if (c < 0) { q.stuck = true; return q; }
+        if (!q.pdf_dead) {
+            const float ratio = (4.0f * r.e[c]) / r.own;
+            q.pdf_path = q.pdf_path * ratio;
+            if (q.pdf_path != q.pdf_path) { q.pdf_path = 0.0f; q.pdf_dead = true; }
+        }
+        q.node = r.child_base + (uint32_t)c;
+        sdt_quadrant(c, q.lox, q.loy, q.hix, q.hiy);
+        ri = sdt_child_rec(r, c);
+    }
+    q.stuck = true;   // deeper than SDT_MAX_LEVELS: impossible for a valid tree
+    return q;
+}
+
+// KDTree.sample after the spatial descent (src/kdtree.py:482-485).
+struct GuidedSample { float dx, dy, dz, pdf; uint32_t sample_node, pdf_node; };
+
+SDT_HD GuidedSample sdt_sample_tree(const TreeView& t, uint32_t root, const LaneRng& rng, bool fuse) {
+    GuidedSample g;
+    const uint32_t ri = SDT_LDG(t.root_iidx + root);
+    const QSample q = sdt_quad_sample(t.rec, ri, root, rng);
+    sdt_canonical_to_dir(q.x, q.y, g.dx, g.dy, g.dz);                    // :996
+    float px, py;
+    sdt_dir_to_canonical(g.dx, g.dy, g.dz, px, py);                      // :1016
+    g.sample_node = q.node;
+    if (fuse && !q.stuck && !q.pdf_dead && px > q.lox && px < q.hix && py > q.loy && py < q.hiy) {
+        g.pdf = q.pdf_path * SDT_INV_FOUR_PI;
+        g.pdf_node = q.node;
+    } else {
+        uint32_t nd;
+        g.pdf = sdt_quad_pdf(t.rec, ri, root, px, py, nd);
+        g.pdf_node = nd;
+    }
+    return g;
+}
+
+// Leaf reached by QuadTree.addDataPropagate's descent (src/quadtree.py:401-441) for a
+// canonical direction; SDT_NONE when the root box does not contain it (:405).
+SDT_HD uint32_t sdt_quad_leaf(const QRec* __restrict__ rec, uint32_t ri, uint32_t root_node, float x, float y) {
+    if (!(x >= 0.0f && x <= 1.0f && y >= 0.0f && y <= 1.0f)) return SDT_NONE;
+    float lox = 0.0f, loy = 0.0f, hix = 1.0f, hiy = 1.0f;
+    uint32_t node = root_node;
+    for (int level = 0; level < SDT_MAX_LEVELS && ri != SDT_NONE; ++level) {
+        // only child_base / interior_base / leafmask are needed: 12 of the 32 bytes
+        const uint32_t cb = SDT_LDG(&rec[ri].child_base);
+        const uint32_t ib = SDT_LDG(&rec[ri].interior_base);
+        const uint32_t lm = SDT_LDG(&rec[ri].leafmask);
+        const float mx = (lox + hix) / 2.0f, my = (loy + hiy) / 2.0f;
+        const int cd = sdt_descend_child(x, y, mx, my);
+        node = cb + (uint32_t)cd;
+        sdt_quadrant(cd, lox, loy, hix, hiy);
+        ri = ((lm >> cd) & 1u) ? SDT_NONE : ib + sdt_popc4((~lm) & ((1u << cd) - 1u));
+    }
+    return node;
+}
+
+// power heuristic, src/path_guiding_integrator.py:16-24 (dr.fma(b,b,a*a), NaN -> 0)
+SDT_HD float sdt_mis_weight(float a, float b) {
+    const float a2 = a * a;
+    const float den = fmaf(b, b, a2);
+    float w = (a > 0.0f) ? a2 / den : 0.0f;
+    if (w != w) w = 0.0f;
+    return w;
+}

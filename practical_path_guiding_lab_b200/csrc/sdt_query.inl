@@ -1,0 +1,302 @@
+// Wavefront queries on the frozen `prev` tree: locate / sample / pdf / guided bounce,
+// and the elementwise MIS helpers.  One thread per path vertex; the top of the spatial
+// tree is staged in shared memory by every CTA, the quadtree records stay L2-resident.
+
+// ---------------------------------------------------------------------------- launch
+#ifndef SDT_HOSTEMU
+template <class Lane>
+__global__ void __launch_bounds__(256) k_wavefront(Lane f, uint32_t n, uint32_t smem_cap) {
+    extern __shared__ uint32_t kd_s[];
+    const DevHeader* hdr = f.t.hdr;
+    uint32_t n_smem = hdr->n_kd;
+    if (n_smem > smem_cap) n_smem = smem_cap;
+    for (uint32_t j = threadIdx.x; j < n_smem; j += blockDim.x) kd_s[j] = __ldg(f.t.kd_word + j);
+    __syncthreads();
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+        f(kd_s, n_smem, i);
+}
+
+template <class Lane>
+static int launch_wavefront(sdt_handle h, cudaStream_t st, uint32_t n, const Lane& f, int block, int ctas_per_sm) {
+    if (n == 0) return SDT_OK;
+    uint32_t smem_nodes = (uint32_t)h->kd_smem_nodes;
+    if (smem_nodes > 12288u) smem_nodes = 12288u;     // 48 KB static limit without opt-in
+    const size_t smem = (size_t)smem_nodes * 4u;
+    static int occ_cache[8] = {0};
+    int& occ = occ_cache[(block >> 6) & 7];
+    if (occ == 0) {
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_wavefront<Lane>, block, smem) != cudaSuccess || occ < 1) occ = 1;
+    }
+    int per_sm = ctas_per_sm < occ ? ctas_per_sm : occ;
+    if (per_sm < 1) per_sm = 1;
+    uint32_t grid = (n + (uint32_t)block - 1u) / (uint32_t)block;
+    const uint32_t cap = (uint32_t)(h->num_sms * per_sm);
+    if (grid > cap) grid = cap;
+    k_wavefront<Lane><<<grid, block, smem, st>>>(f, n, smem_nodes);
+    ++h->launches;
+    h->last_stream = st;
+    return sdt_post_launch(h, "k_wavefront");
+}
+#else
+template <class Lane>
+static int launch_wavefront(sdt_handle h, cudaStream_t st, uint32_t n, const Lane& f, int, int) {
+    for (uint32_t i = 0; i < n; ++i) f(f.t.kd_word, 0u, i);
+    ++h->launches;
+    h->last_stream = st;
+    return SDT_OK;
+}
+#endif
+
+// ---------------------------------------------------------------------------- lanes
+struct LocateLane {
+    TreeView t;
+    sdt_vec3 pos; const uint8_t* active; uint32_t* leaf; uint32_t* root;
+    SDT_HD void operator()(const uint32_t* kd, uint32_t n_smem, uint32_t i) const {
+        const bool act = active ? SDT_LDG(active + i) != 0 : true;
+        uint32_t lf = 0, rt = 0;                     // inactive: node 0, masked gather -> 0
+        if (act) {
+            const KdResult r = sdt_kd_descend(kd, n_smem, t.kd_word, t.hdr, sdt_ld(pos.x, pos.stride, i),
+                                              sdt_ld(pos.y, pos.stride, i), sdt_ld(pos.z, pos.stride, i));
+            lf = r.leaf; rt = r.root;
+        }
+        if (leaf) leaf[i] = lf;
+        if (root) root[i] = rt;
+    }
+};
+
+struct SampleLane {
+    TreeView t;
+    sdt_vec3 pos; const uint8_t* active;
+    const float* u; uint32_t u_stride, seed, lane_offset;
+    sdt_vec3_out dir; float* pdf; uint32_t* dbg; int fuse;
+    SDT_HD void operator()(const uint32_t* kd, uint32_t n_smem, uint32_t i) const {
+        const bool act = active ? SDT_LDG(active + i) != 0 : true;
+        float dx = 0.0f, dy = 0.0f, dz = -1.0f, p = 1.0f;   // inactive lanes: pos (0,0) -> (0,0,-1), pdf 1
+        uint32_t d0 = 0, d1 = 0, d2 = 0, d3 = 0;
+        if (act) {
+            const KdResult r = sdt_kd_descend(kd, n_smem, t.kd_word, t.hdr, sdt_ld(pos.x, pos.stride, i),
+                                              sdt_ld(pos.y, pos.stride, i), sdt_ld(pos.z, pos.stride, i));
+            const LaneRng rng{u, u_stride, seed, lane_offset + i, i};
+            const GuidedSample g = sdt_sample_tree(t, r.root, rng, fuse != 0);
+            dx = g.dx; dy = g.dy; dz = g.dz; p = g.pdf;
+            d0 = r.leaf; d1 = r.root; d2 = g.sample_node; d3 = g.pdf_node;
+        }
+        const int64_t o = (int64_t)i * dir.stride;
+        dir.x[o] = dx; dir.y[o] = dy; dir.z[o] = dz;
+        pdf[i] = p;
+        if (dbg) { dbg[4u * i] = d0; dbg[4u * i + 1u] = d1; dbg[4u * i + 2u] = d2; dbg[4u * i + 3u] = d3; }
+    }
+};
+
+struct PdfLane {
+    TreeView t;
+    sdt_vec3 pos; sdt_vec3 dir; const uint8_t* active; float* pdf; uint32_t* dbg;
+    SDT_HD void operator()(const uint32_t* kd, uint32_t n_smem, uint32_t i) const {
+        const bool act = active ? SDT_LDG(active + i) != 0 : true;
+        float p = 1.0f;
+        uint32_t d0 = 0, d1 = 0, d2 = 0;
+        if (act) {
+            const KdResult r = sdt_kd_descend(kd, n_smem, t.kd_word, t.hdr, sdt_ld(pos.x, pos.stride, i),
+                                              sdt_ld(pos.y, pos.stride, i), sdt_ld(pos.z, pos.stride, i));
+            float x, y;
+            sdt_dir_to_canonical(sdt_ld(dir.x, dir.stride, i), sdt_ld(dir.y, dir.stride, i), sdt_ld(dir.z, dir.stride, i), x, y);
+            uint32_t nd;
+            p = sdt_quad_pdf(t.rec, SDT_LDG(t.root_iidx + r.root), r.root, x, y, nd);
+            d0 = r.leaf; d1 = r.root; d2 = nd;
+        }
+        pdf[i] = p;
+        if (dbg) { dbg[3u * i] = d0; dbg[3u * i + 1u] = d1; dbg[3u * i + 2u] = d2; }
+    }
+};
+
+// one bounce: mode 1 = sample the tree (src/path_guiding_integrator.py:301),
+// mode 2 = tree pdf of the BSDF-sampled direction (:307) + fused mixture (:310-311)
+struct GuidedLane {
+    TreeView t;
+    sdt_guided_args a; int fuse;
+    SDT_HD void operator()(const uint32_t* kd, uint32_t n_smem, uint32_t i) const {
+        const uint32_t m = SDT_LDG(a.mode + i);
+        if (m != 1u && m != 2u) return;
+        const KdResult r = sdt_kd_descend(kd, n_smem, t.kd_word, t.hdr, sdt_ld(a.pos.x, a.pos.stride, i),
+                                          sdt_ld(a.pos.y, a.pos.stride, i), sdt_ld(a.pos.z, a.pos.stride, i));
+        if (m == 1u) {
+            const LaneRng rng{a.u, a.u_stride, a.seed, a.lane_offset + i, i};
+            const GuidedSample g = sdt_sample_tree(t, r.root, rng, fuse != 0);
+            const int64_t o = (int64_t)i * a.dir.stride;
+            a.dir.x[o] = g.dx; a.dir.y[o] = g.dy; a.dir.z[o] = g.dz;
+            a.sdtree_pdf[i] = g.pdf;
+        } else {
+            float x, y;
+            sdt_dir_to_canonical(sdt_ld(a.wo.x, a.wo.stride, i), sdt_ld(a.wo.y, a.wo.stride, i), sdt_ld(a.wo.z, a.wo.stride, i), x, y);
+            uint32_t nd;
+            const float p = sdt_quad_pdf(t.rec, SDT_LDG(t.root_iidx + r.root), r.root, x, y, nd);
+            a.sdtree_pdf[i] = p;
+            if (a.bsdf_pdf && a.wo_pdf) {
+                const float f = a.bsdf_sampling_fraction;
+                const float wp = (f * SDT_LDG(a.bsdf_pdf + i)) + (1.0f - f) * p;       // :310
+                a.wo_pdf[i] = wp;
+                if (a.bsdf_value.x && a.weight.x) {
+                    const int64_t o = (int64_t)i * a.weight.stride;
+                    a.weight.x[o] = sdt_ld(a.bsdf_value.x, a.bsdf_value.stride, i) / wp;   // :311
+                    a.weight.y[o] = sdt_ld(a.bsdf_value.y, a.bsdf_value.stride, i) / wp;
+                    a.weight.z[o] = sdt_ld(a.bsdf_value.z, a.bsdf_value.stride, i) / wp;
+                }
+            }
+        }
+    }
+};
+
+struct MisNeeItem {
+    const float* bsdf_pdf_em; const float* sdtree_pdf_em; const float* pdf_with_delta; const float* pdf_without_delta;
+    const float* ds_pdf; const uint8_t* ds_delta; float f; int32_t iteration; float* surface_pdf_em; float* mis_em;
+    SDT_HD void operator()(uint32_t i) const {
+        const float bp = SDT_LDG(bsdf_pdf_em + i);
+        float surface = bp;
+        if (iteration > 1) {                                                            // :250
+            const float eps = 0.00001f;
+            const float pdf_diffuse = (SDT_LDG(pdf_with_delta + i) + eps) / (SDT_LDG(pdf_without_delta + i) + eps);   // :241
+            surface = f * bp + ((1.0f - f) * SDT_LDG(sdtree_pdf_em + i)) * pdf_diffuse;    // :247
+        }
+        if (surface_pdf_em) surface_pdf_em[i] = surface;
+        if (mis_em) {
+            const bool delta = ds_delta ? SDT_LDG(ds_delta + i) != 0 : false;
+            mis_em[i] = delta ? 1.0f : sdt_mis_weight(SDT_LDG(ds_pdf + i), surface);    // :253
+        }
+    }
+};
+
+struct MisMixtureItem {
+    const float* bsdf_pdf; const float* sdtree_pdf; sdt_vec3 bsdf_value; const uint8_t* do_mis; float f;
+    float* wo_pdf; sdt_vec3_out weight;
+    SDT_HD void operator()(uint32_t i) const {
+        const float bp = SDT_LDG(bsdf_pdf + i);
+        const bool mis = do_mis ? SDT_LDG(do_mis + i) != 0 : true;
+        const float wp = mis ? (f * bp) + (1.0f - f) * SDT_LDG(sdtree_pdf + i) : bp;
+        if (wo_pdf) wo_pdf[i] = wp;
+        if (weight.x && bsdf_value.x) {
+            const int64_t o = (int64_t)i * weight.stride;
+            weight.x[o] = sdt_ld(bsdf_value.x, bsdf_value.stride, i) / wp;
+            weight.y[o] = sdt_ld(bsdf_value.y, bsdf_value.stride, i) / wp;
+            weight.z[o] = sdt_ld(bsdf_value.z, bsdf_value.stride, i) / wp;
+        }
+    }
+};
+
+// ---------------------------------------------------------------------------- entry points
+extern "C" int sdt_locate(sdt_handle h, const sdt_vec3* pos, const uint8_t* active, uint32_t n,
+                          uint32_t* leaf, uint32_t* root, uint32_t flags, sdt_stream stream) {
+    if (!h) return SDT_ERR_INVALID;
+    SDT_CHECK(h, pos && pos->x, SDT_ERR_INVALID, "sdt_locate: pos is NULL");
+    cudaStream_t st = (cudaStream_t)stream;
+    Stager sg(h, st, flags);
+    SDT_TRY(sg.reserve((size_t)n * (12 + 1 + 8) + 4096));
+    LocateLane f{tree_view(h), sg.in3(*pos, n), sg.in_t(active, n), sg.out_t(leaf, n), sg.out_t(root, n)};
+    if (sg.status != SDT_OK) return sg.status;
+    SDT_TRY(launch_wavefront(h, st, n, f, h->query_block, h->query_ctas_per_sm));
+    return sg.finish(flags);
+}
+
+extern "C" int sdt_sample(sdt_handle h, const sdt_vec3* pos, const uint8_t* active, uint32_t n,
+                          const float* u, uint32_t u_stride, uint32_t seed, uint32_t lane_offset,
+                          const sdt_vec3_out* dir, float* pdf, uint32_t* dbg, uint32_t flags, sdt_stream stream) {
+    if (!h) return SDT_ERR_INVALID;
+    SDT_CHECK(h, pos && pos->x && dir && dir->x && pdf, SDT_ERR_INVALID, "sdt_sample: pos / dir / pdf is NULL");
+    SDT_CHECK(h, !u || u_stride >= 3, SDT_ERR_INVALID, "sdt_sample: u_stride must be >= 3");
+    cudaStream_t st = (cudaStream_t)stream;
+    Stager sg(h, st, flags);
+    SDT_TRY(sg.reserve((size_t)n * (12 + 1 + 12 + 4 + 16 + (u ? 4ull * u_stride : 0)) + 8192));
+    SampleLane f{tree_view(h), sg.in3(*pos, n), sg.in_t(active, n), sg.in_t(u, (size_t)n * u_stride), u_stride, seed, lane_offset,
+                 sg.out3(*dir, n), sg.out_t(pdf, n), sg.out_t(dbg, (size_t)n * 4), h->fuse_sample_pdf};
+    if (sg.status != SDT_OK) return sg.status;
+    SDT_TRY(launch_wavefront(h, st, n, f, h->query_block, h->query_ctas_per_sm));
+    return sg.finish(flags);
+}
+
+extern "C" int sdt_pdf(sdt_handle h, const sdt_vec3* pos, const sdt_vec3* dir, const uint8_t* active,
+                       uint32_t n, float* pdf, uint32_t* dbg, uint32_t flags, sdt_stream stream) {
+    if (!h) return SDT_ERR_INVALID;
+    SDT_CHECK(h, pos && pos->x && dir && dir->x && pdf, SDT_ERR_INVALID, "sdt_pdf: pos / dir / pdf is NULL");
+    cudaStream_t st = (cudaStream_t)stream;
+    Stager sg(h, st, flags);
+    SDT_TRY(sg.reserve((size_t)n * (24 + 1 + 4 + 12) + 8192));
+    PdfLane f{tree_view(h), sg.in3(*pos, n), sg.in3(*dir, n), sg.in_t(active, n), sg.out_t(pdf, n), sg.out_t(dbg, (size_t)n * 3)};
+    if (sg.status != SDT_OK) return sg.status;
+    SDT_TRY(launch_wavefront(h, st, n, f, h->query_block, h->query_ctas_per_sm));
+    return sg.finish(flags);
+}
+
+extern "C" int sdt_guided(sdt_handle h, const sdt_guided_args* a, uint32_t n, uint32_t flags, sdt_stream stream) {
+    if (!h) return SDT_ERR_INVALID;
+    SDT_CHECK(h, a && a->pos.x && a->mode && a->sdtree_pdf && a->dir.x, SDT_ERR_INVALID, "sdt_guided: pos / mode / dir / sdtree_pdf is NULL");
+    SDT_CHECK(h, !a->u || a->u_stride >= 3, SDT_ERR_INVALID, "sdt_guided: u_stride must be >= 3");
+    cudaStream_t st = (cudaStream_t)stream;
+    Stager sg(h, st, flags);
+    SDT_TRY(sg.reserve((size_t)n * (12 + 12 + 1 + 4 + 12 + 12 + 4 + 4 + 12 + (a->u ? 4ull * a->u_stride : 0)) + 16384));
+    sdt_guided_args d = *a;
+    d.pos = sg.in3(a->pos, n);
+    d.wo = sg.in3(a->wo, n);
+    d.mode = sg.in_t(a->mode, n);
+    d.u = sg.in_t(a->u, (size_t)n * a->u_stride);
+    d.bsdf_pdf = sg.in_t(a->bsdf_pdf, n);
+    d.bsdf_value = sg.in3(a->bsdf_value, n);
+    if (sg.host) {
+        // outputs are partial (mode-dependent): stage the caller's current contents first
+        SDT_CHECK(h, a->dir.stride == 3 || a->dir.stride == 1, SDT_ERR_INVALID, "sdt_guided: host dir must have stride 3 or 1");
+        sdt_vec3 cur_dir{a->dir.x, a->dir.y, a->dir.z, a->dir.stride};
+        sdt_vec3 dd = sg.in3(cur_dir, n);
+        d.dir = sdt_vec3_out{(float*)dd.x, (float*)dd.y, (float*)dd.z, dd.stride};
+        if (dd.stride == 3) sg.outs.push_back(Stager::Out{a->dir.x, (void*)dd.x, (size_t)n * 12});
+        else { sg.outs.push_back(Stager::Out{a->dir.x, (void*)dd.x, (size_t)n * 4}); sg.outs.push_back(Stager::Out{a->dir.y, (void*)dd.y, (size_t)n * 4}); sg.outs.push_back(Stager::Out{a->dir.z, (void*)dd.z, (size_t)n * 4}); }
+        const float* sp = sg.in_t((const float*)a->sdtree_pdf, n);
+        d.sdtree_pdf = (float*)sp; sg.outs.push_back(Stager::Out{a->sdtree_pdf, (void*)sp, (size_t)n * 4});
+        if (a->wo_pdf) { const float* wp = sg.in_t((const float*)a->wo_pdf, n); d.wo_pdf = (float*)wp; sg.outs.push_back(Stager::Out{a->wo_pdf, (void*)wp, (size_t)n * 4}); }
+        if (a->weight.x) {
+            SDT_CHECK(h, a->weight.stride == 3, SDT_ERR_INVALID, "sdt_guided: host weight must be interleaved (stride 3)");
+            const float* ww = sg.in_t((const float*)a->weight.x, (size_t)n * 3);
+            d.weight = sdt_vec3_out{(float*)ww, (float*)ww + 1, (float*)ww + 2, 3};
+            sg.outs.push_back(Stager::Out{a->weight.x, (void*)ww, (size_t)n * 12});
+        }
+    }
+    if (sg.status != SDT_OK) return sg.status;
+    GuidedLane f{tree_view(h), d, h->fuse_sample_pdf};
+    SDT_TRY(launch_wavefront(h, st, n, f, h->query_block, h->query_ctas_per_sm));
+    return sg.finish(flags);
+}
+
+extern "C" int sdt_mis_nee(sdt_handle h, uint32_t n, const float* bsdf_pdf_em, const float* sdtree_pdf_em,
+                           const float* pdf_with_delta, const float* pdf_without_delta, const float* ds_pdf,
+                           const uint8_t* ds_delta, float bsdf_sampling_fraction, int32_t iteration,
+                           float* surface_pdf_em, float* mis_em, uint32_t flags, sdt_stream stream) {
+    if (!h) return SDT_ERR_INVALID;
+    SDT_CHECK(h, bsdf_pdf_em && (iteration <= 1 || (sdtree_pdf_em && pdf_with_delta && pdf_without_delta)) && (!mis_em || ds_pdf),
+              SDT_ERR_INVALID, "sdt_mis_nee: missing input");
+    cudaStream_t st = (cudaStream_t)stream;
+    Stager sg(h, st, flags);
+    SDT_TRY(sg.reserve((size_t)n * 32 + 16384));
+    MisNeeItem f{sg.in_t(bsdf_pdf_em, n), sg.in_t(sdtree_pdf_em, n), sg.in_t(pdf_with_delta, n), sg.in_t(pdf_without_delta, n),
+                 sg.in_t(ds_pdf, n), sg.in_t(ds_delta, n), bsdf_sampling_fraction, iteration,
+                 sg.out_t(surface_pdf_em, n), sg.out_t(mis_em, n)};
+    if (sg.status != SDT_OK) return sg.status;
+    launch_items(exec_ctx(h, st), nullptr, n, f);
+    SDT_TRY(sdt_post_launch(h, "sdt_mis_nee"));
+    return sg.finish(flags);
+}
+
+extern "C" int sdt_mis_mixture(sdt_handle h, uint32_t n, const float* bsdf_pdf, const float* sdtree_pdf,
+                               const sdt_vec3* bsdf_value, const uint8_t* do_mis, float bsdf_sampling_fraction,
+                               float* wo_pdf, const sdt_vec3_out* weight, uint32_t flags, sdt_stream stream) {
+    if (!h) return SDT_ERR_INVALID;
+    SDT_CHECK(h, bsdf_pdf && sdtree_pdf, SDT_ERR_INVALID, "sdt_mis_mixture: missing input");
+    cudaStream_t st = (cudaStream_t)stream;
+    Stager sg(h, st, flags);
+    SDT_TRY(sg.reserve((size_t)n * 40 + 16384));
+    sdt_vec3 bv{nullptr, nullptr, nullptr, 0};
+    sdt_vec3_out wv{nullptr, nullptr, nullptr, 0};
+    if (bsdf_value) bv = sg.in3(*bsdf_value, n);
+    if (weight) wv = sg.out3(*weight, n);
+    MisMixtureItem f{sg.in_t(bsdf_pdf, n), sg.in_t(sdtree_pdf, n), bv, sg.in_t(do_mis, n), bsdf_sampling_fraction, sg.out_t(wo_pdf, n), wv};
+    if (sg.status != SDT_OK) return sg.status;
+    launch_items(exec_ctx(h, st), nullptr, n, f);
+    SDT_TRY(sdt_post_launch(h, "sdt_mis_mixture"));
+    return sg.finish(flags);
+}

@@ -1,0 +1,348 @@
+// Per-iteration refine, entirely on the device: refineAndPrepareSDTreeForNextIteration
+// (src/path_guiding_integrator.py:566-586).  The reference runs host loops with one
+// round trip and one reallocation per BFS level; here every pass is a grid-wide
+// "items" or "exclusive scan" launch whose sizes are read from the device header, so the
+// whole refine is one stream of launches with no host synchronisation.
+//
+//  spatial split  (KDTree.refine/split, src/kdtree.py:229-358): a leaf with count C at
+//     depth d ends up as a perfect subtree of s = min{s : C/2^s <= T} (capped by
+//     maxDepth-d) levels.  Round r of the reference's loop appends, for every original
+//     leaf with s >= r in ascending id, the 2^r children of its level-(r-1) descendants in
+//     path order -- so one scan over the original leaves per round yields every new node
+//     id and every new quadtree root id in the reference's numbering.
+//  quadtrees  (setRefinementThreshold :512-560, refine :563-637, clearTreeUnusedNode
+//     :844-851, copyTree :695-828): the new forest is built level by level straight into
+//     the canonical layout; a level's nodes decide (merge / keep / split) and one scan of
+//     the non-leaf flags places their children.  A leaf with energy E at depth d becomes a
+//     perfect 4-ary subtree of s = min{s : E/4^s <= thr} (capped by maxDepth-d) levels.
+
+#define SDT_KIND_VIRTUAL 1u   // node created by a split in this refine (no source node)
+#define SDT_KIND_REACHED 2u   // the reference's merge BFS reaches this node (:574-611)
+
+struct RefineCtx {
+    DevHeader* H0;            // header of the tree being refined
+    DevHeader* H1;            // header of the tree being built (also holds the scratch counters)
+    // spatial
+    uint32_t* kd_word; float* kd_count; uint32_t* kd_depth; uint32_t* kd_root; float* kd_bmin; float* kd_bmax;
+    float* kd_prev_count; uint8_t* kd_s; uint32_t* kd_sel; uint32_t* kd_rank_cur; uint32_t* kd_rank_prev; uint32_t* root_src;
+    // quadtrees: old set + current statistics, new set + scratch
+    const uint32_t* child0; const float* thr0; const float* e_cur;
+    uint32_t* child1; float* energy1; float* thr1; uint32_t* iidx1; QRec* rec1; uint32_t* root_iidx1;
+    uint32_t* s_src; uint8_t* s_kind; uint8_t* s_srem;
+    uint32_t no_quad;
+};
+
+struct RefineInit {
+    RefineCtx c;
+    SDT_HD void operator()() const {
+        *c.H1 = *c.H0;
+        DevHeader* H = c.H1;
+        H->kd_n_old = H->n_kd; H->n_roots_old = H->n_roots; H->n_quad_old = H->n_quad;
+        H->kd_sel = 0; H->kd_round_new = 0; H->kd_round_base = H->n_kd; H->kd_prev_round_base = H->n_kd;
+        H->kd_round_root_base = H->n_roots; H->kd_stop = 0; H->lvl_trunc = 0;
+        H->refine_count = H->refine_count + 1u;
+    }
+};
+
+// ---- spatial --------------------------------------------------------------------
+struct KdLevelsItem {       // s per original leaf (KDTree.refine's condition, :346-347)
+    RefineCtx c;
+    SDT_HD void operator()(uint32_t i) const {
+        uint32_t s = 0;
+        if (c.kd_word[i] & SDT_KD_LEAF_BIT) {
+            const float T = c.H1->max_leaf_size;
+            const uint32_t d = c.kd_depth[i], maxd = c.H1->kd_max_depth;
+            float v = c.kd_count[i];
+            while (v > T && d + s < maxd) { if (v > 0.0f) v = v / 2.0f; ++s; }    // :261-264
+        }
+        c.kd_s[i] = (uint8_t)s;
+    }
+};
+struct RootIdentityItem { uint32_t* root_src; SDT_HD void operator()(uint32_t r) const { root_src[r] = r; } };
+
+struct KdRoundFlag {
+    RefineCtx c; uint32_t r;
+    SDT_HD uint32_t operator()(uint32_t i) const { return (!c.H1->kd_stop && c.kd_s[i] >= r) ? 1u : 0u; }
+};
+struct KdRoundEmit {
+    RefineCtx c;
+    SDT_HD void operator()(uint32_t i, uint32_t rank, uint32_t v) const {
+        if (v) { c.kd_sel[rank] = i; c.kd_rank_cur[i] = rank; }
+    }
+};
+struct KdRoundFin {
+    RefineCtx c; uint32_t r;
+    SDT_HD void operator()(uint32_t total) const {
+        DevHeader* H = c.H1;
+        uint64_t splits = (uint64_t)total << (r - 1u);
+        if ((uint64_t)H->n_kd + 2u * splits > H->kd_cap) {     // arena exhausted: stop splitting, flag it
+            if (total) { H->error |= DEV_ERR_KD_CAPACITY; H->kd_stop = 1; }
+            splits = 0; total = 0;
+        }
+        H->kd_sel = total;
+        H->kd_round_new = (uint32_t)(2u * splits);
+        H->kd_prev_round_base = H->kd_round_base;
+        H->kd_round_base = H->n_kd;
+        H->kd_round_root_base = H->n_roots;
+        H->n_kd += (uint32_t)(2u * splits);
+        H->n_roots += (uint32_t)splits;
+    }
+};
+// one thread per node appended in round r (KDTree.split, :229-323)
+struct KdMakeNodeItem {
+    RefineCtx c; uint32_t r;
+    SDT_HD void operator()(uint32_t j) const {
+        const DevHeader* H = c.H1;
+        const uint32_t i = j >> 1, b = j & 1u;                 // i-th split node of the round, left/right
+        const uint32_t sh = r - 1u;
+        const uint32_t lr = i >> sh, k = i & ((1u << sh) - 1u);
+        const uint32_t leaf0 = c.kd_sel[lr];                   // original leaf this subtree hangs from
+        uint32_t parent = leaf0;
+        if (r > 1u) parent = H->kd_prev_round_base + 2u * ((c.kd_rank_prev[leaf0] << (sh - 1u)) + (k >> 1)) + (k & 1u);
+        const uint32_t node = H->kd_round_base + j;
+        if (b == 0u) c.kd_word[parent] = H->kd_round_base + 2u * i;       // :243-249, isLeaf <- False
+        const uint32_t d = c.kd_depth[parent];
+        c.kd_depth[node] = d + 1u;                                        // :255-258
+        const float v = c.kd_count[parent];
+        c.kd_count[node] = v > 0.0f ? v / 2.0f : v;                       // :261-264
+        const uint32_t axis = d % 3u;                                     // :277
+        for (uint32_t a = 0; a < 3u; ++a) {
+            const float lo = c.kd_bmin[3u * parent + a], hi = c.kd_bmax[3u * parent + a];
+            const float mid = (lo + hi) / 2.0f;                           // :270
+            c.kd_bmin[3u * node + a] = (a == axis && b == 1u) ? mid : lo;
+            c.kd_bmax[3u * node + a] = (a == axis && b == 0u) ? mid : hi;
+        }
+        // left inherits the parent's quadtree, right owns a copy with a new root id (:316-323)
+        uint32_t root = c.kd_root[parent];
+        if (b == 1u) {
+            root = H->kd_round_root_base + i;
+            c.root_src[root] = c.kd_root[leaf0];
+        }
+        c.kd_root[node] = root;
+        c.kd_word[node] = SDT_KD_LEAF_BIT | root;
+    }
+};
+
+// ---- quadtrees --------------------------------------------------------------------
+struct QInit {
+    RefineCtx c;
+    SDT_HD void operator()() const {
+        DevHeader* H = c.H1;
+        uint32_t R = H->n_roots;
+        if (R > H->quad_cap) { H->error |= DEV_ERR_QUAD_CAPACITY; R = H->quad_cap; }
+        for (int l = 0; l < SDT_MAX_LEVELS + 2; ++l) { H->level_off[l] = R; H->level_cnt[l] = 0; }
+        H->level_off[0] = 0;
+        H->lvl_n[0] = R; H->lvl_n[1] = 0; H->lvl_trunc = 0;
+    }
+};
+struct QRootItem {          // level 0: tree r copies the tree of root_src[r]; thr = E_root/100 (:519)
+    RefineCtx c;
+    SDT_HD void operator()(uint32_t r) const {
+        const uint32_t src = c.root_src[r];
+        c.s_src[r] = src;
+        c.s_kind[r] = SDT_KIND_REACHED;
+        const float e = c.e_cur[src];
+        c.energy1[r] = e;
+        c.thr1[r] = c.no_quad ? c.thr0[src] : e / 100.0f;
+    }
+};
+
+struct QDecision { uint32_t nonleaf; uint32_t virt; uint32_t srem; uint32_t reached; uint32_t old_cb; };
+
+SDT_HD QDecision sdt_q_decide(const RefineCtx& c, uint32_t id, uint32_t level) {
+    QDecision d;
+    d.nonleaf = 0; d.virt = 0; d.srem = 0; d.reached = 0; d.old_cb = 0;
+    const uint32_t kind = c.s_kind[id];
+    if (kind & SDT_KIND_VIRTUAL) {
+        const uint32_t s = c.s_srem[id];
+        d.nonleaf = s > 0u; d.virt = 1; d.srem = s ? s - 1u : 0u;
+        return d;
+    }
+    const uint32_t cb = c.child0[c.s_src[id]];
+    const float e = c.energy1[id], thr = c.thr1[id];
+    const bool reached = (kind & SDT_KIND_REACHED) != 0u;
+    if (c.no_quad) { d.nonleaf = cb != 0u; d.old_cb = cb; d.reached = reached; return d; }
+    // merge pass (:574-611): a reached non-leaf below the threshold becomes a leaf
+    const bool merged = cb != 0u && reached && (e < thr);
+    if (cb != 0u && !merged) {
+        d.nonleaf = 1; d.old_cb = cb; d.reached = reached && (e >= thr);
+        return d;
+    }
+    // split pass (:617-637): E > thr and depth < maxDepth, children get E/4
+    uint32_t s = 0;
+    float v = e;
+    const uint32_t maxd = c.H1->quad_max_depth;
+    while (v > thr && level + s < maxd) { v = v / 4.0f; ++s; }
+    d.nonleaf = s > 0u; d.virt = 1; d.srem = s ? s - 1u : 0u;
+    return d;
+}
+
+struct QLevelFlag {
+    RefineCtx c; uint32_t level; uint32_t last;   // last: deepest level the arena layout allows
+    SDT_HD uint32_t operator()(uint32_t i) const {
+        if (c.H1->lvl_trunc || last) return 0u;
+        return sdt_q_decide(c, c.H1->level_off[level] + i, level).nonleaf;
+    }
+};
+struct QLevelFin {
+    RefineCtx c; uint32_t level;
+    SDT_HD void operator()(uint32_t total) const {
+        DevHeader* H = c.H1;
+        const uint32_t next_off = H->level_off[level + 1u];
+        if ((uint64_t)next_off + 4ull * total > H->quad_cap) {   // arena exhausted: cut the forest here
+            if (total) { H->error |= DEV_ERR_QUAD_CAPACITY; H->lvl_trunc = 1; }
+            total = 0;
+        }
+        H->level_cnt[level] = H->level_off[level + 1u] - H->level_off[level];
+        H->level_off[level + 2u] = next_off + 4u * total;
+        H->lvl_n[(level + 1u) & 1u] = 4u * total;
+    }
+};
+struct QLevelEmit {
+    RefineCtx c; uint32_t level;
+    SDT_HD void operator()(uint32_t i, uint32_t rank, uint32_t v) const {
+        const DevHeader* H = c.H1;
+        const uint32_t id = H->level_off[level] + i;
+        if (!v) { c.child1[id] = 0u; return; }
+        const QDecision d = sdt_q_decide(c, id, level);
+        const uint32_t cb = H->level_off[level + 1u] + 4u * rank;
+        c.child1[id] = cb;
+        const float thr = c.thr1[id];
+        if (d.virt) {
+            const float e4 = c.energy1[id] / 4.0f;                // :133-134
+            for (uint32_t k = 0; k < 4u; ++k) {
+                c.s_kind[cb + k] = SDT_KIND_VIRTUAL;
+                c.s_srem[cb + k] = (uint8_t)d.srem;
+                c.energy1[cb + k] = e4;
+                c.thr1[cb + k] = thr;                             // :139-143
+            }
+        } else {
+            for (uint32_t k = 0; k < 4u; ++k) {
+                const uint32_t o = d.old_cb + k;
+                c.s_src[cb + k] = o;
+                c.s_kind[cb + k] = d.reached ? SDT_KIND_REACHED : 0u;
+                c.energy1[cb + k] = c.e_cur[o];
+                c.thr1[cb + k] = c.no_quad ? c.thr0[o] : thr;
+            }
+        }
+    }
+};
+struct QFinalize {
+    RefineCtx c; uint32_t levels_bound;
+    SDT_HD void operator()() const {
+        DevHeader* H = c.H1;
+        H->n_quad = H->level_off[levels_bound];
+        uint32_t nl = 0;
+        for (uint32_t l = 0; l < SDT_MAX_LEVELS + 1u; ++l) {
+            if (l >= levels_bound) { H->level_off[l + 1u] = H->n_quad; }
+            H->level_cnt[l] = H->level_off[l + 1u] - H->level_off[l];
+            if (H->level_cnt[l]) nl = l + 1u;
+        }
+        H->n_levels = nl;
+        H->kd_leaves = H->n_roots;
+        H->root_of_node0 = c.kd_root[0];
+    }
+};
+
+// ---- records for the query kernels ----------------------------------------------
+struct RecFlag { const uint32_t* child; SDT_HD uint32_t operator()(uint32_t i) const { return child[i] ? 1u : 0u; } };
+struct RecEmit { uint32_t* iidx; SDT_HD void operator()(uint32_t i, uint32_t rank, uint32_t) const { iidx[i] = rank; } };
+struct RecFin { DevHeader* H; SDT_HD void operator()(uint32_t total) const { H->n_interior = total; } };
+struct RecBuildItem {
+    const DevHeader* H; const uint32_t* child; const float* energy; const uint32_t* iidx; QRec* rec; uint32_t* root_iidx;
+    SDT_HD void operator()(uint32_t i) const {
+        const uint32_t cb = child[i];
+        if (i < H->n_roots) root_iidx[i] = cb ? iidx[i] : SDT_NONE;
+        if (!cb) return;
+        QRec r;
+        r.child_base = cb;
+        r.interior_base = iidx[cb];
+        r.leafmask = 0;
+        for (uint32_t k = 0; k < 4u; ++k) {
+            if (!child[cb + k]) r.leafmask |= 1u << k;
+            r.e[k] = energy[cb + k];
+        }
+        r.own = energy[i];
+        rec[iidx[i]] = r;
+    }
+};
+struct RecEnergyItem {      // refresh own / child energies only (topology unchanged)
+    const uint32_t* child; const float* energy; const uint32_t* iidx; QRec* rec;
+    SDT_HD void operator()(uint32_t i) const {
+        const uint32_t cb = child[i];
+        if (!cb) return;
+        QRec* r = rec + iidx[i];
+        r->own = energy[i];
+        for (uint32_t k = 0; k < 4u; ++k) r->e[k] = energy[cb + k];
+    }
+};
+
+static void sdt_build_records(sdt_handle h, const ExecCtx& x, QuadSet& s) {
+    launch_scan(x, &s.hdr->n_quad, 0, RecFlag{s.child}, RecEmit{s.iidx}, RecFin{s.hdr});
+    launch_items(x, &s.hdr->n_quad, 0, RecBuildItem{s.hdr, s.child, s.energy, s.iidx, s.rec, s.root_iidx});
+}
+
+struct KdRollItem {         // prev.vertCount <- current.vertCount; current <- 0 (:141-153, :401-432)
+    float* cnt; float* prev;
+    SDT_HD void operator()(uint32_t i) const { prev[i] = cnt[i]; cnt[i] = 0.0f; }
+};
+struct ZeroItem { float* p; SDT_HD void operator()(uint32_t i) const { p[i] = 0.0f; } };
+
+extern "C" int sdt_refine(sdt_handle h, uint32_t flags, sdt_stream stream) {
+    if (!h) return SDT_ERR_INVALID;
+    cudaStream_t st = (cudaStream_t)stream;
+    SDT_TRY(sdt_complete_stats(h, st));
+    const ExecCtx x = exec_ctx(h, st);
+    QuadSet& s0 = h->set[h->cur];
+    QuadSet& s1 = h->set[1 - h->cur];
+    RefineCtx c;
+    c.H0 = s0.hdr; c.H1 = s1.hdr;
+    c.kd_word = h->kd_word; c.kd_count = h->kd_count; c.kd_depth = h->kd_depth; c.kd_root = h->kd_root;
+    c.kd_bmin = h->kd_bmin; c.kd_bmax = h->kd_bmax; c.kd_prev_count = h->kd_prev_count; c.kd_s = h->kd_s;
+    c.kd_sel = h->kd_sel; c.kd_rank_cur = h->kd_rank[0]; c.kd_rank_prev = h->kd_rank[1]; c.root_src = h->root_src;
+    c.child0 = s0.child; c.thr0 = s0.thr; c.e_cur = h->q_ecur;
+    c.child1 = s1.child; c.energy1 = s1.energy; c.thr1 = s1.thr; c.iidx1 = s1.iidx; c.rec1 = s1.rec; c.root_iidx1 = s1.root_iidx;
+    c.s_src = h->s_src; c.s_kind = h->s_kind; c.s_srem = h->s_srem;
+    c.no_quad = (flags & SDT_REFINE_NO_QUAD) ? 1u : 0u;
+
+    launch_single(x, RefineInit{c});
+    launch_items(x, &c.H1->n_roots_old, 0, RootIdentityItem{h->root_src});
+    if (!(flags & SDT_REFINE_NO_KD)) {
+        launch_items(x, &c.H1->kd_n_old, 0, KdLevelsItem{c});
+        for (uint32_t r = 1; r <= (uint32_t)h->cfg.kd_max_depth; ++r) {
+            RefineCtx cr = c;
+            cr.kd_rank_cur = h->kd_rank[r & 1u]; cr.kd_rank_prev = h->kd_rank[(r & 1u) ^ 1u];
+            launch_scan(x, &c.H1->kd_n_old, 0, KdRoundFlag{cr, r}, KdRoundEmit{cr}, KdRoundFin{cr, r});
+            launch_items(x, &c.H1->kd_round_new, 0, KdMakeNodeItem{cr, r});
+        }
+    }
+    uint32_t levels_bound = (uint32_t)h->cfg.quad_max_depth + 1u;
+    if (levels_bound < h->levels_hint) levels_bound = h->levels_hint;
+    if (levels_bound > SDT_MAX_LEVELS) levels_bound = SDT_MAX_LEVELS;
+    launch_single(x, QInit{c});
+    launch_items(x, &c.H1->lvl_n[0], 0, QRootItem{c});
+    for (uint32_t l = 0; l < levels_bound; ++l)
+        launch_scan(x, &c.H1->lvl_n[l & 1u], 0, QLevelFlag{c, l, (uint32_t)(l + 1u == levels_bound)}, QLevelEmit{c, l}, QLevelFin{c, l});
+    launch_single(x, QFinalize{c, levels_bound});
+    sdt_build_records(h, x, s1);
+    // prev <- current, then reset current (:582-586)
+    launch_items(x, &c.H1->n_kd, 0, KdRollItem{h->kd_count, h->kd_prev_count});
+    launch_items(x, &c.H1->n_quad, 0, ZeroItem{h->q_ecur});
+    SDT_TRY(sdt_post_launch(h, "sdt_refine"));
+    h->cur = 1 - h->cur;
+    h->levels_hint = levels_bound;
+    h->stats_complete = true;
+    if (flags & SDT_SYNC) SDT_CUDA(h, cudaStreamSynchronize(st));
+    return SDT_OK;
+}
+
+extern "C" int sdt_reset_stats(sdt_handle h, sdt_stream stream) {
+    if (!h) return SDT_ERR_INVALID;
+    cudaStream_t st = (cudaStream_t)stream;
+    const ExecCtx x = exec_ctx(h, st);
+    QuadSet& s = h->set[h->cur];
+    launch_items(x, &s.hdr->n_kd, 0, ZeroItem{h->kd_count});
+    launch_items(x, &s.hdr->n_quad, 0, ZeroItem{h->q_ecur});
+    h->stats_complete = true;
+    return sdt_post_launch(h, "sdt_reset_stats");
+}

@@ -1,0 +1,211 @@
+// Radiance-record splatting into `current` (KDTree.addDataPropagate src/kdtree.py:180-225,
+// QuadTree.addDataPropagate src/quadtree.py:389-464) and the bottom-up sweeps that turn
+// leaf statistics into the per-node statistics the reference accumulates with one
+// atomic per visited node.
+//
+// The reference adds the count / energy at EVERY node of the root->leaf path.  Here a
+// record issues ONE atomic per descent -- on the leaf -- and the interior sums are
+// rebuilt level by level afterwards (interior = sum of its children, in fp32, inside the
+// 1e-4 relative tolerance the reference's own atomic ordering already has).  Lanes of a
+// warp that hit the same leaf are combined first (match_any + shuffle reduction), so a
+// hot leaf costs one atomic per warp instead of 32 serialised ones.
+
+struct SplatTarget {
+    float* kd_count;
+    float* q_ecur;
+    uint32_t store_nee;
+};
+
+// one warp-aggregated fp32 add: lanes with the same address are summed by the lowest lane
+SDT_HD void sdt_splat_add(float* base, uint32_t idx, float v, bool valid) {
+#if defined(__CUDA_ARCH__)
+    const uint32_t act = __ballot_sync(__activemask(), valid);
+    if (!valid) return;
+    const uint32_t peers = __match_any_sync(act, idx);
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t leader = __ffs(peers) - 1u;
+    if (peers == (1u << lane)) { atomicAdd(base + idx, v); return; }
+    // sum the peer group in ascending lane order (deterministic within the warp)
+    float acc = 0.0f;
+    uint32_t rest = peers;
+    while (rest) {
+        const uint32_t src = __ffs(rest) - 1u;
+        acc += __shfl_sync(peers, v, src);
+        rest &= rest - 1u;
+    }
+    if (lane == leader) atomicAdd(base + idx, acc);
+#else
+    if (valid) base[idx] += v;
+#endif
+}
+
+// one record through both trees
+SDT_HD void sdt_splat_one(const TreeView& t, const SplatTarget& tg, const uint32_t* kd, uint32_t n_smem, bool act,
+                          float px, float py, float pz, float dx, float dy, float radiance, float wo_pdf,
+                          float nr, float ng, float nb, float ndx, float ndy) {
+    KdResult r;
+    r.leaf = 0; r.root = 0; r.inbox = false;
+    if (act) r = sdt_kd_descend(kd, n_smem, t.kd_word, t.hdr, px, py, pz);
+    // src/kdtree.py:199: +1.0f (fp32 counter; exact below 2^24, then it sticks like the reference's)
+    sdt_splat_add(tg.kd_count, r.leaf, 1.0f, act && r.inbox);
+    // src/kdtree.py:224: the root id is gathered UNMASKED -- out-of-box records go to the tree of node 0
+    uint32_t ri = SDT_NONE;
+    if (act) ri = SDT_LDG(t.root_iidx + r.root);
+    const float irr = (wo_pdf > 0.0f) ? radiance / wo_pdf : 0.0f;                      // src/quadtree.py:451
+    uint32_t leaf = SDT_NONE;
+    if (act && irr != 0.0f) leaf = sdt_quad_leaf(t.rec, ri, r.root, dx, dy);
+    sdt_splat_add(tg.q_ecur, leaf, irr, leaf != SDT_NONE);
+    if (tg.store_nee) {                                                               // :455-464
+        const float lum = sdt_luminance(nr, ng, nb);
+        const float irr2 = (wo_pdf > 0.0f) ? lum / wo_pdf : 0.0f;
+        uint32_t leaf2 = SDT_NONE;
+        if (act && irr2 != 0.0f) leaf2 = sdt_quad_leaf(t.rec, ri, r.root, ndx, ndy);
+        sdt_splat_add(tg.q_ecur, leaf2, irr2, leaf2 != SDT_NONE);
+    }
+}
+
+struct SplatRecordsLane {
+    TreeView t; SplatTarget tg; sdt_records r;
+    SDT_HD void operator()(const uint32_t* kd, uint32_t n_smem, uint32_t i) const {
+        const bool act = r.active ? SDT_LDG(r.active + i) != 0 : true;
+        float nr = 0.0f, ng = 0.0f, nb = 0.0f, ndx = 0.0f, ndy = 0.0f;
+        if (tg.store_nee && r.radiance_nee.x && r.direction_nee.x) {
+            nr = sdt_ld(r.radiance_nee.x, r.radiance_nee.stride, i);
+            ng = sdt_ld(r.radiance_nee.y, r.radiance_nee.stride, i);
+            nb = sdt_ld(r.radiance_nee.z, r.radiance_nee.stride, i);
+            ndx = sdt_ld(r.direction_nee.x, r.direction_nee.stride, i);
+            ndy = sdt_ld(r.direction_nee.y, r.direction_nee.stride, i);
+        }
+        sdt_splat_one(t, tg, kd, n_smem, act,
+                      sdt_ld(r.position.x, r.position.stride, i), sdt_ld(r.position.y, r.position.stride, i), sdt_ld(r.position.z, r.position.stride, i),
+                      sdt_ld(r.direction.x, r.direction.stride, i), sdt_ld(r.direction.y, r.direction.stride, i),
+                      SDT_LDG(r.radiance + i), SDT_LDG(r.wo_pdf + i), nr, ng, nb, ndx, ndy);
+    }
+};
+
+SDT_HD float sdt_nan0(float v) { return (v != v) ? 0.0f : v; }
+
+// processPathData + scatterDataIntoSDTree (src/path_guiding_integrator.py:434-500) fused
+// in front of the splat: no compaction pass, the filter just masks the lane.
+struct SplatPathLane {
+    TreeView t; SplatTarget tg; sdt_path_data p;
+    SDT_HD void operator()(const uint32_t* kd, uint32_t n_smem, uint32_t i) const {
+        const uint32_t ray = i / p.max_depth;                                          // :440
+        float inc[3];
+        const float* lf[3] = {p.l_final.x, p.l_final.y, p.l_final.z};
+        const float* tr[3] = {p.throughput_radiance.x, p.throughput_radiance.y, p.throughput_radiance.z};
+        const float* tb[3] = {p.throughput_bsdf.x, p.throughput_bsdf.y, p.throughput_bsdf.z};
+        const float* bs[3] = {p.bsdf.x, p.bsdf.y, p.bsdf.z};
+        for (int c = 0; c < 3; ++c) {
+            float out = (sdt_ld(lf[c], p.l_final.stride, ray) - sdt_ld(tr[c], p.throughput_radiance.stride, i))
+                        / sdt_ld(tb[c], p.throughput_bsdf.stride, i);                 // :443
+            out = sdt_nan0(out);                                                       // :444
+            inc[c] = sdt_nan0(out / sdt_ld(bs[c], p.bsdf.stride, i));                  // :448-449
+        }
+        const float radiance = sdt_nan0(sdt_luminance(inc[0], inc[1], inc[2]));       // :452, :466
+        if (p.radiance_out) p.radiance_out[i] = radiance;
+        float nr = 0.0f, ng = 0.0f, nb = 0.0f, ndx = 0.0f, ndy = 0.0f;
+        if (p.radiance_nee.x) {
+            nr = sdt_nan0(sdt_ld(p.radiance_nee.x, p.radiance_nee.stride, i));         // :467
+            ng = sdt_nan0(sdt_ld(p.radiance_nee.y, p.radiance_nee.stride, i));
+            nb = sdt_nan0(sdt_ld(p.radiance_nee.z, p.radiance_nee.stride, i));
+        }
+        if (p.direction_nee.x) {
+            ndx = sdt_ld(p.direction_nee.x, p.direction_nee.stride, i);
+            ndy = sdt_ld(p.direction_nee.y, p.direction_nee.stride, i);
+        }
+        const float wo_pdf = SDT_LDG(p.wo_pdf + i);
+        const bool both_zero = (radiance == 0.0f) && (sdt_luminance(nr, ng, nb) == 0.0f);  // :470-472
+        bool act = p.active ? SDT_LDG(p.active + i) != 0 : true;
+        act = act && !both_zero && !(wo_pdf == 0.0f) && !(wo_pdf != wo_pdf);           // :475-478
+        sdt_splat_one(t, tg, kd, n_smem, act,
+                      sdt_ld(p.position.x, p.position.stride, i), sdt_ld(p.position.y, p.position.stride, i), sdt_ld(p.position.z, p.position.stride, i),
+                      sdt_ld(p.direction.x, p.direction.stride, i), sdt_ld(p.direction.y, p.direction.stride, i),
+                      radiance, wo_pdf, nr, ng, nb, ndx, ndy);
+    }
+};
+
+// ---- bottom-up sweeps -------------------------------------------------------------
+// quadtree level l (deepest first): interior energy = ((c1+c2)+c3)+c4
+struct QuadSweepItem {
+    const DevHeader* hdr; const uint32_t* child; float* e; uint32_t level;
+    SDT_HD void operator()(uint32_t i) const {
+        const uint32_t id = hdr->level_off[level] + i;
+        const uint32_t cb = child[id];
+        if (cb) e[id] = ((e[cb] + e[cb + 1u]) + e[cb + 2u]) + e[cb + 3u];
+    }
+};
+// spatial nodes of depth d: interior count = left + right, sticking at 2^24 like a
+// chain of fp32 "+1.0f" atomics does
+struct KdSweepItem {
+    const uint32_t* kd_word; const uint32_t* kd_depth; float* cnt; uint32_t depth;
+    SDT_HD void operator()(uint32_t i) const {
+        const uint32_t w = kd_word[i];
+        if ((w & SDT_KD_LEAF_BIT) || kd_depth[i] != depth) return;
+        const float s = cnt[w] + cnt[w + 1u];
+        cnt[i] = s > 16777216.0f ? 16777216.0f : s;
+    }
+};
+
+static int sdt_complete_stats(sdt_handle h, cudaStream_t st) {
+    if (h->stats_complete) return SDT_OK;
+    const ExecCtx x = exec_ctx(h, st);
+    const QuadSet& s = h->set[h->cur];
+    // level sizes live on the device
+    for (int l = (int)h->levels_hint - 1; l >= 0; --l)
+        launch_items(x, &s.hdr->level_cnt[l], 0, QuadSweepItem{s.hdr, s.child, h->q_ecur, (uint32_t)l});
+    for (int d = h->cfg.kd_max_depth - 1; d >= 0; --d)
+        launch_items(x, &s.hdr->n_kd, 0, KdSweepItem{h->kd_word, h->kd_depth, h->kd_count, (uint32_t)d});
+    SDT_TRY(sdt_post_launch(h, "sdt_complete_stats"));
+    h->stats_complete = true;
+    return SDT_OK;
+}
+
+// ---------------------------------------------------------------------------- entry points
+extern "C" int sdt_splat_records(sdt_handle h, const sdt_records* rec, uint32_t n, uint32_t flags, sdt_stream stream) {
+    if (!h) return SDT_ERR_INVALID;
+    SDT_CHECK(h, rec && rec->position.x && rec->direction.x && rec->radiance && rec->wo_pdf, SDT_ERR_INVALID, "sdt_splat_records: missing field");
+    cudaStream_t st = (cudaStream_t)stream;
+    Stager sg(h, st, flags);
+    SDT_TRY(sg.reserve((size_t)n * (12 + 8 + 4 + 4 + 12 + 8 + 1) + 16384));
+    sdt_records d = *rec;
+    d.position = sg.in3(rec->position, n);
+    d.direction = sg.in2(rec->direction, n);
+    d.radiance = sg.in_t(rec->radiance, n);
+    d.wo_pdf = sg.in_t(rec->wo_pdf, n);
+    if (h->cfg.store_nee) { d.radiance_nee = sg.in3(rec->radiance_nee, n); d.direction_nee = sg.in2(rec->direction_nee, n); }
+    d.active = sg.in_t(rec->active, n);
+    if (sg.status != SDT_OK) return sg.status;
+    SplatRecordsLane f{tree_view(h), SplatTarget{h->kd_count, h->q_ecur, (uint32_t)(h->cfg.store_nee != 0)}, d};
+    h->stats_complete = false;
+    SDT_TRY(launch_wavefront(h, st, n, f, h->splat_block, h->splat_ctas_per_sm));
+    return sg.finish(flags);
+}
+
+extern "C" int sdt_splat_path_data(sdt_handle h, const sdt_path_data* pd, uint32_t flags, sdt_stream stream) {
+    if (!h) return SDT_ERR_INVALID;
+    SDT_CHECK(h, pd && pd->max_depth > 0 && pd->l_final.x && pd->throughput_radiance.x && pd->throughput_bsdf.x && pd->bsdf.x &&
+                     pd->position.x && pd->direction.x && pd->wo_pdf, SDT_ERR_INVALID, "sdt_splat_path_data: missing field");
+    cudaStream_t st = (cudaStream_t)stream;
+    const uint32_t n = pd->slots;
+    const uint32_t rays = (n + pd->max_depth - 1u) / pd->max_depth;
+    Stager sg(h, st, flags);
+    SDT_TRY(sg.reserve((size_t)n * (36 + 12 + 8 + 4 + 12 + 8 + 1 + 4) + (size_t)rays * 12 + 32768));
+    sdt_path_data d = *pd;
+    d.l_final = sg.in3(pd->l_final, rays);
+    d.throughput_radiance = sg.in3(pd->throughput_radiance, n);
+    d.throughput_bsdf = sg.in3(pd->throughput_bsdf, n);
+    d.bsdf = sg.in3(pd->bsdf, n);
+    d.position = sg.in3(pd->position, n);
+    d.direction = sg.in2(pd->direction, n);
+    d.wo_pdf = sg.in_t(pd->wo_pdf, n);
+    d.radiance_nee = sg.in3(pd->radiance_nee, n);
+    d.direction_nee = sg.in2(pd->direction_nee, n);
+    d.active = sg.in_t(pd->active, n);
+    d.radiance_out = sg.out_t(pd->radiance_out, n);
+    if (sg.status != SDT_OK) return sg.status;
+    SplatPathLane f{tree_view(h), SplatTarget{h->kd_count, h->q_ecur, (uint32_t)(h->cfg.store_nee != 0)}, d};
+    h->stats_complete = false;
+    SDT_TRY(launch_wavefront(h, st, n, f, h->splat_block, h->splat_ctas_per_sm));
+    return sg.finish(flags);
+}

@@ -1,0 +1,406 @@
+"""Parity cases shared by the CPU suite (host emulation of the kernels' index logic,
+tests/test_hostemu_parity.py) and the GPU suite (libsdtree.so on the B200,
+tests/test_gpu_parity.py).  Every case drives the library through its C ABI (via the
+ctypes wrapper) and holds the result against the oracle on the same seeded inputs.
+
+`ctx.make(**cfg)` builds an SDTree on the library under test; `ctx.dev(x)` moves a numpy
+array to where the test wants the call's buffers (numpy = host-pointer path, torch CUDA =
+device-pointer path); `ctx.host(x)` brings a result back as numpy.
+"""
+import numpy as np
+
+from oracle import sdtree_oracle as so
+from oracle import drjit_math as dm
+
+F = np.float32
+U = np.uint32
+
+
+class Ctx:
+    def __init__(self, make, dev=None, host=None):
+        self.make = make
+        self.dev = dev or (lambda x: x)
+        self.host = host or (lambda x: np.asarray(x))
+
+    def u32(self, x):
+        return self.host(x).view(U) if self.host(x).dtype != U else self.host(x)
+
+
+# ------------------------------------------------------------------------------ data
+def dyadic_records(n, seed, lobes=((0.3, 0.7, 0.02),), box=1.0, nee=False):
+    """records whose radiance/woPdf are multiples of 1/16 (<= 8): fp32 sums of up to
+    ~1e5 of them are exact in any order, so splat results are bit-reproducible"""
+    rng = np.random.default_rng(seed)
+    pos = (rng.random((n, 3)) ** 1.5 * box).astype(F)
+    d = rng.random((n, 2)).astype(F)
+    k = rng.integers(0, len(lobes) + 1, n)
+    for j, (cx, cy, s) in enumerate(lobes):
+        m = k == j
+        d[m] = np.clip(np.stack([cx + s * rng.standard_normal(m.sum()), cy + s * rng.standard_normal(m.sum())], 1), 0, 1).astype(F)
+    radiance = (rng.integers(0, 17, n) / 8.0).astype(F)
+    wo = rng.choice(np.array([0.25, 0.5, 1.0, 2.0], F), n).astype(F)
+    rec = so.SurfaceInteractionRecord(pos, d, radiance, wo)
+    if nee:
+        rec.radiance_nee = (rng.integers(0, 3, (n, 3)) * np.array([0, 0, 0], F)).astype(F)
+        rec.direction_nee = rng.random((n, 2)).astype(F)
+    return rec
+
+
+def oracle_pair(bbox_min=(0, 0, 0), bbox_max=(1, 1, 1), kd_max_depth=20, quad_max_depth=20, store_nee=False):
+    cur = so.KDTree(maxDepth=kd_max_depth)
+    cur.setup(bbox_min, bbox_max)
+    cur.quadTree.maxDepth = quad_max_depth
+    cur.quadTree.isStoreNEERadiance = store_nee
+    prev = so.KDTree(maxDepth=kd_max_depth)
+    prev.copyFrom(cur)
+    return cur, prev
+
+
+def oracle_refine(cur, prev, max_leaf_size, kd=True, quad=True):
+    """refineAndPrepareSDTreeForNextIteration with an explicit KDTree.maxLeafSize"""
+    cur.maxLeafSize = max_leaf_size
+    if kd:
+        cur.refine()
+    if quad:
+        cur.setQuadTreeRefinementThreshold()
+        cur.refineAllQuadTree()
+    cur.cleanUnusedQuadTree()
+    prev.copyFrom(cur)
+    cur.resetTreeVertCount()
+    cur.resetAllQuadTreeIrradiance()
+
+
+def splat(tree, ctx, rec, active=None):
+    tree.splat_records(ctx.dev(rec.position), ctx.dev(rec.direction), ctx.dev(rec.radiance), ctx.dev(rec.woPdf),
+                       ctx.dev(rec.radiance_nee), ctx.dev(rec.direction_nee),
+                       None if active is None else ctx.dev(active.astype(np.uint8)))
+
+
+def assert_tree_equal(got, want_tree, exact_energy=True, rtol=1e-4):
+    """got: dict in the npz schema from SDTree.download; want_tree: oracle KDTree"""
+    want = want_tree.to_arrays()
+    for k in so.KDTree.NPZ_KEYS:
+        g, w = np.asarray(got[k]), np.asarray(want[k])
+        if k == 'kdtree_maxLeafSize':
+            assert np.float32(g) == np.float32(w), k
+            continue
+        assert g.shape == w.shape, (k, g.shape, w.shape)
+        if g.dtype.kind == 'f' and not exact_energy and k in ('quadtree_irradiance', 'quadtree_refinementThreshold'):
+            np.testing.assert_allclose(g, w, rtol=rtol, atol=1e-30, err_msg=k)
+        elif g.dtype.kind == 'f':
+            assert np.array_equal(g.view(U) if g.dtype == F else g, w.astype(F).view(U) if g.dtype == F else w), k
+        else:
+            assert np.array_equal(g, w), k
+
+
+def train(ctx, iters=4, n=20000, max_leaf=600, kd_max_depth=20, quad_max_depth=20, store_nee=False, box=1.0, caps=None):
+    """identical splat+refine loop on the library and on the oracle; returns both"""
+    caps = caps or dict(kd_capacity=1 << 14, quad_capacity=1 << 18)
+    t = ctx.make(bbox_min=(0, 0, 0), bbox_max=(box, box, box), kd_max_depth=kd_max_depth, quad_max_depth=quad_max_depth,
+                 store_nee=store_nee, **caps)
+    cur, prev = oracle_pair((0, 0, 0), (box, box, box), kd_max_depth, quad_max_depth, store_nee)
+    lobes = [((0.3, 0.7, 0.02),), ((0.3, 0.7, 0.004), (0.8, 0.2, 0.05)), ((0.8, 0.2, 0.01),), ((0.55, 0.5, 0.001), (0.1, 0.1, 0.1))]
+    for it in range(iters):
+        rec = dyadic_records(n, 100 + it, lobes[it % len(lobes)], box=box, nee=store_nee)
+        splat(t, ctx, rec)
+        cur.addDataPropagate(rec)
+        t.set_max_leaf_size(max_leaf)
+        t.refine()
+        oracle_refine(cur, prev, max_leaf)
+    return t, cur, prev
+
+
+# ------------------------------------------------------------------------------ cases
+def case_initial_tree(ctx):
+    t = ctx.make(bbox_min=(0, 0, 0), bbox_max=(100, 100, 100), kd_max_depth=10, quad_max_depth=20, store_nee=False,
+                 kd_capacity=64, quad_capacity=256)
+    cur, prev = oracle_pair((0, 0, 0), (100, 100, 100), 10, 20, False)
+    cur.maxLeafSize = 1
+    assert_tree_equal(t.download(0), cur)
+    s = t.sizes()
+    assert (s['n_kd'], s['n_quad'], s['n_roots'], s['n_levels'], s['error']) == (1, 1, 1, 1, 0)
+    pos = np.array([[1, 2, 3], [101, 0, 0], [np.nan, 0, 0]], F)
+    d, p = t.sample(ctx.dev(pos), seed=1)
+    np.testing.assert_array_equal(ctx.host(p), np.full(3, dm.INV_FOUR_PI, F))
+
+
+def case_golden_upload_download(ctx):
+    """hand-derived golden trees: upload in the reference schema, queries, download"""
+    k = so.KDTree()
+    k.setup([0, 0, 0], [100, 100, 100])
+    k.split(k.getAllLeafNodeIndex())
+    k.split(k.getAllLeafNodeIndex())
+    # give every tree a different shape: non-canonical node order on purpose
+    q = k.quadTree.quadTreeNode
+    for r in (3, 1):
+        q.split(q.getAllLeafNodeIndex(np.array([r], U)))
+    q.split(q.getAllLeafNodeIndex(np.array([1], U))[1:3])
+    rng = np.random.default_rng(5)
+    q.irradiance[:] = rng.integers(1, 9, q.getWidth()).astype(F)
+    t = ctx.make(bbox_min=(0, 0, 0), bbox_max=(100, 100, 100), kd_max_depth=10, quad_max_depth=20, store_nee=False,
+                 kd_capacity=64, quad_capacity=256)
+    t.upload(k.to_arrays())
+    k.cleanUnusedQuadTree()                       # canonical layout = what download returns
+    assert_tree_equal(t.download(0), k)
+    pos = np.array([[75, 25, 25], [50, 50, 1], [50, 49, 1], [49, 50, 1], [0, 0, 0], [100, 100, 100],
+                    [101, 1, 1], [np.nan, 1, 1], [-1e-3, 5, 5]], F)
+    leaf, root = t.locate(ctx.dev(pos))
+    assert ctx.host(leaf).view(U).tolist() == [5, 6, 5, 4, 3, 6, 0, 0, 0]
+    assert ctx.host(root).view(U).tolist() == [1, 3, 1, 2, 0, 3, 0, 0, 0]
+    act = np.zeros(9, np.uint8)
+    leaf, root = t.locate(ctx.dev(pos), ctx.dev(act))
+    assert ctx.host(leaf).view(U).tolist() == [0] * 9
+
+
+def check_queries(ctx, t, prev, n=4096, seed=7, box=1.0, explicit=True):
+    rng = np.random.default_rng(seed)
+    pos = (rng.random((n, 3)) * box * 1.02 - 0.01 * box).astype(F)      # a few lanes outside the box
+    pos[:8] = np.array([[0.5, 0.5, 0.5], [0.25, 0.5, 0.75], [0, 0, 0], [1, 1, 1], [0.5, 0.25, 0.125],
+                        [np.nan, 0.5, 0.5], [0.75, 0.75, 0.75], [0.5, 0.5, 0.0]], F) * box
+    active = rng.random(n) < 0.9
+    # locate
+    leaf, root = t.locate(ctx.dev(pos), ctx.dev(active.astype(np.uint8)))
+    o_leaf = prev.getLeafNodeIndex(pos, active)
+    o_root = so.gather(prev.kdTreeNode.quadTreeRootIndex, o_leaf, active)
+    assert np.array_equal(ctx.host(leaf).view(U), o_leaf)
+    assert np.array_equal(ctx.host(root).view(U), o_root)
+    # sample
+    depth = prev.quadTree.maxDepth
+    if explicit:
+        u = rng.random((n, 3 * (depth + 2))).astype(F)
+        u[:16, 2::3] = np.array([0.0, 0.25, 0.5, 0.75] * 4, F)[:, None]     # selection uniforms on bin edges
+        sampler = so.ExplicitSampler(u=u)
+        d, p, dbg = t.sample(ctx.dev(pos), ctx.dev(active.astype(np.uint8)), u=ctx.dev(u), debug=True)
+    else:
+        sampler = so.ExplicitSampler(seed=1234, n=n, lane_offset=17)
+        d, p, dbg = t.sample(ctx.dev(pos), ctx.dev(active.astype(np.uint8)), seed=1234, lane_offset=17, debug=True)
+    od, op, odbg = prev.sample(pos, sampler, active, return_debug=True)
+    dbg = ctx.host(dbg).view(U)
+    a = active
+    assert np.array_equal(dbg[a, 0], odbg['leaf'][a])
+    assert np.array_equal(dbg[a, 1], odbg['root'][a])
+    assert np.array_equal(dbg[a, 2], odbg['sample_node'][a]), "sampled quadtree node"
+    assert np.array_equal(dbg[a, 3], odbg['pdf_node'][a]), "node reached by the pdf of the sample"
+    # the oracle's math is restated op for op (no FMA): directions and pdfs are bit-identical
+    assert np.array_equal(ctx.host(d).view(U), od.view(U))
+    assert np.array_equal(ctx.host(p).view(U), op.view(U))
+    np.testing.assert_allclose(ctx.host(d), od, rtol=1e-5, atol=1e-7)       # the north_star tolerance
+    np.testing.assert_allclose(ctx.host(p), op, rtol=1e-5)
+    # pdf of arbitrary directions (+ axis-aligned and degenerate ones: tie rules, NaN, zero)
+    dirs = rng.standard_normal((n, 3)).astype(F)
+    dirs /= np.linalg.norm(dirs, axis=1, keepdims=True)
+    dirs[:10] = np.array([[1, 0, 0], [0, 1, 0], [-1, 0, 0], [0, -1, 0], [0, 0, 1], [0, 0, -1], [0, 0, 0],
+                          [np.nan, 0, 1], [np.inf, 0, 0], [0.70710678, 0.70710678, 0]], F)
+    pp, pdbg = t.pdf(ctx.dev(pos), ctx.dev(dirs), ctx.dev(active.astype(np.uint8)), debug=True)
+    opp, opdbg = prev.pdf(pos, dirs, active, return_debug=True)
+    pdbg = ctx.host(pdbg).view(U)
+    assert np.array_equal(pdbg[a, 2], opdbg['pdf_node'][a])
+    assert np.array_equal(ctx.host(pp).view(U), opp.view(U))
+    return dict(pos=pos, active=active, dirs=dirs)
+
+
+def case_train_refine_topology(ctx):
+    """splat + refine x4: post-refine topology (all 23 arrays) bit-exact; then queries"""
+    t, cur, prev = train(ctx, iters=4)
+    s = t.sizes()
+    assert s['error'] == 0
+    assert s['n_kd'] == prev.kdTreeNode.getWidth() > 15
+    assert s['n_quad'] == prev.quadTree.quadTreeNode.getWidth() > 200
+    assert_tree_equal(t.download(0), prev)
+    assert_tree_equal(t.download(1), cur)
+    assert prev.validateTreeNodeBBox() and prev.quadTree.validateQuadTreeNodeBBox()
+    check_queries(ctx, t, prev, explicit=True)
+    check_queries(ctx, t, prev, explicit=False)
+
+
+def case_train_refine_nee_shallow(ctx):
+    """NEE storage on, shallow depth caps (maxDepth limits bite), non-unit box"""
+    t, cur, prev = train(ctx, iters=3, n=15000, max_leaf=300, kd_max_depth=5, quad_max_depth=4, store_nee=True, box=100.0)
+    assert_tree_equal(t.download(0), prev)
+    assert int(prev.kdTreeNode.depth.max()) == 5 and int(prev.quadTree.quadTreeNode.depth.max()) == 4
+    check_queries(ctx, t, prev, box=100.0)
+
+
+def case_fused_equals_two_descents(ctx):
+    t, cur, prev = train(ctx, iters=3)
+    rng = np.random.default_rng(3)
+    n = 8192
+    pos = rng.random((n, 3)).astype(F)
+    t.set_tuning("fuse_sample_pdf", 1)
+    d1, p1, g1 = t.sample(ctx.dev(pos), seed=9, debug=True)
+    t.set_tuning("fuse_sample_pdf", 0)
+    d0, p0, g0 = t.sample(ctx.dev(pos), seed=9, debug=True)
+    assert np.array_equal(ctx.host(d1).view(U), ctx.host(d0).view(U))
+    assert np.array_equal(ctx.host(p1).view(U), ctx.host(p0).view(U))
+    assert np.array_equal(ctx.host(g1), ctx.host(g0))
+    t.set_tuning("fuse_sample_pdf", 1)
+
+
+def case_splat_float_tolerance(ctx):
+    """general fp32 radiance: energies within 1e-4 relative of the exactly-rounded sums;
+    conservation root = sum leaves = sum radiance/woPdf (src/quadtree.py:1205-1218)"""
+    t, cur, prev = train(ctx, iters=3)
+    rng = np.random.default_rng(11)
+    n = 50000
+    rec = so.SurfaceInteractionRecord(rng.random((n, 3)).astype(F) * 1.05 - 0.02, rng.random((n, 2)).astype(F),
+                                      rng.lognormal(0, 1, n).astype(F), (rng.random(n) * 1.95 + 0.05).astype(F))
+    rec.direction[:5] = np.array([[0.5, 0.5], [0, 0], [1, 1], [1.5, 0.5], [np.nan, 0.2]], F)
+    active = rng.random(n) < 0.95
+    splat(t, ctx, rec, active)
+    sub = so.SurfaceInteractionRecord(rec.position[active], rec.direction[active], rec.radiance[active], rec.woPdf[active])
+    cur.addDataPropagate(sub, exact=True)
+    got = t.download(1)
+    np.testing.assert_array_equal(got['kdtree_vertCount'], cur.kdTreeNode.vertCount)
+    np.testing.assert_allclose(got['quadtree_irradiance'], cur.quadTree.quadTreeNode.irradiance, rtol=1e-4, atol=1e-6)
+    q = cur.quadTree.quadTreeNode
+    roots = got['quadtree_irradiance'][:q.rootNodeIndex.shape[0]].astype(np.float64).sum()
+    leaves = got['quadtree_irradiance'][got['quadtree_isLeaf']].astype(np.float64).sum()
+    inside = dm_inside(sub.direction)
+    truth = (sub.radiance[inside].astype(np.float64) / sub.woPdf[inside]).sum()
+    assert abs(roots - truth) <= 1e-4 * truth and abs(leaves - truth) <= 1e-4 * truth
+    inbox = so.bbox_contains(F(0), F(1), sub.position)
+    assert got['kdtree_vertCount'][got['kdtree_isLeaf']].sum() == inbox.sum() == got['kdtree_vertCount'][0]
+
+
+def dm_inside(d):
+    with np.errstate(invalid='ignore'):
+        return np.all((d >= 0) & (d <= 1), axis=1)
+
+
+def case_path_data(ctx):
+    """processPathData + filter + splat in one call vs the oracle's three steps"""
+    t, cur, prev = train(ctx, iters=2, store_nee=True)
+    rng = np.random.default_rng(21)
+    rays, md = 3000, 5
+    n = rays * md
+    Lf = rng.random((rays, 3)).astype(F) * 4
+    tr = (rng.random((n, 3)) * 2).astype(F)
+    tb = rng.random((n, 3)).astype(F)
+    bsdf = rng.random((n, 3)).astype(F)
+    tb[rng.random(n) < 0.1] = 0           # -> inf / NaN scrubbing
+    bsdf[rng.random(n) < 0.1] = 0
+    tr[rng.random(n) < 0.05] = np.nan
+    pos = rng.random((n, 3)).astype(F)
+    d = rng.random((n, 2)).astype(F)
+    wo = (rng.random(n) * 2).astype(F)
+    wo[rng.random(n) < 0.1] = 0
+    wo[rng.random(n) < 0.05] = np.nan
+    nee = (rng.random((n, 3)) * (rng.random((n, 1)) < 0.5)).astype(F)
+    nee[rng.random(n) < 0.05, 1] = np.nan
+    dnee = rng.random((n, 2)).astype(F)
+    active = rng.random(n) < 0.7
+    rad = t.splat_path_data(md, ctx.dev(Lf), ctx.dev(tr), ctx.dev(tb), ctx.dev(bsdf), ctx.dev(pos), ctx.dev(d), ctx.dev(wo),
+                            ctx.dev(nee), ctx.dev(dnee), ctx.dev(active.astype(np.uint8)), want_radiance=True)
+    _, orad = so.process_path_data(Lf, tr, tb, bsdf, md)
+    keep, orad2, onee = so.filter_records(active, orad, nee, wo)
+    assert np.array_equal(ctx.host(rad).view(U), orad2.view(U))
+    sub = so.SurfaceInteractionRecord(pos[keep], d[keep], orad2[keep], wo[keep], onee[keep], dnee[keep])
+    cur.addDataPropagate(sub, exact=True)
+    got = t.download(1)
+    np.testing.assert_array_equal(got['kdtree_vertCount'], cur.kdTreeNode.vertCount)
+    e = cur.quadTree.quadTreeNode.irradiance
+    with np.errstate(invalid='ignore'):
+        fin = np.isfinite(e)
+    assert np.array_equal(np.isfinite(got['quadtree_irradiance']), fin)
+    np.testing.assert_allclose(got['quadtree_irradiance'][fin], e[fin], rtol=1e-4, atol=1e-6)
+
+
+def case_mis(ctx):
+    rng = np.random.default_rng(4)
+    n = 5000
+    a = [rng.random(n).astype(F) * 3 for _ in range(5)]
+    a[0][:5] = [0, 1, np.inf, 0, np.nan]
+    a[4][:5] = [0, 0, np.inf, 1, 1]
+    delta = rng.random(n) < 0.2
+    t = ctx.make(kd_capacity=16, quad_capacity=64)
+    for it in (1, 2):
+        s, m = t.mis_nee(ctx.dev(a[0]), ctx.dev(a[1]), ctx.dev(a[2]), ctx.dev(a[3]), ctx.dev(a[4]),
+                         ctx.dev(delta.astype(np.uint8)), 0.5, it)
+        os_, om = so.nee_mis(a[0], a[1], a[2], a[3], a[4], delta, 0.5, it)
+        assert np.array_equal(ctx.host(s).view(U), os_.view(U))
+        assert np.array_equal(ctx.host(m).view(U), om.view(U))
+    val = rng.random((n, 3)).astype(F)
+    do = rng.random(n) < 0.6
+    wo, w = t.mis_mixture(ctx.dev(a[0]), ctx.dev(a[1]), ctx.dev(val), ctx.dev(do.astype(np.uint8)), 0.5)
+    owo, ow = so.mixture(a[0], a[1], val, do, 0.5)
+    assert np.array_equal(ctx.host(wo).view(U), owo.view(U))
+    assert np.array_equal(ctx.host(w).view(U), ow.view(U))
+
+
+def case_guided_bounce(ctx):
+    """sdt_guided = sample on mode-1 lanes, pdf + fused mixture on mode-2 lanes, in one pass"""
+    t, cur, prev = train(ctx, iters=3)
+    rng = np.random.default_rng(8)
+    n = 6000
+    pos = rng.random((n, 3)).astype(F)
+    mode = rng.integers(0, 3, n).astype(np.uint8)
+    wo = rng.standard_normal((n, 3)).astype(F)
+    wo /= np.linalg.norm(wo, axis=1, keepdims=True)
+    bp = (rng.random(n) * 2).astype(F)
+    bv = rng.random((n, 3)).astype(F)
+    d, sp, wp, wt = t.guided(ctx.dev(pos), ctx.dev(mode), wo=ctx.dev(wo), seed=77, bsdf_pdf=ctx.dev(bp), bsdf_value=ctx.dev(bv))
+    d, sp, wp, wt = ctx.host(d), ctx.host(sp), ctx.host(wp), ctx.host(wt)
+    m1, m2 = mode == 1, mode == 2
+    od, op = prev.sample(pos, so.ExplicitSampler(seed=77, n=n), m1)
+    assert np.array_equal(d[m1].view(U), od[m1].view(U)) and np.array_equal(sp[m1].view(U), op[m1].view(U))
+    op2 = prev.pdf(pos, wo, m2)
+    assert np.array_equal(sp[m2].view(U), op2[m2].view(U))
+    owo, ow = so.mixture(bp, op2, bv, m2, 0.5)
+    assert np.array_equal(wp[m2].view(U), owo[m2].view(U)) and np.array_equal(wt[m2].view(U), ow[m2].view(U))
+    assert not d[mode == 0].any() and not sp[mode == 0].any()
+
+
+def case_refine_flags_and_frozen_stats(ctx):
+    """refine from frozen stat buffers (sdt_upload_stats), KD-only and quad-only"""
+    t, cur, prev = train(ctx, iters=2)
+    rng = np.random.default_rng(31)
+    k, q = cur.kdTreeNode, cur.quadTree.quadTreeNode
+    # arbitrary (non-additive) frozen statistics, interior values included
+    q.irradiance[:] = (rng.random(q.getWidth()) ** 4 * 50).astype(F)
+    k.vertCount[:] = rng.integers(0, 4000, k.getWidth()).astype(F)
+    t.upload_stats(q.irradiance, k.vertCount)
+    t.set_max_leaf_size(700)
+    t.refine(kd=True, quad=False)
+    oracle_refine(cur, prev, 700, kd=True, quad=False)
+    assert_tree_equal(t.download(0), prev)
+    q = cur.quadTree.quadTreeNode
+    q.irradiance[:] = (rng.random(q.getWidth()) ** 6 * 80).astype(F)
+    R = q.rootNodeIndex.shape[0]
+    q.irradiance[:R] = (2000 * (0.5 + rng.random(R))).astype(F)      # thr 10..30: leaves split 0..2 levels
+    t.upload_stats(q.irradiance, None)
+    t.refine(kd=False, quad=True)
+    oracle_refine(cur, prev, 700, kd=False, quad=True)
+    assert_tree_equal(t.download(0), prev)
+
+
+def case_capacity_error(ctx):
+    t = ctx.make(kd_capacity=8, quad_capacity=64, kd_max_depth=20, quad_max_depth=20, store_nee=False)
+    rec = dyadic_records(20000, 1)
+    splat(t, ctx, rec)
+    t.set_max_leaf_size(100)
+    t.refine()
+    s = t.sizes()
+    assert s['error'] != 0 and s['n_kd'] <= 8 and s['n_quad'] <= 64
+    # the tree is still a valid tree: queries run
+    leaf, root = t.locate(ctx.dev(rec.position[:100]))
+    assert ctx.host(root).view(U).max() < s['n_roots']
+
+
+def case_npz_roundtrip(ctx, tmp_path):
+    t, cur, prev = train(ctx, iters=2)
+    f = str(tmp_path / "tree.npz")
+    t.save_npz(f)
+    d = np.load(f)
+    assert set(d.files) == set(so.KDTree.NPZ_KEYS)
+    o = so.KDTree()
+    o.loadFromFile(f)                      # the oracle's reader follows src/kdtree.py:156-170
+    t2 = ctx.make(kd_capacity=1 << 14, quad_capacity=1 << 18)
+    t2.load_npz(f)
+    assert_tree_equal(t2.download(0), o)
+    check_queries(ctx, t2, o, n=1024)
+
+
+ALL_CASES = [case_initial_tree, case_golden_upload_download, case_train_refine_topology,
+             case_train_refine_nee_shallow, case_fused_equals_two_descents, case_splat_float_tolerance,
+             case_path_data, case_mis, case_guided_bounce, case_refine_flags_and_frozen_stats,
+             case_capacity_error]

@@ -1,0 +1,98 @@
+"""GPU suite (-m gpu): the parity cases of tests/sdt_cases.py on libsdtree.so, called
+through the C ABI, against the oracle.  Two buffer modes: torch CUDA tensors (device
+pointers, the integrator's path) and numpy arrays (host pointers staged by the library,
+SDT_HOST_PTRS -- the path bench.py's e2e number times)."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+import sdt_cases as cases  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+
+
+def _ctx(mode):
+    import torch
+    from practical_path_guiding_lab_b200 import SDTree
+    from practical_path_guiding_lab_b200.build import build
+    build()
+    make = lambda **kw: SDTree(device=0, **kw)
+    if mode == "host":
+        return cases.Ctx(make=make)
+
+    def dev(x):
+        if x is None:
+            return None
+        a = np.ascontiguousarray(x)
+        if a.dtype == np.uint32:
+            a = a.view(np.int32)
+        return torch.from_numpy(a).cuda()
+
+    def host(x):
+        if x is None:
+            return None
+        if isinstance(x, np.ndarray):
+            return x
+        torch.cuda.synchronize()
+        return x.cpu().numpy()
+    return cases.Ctx(make=make, dev=dev, host=host)
+
+
+@pytest.fixture(scope="module", params=["device", "host"])
+def ctx(request):
+    return _ctx(request.param)
+
+
+@pytest.mark.parametrize("case", cases.ALL_CASES, ids=lambda c: c.__name__)
+def test_case(ctx, case):
+    case(ctx)
+
+
+def test_npz_roundtrip(ctx, tmp_path):
+    cases.case_npz_roundtrip(ctx, tmp_path)
+
+
+def test_library_is_cuda():
+    """the product path is the CUDA library: kernels were launched, an L2 probe runs"""
+    c = _ctx("device")
+    t = c.make(kd_capacity=64, quad_capacity=256)
+    before = t.kernel_launches()
+    import torch
+    pos = torch.rand(1000, 3, device="cuda")
+    t.sample(pos, seed=1)
+    torch.cuda.synchronize()
+    assert t.kernel_launches() > before
+    assert t.measure_l2(16 << 20, 20) > 500.0      # GB/s; anything CPU-like would be far below
+
+
+def test_large_wavefront_properties():
+    """full-size wavefront (2^22 lanes): size-independent properties -- determinism,
+    pdf(sample) consistency, conservation of splatted energy and counts"""
+    import torch
+    c = _ctx("device")
+    t, cur, prev = cases.train(c, iters=3)
+    n = 1 << 22
+    g = torch.Generator(device="cuda").manual_seed(5)
+    pos = torch.rand(n, 3, device="cuda", generator=g)
+    d1, p1 = t.sample(pos, seed=42)
+    d2, p2 = t.sample(pos, seed=42)
+    assert torch.equal(d1, d2) and torch.equal(p1, p2)
+    p3 = t.pdf(pos, d1)
+    assert torch.equal(p1, p3)                      # KDTree.sample's pdf IS KDTree.pdf of the sampled direction
+    assert torch.isfinite(p1).all() and (p1 >= 0).all()
+    nrm = d1.norm(dim=1)
+    assert (nrm - 1).abs().max() < 1e-5
+    # splat: dyadic energies -> exact, order-independent sums
+    dirs = torch.rand(n, 2, device="cuda", generator=g)
+    rad = torch.randint(0, 9, (n,), device="cuda", generator=g).float() / 8
+    wo = torch.full((n,), 0.5, device="cuda")
+    t.splat_records(pos, dirs, rad, wo)
+    got = t.download(1)
+    R = t.sizes()['n_roots']
+    total = float((rad.double() / 0.5).sum())
+    assert float(got['quadtree_irradiance'][:R].astype(np.float64).sum()) == total
+    assert float(got['quadtree_irradiance'][got['quadtree_isLeaf']].astype(np.float64).sum()) == total
+    assert got['kdtree_vertCount'][0] == n == got['kdtree_vertCount'][got['kdtree_isLeaf']].sum()
