@@ -1,0 +1,373 @@
+#!/usr/bin/env python
+"""bench.py -- guided samples/s of the SD-tree hot path on the synthetic frozen-tree
+workload of BASELINE.json configs[1].
+
+One STEP = one pass of the hot path over one wavefront of n = 2^24 path vertices:
+    sdt_sample (spatial descent + quadtree sample + pdf of the sample, A1+A3+A4)
+  + sdt_pdf    (spatial descent + quadtree pdf of a given direction,   A1+A4)
+  + sdt_splat_records (spatial descent + quadtree descent + accumulation, A6+A7)
+on a frozen tree (~4k spatial leaves, quadtree depth <= 20) that the library itself
+trained on the synthetic records (splat + device-side refine, 6 iterations).
+`value` = vertices through the whole step per second with inputs resident in HBM;
+`e2e` = the same three C-ABI calls with HOST buffers (pinned), H2D/D2H inside the timed
+region.  `--impl reference` times the CPU restatement of the reference (oracle/) on a
+bounded sample of the same workload.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--n LANES]
+    torchrun --nproc-per-node N bench.py --gpus N ...        (one rank per GPU)
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "guided samples/s (sample + pdf + splat per path vertex, synthetic frozen SD-tree)"
+UNIT = "samples/s"
+N_DEFAULT = 1 << 24
+CPU_SAMPLE = 1 << 17
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--n", type=int, default=N_DEFAULT, help="path vertices per step per GPU")
+    ap.add_argument("--cpu-sample", type=int, default=CPU_SAMPLE)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def workload_config(n, world):
+    from practical_path_guiding_lab_b200 import synthetic as syn
+    return {"workload": "synthetic frozen SD-tree microbench (BASELINE configs[1])",
+            "queries_per_step_per_gpu": n, "ops_per_query": ["sample", "pdf", "splat"],
+            "tree_build": {"iterations": syn.BUILD_ITERS, "records_iter0": syn.BUILD_N0, "c": syn.BUILD_C,
+                           "seed": syn.BUILD_SEED},
+            "l2_policy": "inputs (>= 200 MB per array set) larger than the 126 MB L2; the tree (~13 MB of records) is meant to stay L2-resident",
+            "parallelism": f"replicated tree, vertices sharded x{world}"}
+
+
+# ------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index = index
+        self.rows = []
+        self.stop = False
+        self.th = None
+
+    def _run(self):
+        while not self.stop:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.05)
+
+    def __enter__(self):
+        self.th = threading.Thread(target=self._run, daemon=True)
+        self.th.start()
+        return self
+
+    def __exit__(self, *a):
+        self.stop = True
+        self.th.join(timeout=10)
+
+    def summary(self):
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        sm = sorted(float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for k, n in enumerate(names) if any(len(r) > 2 + k and r[2 + k].lower().startswith("active") for r in self.rows)]
+        mx = [float(r[1]) for r in self.rows if r[1].replace(".", "").isdigit()]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(self.rows)}
+
+
+# ------------------------------------------------------------------------------ CPU port (oracle) arm
+def oracle_tree():
+    """the frozen tree, built by the oracle itself (numpy restatement of the reference)"""
+    from oracle import sdtree_oracle as so
+    from practical_path_guiding_lab_b200 import synthetic as syn
+    cur = so.KDTree(maxDepth=20)
+    cur.setup([0, 0, 0], [1, 1, 1])
+    cur.quadTree.maxDepth = 20
+    cur.quadTree.isStoreNEERadiance = False
+    prev = so.KDTree(maxDepth=20)
+    prev.copyFrom(cur)
+    scene = syn.Scene()
+    for it in syn.build_schedule():
+        r = scene.records(it['seed'], it['n'])
+        cur.addDataPropagate(so.SurfaceInteractionRecord(r['position'], r['direction'], r['radiance'], r['wo_pdf']))
+        cur.maxLeafSize = it['max_leaf_size']
+        cur.refine()
+        cur.setQuadTreeRefinementThreshold()
+        cur.refineAllQuadTree()
+        cur.cleanUnusedQuadTree()
+        prev.copyFrom(cur)
+        cur.resetTreeVertCount()
+        cur.resetAllQuadTreeIrradiance()
+    return cur, prev
+
+
+def oracle_step(cur, prev, pos, dirs, rec, seed):
+    from oracle import sdtree_oracle as so
+    n = pos.shape[0]
+    prev.sample(pos, so.ExplicitSampler(seed=seed, n=n), True)
+    prev.pdf(pos, dirs, True)
+    cur.addDataPropagate(so.SurfaceInteractionRecord(rec['position'], rec['direction'], rec['radiance'], rec['wo_pdf']))
+
+
+def cpu_inputs(m):
+    from practical_path_guiding_lab_b200 import synthetic as syn
+    return syn.uniform_box(1, m), syn.uniform_sphere(2, m), syn.Scene().records(4, m)
+
+
+def run_reference(args):
+    """reference arm: the CPU restatement of the reference's algorithm (oracle/, numpy --
+    Mitsuba 3 / Dr.Jit are not installable in this image) on the host cores"""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    m = args.cpu_sample
+    cur, prev = oracle_tree()
+    pos, dirs, rec = cpu_inputs(m)
+    for _ in range(args.warmup):
+        oracle_step(cur, prev, pos, dirs, rec, 3)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        oracle_step(cur, prev, pos, dirs, rec, 3)
+    dt = (time.perf_counter() - t0) / args.steps
+    v = m / dt
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": workload_config(args.n, args.gpus),
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": 1, "kind": "port",
+                             "sample": f"{m} of the {args.n} vertices per step (numpy oracle, one process; host has {os.cpu_count()} cores)"},
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------ B200 arm
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    from practical_path_guiding_lab_b200 import SDTree, synthetic as syn
+    from practical_path_guiding_lab_b200.build import build
+    build()
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the product has no CPU fallback; use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    n = args.n
+    tree = SDTree(device=local, kd_max_depth=20, quad_max_depth=20, store_nee=False)
+    to_dev = lambda x: torch.from_numpy(np.ascontiguousarray(x)).to(dev)
+    allreduce = None
+    if world > 1:
+        ids = [tree.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(ids, src=0)
+        tree.comm_init(ids[0], rank, world)
+        allreduce = lambda: tree.allreduce(torch.cuda.current_stream().cuda_stream)
+    t_build0 = time.perf_counter()
+    syn.build_tree(tree, to_dev=to_dev, rank=rank, world=world, allreduce=allreduce)
+    torch.cuda.synchronize()
+    sizes = tree.sizes()
+    t_build = time.perf_counter() - t_build0
+    assert sizes["error"] == 0, sizes
+
+    # inputs of this rank's shard (host, pinned for the e2e arm) and their device copies
+    scene = syn.Scene()
+    pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+    h_pos = pin(syn.uniform_box(1 + 1000 * rank, n))
+    h_dir = pin(syn.uniform_sphere(2 + 1000 * rank, n))
+    rec = scene.records(4 + 1000 * rank, n)
+    h_rec = {k: pin(v) for k, v in rec.items()}
+    d_pos, d_dir = h_pos.to(dev), h_dir.to(dev)
+    d_rec = {k: v.to(dev) for k, v in h_rec.items()}
+    o_dir = torch.empty(n, 3, device=dev)
+    o_pdf = torch.empty(n, device=dev)
+    o_pdf2 = torch.empty(n, device=dev)
+    lane0 = rank * n
+
+    def step(ev=None):
+        if ev:
+            ev[0].record()
+        tree.sample(d_pos, seed=3, lane_offset=lane0, out=(o_dir, o_pdf))
+        if ev:
+            ev[1].record()
+        tree.pdf(d_pos, d_dir, out=o_pdf2)
+        if ev:
+            ev[2].record()
+        tree.splat_records(d_rec['position'], d_rec['direction'], d_rec['radiance'], d_rec['wo_pdf'])
+        if ev:
+            ev[3].record()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(args.steps)]
+    barrier()
+    launches0 = tree.kernel_launches()
+    with ClockSampler(local) as clk:
+        barrier()
+        for k in range(args.steps):
+            step(evs[k])
+        barrier()
+    launches = tree.kernel_launches() - launches0
+    total_ms = evs[0][0].elapsed_time(evs[-1][3])
+    k_ms = [float(np.mean([e[j].elapsed_time(e[j + 1]) for e in evs])) for j in range(3)]
+    t = torch.tensor([total_ms], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_per_step = float(t.item()) / args.steps
+    value = n * world / (ms_per_step * 1e-3)
+
+    # ---- algorithmic bytes from the measured depths of a 2^20-lane subset
+    m = min(n, 1 << 20)
+    tr = tree.download(0)
+    leaf, _ = tree.locate(d_pos[:m])
+    ds = tr['kdtree_depth'][leaf.cpu().numpy().view(np.uint32)].astype(np.float64).mean()
+    _, _, dbg = tree.sample(d_pos[:m], seed=3, lane_offset=lane0, debug=True)
+    dbg = dbg.cpu().numpy().view(np.uint32)
+    dq_s = tr['quadtree_depth'][dbg[:, 2]].astype(np.float64).mean()
+    redescend = float((dbg[:, 2] != dbg[:, 3]).mean())
+    _, dbgp = tree.pdf(d_pos[:m], d_dir[:m], debug=True)
+    dq_p = tr['quadtree_depth'][dbgp.cpu().numpy().view(np.uint32)[:, 2]].astype(np.float64).mean()
+    bytes_q = {"sample": 28 + 4 * ds + 4 + 20 * dq_s,            # ONE quadtree descent (fused pdf); re-descents not counted
+               "pdf": 28 + 4 * ds + 4 + 20 * dq_p + 4,
+               "splat": 28 + 4 * ds + 4 + 4 * dq_p + 8}            # leaf-only update + sweep (Dq ~ pdf's for iid directions)
+    names = ["sample", "pdf", "splat"]
+    dom = int(np.argmax(k_ms))
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    achieved = bytes_q[names[dom]] * n / (k_ms[dom] * 1e-3) / 1e9
+    l2_gbs = tree.measure_l2(32 << 20, 50)
+    roof = {"bound": "hbm", "kernel": f"k_wavefront<{['SampleLane', 'PdfLane', 'SplatRecordsLane'][dom]}>", "achieved": achieved, "peak": peak,
+            "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+            "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if "hbm_gbs" in peaks else "fallback 6650",
+            "algorithmic_bytes_per_query": bytes_q[names[dom]], "kernel_ms": k_ms[dom],
+            "l2": {"measured_read_gbs": l2_gbs, "frac_of_l2": achieved / l2_gbs if l2_gbs else None,
+                   "how": "sdt_measure_l2: 32 MiB resident set, 50 passes, ld.global.cg"},
+            "per_kernel": {names[j]: {"ms": k_ms[j], "bytes_per_query": bytes_q[names[j]],
+                                      "achieved_gbs": bytes_q[names[j]] * n / (k_ms[j] * 1e-3) / 1e9,
+                                      "queries_per_s": n / (k_ms[j] * 1e-3)} for j in range(3)},
+            "mean_depths": {"spatial": ds, "quad_sample": dq_s, "quad_pdf": dq_p, "sample_redescend_frac": redescend}}
+
+    # ---- refine + allreduce wall time (per training iteration, not part of a step)
+    e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+    torch.cuda.synchronize()
+    e0.record()
+    if allreduce:
+        allreduce()
+    e1.record()
+    tree.set_max_leaf_size(1e9)            # statistics are K steps of the same records: keep the spatial tree frozen
+    tree.refine()
+    e2.record()
+    torch.cuda.synchronize()
+    per_iter = {"allreduce_ms": e0.elapsed_time(e1) if allreduce else 0.0, "refine_ms": e1.elapsed_time(e2)}
+
+    # ---- end to end: the same three C-ABI calls on HOST buffers (pinned)
+    e2e = None
+    if not args.no_e2e:
+        tree2 = tree
+        hp, hd = h_pos.numpy(), h_dir.numpy()
+        hr = {k: v.numpy() for k, v in h_rec.items()}
+        ho_dir = torch.empty(n, 3).pin_memory().numpy()
+        ho_pdf = torch.empty(n).pin_memory().numpy()
+        ho_pdf2 = torch.empty(n).pin_memory().numpy()
+
+        def step_host():
+            tree2.sample(hp, seed=3, lane_offset=lane0, out=(ho_dir, ho_pdf))
+            tree2.pdf(hp, hd, out=ho_pdf2)
+            tree2.splat_records(hr['position'], hr['direction'], hr['radiance'], hr['wo_pdf'])
+            torch.cuda.synchronize()
+        ke = max(1, min(args.steps, 5))
+        for _ in range(2):
+            step_host()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(ke):
+            step_host()
+        barrier()
+        dt = torch.tensor([(time.perf_counter() - t0) / ke], device=dev)
+        if world > 1:
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        e2e = {"value": n * world / float(dt.item()), "unit": UNIT, "ms_per_step": float(dt.item()) * 1e3,
+               "h2d_bytes_per_step": n * (12 + 24 + 28), "d2h_bytes_per_step": n * (16 + 4),
+               "how": "sdt_sample + sdt_pdf + sdt_splat_records with SDT_HOST_PTRS on pinned host arrays; staging copies inside the calls"}
+
+    # ---- CPU port of the reference, timed beside it (rank 0, N=1)
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        from oracle import sdtree_oracle as so
+        mc = args.cpu_sample
+        prev = so.KDTree()
+        prev.loadFromArrays(tr)
+        cur = so.KDTree()
+        cur.copyFrom(prev)
+        cur.resetTreeVertCount()
+        cur.resetAllQuadTreeIrradiance()
+        pos, dirs, crec = h_pos.numpy()[:mc], h_dir.numpy()[:mc], {k: v.numpy()[:mc] for k, v in h_rec.items()}
+        oracle_step(cur, prev, pos[:4096], dirs[:4096], {k: v[:4096] for k, v in crec.items()}, 3)
+        t0 = time.perf_counter()
+        reps = 0
+        while reps < 2 or time.perf_counter() - t0 < 10.0:
+            oracle_step(cur, prev, pos, dirs, crec, 3)
+            reps += 1
+        dt = (time.perf_counter() - t0) / reps
+        cpu = {"value": mc / dt, "unit": UNIT, "cores": 1, "kind": "port",
+               "sample": f"first {mc} of the {n} vertices per step, {reps} repetitions (numpy oracle, one process; host has {os.cpu_count()} cores)"}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+                "data": "synthetic", "config": workload_config(n, world), "clocks": clk.summary(), "e2e": e2e,
+                "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu,
+                "tree": {k: sizes[k] for k in ("n_kd", "kd_leaves", "n_quad", "n_interior", "n_levels")},
+                "tree_build_s": t_build, "per_iteration": per_iter}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()
