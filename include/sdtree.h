@@ -190,6 +190,14 @@ int sdt_mis_mixture(sdt_handle h, uint32_t n, const float* bsdf_pdf, const float
                     const sdt_vec3* bsdf_value, const uint8_t* do_mis, float bsdf_sampling_fraction,
                     float* wo_pdf, const sdt_vec3_out* weight, uint32_t flags, sdt_stream stream);
 
+/* dirToCanonical / canonicalToDir (src/common.py:100-158) on n vectors: what the integrator
+ * stores in SurfaceInteractionRecord.direction / direction_nee
+ * (src/path_guiding_integrator.py:325,338). */
+int sdt_dir_to_canonical(sdt_handle h, const sdt_vec3* dir, uint32_t n, float* out_xy /* n*2 */,
+                         uint32_t flags, sdt_stream stream);
+int sdt_canonical_to_dir(sdt_handle h, const sdt_vec2* pos, uint32_t n, const sdt_vec3_out* dir,
+                         uint32_t flags, sdt_stream stream);
+
 /* ---- splat into `current` ---------------------------------------------------- */
 /* KDTree.addDataPropagate + QuadTree.addDataPropagate (src/kdtree.py:180-225,
  * src/quadtree.py:389-464) on already-filtered records.  radiance_nee / direction_nee

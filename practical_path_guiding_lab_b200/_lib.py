@@ -95,6 +95,8 @@ SYMBOLS = {
                               C.c_float, C.c_int32, C.c_void_p, C.c_void_p, C.c_uint32, _S]),
     "sdt_mis_mixture": (C.c_int, [_H, C.c_uint32, C.c_void_p, C.c_void_p, C.POINTER(Vec3), C.c_void_p, C.c_float,
                                   C.c_void_p, C.POINTER(Vec3), C.c_uint32, _S]),
+    "sdt_dir_to_canonical": (C.c_int, [_H, C.POINTER(Vec3), C.c_uint32, C.c_void_p, C.c_uint32, _S]),
+    "sdt_canonical_to_dir": (C.c_int, [_H, C.POINTER(Vec2), C.c_uint32, C.POINTER(Vec3), C.c_uint32, _S]),
     "sdt_splat_records": (C.c_int, [_H, C.POINTER(Records), C.c_uint32, C.c_uint32, _S]),
     "sdt_splat_path_data": (C.c_int, [_H, C.POINTER(PathData), C.c_uint32, _S]),
     "sdt_set_iteration_threshold": (C.c_int, [_H, C.c_int32]),

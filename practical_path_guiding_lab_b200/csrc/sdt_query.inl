@@ -300,3 +300,47 @@ extern "C" int sdt_mis_mixture(sdt_handle h, uint32_t n, const float* bsdf_pdf, 
     SDT_TRY(sdt_post_launch(h, "sdt_mis_mixture"));
     return sg.finish(flags);
 }
+
+struct DirToCanonicalItem {
+    sdt_vec3 d; float* out;
+    SDT_HD void operator()(uint32_t i) const {
+        float x, y;
+        sdt_dir_to_canonical(sdt_ld(d.x, d.stride, i), sdt_ld(d.y, d.stride, i), sdt_ld(d.z, d.stride, i), x, y);
+        out[2u * i] = x; out[2u * i + 1u] = y;
+    }
+};
+struct CanonicalToDirItem {
+    sdt_vec2 p; sdt_vec3_out d;
+    SDT_HD void operator()(uint32_t i) const {
+        float x, y, z;
+        sdt_canonical_to_dir(sdt_ld(p.x, p.stride, i), sdt_ld(p.y, p.stride, i), x, y, z);
+        const int64_t o = (int64_t)i * d.stride;
+        d.x[o] = x; d.y[o] = y; d.z[o] = z;
+    }
+};
+
+extern "C" int sdt_dir_to_canonical(sdt_handle h, const sdt_vec3* dir, uint32_t n, float* out_xy, uint32_t flags, sdt_stream stream) {
+    if (!h) return SDT_ERR_INVALID;
+    SDT_CHECK(h, dir && dir->x && out_xy, SDT_ERR_INVALID, "sdt_dir_to_canonical: NULL argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    Stager sg(h, st, flags);
+    SDT_TRY(sg.reserve((size_t)n * 20 + 8192));
+    DirToCanonicalItem f{sg.in3(*dir, n), sg.out_t(out_xy, (size_t)n * 2)};
+    if (sg.status != SDT_OK) return sg.status;
+    launch_items(exec_ctx(h, st), nullptr, n, f);
+    SDT_TRY(sdt_post_launch(h, "sdt_dir_to_canonical"));
+    return sg.finish(flags);
+}
+
+extern "C" int sdt_canonical_to_dir(sdt_handle h, const sdt_vec2* pos, uint32_t n, const sdt_vec3_out* dir, uint32_t flags, sdt_stream stream) {
+    if (!h) return SDT_ERR_INVALID;
+    SDT_CHECK(h, pos && pos->x && dir && dir->x, SDT_ERR_INVALID, "sdt_canonical_to_dir: NULL argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    Stager sg(h, st, flags);
+    SDT_TRY(sg.reserve((size_t)n * 20 + 8192));
+    CanonicalToDirItem f{sg.in2(*pos, n), sg.out3(*dir, n)};
+    if (sg.status != SDT_OK) return sg.status;
+    launch_items(exec_ctx(h, st), nullptr, n, f);
+    SDT_TRY(sdt_post_launch(h, "sdt_canonical_to_dir"));
+    return sg.finish(flags);
+}

@@ -305,6 +305,25 @@ class SDTree:
                                            C.byref(wv), b.flags(), b.stream()))
         return wo, w
 
+    def dir_to_canonical(self, direction):
+        """dirToCanonical (src/common.py:132-158): (n,3) -> (n,2)"""
+        b = _Buf()
+        n = _n_of(direction)
+        dv = b.vec(direction, 3)
+        o, op = b.new((n, 2), np.float32)
+        self._ck(self._lib.sdt_dir_to_canonical(self._h, C.byref(dv), n, op, b.flags(), b.stream()))
+        return o
+
+    def canonical_to_dir(self, pos2):
+        """canonicalToDir (src/common.py:100-129): (n,2) -> (n,3)"""
+        b = _Buf()
+        n = _n_of(pos2)
+        pv = b.vec(pos2, 2)
+        o, op = b.new((n, 3), np.float32)
+        ov = L.Vec3(op, op + 4, op + 8, 3)
+        self._ck(self._lib.sdt_canonical_to_dir(self._h, C.byref(pv), n, C.byref(ov), b.flags(), b.stream()))
+        return o
+
     # ---- splat into current -----------------------------------------------------------
     def splat_records(self, position, direction, radiance, wo_pdf, radiance_nee=None, direction_nee=None, active=None):
         """KDTree.addDataPropagate on already-filtered records"""

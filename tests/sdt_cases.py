@@ -16,6 +16,15 @@ F = np.float32
 U = np.uint32
 
 
+def beq(a, b):
+    """bit-exact fp32 equality; NaNs match NaNs (their payload/sign differs between x86 and sm_100)"""
+    a = np.ascontiguousarray(a, F)
+    b = np.ascontiguousarray(b, F)
+    if a.shape != b.shape:
+        return False
+    return bool(np.all((a.view(U) == b.view(U)) | (np.isnan(a) & np.isnan(b))))
+
+
 class Ctx:
     def __init__(self, make, dev=None, host=None):
         self.make = make
@@ -88,7 +97,7 @@ def assert_tree_equal(got, want_tree, exact_energy=True, rtol=1e-4):
         if g.dtype.kind == 'f' and not exact_energy and k in ('quadtree_irradiance', 'quadtree_refinementThreshold'):
             np.testing.assert_allclose(g, w, rtol=rtol, atol=1e-30, err_msg=k)
         elif g.dtype.kind == 'f':
-            assert np.array_equal(g.view(U) if g.dtype == F else g, w.astype(F).view(U) if g.dtype == F else w), k
+            assert (beq(g, w) if g.dtype == F else np.array_equal(g, w)), k
         else:
             assert np.array_equal(g, w), k
 
@@ -182,8 +191,8 @@ def check_queries(ctx, t, prev, n=4096, seed=7, box=1.0, explicit=True):
     assert np.array_equal(dbg[a, 2], odbg['sample_node'][a]), "sampled quadtree node"
     assert np.array_equal(dbg[a, 3], odbg['pdf_node'][a]), "node reached by the pdf of the sample"
     # the oracle's math is restated op for op (no FMA): directions and pdfs are bit-identical
-    assert np.array_equal(ctx.host(d).view(U), od.view(U))
-    assert np.array_equal(ctx.host(p).view(U), op.view(U))
+    assert beq(ctx.host(d), od)
+    assert beq(ctx.host(p), op)
     np.testing.assert_allclose(ctx.host(d), od, rtol=1e-5, atol=1e-7)       # the north_star tolerance
     np.testing.assert_allclose(ctx.host(p), op, rtol=1e-5)
     # pdf of arbitrary directions (+ axis-aligned and degenerate ones: tie rules, NaN, zero)
@@ -195,7 +204,7 @@ def check_queries(ctx, t, prev, n=4096, seed=7, box=1.0, explicit=True):
     opp, opdbg = prev.pdf(pos, dirs, active, return_debug=True)
     pdbg = ctx.host(pdbg).view(U)
     assert np.array_equal(pdbg[a, 2], opdbg['pdf_node'][a])
-    assert np.array_equal(ctx.host(pp).view(U), opp.view(U))
+    assert beq(ctx.host(pp), opp)
     return dict(pos=pos, active=active, dirs=dirs)
 
 
@@ -293,7 +302,7 @@ def case_path_data(ctx):
                             ctx.dev(nee), ctx.dev(dnee), ctx.dev(active.astype(np.uint8)), want_radiance=True)
     _, orad = so.process_path_data(Lf, tr, tb, bsdf, md)
     keep, orad2, onee = so.filter_records(active, orad, nee, wo)
-    assert np.array_equal(ctx.host(rad).view(U), orad2.view(U))
+    assert beq(ctx.host(rad), orad2)
     sub = so.SurfaceInteractionRecord(pos[keep], d[keep], orad2[keep], wo[keep], onee[keep], dnee[keep])
     cur.addDataPropagate(sub, exact=True)
     got = t.download(1)
@@ -317,14 +326,14 @@ def case_mis(ctx):
         s, m = t.mis_nee(ctx.dev(a[0]), ctx.dev(a[1]), ctx.dev(a[2]), ctx.dev(a[3]), ctx.dev(a[4]),
                          ctx.dev(delta.astype(np.uint8)), 0.5, it)
         os_, om = so.nee_mis(a[0], a[1], a[2], a[3], a[4], delta, 0.5, it)
-        assert np.array_equal(ctx.host(s).view(U), os_.view(U))
-        assert np.array_equal(ctx.host(m).view(U), om.view(U))
+        assert beq(ctx.host(s), os_)
+        assert beq(ctx.host(m), om)
     val = rng.random((n, 3)).astype(F)
     do = rng.random(n) < 0.6
     wo, w = t.mis_mixture(ctx.dev(a[0]), ctx.dev(a[1]), ctx.dev(val), ctx.dev(do.astype(np.uint8)), 0.5)
     owo, ow = so.mixture(a[0], a[1], val, do, 0.5)
-    assert np.array_equal(ctx.host(wo).view(U), owo.view(U))
-    assert np.array_equal(ctx.host(w).view(U), ow.view(U))
+    assert beq(ctx.host(wo), owo)
+    assert beq(ctx.host(w), ow)
 
 
 def case_guided_bounce(ctx):
@@ -342,11 +351,11 @@ def case_guided_bounce(ctx):
     d, sp, wp, wt = ctx.host(d), ctx.host(sp), ctx.host(wp), ctx.host(wt)
     m1, m2 = mode == 1, mode == 2
     od, op = prev.sample(pos, so.ExplicitSampler(seed=77, n=n), m1)
-    assert np.array_equal(d[m1].view(U), od[m1].view(U)) and np.array_equal(sp[m1].view(U), op[m1].view(U))
+    assert beq(d[m1], od[m1]) and beq(sp[m1], op[m1])
     op2 = prev.pdf(pos, wo, m2)
-    assert np.array_equal(sp[m2].view(U), op2[m2].view(U))
+    assert beq(sp[m2], op2[m2])
     owo, ow = so.mixture(bp, op2, bv, m2, 0.5)
-    assert np.array_equal(wp[m2].view(U), owo[m2].view(U)) and np.array_equal(wt[m2].view(U), ow[m2].view(U))
+    assert beq(wp[m2], owo[m2]) and beq(wt[m2], ow[m2])
     assert not d[mode == 0].any() and not sp[mode == 0].any()
 
 
