@@ -311,6 +311,7 @@ extern "C" int sdt_stat_buffers(sdt_handle h, float** q_energy, uint32_t* n_quad
     if (n_quad) *n_quad = H.n_quad;
     if (kd_count) *kd_count = h->kd_count;
     if (n_kd) *n_kd = H.n_kd;
+    h->stats_complete = false;      // the caller may reduce into the buffers: interiors are re-swept from the leaves
     return SDT_OK;
 }
 

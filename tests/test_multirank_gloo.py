@@ -1,0 +1,67 @@
+"""N>1 path on CPU: world_size-2 `gloo` run of the sharded training iteration -- every rank
+splats its slice of the records into its replica, the LEAF statistics are all-reduced
+(here through sdt_stat_buffers + torch.distributed, on the GPU through sdt_allreduce/NCCL),
+the deterministic refine then yields the same tree on every rank, equal to the tree a
+single rank builds from all the records.  Uses the host emulation of the kernels."""
+import ctypes
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+
+def _worker(rank, world, port, lib, out_dir):
+    import torch
+    import torch.distributed as dist
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import sdt_cases as cases
+    from practical_path_guiding_lab_b200 import SDTree
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    t = SDTree(lib_path=lib, store_nee=False, kd_capacity=1 << 12, quad_capacity=1 << 17)
+    for it in range(3):
+        rec = cases.dyadic_records(16000, 300 + it, ((0.3, 0.7, 0.02), (0.8, 0.2, 0.005)))
+        n = rec.position.shape[0]
+        sl = slice(rank * n // world, (rank + 1) * n // world)
+        t.splat_records(rec.position[sl], rec.direction[sl], rec.radiance[sl], rec.woPdf[sl])
+        qp, nq, kp, nk = t.stat_buffers()
+        q = np.ctypeslib.as_array(ctypes.cast(qp, ctypes.POINTER(ctypes.c_float)), shape=(nq,))
+        k = np.ctypeslib.as_array(ctypes.cast(kp, ctypes.POINTER(ctypes.c_float)), shape=(nk,))
+        buf = torch.from_numpy(np.concatenate([q, k]))
+        dist.all_reduce(buf)                                  # one exchange per training iteration
+        q[:] = buf[:nq].numpy()
+        k[:] = buf[nq:].numpy()
+        t.set_max_leaf_size(500)
+        t.refine()
+    d = t.download(0)
+    np.savez(os.path.join(out_dir, f"rank{rank}.npz"), **d)
+    dist.destroy_process_group()
+
+
+def test_two_rank_training_matches_single_rank(tmp_path):
+    import torch.multiprocessing as mp
+    from hostemu.build_hostemu import build as build_hostemu
+    import sdt_cases as cases
+    from practical_path_guiding_lab_b200 import SDTree
+    lib = build_hostemu()
+    port = 29500 + os.getpid() % 2000
+    mp.spawn(_worker, args=(2, port, lib, str(tmp_path)), nprocs=2, join=True)
+    t = SDTree(lib_path=lib, store_nee=False, kd_capacity=1 << 12, quad_capacity=1 << 17)
+    for it in range(3):
+        rec = cases.dyadic_records(16000, 300 + it, ((0.3, 0.7, 0.02), (0.8, 0.2, 0.005)))
+        t.splat_records(rec.position, rec.direction, rec.radiance, rec.woPdf)
+        t.set_max_leaf_size(500)
+        t.refine()
+    one = t.download(0)
+    assert one['kdtree_depth'].shape[0] > 31
+    for r in range(2):
+        d = np.load(os.path.join(str(tmp_path), f"rank{r}.npz"))
+        for k in one:
+            a, b = np.asarray(one[k]), np.asarray(d[k])
+            assert a.shape == b.shape and np.array_equal(a, b), (r, k)
