@@ -30,7 +30,7 @@
 struct __align__(32) QRec {
     uint32_t child_base;     // canonical node id of child_1; children are base..base+3
     uint32_t interior_base;  // record index of the first non-leaf child
-    uint32_t leafmask;       // bit c set: child c is a leaf (has no record)
+    uint32_t cinfo;          // bits 0-3: child c is a leaf (no record); bits 8-15: see sdt_make_cinfo
     float own;               // this node's stored energy (pdf denominator, :1056)
     float e[4];              // the four children's stored energies (:969-972, :1057-1060)
 };
@@ -180,106 +180,167 @@ SDT_HD float sdt_ld(const float* p, int64_t stride, uint32_t i) { return SDT_LDG
 
 // ---- spatial descent: KDTree.getLeafNodeIndex, src/kdtree.py:435-470 --------
 // Returns the leaf node id (0 for lanes outside the root box, like the reference).
-// `kd` is the smem-staged prefix of kd_word (n_smem words), `kdg` the full array.
+// `kd` is the smem-staged prefix of kd_word (n_smem words), `kdg` the full array;
+// ALL_SMEM: the whole tree is staged (no range check, no global path in the loop).
 struct KdResult { uint32_t leaf; uint32_t root; bool inbox; };
 
-SDT_HD KdResult sdt_kd_descend(const uint32_t* __restrict__ kd, uint32_t n_smem,
-                               const uint32_t* __restrict__ kdg, const DevHeader* __restrict__ hdr,
-                               float px, float py, float pz) {
+template <bool ALL_SMEM>
+SDT_HD uint32_t sdt_kd_load(const uint32_t* __restrict__ kd, uint32_t n_smem, const uint32_t* __restrict__ kdg, uint32_t node) {
+    if (ALL_SMEM) return kd[node];
+    return (node < n_smem) ? kd[node] : SDT_LDG(kdg + node);
+}
+
+// one level on one axis: children are left [lo, mid] and right [mid, hi]; the reference assigns
+// left first, right second, so the right child wins on the plane (:462-468)
+#define SDT_KD_STEP(P, LO, HI)                                              \
+    {                                                                       \
+        const float mid = (LO + HI) / 2.0f;                                 \
+        const bool right = P >= mid;                                        \
+        LO = right ? mid : LO;                                              \
+        HI = right ? HI : mid;                                              \
+        node = w + (right ? 1u : 0u);                                       \
+        w = sdt_kd_load<ALL_SMEM>(kd, n_smem, kdg, node);                   \
+        if (w & SDT_KD_LEAF_BIT) break;                                     \
+    }
+
+// per-thread constants of the spatial descent (loaded once per thread, not per vertex)
+struct KdCtx {
+    const uint32_t* kd;       // smem-staged prefix of kd_word
+    uint32_t n_smem;
+    const uint32_t* kdg;      // full array
+    float lo[3], hi[3];       // root box
+    uint32_t root0;           // quadTreeRootIndex[0]
+};
+SDT_HD KdCtx sdt_kd_ctx(const uint32_t* kd, uint32_t n_smem, const uint32_t* kdg, const DevHeader* hdr) {
+    KdCtx k;
+    k.kd = kd; k.n_smem = n_smem; k.kdg = kdg;
+    for (int a = 0; a < 3; ++a) { k.lo[a] = hdr->bbox_min[a]; k.hi[a] = hdr->bbox_max[a]; }
+    k.root0 = hdr->root_of_node0;
+    return k;
+}
+
+template <bool ALL_SMEM>
+SDT_HD KdResult sdt_kd_descend(const KdCtx& k, float px, float py, float pz) {
+    const uint32_t* __restrict__ kd = k.kd;
+    const uint32_t* __restrict__ kdg = k.kdg;
+    const uint32_t n_smem = k.n_smem;
     KdResult r;
-    float lo0 = hdr->bbox_min[0], lo1 = hdr->bbox_min[1], lo2 = hdr->bbox_min[2];
-    float hi0 = hdr->bbox_max[0], hi1 = hdr->bbox_max[1], hi2 = hdr->bbox_max[2];
+    float lo0 = k.lo[0], lo1 = k.lo[1], lo2 = k.lo[2];
+    float hi0 = k.hi[0], hi1 = k.hi[1], hi2 = k.hi[2];
     // BoundingBox3f.contains: inclusive; NaN fails every comparison
     r.inbox = (px >= lo0) && (px <= hi0) && (py >= lo1) && (py <= hi1) && (pz >= lo2) && (pz <= hi2);
     r.leaf = 0;
-    r.root = hdr->root_of_node0;
+    r.root = k.root0;
     if (!r.inbox) return r;
     uint32_t node = 0;
-    uint32_t w = n_smem ? kd[0] : SDT_LDG(kdg);
-    int axis = 0;
-    while (!(w & SDT_KD_LEAF_BIT)) {
-        // children: left [lo, mid], right [mid, hi] on `axis`; left is assigned first,
-        // right second, so the right child wins on the plane (:462-468)
-        bool right;
-        if (axis == 0) { const float mid = (lo0 + hi0) / 2.0f; right = px >= mid; if (right) lo0 = mid; else hi0 = mid; }
-        else if (axis == 1) { const float mid = (lo1 + hi1) / 2.0f; right = py >= mid; if (right) lo1 = mid; else hi1 = mid; }
-        else { const float mid = (lo2 + hi2) / 2.0f; right = pz >= mid; if (right) lo2 = mid; else hi2 = mid; }
-        node = w + (right ? 1u : 0u);
-        w = (node < n_smem) ? kd[node] : SDT_LDG(kdg + node);
-        axis = (axis == 2) ? 0 : axis + 1;
+    uint32_t w = sdt_kd_load<ALL_SMEM>(kd, n_smem, kdg, 0u);
+    if (!(w & SDT_KD_LEAF_BIT)) {
+        for (int guard = 0; guard < SDT_KD_MAX_DEPTH; guard += 3) {   // axis = depth % 3 (:277)
+            SDT_KD_STEP(px, lo0, hi0)
+            SDT_KD_STEP(py, lo1, hi1)
+            SDT_KD_STEP(pz, lo2, hi2)
+        }
     }
     r.leaf = node;
     r.root = w & ~SDT_KD_LEAF_BIT;
     return r;
 }
 
-SDT_HD void sdt_load_rec(const QRec* __restrict__ rec, uint32_t i, QRec& out) {
+struct __align__(16) SdtF4 { float x, y, z, w; };
+
+// record words 0..3 {child_base, interior_base, cinfo, own}
+struct QHead { uint32_t child_base, interior_base, cinfo; float own; };
+
+SDT_HD QHead sdt_load_head(const QRec* __restrict__ rec, uint32_t i) {
+    QHead h;
 #if defined(__CUDA_ARCH__)
-    const float4* p = reinterpret_cast<const float4*>(rec + i);
-    const float4 a = __ldg(p), b = __ldg(p + 1);
-    out.child_base = __float_as_uint(a.x);
-    out.interior_base = __float_as_uint(a.y);
-    out.leafmask = __float_as_uint(a.z);
-    out.own = a.w;
-    out.e[0] = b.x; out.e[1] = b.y; out.e[2] = b.z; out.e[3] = b.w;
+    const uint4 a = __ldg(reinterpret_cast<const uint4*>(rec + i));
+    h.child_base = a.x; h.interior_base = a.y; h.cinfo = a.z; h.own = __uint_as_float(a.w);
 #else
-    out = rec[i];
+    h.child_base = rec[i].child_base; h.interior_base = rec[i].interior_base; h.cinfo = rec[i].cinfo; h.own = rec[i].own;
 #endif
+    return h;
+}
+SDT_HD SdtF4 sdt_load_f4(const float* __restrict__ p) {
+    SdtF4 v;
+#if defined(__CUDA_ARCH__)
+    const float4 a = __ldg(reinterpret_cast<const float4*>(p));
+    v.x = a.x; v.y = a.y; v.z = a.z; v.w = a.w;
+#else
+    v.x = p[0]; v.y = p[1]; v.z = p[2]; v.w = p[3];
+#endif
+    return v;
 }
 
-SDT_HD uint32_t sdt_popc4(uint32_t v) {
-    v &= 0xFu;
-    return (v & 1u) + ((v >> 1) & 1u) + ((v >> 2) & 1u) + ((v >> 3) & 1u);
+// cinfo: bits 0..3 = child c is a leaf; bits 8+2c..9+2c = rank of child c among the
+// non-leaf children (its record is interior_base + rank)
+SDT_HD uint32_t sdt_make_cinfo(uint32_t leafmask) {
+    uint32_t ci = leafmask & 0xFu, run = 0;
+    for (uint32_t c = 0; c < 4u; ++c) {
+        ci |= run << (8u + 2u * c);
+        if (!((leafmask >> c) & 1u)) ++run;
+    }
+    return ci;
+}
+// record index of child c, or SDT_NONE when it is a leaf
+SDT_HD uint32_t sdt_child_rec(uint32_t cinfo, uint32_t interior_base, uint32_t c) {
+    const uint32_t off = (cinfo >> (8u + 2u * c)) & 3u;
+    return ((cinfo >> c) & 1u) ? SDT_NONE : interior_base + off;
 }
 
 // quadrant c (0..3 = child_1..child_4) of [lo,hi], src/quadtree.py:153-175:
-// c1 = [mid,max], c2 = upper-left, c3 = [min,mid], c4 = lower-right
-SDT_HD void sdt_quadrant(int c, float& lox, float& loy, float& hix, float& hiy) {
-    const float mx = (lox + hix) / 2.0f, my = (loy + hiy) / 2.0f;
-    if (c == 0) { lox = mx; loy = my; }
-    else if (c == 1) { hix = mx; loy = my; }
-    else if (c == 2) { hix = mx; hiy = my; }
-    else { lox = mx; hiy = my; }
+// c1 = [mid,max] upper-right, c2 upper-left, c3 = [min,mid] lower-left, c4 lower-right
+SDT_HD void sdt_quadrant_m(uint32_t c, float mx, float my, float& lox, float& loy, float& hix, float& hiy) {
+    const bool right = (c == 0u) || (c == 3u);
+    const bool top = c < 2u;
+    lox = right ? mx : lox;
+    hix = right ? hix : mx;
+    loy = top ? my : loy;
+    hiy = top ? hiy : my;
 }
-
-// record index of child c, or SDT_NONE when it is a leaf
-SDT_HD uint32_t sdt_child_rec(const QRec& r, int c) {
-    if ((r.leafmask >> c) & 1u) return SDT_NONE;
-    return r.interior_base + sdt_popc4((~r.leafmask) & ((1u << c) - 1u));
+SDT_HD void sdt_quadrant(int c, float& lox, float& loy, float& hix, float& hiy) {
+    sdt_quadrant_m((uint32_t)c, (lox + hix) / 2.0f, (loy + hiy) / 2.0f, lox, loy, hix, hiy);
 }
 
 // child that the DESCENT follows for a point of the node box: the reference assigns
 // c1..c4 in turn, so the LAST matching (inclusive) child box wins
 // (src/quadtree.py:1095-1098 for pdf, :424-438 for splat)
-SDT_HD int sdt_descend_child(float x, float y, float mx, float my) {
-    return (y <= my) ? ((x >= mx) ? 3 : 2) : ((x <= mx) ? 1 : 0);
+SDT_HD uint32_t sdt_descend_child(float x, float y, float mx, float my) {
+    return (y <= my) ? ((x >= mx) ? 3u : 2u) : ((x <= mx) ? 1u : 0u);
 }
 // child whose ENERGY enters the pdf: FIRST matching child box (src/quadtree.py:1063-1075)
-SDT_HD int sdt_energy_child(float x, float y, float mx, float my) {
-    return (y >= my) ? ((x >= mx) ? 0 : 1) : ((x <= mx) ? 2 : 3);
+SDT_HD uint32_t sdt_energy_child(float x, float y, float mx, float my) {
+    return (y >= my) ? ((x >= mx) ? 0u : 1u) : ((x <= mx) ? 2u : 3u);
+}
+SDT_HD float sdt_pick4(const SdtF4& v, uint32_t c) {
+    const float a = (c & 1u) ? v.y : v.x;
+    const float b = (c & 1u) ? v.w : v.z;
+    return (c & 2u) ? b : a;
 }
 
 // QuadTree.pdfQuadTree, src/quadtree.py:1001-1101, from canonical position (x,y) in
-// [0,1]^2.  ri = record index of the root (SDT_NONE: single-leaf tree).
+// [0,1]^2.  ri = record index of the root (SDT_NONE: single-leaf tree).  One 32-byte record
+// (one L2 sector) per level carries everything: child ids, own energy, child energies.
 SDT_HD float sdt_quad_pdf(const QRec* __restrict__ rec, uint32_t ri, uint32_t root_node,
                           float x, float y, uint32_t& node_out) {
     float pdf = 1.0f;
     float lox = 0.0f, loy = 0.0f, hix = 1.0f, hiy = 1.0f;
     uint32_t node = root_node;
+    bool dead = false;
     for (int level = 0; level < SDT_MAX_LEVELS; ++level) {
-        if (ri == SDT_NONE) { pdf = pdf * SDT_INV_FOUR_PI; break; }     // :1030
-        QRec r;
-        sdt_load_rec(rec, ri, r);
+        if (ri == SDT_NONE) break;
+        const QHead h = sdt_load_head(rec, ri);
+        const SdtF4 e = sdt_load_f4(rec[ri].e);
         const float mx = (lox + hix) / 2.0f, my = (loy + hiy) / 2.0f;
-        const int ce = sdt_energy_child(x, y, mx, my);
-        const int cd = sdt_descend_child(x, y, mx, my);
-        const float ratio = (4.0f * r.e[ce]) / r.own;                   // :1084
-        pdf = pdf * ratio;
-        if (pdf != pdf) { pdf = 0.0f; break; }                          // :1090-1092
-        node = r.child_base + cd;
-        sdt_quadrant(cd, lox, loy, hix, hiy);
-        ri = sdt_child_rec(r, cd);
+        const uint32_t ce = sdt_energy_child(x, y, mx, my);
+        const uint32_t cd = sdt_descend_child(x, y, mx, my);
+        pdf = pdf * ((4.0f * sdt_pick4(e, ce)) / h.own);                // :1084
+        if (pdf != pdf) { dead = true; break; }                         // :1090-1092
+        node = h.child_base + cd;
+        sdt_quadrant_m(cd, mx, my, lox, loy, hix, hiy);
+        ri = sdt_child_rec(h.cinfo, h.interior_base, cd);
     }
+    pdf = dead ? 0.0f : pdf * SDT_INV_FOUR_PI;                          // :1030
     node_out = node;
     return pdf;
 }
@@ -304,36 +365,39 @@ SDT_HD QSample sdt_quad_sample(const QRec* __restrict__ rec, uint32_t ri, uint32
     QSample q;
     q.x = 0.0f; q.y = 0.0f; q.node = root_node; q.pdf_path = 1.0f; q.pdf_dead = false; q.stuck = false;
     q.lox = 0.0f; q.loy = 0.0f; q.hix = 1.0f; q.hiy = 1.0f;
-    for (uint32_t level = 0; level < SDT_MAX_LEVELS; ++level) {
-        if (ri == SDT_NONE) {
-            const float ux = rng.get(3u * level), uy = rng.get(3u * level + 1u);
-            q.x = q.lox + ux * (q.hix - q.lox);                          // :960-962
-            q.y = q.loy + uy * (q.hiy - q.loy);
-            return q;
-        }
-        QRec r;
-        sdt_load_rec(rec, ri, r);
-        const float e1 = r.e[0];
-        const float e2 = r.e[1] + e1;                                    // :975-977
-        const float e3 = r.e[2] + e2;
-        const float e4 = r.e[3] + e3;
+    uint32_t level = 0;
+    // the loop only descends; the leaf position is drawn after it, where the warp has reconverged
+    for (; level < SDT_MAX_LEVELS; ++level) {
+        if (ri == SDT_NONE) break;
+        const QHead h = sdt_load_head(rec, ri);
+        const SdtF4 e = sdt_load_f4(rec[ri].e);
+        const float e1 = e.x;
+        const float e2 = e.y + e1;                                       // :975-977
+        const float e3 = e.z + e2;
+        const float e4 = e.w + e3;
         const float s = rng.get(3u * level + 2u) * e4;                   // :980
         int c = -1;                                                      // :983-991, later bins override
         if (s < e1) c = 0;
         if (e1 <= s && s < e2) c = 1;
         if (e2 <= s && s < e3) c = 2;
         if (e3 <= s) c = 3;
-        if (c < 0) { q.stuck = true; return q; }
+        if (c < 0) { q.stuck = true; break; }
+        const uint32_t cu = (uint32_t)c;
+        const float f = q.pdf_path * ((4.0f * sdt_pick4(e, cu)) / h.own);   // :1084
         if (!q.pdf_dead) {
-            const float ratio = (4.0f * r.e[c]) / r.own;
-            q.pdf_path = q.pdf_path * ratio;
-            if (q.pdf_path != q.pdf_path) { q.pdf_path = 0.0f; q.pdf_dead = true; }
+            q.pdf_dead = f != f;                                         // :1090-1092
+            q.pdf_path = q.pdf_dead ? 0.0f : f;
         }
-        q.node = r.child_base + (uint32_t)c;
-        sdt_quadrant(c, q.lox, q.loy, q.hix, q.hiy);
-        ri = sdt_child_rec(r, c);
+        q.node = h.child_base + cu;
+        sdt_quadrant_m(cu, (q.lox + q.hix) / 2.0f, (q.loy + q.hiy) / 2.0f, q.lox, q.loy, q.hix, q.hiy);
+        ri = sdt_child_rec(h.cinfo, h.interior_base, cu);
     }
-    q.stuck = true;   // deeper than SDT_MAX_LEVELS: impossible for a valid tree
+    if (level >= SDT_MAX_LEVELS) q.stuck = true;   // deeper than SDT_MAX_LEVELS: impossible for a valid tree
+    if (!q.stuck) {
+        const float ux = rng.get(3u * level), uy = rng.get(3u * level + 1u);
+        q.x = q.lox + ux * (q.hix - q.lox);                              // :960-962
+        q.y = q.loy + uy * (q.hiy - q.loy);
+    }
     return q;
 }
 
@@ -366,15 +430,12 @@ SDT_HD uint32_t sdt_quad_leaf(const QRec* __restrict__ rec, uint32_t ri, uint32_
     float lox = 0.0f, loy = 0.0f, hix = 1.0f, hiy = 1.0f;
     uint32_t node = root_node;
     for (int level = 0; level < SDT_MAX_LEVELS && ri != SDT_NONE; ++level) {
-        // only child_base / interior_base / leafmask are needed: 12 of the 32 bytes
-        const uint32_t cb = SDT_LDG(&rec[ri].child_base);
-        const uint32_t ib = SDT_LDG(&rec[ri].interior_base);
-        const uint32_t lm = SDT_LDG(&rec[ri].leafmask);
+        const QHead h = sdt_load_head(rec, ri);      // 16 of the record's 32 bytes
         const float mx = (lox + hix) / 2.0f, my = (loy + hiy) / 2.0f;
-        const int cd = sdt_descend_child(x, y, mx, my);
-        node = cb + (uint32_t)cd;
-        sdt_quadrant(cd, lox, loy, hix, hiy);
-        ri = ((lm >> cd) & 1u) ? SDT_NONE : ib + sdt_popc4((~lm) & ((1u << cd) - 1u));
+        const uint32_t cd = sdt_descend_child(x, y, mx, my);
+        node = h.child_base + cd;
+        sdt_quadrant_m(cd, mx, my, lox, loy, hix, hiy);
+        ri = sdt_child_rec(h.cinfo, h.interior_base, cd);
     }
     return node;
 }

@@ -51,6 +51,9 @@ struct sdt_tree_s {
     cudaStream_t last_stream = nullptr;
     uint64_t launches = 0;
     uint32_t levels_hint = 1;       // upper bound of quadtree levels in use
+    uint32_t kd_nodes_known = 1;    // last spatial node count seen by the host (sizes the smem staging)
+    cudaEvent_t hdr_event = nullptr;
+    bool hdr_pending = false;       // an async header read-back (after refine) is in flight
 
     // staging for SDT_HOST_PTRS
     char* stage = nullptr;
@@ -59,7 +62,7 @@ struct sdt_tree_s {
     // tuning
     int query_block = 256;
     int query_ctas_per_sm = 8;
-    int kd_smem_nodes = 8192;
+    int kd_smem_nodes = 24576;      // cap of the smem-staged prefix of the spatial tree (96 KB)
     int splat_block = 256;
     int splat_ctas_per_sm = 8;
     int fuse_sample_pdf = 1;

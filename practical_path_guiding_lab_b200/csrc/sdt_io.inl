@@ -17,6 +17,7 @@ static int sdt_free_all(sdt_handle h) {
         for (void* p : q) if (p) cudaFree(p);
     }
     if (h->h_hdr) cudaFreeHost(h->h_hdr);
+    if (h->hdr_event) cudaEventDestroy(h->hdr_event);
     return SDT_OK;
 }
 
@@ -71,6 +72,7 @@ extern "C" int sdt_create(const sdt_config* cfg, sdt_handle* out) {
     }
 #undef A
     if (st == SDT_OK && cudaMallocHost((void**)&h->h_hdr, sizeof(DevHeader)) != cudaSuccess) st = sdt_fail(h, SDT_ERR_CUDA, "cudaMallocHost failed");
+    if (st == SDT_OK && cudaEventCreate(&h->hdr_event) != cudaSuccess) st = sdt_fail(h, SDT_ERR_CUDA, "cudaEventCreate failed");
     if (st == SDT_OK) {
         // initial tree: src/kdtree.py:117-130, src/quadtree.py:350-362
         DevHeader H;
@@ -105,6 +107,8 @@ static int sdt_read_header(sdt_handle h, DevHeader& H) {
     SDT_CUDA(h, cudaStreamSynchronize(h->last_stream));
     SDT_CUDA(h, cudaMemcpy(h->h_hdr, h->set[h->cur].hdr, sizeof(DevHeader), cudaMemcpyDeviceToHost));
     H = *h->h_hdr;
+    h->hdr_pending = false;
+    h->kd_nodes_known = H.n_kd;
     return SDT_OK;
 }
 
@@ -221,6 +225,8 @@ extern "C" int sdt_upload(sdt_handle h, const sdt_arrays* a) {
     SDT_TRY(sdt_post_launch(h, "sdt_upload"));
     SDT_CUDA(h, cudaStreamSynchronize(nullptr));
     h->levels_hint = nlev > 0 ? nlev : 1;
+    h->kd_nodes_known = nk;
+    h->hdr_pending = false;
     h->stats_complete = true;
     return SDT_OK;
 }
@@ -320,7 +326,7 @@ extern "C" int sdt_set_tuning(sdt_handle h, const char* key, int64_t value) {
     const std::string k(key);
     if (k == "query_block") { SDT_CHECK(h, value >= 64 && value <= 256 && value % 32 == 0, SDT_ERR_INVALID, "query_block must be 64..256, multiple of 32"); h->query_block = (int)value; }
     else if (k == "query_ctas_per_sm") { SDT_CHECK(h, value >= 1 && value <= 32, SDT_ERR_INVALID, "query_ctas_per_sm must be 1..32"); h->query_ctas_per_sm = (int)value; }
-    else if (k == "kd_smem_nodes") { SDT_CHECK(h, value >= 0 && value <= 12288, SDT_ERR_INVALID, "kd_smem_nodes must be 0..12288"); h->kd_smem_nodes = (int)value; }
+    else if (k == "kd_smem_nodes") { SDT_CHECK(h, value >= 0 && value <= 49152, SDT_ERR_INVALID, "kd_smem_nodes must be 0..49152"); h->kd_smem_nodes = (int)value; }
     else if (k == "splat_block") { SDT_CHECK(h, value >= 64 && value <= 256 && value % 32 == 0, SDT_ERR_INVALID, "splat_block must be 64..256, multiple of 32"); h->splat_block = (int)value; }
     else if (k == "splat_ctas_per_sm") { SDT_CHECK(h, value >= 1 && value <= 32, SDT_ERR_INVALID, "splat_ctas_per_sm must be 1..32"); h->splat_ctas_per_sm = (int)value; }
     else if (k == "fuse_sample_pdf") h->fuse_sample_pdf = value != 0;

@@ -8,26 +8,48 @@ template <class Lane>
 __global__ void __launch_bounds__(256) k_wavefront(Lane f, uint32_t n, uint32_t smem_cap) {
     extern __shared__ uint32_t kd_s[];
     const DevHeader* hdr = f.t.hdr;
-    uint32_t n_smem = hdr->n_kd;
-    if (n_smem > smem_cap) n_smem = smem_cap;
+    const uint32_t n_kd = hdr->n_kd;
+    const uint32_t n_smem = n_kd < smem_cap ? n_kd : smem_cap;
     for (uint32_t j = threadIdx.x; j < n_smem; j += blockDim.x) kd_s[j] = __ldg(f.t.kd_word + j);
+    const KdCtx k = sdt_kd_ctx(kd_s, n_smem, f.t.kd_word, hdr);
     __syncthreads();
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
-        f(kd_s, n_smem, i);
+    if (n_smem == n_kd) {           // whole spatial tree staged: descent loop without the global path
+        for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+            f.template run<true>(k, i);
+    } else {
+        for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+            f.template run<false>(k, i);
+    }
 }
 
+// Persistent grid: 148 SMs x resident CTAs.  The smem staging is sized to the spatial tree the
+// host last saw (exact after upload / get_sizes; after a refine a non-blocking header read-back
+// refreshes it), capped by the "kd_smem_nodes" tuning; a larger tree falls back to global loads
+// for the nodes beyond the staged prefix.
 template <class Lane>
 static int launch_wavefront(sdt_handle h, cudaStream_t st, uint32_t n, const Lane& f, int block, int ctas_per_sm) {
     if (n == 0) return SDT_OK;
-    uint32_t smem_nodes = (uint32_t)h->kd_smem_nodes;
-    if (smem_nodes > 12288u) smem_nodes = 12288u;     // 48 KB static limit without opt-in
-    const size_t smem = (size_t)smem_nodes * 4u;
-    static int occ_cache[8] = {0};
-    int& occ = occ_cache[(block >> 6) & 7];
-    if (occ == 0) {
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_wavefront<Lane>, block, smem) != cudaSuccess || occ < 1) occ = 1;
+    if (h->hdr_pending && cudaEventQuery(h->hdr_event) == cudaSuccess) {
+        h->hdr_pending = false;
+        h->kd_nodes_known = h->h_hdr->n_kd;
     }
-    int per_sm = ctas_per_sm < occ ? ctas_per_sm : occ;
+    uint32_t want = h->hdr_pending ? 2u * h->kd_nodes_known + 2u : h->kd_nodes_known;   // a refine at most... unknown: be generous
+    uint32_t smem_nodes = (want + 255u) & ~255u;
+    if (smem_nodes > (uint32_t)h->kd_smem_nodes) smem_nodes = (uint32_t)h->kd_smem_nodes;
+    const size_t smem = (size_t)smem_nodes * 4u;
+    static size_t attr_set = 0;
+    if (smem > 48u * 1024u && smem > attr_set) {
+        if (cudaFuncSetAttribute(k_wavefront<Lane>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess)
+            return sdt_fail(h, SDT_ERR_CUDA, "cudaFuncSetAttribute(MaxDynamicSharedMemorySize) failed");
+        attr_set = 200 * 1024;
+    }
+    static int occ_cache = 0, occ_block = 0;
+    static size_t occ_smem = ~(size_t)0;
+    if (occ_smem != smem || occ_block != block) {
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_cache, k_wavefront<Lane>, block, smem) != cudaSuccess || occ_cache < 1) occ_cache = 1;
+        occ_smem = smem; occ_block = block;
+    }
+    int per_sm = ctas_per_sm < occ_cache ? ctas_per_sm : occ_cache;
     if (per_sm < 1) per_sm = 1;
     uint32_t grid = (n + (uint32_t)block - 1u) / (uint32_t)block;
     const uint32_t cap = (uint32_t)(h->num_sms * per_sm);
@@ -40,7 +62,8 @@ static int launch_wavefront(sdt_handle h, cudaStream_t st, uint32_t n, const Lan
 #else
 template <class Lane>
 static int launch_wavefront(sdt_handle h, cudaStream_t st, uint32_t n, const Lane& f, int, int) {
-    for (uint32_t i = 0; i < n; ++i) f(f.t.kd_word, 0u, i);
+    const KdCtx k = sdt_kd_ctx(f.t.kd_word, 0u, f.t.kd_word, f.t.hdr);
+    for (uint32_t i = 0; i < n; ++i) f.template run<false>(k, i);
     ++h->launches;
     h->last_stream = st;
     return SDT_OK;
@@ -51,11 +74,12 @@ static int launch_wavefront(sdt_handle h, cudaStream_t st, uint32_t n, const Lan
 struct LocateLane {
     TreeView t;
     sdt_vec3 pos; const uint8_t* active; uint32_t* leaf; uint32_t* root;
-    SDT_HD void operator()(const uint32_t* kd, uint32_t n_smem, uint32_t i) const {
+    template <bool ALL_SMEM>
+    SDT_HD void run(const KdCtx& k, uint32_t i) const {
         const bool act = active ? SDT_LDG(active + i) != 0 : true;
         uint32_t lf = 0, rt = 0;                     // inactive: node 0, masked gather -> 0
         if (act) {
-            const KdResult r = sdt_kd_descend(kd, n_smem, t.kd_word, t.hdr, sdt_ld(pos.x, pos.stride, i),
+            const KdResult r = sdt_kd_descend<ALL_SMEM>(k, sdt_ld(pos.x, pos.stride, i),
                                               sdt_ld(pos.y, pos.stride, i), sdt_ld(pos.z, pos.stride, i));
             lf = r.leaf; rt = r.root;
         }
@@ -69,12 +93,13 @@ struct SampleLane {
     sdt_vec3 pos; const uint8_t* active;
     const float* u; uint32_t u_stride, seed, lane_offset;
     sdt_vec3_out dir; float* pdf; uint32_t* dbg; int fuse;
-    SDT_HD void operator()(const uint32_t* kd, uint32_t n_smem, uint32_t i) const {
+    template <bool ALL_SMEM>
+    SDT_HD void run(const KdCtx& k, uint32_t i) const {
         const bool act = active ? SDT_LDG(active + i) != 0 : true;
         float dx = 0.0f, dy = 0.0f, dz = -1.0f, p = 1.0f;   // inactive lanes: pos (0,0) -> (0,0,-1), pdf 1
         uint32_t d0 = 0, d1 = 0, d2 = 0, d3 = 0;
         if (act) {
-            const KdResult r = sdt_kd_descend(kd, n_smem, t.kd_word, t.hdr, sdt_ld(pos.x, pos.stride, i),
+            const KdResult r = sdt_kd_descend<ALL_SMEM>(k, sdt_ld(pos.x, pos.stride, i),
                                               sdt_ld(pos.y, pos.stride, i), sdt_ld(pos.z, pos.stride, i));
             const LaneRng rng{u, u_stride, seed, lane_offset + i, i};
             const GuidedSample g = sdt_sample_tree(t, r.root, rng, fuse != 0);
@@ -91,12 +116,13 @@ struct SampleLane {
 struct PdfLane {
     TreeView t;
     sdt_vec3 pos; sdt_vec3 dir; const uint8_t* active; float* pdf; uint32_t* dbg;
-    SDT_HD void operator()(const uint32_t* kd, uint32_t n_smem, uint32_t i) const {
+    template <bool ALL_SMEM>
+    SDT_HD void run(const KdCtx& k, uint32_t i) const {
         const bool act = active ? SDT_LDG(active + i) != 0 : true;
         float p = 1.0f;
         uint32_t d0 = 0, d1 = 0, d2 = 0;
         if (act) {
-            const KdResult r = sdt_kd_descend(kd, n_smem, t.kd_word, t.hdr, sdt_ld(pos.x, pos.stride, i),
+            const KdResult r = sdt_kd_descend<ALL_SMEM>(k, sdt_ld(pos.x, pos.stride, i),
                                               sdt_ld(pos.y, pos.stride, i), sdt_ld(pos.z, pos.stride, i));
             float x, y;
             sdt_dir_to_canonical(sdt_ld(dir.x, dir.stride, i), sdt_ld(dir.y, dir.stride, i), sdt_ld(dir.z, dir.stride, i), x, y);
@@ -114,10 +140,11 @@ struct PdfLane {
 struct GuidedLane {
     TreeView t;
     sdt_guided_args a; int fuse;
-    SDT_HD void operator()(const uint32_t* kd, uint32_t n_smem, uint32_t i) const {
+    template <bool ALL_SMEM>
+    SDT_HD void run(const KdCtx& k, uint32_t i) const {
         const uint32_t m = SDT_LDG(a.mode + i);
         if (m != 1u && m != 2u) return;
-        const KdResult r = sdt_kd_descend(kd, n_smem, t.kd_word, t.hdr, sdt_ld(a.pos.x, a.pos.stride, i),
+        const KdResult r = sdt_kd_descend<ALL_SMEM>(k, sdt_ld(a.pos.x, a.pos.stride, i),
                                           sdt_ld(a.pos.y, a.pos.stride, i), sdt_ld(a.pos.z, a.pos.stride, i));
         if (m == 1u) {
             const LaneRng rng{a.u, a.u_stride, a.seed, a.lane_offset + i, i};

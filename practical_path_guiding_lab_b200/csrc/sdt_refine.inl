@@ -257,23 +257,14 @@ struct RecBuildItem {
         QRec r;
         r.child_base = cb;
         r.interior_base = iidx[cb];
-        r.leafmask = 0;
+        uint32_t leafmask = 0;
         for (uint32_t k = 0; k < 4u; ++k) {
-            if (!child[cb + k]) r.leafmask |= 1u << k;
+            if (!child[cb + k]) leafmask |= 1u << k;
             r.e[k] = energy[cb + k];
         }
+        r.cinfo = sdt_make_cinfo(leafmask);
         r.own = energy[i];
         rec[iidx[i]] = r;
-    }
-};
-struct RecEnergyItem {      // refresh own / child energies only (topology unchanged)
-    const uint32_t* child; const float* energy; const uint32_t* iidx; QRec* rec;
-    SDT_HD void operator()(uint32_t i) const {
-        const uint32_t cb = child[i];
-        if (!cb) return;
-        QRec* r = rec + iidx[i];
-        r->own = energy[i];
-        for (uint32_t k = 0; k < 4u; ++k) r->e[k] = energy[cb + k];
     }
 };
 
@@ -332,6 +323,9 @@ extern "C" int sdt_refine(sdt_handle h, uint32_t flags, sdt_stream stream) {
     h->cur = 1 - h->cur;
     h->levels_hint = levels_bound;
     h->stats_complete = true;
+    // non-blocking read-back of the new sizes (only used to size the smem staging of later launches)
+    if (cudaMemcpyAsync(h->h_hdr, s1.hdr, sizeof(DevHeader), cudaMemcpyDeviceToHost, st) == cudaSuccess &&
+        cudaEventRecord(h->hdr_event, st) == cudaSuccess) h->hdr_pending = true;
     if (flags & SDT_SYNC) SDT_CUDA(h, cudaStreamSynchronize(st));
     return SDT_OK;
 }

@@ -40,12 +40,13 @@ SDT_HD void sdt_splat_add(float* base, uint32_t idx, float v, bool valid) {
 }
 
 // one record through both trees
-SDT_HD void sdt_splat_one(const TreeView& t, const SplatTarget& tg, const uint32_t* kd, uint32_t n_smem, bool act,
+template <bool ALL_SMEM>
+SDT_HD void sdt_splat_one(const TreeView& t, const SplatTarget& tg, const KdCtx& k, bool act,
                           float px, float py, float pz, float dx, float dy, float radiance, float wo_pdf,
                           float nr, float ng, float nb, float ndx, float ndy) {
     KdResult r;
     r.leaf = 0; r.root = 0; r.inbox = false;
-    if (act) r = sdt_kd_descend(kd, n_smem, t.kd_word, t.hdr, px, py, pz);
+    if (act) r = sdt_kd_descend<ALL_SMEM>(k, px, py, pz);
     // src/kdtree.py:199: +1.0f (fp32 counter; exact below 2^24, then it sticks like the reference's)
     sdt_splat_add(tg.kd_count, r.leaf, 1.0f, act && r.inbox);
     // src/kdtree.py:224: the root id is gathered UNMASKED -- out-of-box records go to the tree of node 0
@@ -66,7 +67,8 @@ SDT_HD void sdt_splat_one(const TreeView& t, const SplatTarget& tg, const uint32
 
 struct SplatRecordsLane {
     TreeView t; SplatTarget tg; sdt_records r;
-    SDT_HD void operator()(const uint32_t* kd, uint32_t n_smem, uint32_t i) const {
+    template <bool ALL_SMEM>
+    SDT_HD void run(const KdCtx& k, uint32_t i) const {
         const bool act = r.active ? SDT_LDG(r.active + i) != 0 : true;
         float nr = 0.0f, ng = 0.0f, nb = 0.0f, ndx = 0.0f, ndy = 0.0f;
         if (tg.store_nee && r.radiance_nee.x && r.direction_nee.x) {
@@ -76,7 +78,7 @@ struct SplatRecordsLane {
             ndx = sdt_ld(r.direction_nee.x, r.direction_nee.stride, i);
             ndy = sdt_ld(r.direction_nee.y, r.direction_nee.stride, i);
         }
-        sdt_splat_one(t, tg, kd, n_smem, act,
+        sdt_splat_one<ALL_SMEM>(t, tg, k, act,
                       sdt_ld(r.position.x, r.position.stride, i), sdt_ld(r.position.y, r.position.stride, i), sdt_ld(r.position.z, r.position.stride, i),
                       sdt_ld(r.direction.x, r.direction.stride, i), sdt_ld(r.direction.y, r.direction.stride, i),
                       SDT_LDG(r.radiance + i), SDT_LDG(r.wo_pdf + i), nr, ng, nb, ndx, ndy);
@@ -89,7 +91,8 @@ SDT_HD float sdt_nan0(float v) { return (v != v) ? 0.0f : v; }
 // in front of the splat: no compaction pass, the filter just masks the lane.
 struct SplatPathLane {
     TreeView t; SplatTarget tg; sdt_path_data p;
-    SDT_HD void operator()(const uint32_t* kd, uint32_t n_smem, uint32_t i) const {
+    template <bool ALL_SMEM>
+    SDT_HD void run(const KdCtx& k, uint32_t i) const {
         const uint32_t ray = i / p.max_depth;                                          // :440
         float inc[3];
         const float* lf[3] = {p.l_final.x, p.l_final.y, p.l_final.z};
@@ -118,7 +121,7 @@ struct SplatPathLane {
         const bool both_zero = (radiance == 0.0f) && (sdt_luminance(nr, ng, nb) == 0.0f);  // :470-472
         bool act = p.active ? SDT_LDG(p.active + i) != 0 : true;
         act = act && !both_zero && !(wo_pdf == 0.0f) && !(wo_pdf != wo_pdf);           // :475-478
-        sdt_splat_one(t, tg, kd, n_smem, act,
+        sdt_splat_one<ALL_SMEM>(t, tg, k, act,
                       sdt_ld(p.position.x, p.position.stride, i), sdt_ld(p.position.y, p.position.stride, i), sdt_ld(p.position.z, p.position.stride, i),
                       sdt_ld(p.direction.x, p.direction.stride, i), sdt_ld(p.direction.y, p.direction.stride, i),
                       radiance, wo_pdf, nr, ng, nb, ndx, ndy);
