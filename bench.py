@@ -40,12 +40,13 @@ CPU_SAMPLE = 1 << 17
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--n", type=int, default=N_DEFAULT, help="path vertices per step per GPU")
     ap.add_argument("--cpu-sample", type=int, default=CPU_SAMPLE)
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--tune", action="append", default=[], help="key=value passed to sdt_set_tuning (repeatable)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
 
@@ -62,43 +63,53 @@ def workload_config(n, world):
 
 # ------------------------------------------------------------------------------ clocks
 class ClockSampler:
-    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    """SM clock and throttle reasons sampled DURING the timed region (NVML, every ~2 ms)."""
 
     def __init__(self, index):
         self.index = index
-        self.rows = []
+        self.sm, self.reasons, self.mx = [], 0, None
         self.stop = False
         self.th = None
+        self.nv = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.mx = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.nv = None
 
     def _run(self):
+        nv = self.nv
         while not self.stop:
             try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits"],
-                                     capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([c.strip() for c in out.split(",")])
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                self.reasons |= int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
             except Exception:
                 pass
-            time.sleep(0.05)
+            time.sleep(0.002)
 
     def __enter__(self):
-        self.th = threading.Thread(target=self._run, daemon=True)
-        self.th.start()
+        if self.nv is not None:
+            self.th = threading.Thread(target=self._run, daemon=True)
+            self.th.start()
         return self
 
     def __exit__(self, *a):
         self.stop = True
-        self.th.join(timeout=10)
+        if self.th is not None:
+            self.th.join(timeout=10)
 
     def summary(self):
-        if not self.rows:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
-        sm = sorted(float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit())
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for k, n in enumerate(names) if any(len(r) > 2 + k and r[2 + k].lower().startswith("active") for r in self.rows)]
-        mx = [float(r[1]) for r in self.rows if r[1].replace(".", "").isdigit()]
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
-                "samples": len(self.rows)}
+        if self.nv is None or not self.sm:
+            return {"sm_mhz": None, "sm_max_mhz": self.mx, "reasons": ["unavailable"]}
+        nv = self.nv
+        names = {"hw_slowdown": nv.nvmlClocksThrottleReasonHwSlowdown, "hw_thermal_slowdown": nv.nvmlClocksThrottleReasonHwThermalSlowdown,
+                 "sw_thermal_slowdown": nv.nvmlClocksThrottleReasonSwThermalSlowdown, "sw_power_cap": nv.nvmlClocksThrottleReasonSwPowerCap}
+        sm = sorted(self.sm)
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": self.mx, "reasons": [k for k, bit in names.items() if self.reasons & bit],
+                "samples": len(sm), "sm_mhz_min": sm[0]}
 
 
 # ------------------------------------------------------------------------------ CPU port (oracle) arm
@@ -146,7 +157,8 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    m = args.cpu_sample
+    # bounded sample: the whole run (warm-up + steps) stays around 1-2 minutes of CPU work
+    m = int(min(args.cpu_sample, max(8192, args.cpu_sample * 12 // max(1, args.steps + args.warmup))))
     cur, prev = oracle_tree()
     pos, dirs, rec = cpu_inputs(m)
     for _ in range(args.warmup):
@@ -184,6 +196,9 @@ def run_b200(args):
         dist.init_process_group("nccl", device_id=dev)
     n = args.n
     tree = SDTree(device=local, kd_max_depth=20, quad_max_depth=20, store_nee=False)
+    for kv in args.tune:
+        key, val = kv.split("=")
+        tree.set_tuning(key, int(val))
     to_dev = lambda x: torch.from_numpy(np.ascontiguousarray(x)).to(dev)
     allreduce = None
     if world > 1:

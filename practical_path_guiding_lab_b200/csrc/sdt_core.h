@@ -18,7 +18,9 @@
 // Spatial binary tree: ONE 32-bit word per node (4 B per descent level):
 //   interior: child_base (left = base, right = base+1; the reference appends both
 //             children adjacently, src/kdtree.py:243-245)
-//   leaf    : SDT_KD_LEAF_BIT | quadTreeRootIndex
+//   leaf    : SDT_KD_LEAF_BIT | record index of its quadtree's root (0x7FFFFFFF: single-leaf
+//             tree) -- the descent lands directly on the first quadtree record; the root ID
+//             (= canonical node id of the root) is in kd_root[] for the callers that need it
 // The split plane is never stored: children partition axis depth%3 at
 // (min+max)/2 (src/kdtree.py:268-304), so the running box reproduces the
 // reference's stored child boxes bit for bit.
@@ -41,6 +43,8 @@ struct DevHeader {
     uint32_t n_kd, n_quad, n_roots, n_interior, n_levels, kd_leaves, error, refine_count;
     uint32_t root_of_node0;                 // quadTreeRootIndex[0] (out-of-box lanes, :224,:482)
     uint32_t kd_max_depth, quad_max_depth, store_nee;
+    uint32_t rootrec_of_node0;              // record index of that tree's root (SDT_NONE: single-leaf tree)
+    uint32_t pad0[3];
     float bbox_min[3], bbox_max[3];         // spatial root box
     float max_leaf_size;                    // KDTree.maxLeafSize as fp32
     uint32_t pad1;
@@ -69,7 +73,7 @@ enum DevError : uint32_t {
 struct TreeView {
     const DevHeader* hdr;
     const uint32_t* kd_word;
-    const uint32_t* root_iidx;  // per root id: record index of the root node or SDT_NONE
+    const uint32_t* kd_root;    // per spatial node: quadTreeRootIndex (= canonical node id of the tree's root)
     const QRec* rec;
 };
 
@@ -182,7 +186,7 @@ SDT_HD float sdt_ld(const float* p, int64_t stride, uint32_t i) { return SDT_LDG
 // Returns the leaf node id (0 for lanes outside the root box, like the reference).
 // `kd` is the smem-staged prefix of kd_word (n_smem words), `kdg` the full array;
 // ALL_SMEM: the whole tree is staged (no range check, no global path in the loop).
-struct KdResult { uint32_t leaf; uint32_t root; bool inbox; };
+struct KdResult { uint32_t leaf; uint32_t rootrec; bool inbox; };   // rootrec: record index of the quadtree root or SDT_NONE
 
 template <bool ALL_SMEM>
 SDT_HD uint32_t sdt_kd_load(const uint32_t* __restrict__ kd, uint32_t n_smem, const uint32_t* __restrict__ kdg, uint32_t node) {
@@ -209,13 +213,13 @@ struct KdCtx {
     uint32_t n_smem;
     const uint32_t* kdg;      // full array
     float lo[3], hi[3];       // root box
-    uint32_t root0;           // quadTreeRootIndex[0]
+    uint32_t rootrec0;        // root record of the tree owned by node 0 (out-of-box lanes, :224,:482)
 };
 SDT_HD KdCtx sdt_kd_ctx(const uint32_t* kd, uint32_t n_smem, const uint32_t* kdg, const DevHeader* hdr) {
     KdCtx k;
     k.kd = kd; k.n_smem = n_smem; k.kdg = kdg;
     for (int a = 0; a < 3; ++a) { k.lo[a] = hdr->bbox_min[a]; k.hi[a] = hdr->bbox_max[a]; }
-    k.root0 = hdr->root_of_node0;
+    k.rootrec0 = hdr->rootrec_of_node0;
     return k;
 }
 
@@ -230,7 +234,7 @@ SDT_HD KdResult sdt_kd_descend(const KdCtx& k, float px, float py, float pz) {
     // BoundingBox3f.contains: inclusive; NaN fails every comparison
     r.inbox = (px >= lo0) && (px <= hi0) && (py >= lo1) && (py <= hi1) && (pz >= lo2) && (pz <= hi2);
     r.leaf = 0;
-    r.root = k.root0;
+    r.rootrec = k.rootrec0;
     if (!r.inbox) return r;
     uint32_t node = 0;
     uint32_t w = sdt_kd_load<ALL_SMEM>(kd, n_smem, kdg, 0u);
@@ -242,7 +246,8 @@ SDT_HD KdResult sdt_kd_descend(const KdCtx& k, float px, float py, float pz) {
         }
     }
     r.leaf = node;
-    r.root = w & ~SDT_KD_LEAF_BIT;
+    r.rootrec = w & ~SDT_KD_LEAF_BIT;
+    if (r.rootrec == 0x7FFFFFFFu) r.rootrec = SDT_NONE;
     return r;
 }
 
@@ -260,6 +265,20 @@ SDT_HD QHead sdt_load_head(const QRec* __restrict__ rec, uint32_t i) {
     h.child_base = rec[i].child_base; h.interior_base = rec[i].interior_base; h.cinfo = rec[i].cinfo; h.own = rec[i].own;
 #endif
     return h;
+}
+// the whole 32-byte record with ONE load instruction (sm_100 256-bit global load): for a
+// divergent gather the L1 tag stage is charged per instruction and lane, so one LDG.256
+// costs half of two LDG.128 on the same sector
+SDT_HD void sdt_load_rec(const QRec* __restrict__ rec, uint32_t i, QHead& h, SdtF4& e) {
+#if defined(__CUDA_ARCH__)
+    uint32_t a, b, c, d;
+    asm("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+        : "=r"(a), "=r"(b), "=r"(c), "=r"(d), "=f"(e.x), "=f"(e.y), "=f"(e.z), "=f"(e.w) : "l"(rec + i));
+    h.child_base = a; h.interior_base = b; h.cinfo = c; h.own = __uint_as_float(d);
+#else
+    h.child_base = rec[i].child_base; h.interior_base = rec[i].interior_base; h.cinfo = rec[i].cinfo; h.own = rec[i].own;
+    e.x = rec[i].e[0]; e.y = rec[i].e[1]; e.z = rec[i].e[2]; e.w = rec[i].e[3];
+#endif
 }
 SDT_HD SdtF4 sdt_load_f4(const float* __restrict__ p) {
     SdtF4 v;
@@ -329,8 +348,8 @@ SDT_HD float sdt_quad_pdf(const QRec* __restrict__ rec, uint32_t ri, uint32_t ro
     bool dead = false;
     for (int level = 0; level < SDT_MAX_LEVELS; ++level) {
         if (ri == SDT_NONE) break;
-        const QHead h = sdt_load_head(rec, ri);
-        const SdtF4 e = sdt_load_f4(rec[ri].e);
+        QHead h; SdtF4 e;
+        sdt_load_rec(rec, ri, h, e);
         const float mx = (lox + hix) / 2.0f, my = (loy + hiy) / 2.0f;
         const uint32_t ce = sdt_energy_child(x, y, mx, my);
         const uint32_t cd = sdt_descend_child(x, y, mx, my);
@@ -369,8 +388,8 @@ SDT_HD QSample sdt_quad_sample(const QRec* __restrict__ rec, uint32_t ri, uint32
     // the loop only descends; the leaf position is drawn after it, where the warp has reconverged
     for (; level < SDT_MAX_LEVELS; ++level) {
         if (ri == SDT_NONE) break;
-        const QHead h = sdt_load_head(rec, ri);
-        const SdtF4 e = sdt_load_f4(rec[ri].e);
+        QHead h; SdtF4 e;
+        sdt_load_rec(rec, ri, h, e);
         const float e1 = e.x;
         const float e2 = e.y + e1;                                       // :975-977
         const float e3 = e.z + e2;
@@ -404,9 +423,10 @@ SDT_HD QSample sdt_quad_sample(const QRec* __restrict__ rec, uint32_t ri, uint32
 // KDTree.sample after the spatial descent (src/kdtree.py:482-485).
 struct GuidedSample { float dx, dy, dz, pdf; uint32_t sample_node, pdf_node; };
 
-SDT_HD GuidedSample sdt_sample_tree(const TreeView& t, uint32_t root, const LaneRng& rng, bool fuse) {
+// ri = record of the tree's root (from the spatial leaf word); root = its node id, only used for
+// the node ids reported to dbg (pass 0 when not needed)
+SDT_HD GuidedSample sdt_sample_tree(const TreeView& t, uint32_t ri, uint32_t root, const LaneRng& rng, bool fuse) {
     GuidedSample g;
-    const uint32_t ri = SDT_LDG(t.root_iidx + root);
     const QSample q = sdt_quad_sample(t.rec, ri, root, rng);
     sdt_canonical_to_dir(q.x, q.y, g.dx, g.dy, g.dz);                    // :996
     float px, py;

@@ -60,11 +60,11 @@ struct sdt_tree_s {
     size_t stage_cap = 0, stage_off = 0;
 
     // tuning
-    int query_block = 256;
-    int query_ctas_per_sm = 8;
+    int query_block = 512;
+    int query_ctas_per_sm = 4;
     int kd_smem_nodes = 24576;      // cap of the smem-staged prefix of the spatial tree (96 KB)
-    int splat_block = 256;
-    int splat_ctas_per_sm = 8;
+    int splat_block = 512;
+    int splat_ctas_per_sm = 4;
     int fuse_sample_pdf = 1;
     int splat_all_levels = 0;       // 1: atomics at every level like the reference (no sweep)
 
@@ -97,7 +97,7 @@ static inline ExecCtx exec_ctx(sdt_handle h, cudaStream_t st) {
 
 static inline TreeView tree_view(const sdt_tree_s* h) {
     const QuadSet& s = h->set[h->cur];
-    return TreeView{s.hdr, h->kd_word, s.root_iidx, s.rec};
+    return TreeView{s.hdr, h->kd_word, h->kd_root, s.rec};
 }
 
 static int sdt_read_header(sdt_handle h, DevHeader& H);

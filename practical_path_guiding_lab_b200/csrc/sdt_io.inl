@@ -35,6 +35,7 @@ static void sdt_initial_header(sdt_handle h, DevHeader& H) {
     for (int a = 0; a < 3; ++a) { H.bbox_min[a] = h->cfg.bbox_min[a]; H.bbox_max[a] = h->cfg.bbox_max[a]; }
     H.max_leaf_size = 1.0f;                      // KDTree(max_leaf_size=1), src/kdtree.py:117
     H.kd_cap = h->kd_cap; H.quad_cap = h->quad_cap;
+    H.rootrec_of_node0 = SDT_NONE;
     for (int l = 1; l < SDT_MAX_LEVELS + 2; ++l) H.level_off[l] = 1;
     H.level_cnt[0] = 1;
 }
@@ -77,7 +78,7 @@ extern "C" int sdt_create(const sdt_config* cfg, sdt_handle* out) {
         // initial tree: src/kdtree.py:117-130, src/quadtree.py:350-362
         DevHeader H;
         sdt_initial_header(h, H);
-        const uint32_t word0 = SDT_KD_LEAF_BIT | 0u, none = SDT_NONE;
+        const uint32_t word0 = SDT_KD_LEAF_BIT | 0x7FFFFFFFu, none = SDT_NONE;
         const float inf = INFINITY;
         cudaMemcpy(h->set[0].hdr, &H, sizeof(H), cudaMemcpyHostToDevice);
         cudaMemcpy(h->set[1].hdr, &H, sizeof(H), cudaMemcpyHostToDevice);
@@ -324,10 +325,10 @@ extern "C" int sdt_stat_buffers(sdt_handle h, float** q_energy, uint32_t* n_quad
 extern "C" int sdt_set_tuning(sdt_handle h, const char* key, int64_t value) {
     if (!h || !key) return SDT_ERR_INVALID;
     const std::string k(key);
-    if (k == "query_block") { SDT_CHECK(h, value >= 64 && value <= 256 && value % 32 == 0, SDT_ERR_INVALID, "query_block must be 64..256, multiple of 32"); h->query_block = (int)value; }
+    if (k == "query_block") { SDT_CHECK(h, value >= 64 && value <= 512 && value % 32 == 0, SDT_ERR_INVALID, "query_block must be 64..512, multiple of 32"); h->query_block = (int)value; }
     else if (k == "query_ctas_per_sm") { SDT_CHECK(h, value >= 1 && value <= 32, SDT_ERR_INVALID, "query_ctas_per_sm must be 1..32"); h->query_ctas_per_sm = (int)value; }
     else if (k == "kd_smem_nodes") { SDT_CHECK(h, value >= 0 && value <= 49152, SDT_ERR_INVALID, "kd_smem_nodes must be 0..49152"); h->kd_smem_nodes = (int)value; }
-    else if (k == "splat_block") { SDT_CHECK(h, value >= 64 && value <= 256 && value % 32 == 0, SDT_ERR_INVALID, "splat_block must be 64..256, multiple of 32"); h->splat_block = (int)value; }
+    else if (k == "splat_block") { SDT_CHECK(h, value >= 64 && value <= 512 && value % 32 == 0, SDT_ERR_INVALID, "splat_block must be 64..512, multiple of 32"); h->splat_block = (int)value; }
     else if (k == "splat_ctas_per_sm") { SDT_CHECK(h, value >= 1 && value <= 32, SDT_ERR_INVALID, "splat_ctas_per_sm must be 1..32"); h->splat_ctas_per_sm = (int)value; }
     else if (k == "fuse_sample_pdf") h->fuse_sample_pdf = value != 0;
     else return sdt_fail(h, SDT_ERR_INVALID, "sdt_set_tuning: unknown key " + k);

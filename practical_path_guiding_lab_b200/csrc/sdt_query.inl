@@ -5,7 +5,7 @@
 // ---------------------------------------------------------------------------- launch
 #ifndef SDT_HOSTEMU
 template <class Lane>
-__global__ void __launch_bounds__(256) k_wavefront(Lane f, uint32_t n, uint32_t smem_cap) {
+__global__ void __launch_bounds__(512, 4) k_wavefront(Lane f, uint32_t n, uint32_t smem_cap) {
     extern __shared__ uint32_t kd_s[];
     const DevHeader* hdr = f.t.hdr;
     const uint32_t n_kd = hdr->n_kd;
@@ -81,7 +81,7 @@ struct LocateLane {
         if (act) {
             const KdResult r = sdt_kd_descend<ALL_SMEM>(k, sdt_ld(pos.x, pos.stride, i),
                                               sdt_ld(pos.y, pos.stride, i), sdt_ld(pos.z, pos.stride, i));
-            lf = r.leaf; rt = r.root;
+            lf = r.leaf; rt = SDT_LDG(t.kd_root + r.leaf);
         }
         if (leaf) leaf[i] = lf;
         if (root) root[i] = rt;
@@ -102,9 +102,10 @@ struct SampleLane {
             const KdResult r = sdt_kd_descend<ALL_SMEM>(k, sdt_ld(pos.x, pos.stride, i),
                                               sdt_ld(pos.y, pos.stride, i), sdt_ld(pos.z, pos.stride, i));
             const LaneRng rng{u, u_stride, seed, lane_offset + i, i};
-            const GuidedSample g = sdt_sample_tree(t, r.root, rng, fuse != 0);
+            const uint32_t root = dbg ? SDT_LDG(t.kd_root + r.leaf) : 0u;
+            const GuidedSample g = sdt_sample_tree(t, r.rootrec, root, rng, fuse != 0);
             dx = g.dx; dy = g.dy; dz = g.dz; p = g.pdf;
-            d0 = r.leaf; d1 = r.root; d2 = g.sample_node; d3 = g.pdf_node;
+            d0 = r.leaf; d1 = root; d2 = g.sample_node; d3 = g.pdf_node;
         }
         const int64_t o = (int64_t)i * dir.stride;
         dir.x[o] = dx; dir.y[o] = dy; dir.z[o] = dz;
@@ -127,8 +128,9 @@ struct PdfLane {
             float x, y;
             sdt_dir_to_canonical(sdt_ld(dir.x, dir.stride, i), sdt_ld(dir.y, dir.stride, i), sdt_ld(dir.z, dir.stride, i), x, y);
             uint32_t nd;
-            p = sdt_quad_pdf(t.rec, SDT_LDG(t.root_iidx + r.root), r.root, x, y, nd);
-            d0 = r.leaf; d1 = r.root; d2 = nd;
+            const uint32_t root = dbg ? SDT_LDG(t.kd_root + r.leaf) : 0u;
+            p = sdt_quad_pdf(t.rec, r.rootrec, root, x, y, nd);
+            d0 = r.leaf; d1 = root; d2 = nd;
         }
         pdf[i] = p;
         if (dbg) { dbg[3u * i] = d0; dbg[3u * i + 1u] = d1; dbg[3u * i + 2u] = d2; }
@@ -148,7 +150,7 @@ struct GuidedLane {
                                           sdt_ld(a.pos.y, a.pos.stride, i), sdt_ld(a.pos.z, a.pos.stride, i));
         if (m == 1u) {
             const LaneRng rng{a.u, a.u_stride, a.seed, a.lane_offset + i, i};
-            const GuidedSample g = sdt_sample_tree(t, r.root, rng, fuse != 0);
+            const GuidedSample g = sdt_sample_tree(t, r.rootrec, 0u, rng, fuse != 0);
             const int64_t o = (int64_t)i * a.dir.stride;
             a.dir.x[o] = g.dx; a.dir.y[o] = g.dy; a.dir.z[o] = g.dz;
             a.sdtree_pdf[i] = g.pdf;
@@ -156,7 +158,7 @@ struct GuidedLane {
             float x, y;
             sdt_dir_to_canonical(sdt_ld(a.wo.x, a.wo.stride, i), sdt_ld(a.wo.y, a.wo.stride, i), sdt_ld(a.wo.z, a.wo.stride, i), x, y);
             uint32_t nd;
-            const float p = sdt_quad_pdf(t.rec, SDT_LDG(t.root_iidx + r.root), r.root, x, y, nd);
+            const float p = sdt_quad_pdf(t.rec, r.rootrec, 0u, x, y, nd);
             a.sdtree_pdf[i] = p;
             if (a.bsdf_pdf && a.wo_pdf) {
                 const float f = a.bsdf_sampling_fraction;

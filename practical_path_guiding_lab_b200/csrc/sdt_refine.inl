@@ -268,9 +268,20 @@ struct RecBuildItem {
     }
 };
 
+// spatial leaf word <- record of the root of the leaf's quadtree (see the layout note in sdt_core.h)
+struct KdLeafWordItem {
+    DevHeader* H; uint32_t* kd_word; const uint32_t* kd_root; const uint32_t* root_iidx;
+    SDT_HD void operator()(uint32_t i) const {
+        const uint32_t ri = root_iidx[kd_root[i]];
+        if (i == 0u) H->rootrec_of_node0 = ri;
+        if (kd_word[i] & SDT_KD_LEAF_BIT) kd_word[i] = SDT_KD_LEAF_BIT | (ri == SDT_NONE ? 0x7FFFFFFFu : ri);
+    }
+};
+
 static void sdt_build_records(sdt_handle h, const ExecCtx& x, QuadSet& s) {
     launch_scan(x, &s.hdr->n_quad, 0, RecFlag{s.child}, RecEmit{s.iidx}, RecFin{s.hdr});
     launch_items(x, &s.hdr->n_quad, 0, RecBuildItem{s.hdr, s.child, s.energy, s.iidx, s.rec, s.root_iidx});
+    launch_items(x, &s.hdr->n_kd, 0, KdLeafWordItem{s.hdr, h->kd_word, h->kd_root, s.root_iidx});
 }
 
 struct KdRollItem {         // prev.vertCount <- current.vertCount; current <- 0 (:141-153, :401-432)

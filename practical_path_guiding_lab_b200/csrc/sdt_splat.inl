@@ -45,22 +45,24 @@ SDT_HD void sdt_splat_one(const TreeView& t, const SplatTarget& tg, const KdCtx&
                           float px, float py, float pz, float dx, float dy, float radiance, float wo_pdf,
                           float nr, float ng, float nb, float ndx, float ndy) {
     KdResult r;
-    r.leaf = 0; r.root = 0; r.inbox = false;
+    r.leaf = 0; r.rootrec = SDT_NONE; r.inbox = false;
     if (act) r = sdt_kd_descend<ALL_SMEM>(k, px, py, pz);
     // src/kdtree.py:199: +1.0f (fp32 counter; exact below 2^24, then it sticks like the reference's)
     sdt_splat_add(tg.kd_count, r.leaf, 1.0f, act && r.inbox);
     // src/kdtree.py:224: the root id is gathered UNMASKED -- out-of-box records go to the tree of node 0
-    uint32_t ri = SDT_NONE;
-    if (act) ri = SDT_LDG(t.root_iidx + r.root);
+    const uint32_t ri = r.rootrec;
+    // a single-leaf tree has no record: its only node is the root, whose id is in kd_root
+    uint32_t root = 0;
+    if (act && ri == SDT_NONE) root = SDT_LDG(t.kd_root + r.leaf);
     const float irr = (wo_pdf > 0.0f) ? radiance / wo_pdf : 0.0f;                      // src/quadtree.py:451
     uint32_t leaf = SDT_NONE;
-    if (act && irr != 0.0f) leaf = sdt_quad_leaf(t.rec, ri, r.root, dx, dy);
+    if (act && irr != 0.0f) leaf = sdt_quad_leaf(t.rec, ri, root, dx, dy);
     sdt_splat_add(tg.q_ecur, leaf, irr, leaf != SDT_NONE);
     if (tg.store_nee) {                                                               // :455-464
         const float lum = sdt_luminance(nr, ng, nb);
         const float irr2 = (wo_pdf > 0.0f) ? lum / wo_pdf : 0.0f;
         uint32_t leaf2 = SDT_NONE;
-        if (act && irr2 != 0.0f) leaf2 = sdt_quad_leaf(t.rec, ri, r.root, ndx, ndy);
+        if (act && irr2 != 0.0f) leaf2 = sdt_quad_leaf(t.rec, ri, root, ndx, ndy);
         sdt_splat_add(tg.q_ecur, leaf2, irr2, leaf2 != SDT_NONE);
     }
 }
