@@ -167,17 +167,20 @@ SDT_HD float sdt_uniform(uint32_t seed, uint32_t lane, uint32_t idx) {
     return (float)(h >> 8) * 5.9604644775390625e-08f;
 }
 
-// Uniform stream of one lane: explicit u[lane*stride + idx] (clamped like the oracle's
-// ExplicitSampler) or the counter generator.
-struct LaneRng {
-    const float* u; uint32_t u_stride; uint32_t seed; uint32_t lane_id; uint32_t lane_index;
+// Uniform stream of one lane.  CounterRng: the counter generator (the lane hash is computed
+// once).  ExplicitRng: u[lane*stride + idx], clamped like the oracle's ExplicitSampler.
+struct CounterRng {
+    uint32_t h0;
+    SDT_HD CounterRng(uint32_t seed, uint32_t lane_id) : h0(sdt_fmix(seed + lane_id * 0x9E3779B1u)) {}
     SDT_HD float get(uint32_t idx) const {
-        if (u) {
-            const uint32_t c = idx < u_stride ? idx : u_stride - 1u;
-            return SDT_LDG(u + (size_t)lane_index * u_stride + c);
-        }
-        return sdt_uniform(seed, lane_id, idx);
+        const uint32_t h = sdt_fmix(h0 ^ (idx * 0x85EBCA77u + 0x165667B1u));
+        return (float)(h >> 8) * 5.9604644775390625e-08f;
     }
+};
+struct ExplicitRng {
+    const float* row; uint32_t u_stride;
+    SDT_HD ExplicitRng(const float* u, uint32_t stride, uint32_t lane_index) : row(u + (size_t)lane_index * stride), u_stride(stride) {}
+    SDT_HD float get(uint32_t idx) const { return SDT_LDG(row + (idx < u_stride ? idx : u_stride - 1u)); }
 };
 
 SDT_HD float sdt_ld(const float* p, int64_t stride, uint32_t i) { return SDT_LDG(p + (int64_t)i * stride); }
@@ -380,7 +383,8 @@ struct QSample {
     float lox, loy, hix, hiy;   // leaf cell
 };
 
-SDT_HD QSample sdt_quad_sample(const QRec* __restrict__ rec, uint32_t ri, uint32_t root_node, const LaneRng& rng) {
+template <class Rng>
+SDT_HD QSample sdt_quad_sample(const QRec* __restrict__ rec, uint32_t ri, uint32_t root_node, const Rng& rng) {
     QSample q;
     q.x = 0.0f; q.y = 0.0f; q.node = root_node; q.pdf_path = 1.0f; q.pdf_dead = false; q.stuck = false;
     q.lox = 0.0f; q.loy = 0.0f; q.hix = 1.0f; q.hiy = 1.0f;
@@ -395,13 +399,12 @@ SDT_HD QSample sdt_quad_sample(const QRec* __restrict__ rec, uint32_t ri, uint32
         const float e3 = e.z + e2;
         const float e4 = e.w + e3;
         const float s = rng.get(3u * level + 2u) * e4;                   // :980
-        int c = -1;                                                      // :983-991, later bins override
-        if (s < e1) c = 0;
-        if (e1 <= s && s < e2) c = 1;
-        if (e2 <= s && s < e3) c = 2;
-        if (e3 <= s) c = 3;
-        if (c < 0) { q.stuck = true; break; }
-        const uint32_t cu = (uint32_t)c;
+        // :983-991: four masked assignments in turn, a later bin overrides an earlier one
+        // (they only overlap for negative energies); no bin (NaN) -> the lane is stuck
+        const bool b1 = e1 <= s, b2 = e2 <= s, b3 = e3 <= s;
+        const bool m0 = s < e1, m1 = b1 && (s < e2), m2 = b2 && (s < e3);
+        if (!(m0 || m1 || m2 || b3)) { q.stuck = true; break; }
+        const uint32_t cu = b3 ? 3u : (m2 ? 2u : (m1 ? 1u : 0u));
         const float f = q.pdf_path * ((4.0f * sdt_pick4(e, cu)) / h.own);   // :1084
         if (!q.pdf_dead) {
             q.pdf_dead = f != f;                                         // :1090-1092
@@ -425,7 +428,8 @@ struct GuidedSample { float dx, dy, dz, pdf; uint32_t sample_node, pdf_node; };
 
 // ri = record of the tree's root (from the spatial leaf word); root = its node id, only used for
 // the node ids reported to dbg (pass 0 when not needed)
-SDT_HD GuidedSample sdt_sample_tree(const TreeView& t, uint32_t ri, uint32_t root, const LaneRng& rng, bool fuse) {
+template <class Rng>
+SDT_HD GuidedSample sdt_sample_tree(const TreeView& t, uint32_t ri, uint32_t root, const Rng& rng, bool fuse) {
     GuidedSample g;
     const QSample q = sdt_quad_sample(t.rec, ri, root, rng);
     sdt_canonical_to_dir(q.x, q.y, g.dx, g.dy, g.dz);                    // :996

@@ -61,10 +61,10 @@ struct sdt_tree_s {
 
     // tuning
     int query_block = 512;
-    int query_ctas_per_sm = 4;
+    int query_ctas_per_sm = 3;
     int kd_smem_nodes = 24576;      // cap of the smem-staged prefix of the spatial tree (96 KB)
     int splat_block = 512;
-    int splat_ctas_per_sm = 4;
+    int splat_ctas_per_sm = 3;
     int fuse_sample_pdf = 1;
     int splat_all_levels = 0;       // 1: atomics at every level like the reference (no sweep)
 

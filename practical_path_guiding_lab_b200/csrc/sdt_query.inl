@@ -5,7 +5,7 @@
 // ---------------------------------------------------------------------------- launch
 #ifndef SDT_HOSTEMU
 template <class Lane>
-__global__ void __launch_bounds__(512, 4) k_wavefront(Lane f, uint32_t n, uint32_t smem_cap) {
+__global__ void __launch_bounds__(512, 3) k_wavefront(Lane f, uint32_t n, uint32_t smem_cap) {
     extern __shared__ uint32_t kd_s[];
     const DevHeader* hdr = f.t.hdr;
     const uint32_t n_kd = hdr->n_kd;
@@ -88,6 +88,7 @@ struct LocateLane {
     }
 };
 
+template <bool EXPLICIT_U>
 struct SampleLane {
     TreeView t;
     sdt_vec3 pos; const uint8_t* active;
@@ -101,9 +102,10 @@ struct SampleLane {
         if (act) {
             const KdResult r = sdt_kd_descend<ALL_SMEM>(k, sdt_ld(pos.x, pos.stride, i),
                                               sdt_ld(pos.y, pos.stride, i), sdt_ld(pos.z, pos.stride, i));
-            const LaneRng rng{u, u_stride, seed, lane_offset + i, i};
             const uint32_t root = dbg ? SDT_LDG(t.kd_root + r.leaf) : 0u;
-            const GuidedSample g = sdt_sample_tree(t, r.rootrec, root, rng, fuse != 0);
+            GuidedSample g;
+            if (EXPLICIT_U) g = sdt_sample_tree(t, r.rootrec, root, ExplicitRng(u, u_stride, i), fuse != 0);
+            else g = sdt_sample_tree(t, r.rootrec, root, CounterRng(seed, lane_offset + i), fuse != 0);
             dx = g.dx; dy = g.dy; dz = g.dz; p = g.pdf;
             d0 = r.leaf; d1 = root; d2 = g.sample_node; d3 = g.pdf_node;
         }
@@ -139,6 +141,7 @@ struct PdfLane {
 
 // one bounce: mode 1 = sample the tree (src/path_guiding_integrator.py:301),
 // mode 2 = tree pdf of the BSDF-sampled direction (:307) + fused mixture (:310-311)
+template <bool EXPLICIT_U>
 struct GuidedLane {
     TreeView t;
     sdt_guided_args a; int fuse;
@@ -149,8 +152,9 @@ struct GuidedLane {
         const KdResult r = sdt_kd_descend<ALL_SMEM>(k, sdt_ld(a.pos.x, a.pos.stride, i),
                                           sdt_ld(a.pos.y, a.pos.stride, i), sdt_ld(a.pos.z, a.pos.stride, i));
         if (m == 1u) {
-            const LaneRng rng{a.u, a.u_stride, a.seed, a.lane_offset + i, i};
-            const GuidedSample g = sdt_sample_tree(t, r.rootrec, 0u, rng, fuse != 0);
+            GuidedSample g;
+            if (EXPLICIT_U) g = sdt_sample_tree(t, r.rootrec, 0u, ExplicitRng(a.u, a.u_stride, i), fuse != 0);
+            else g = sdt_sample_tree(t, r.rootrec, 0u, CounterRng(a.seed, a.lane_offset + i), fuse != 0);
             const int64_t o = (int64_t)i * a.dir.stride;
             a.dir.x[o] = g.dx; a.dir.y[o] = g.dy; a.dir.z[o] = g.dz;
             a.sdtree_pdf[i] = g.pdf;
@@ -234,10 +238,15 @@ extern "C" int sdt_sample(sdt_handle h, const sdt_vec3* pos, const uint8_t* acti
     cudaStream_t st = (cudaStream_t)stream;
     Stager sg(h, st, flags);
     SDT_TRY(sg.reserve((size_t)n * (12 + 1 + 12 + 4 + 16 + (u ? 4ull * u_stride : 0)) + 8192));
-    SampleLane f{tree_view(h), sg.in3(*pos, n), sg.in_t(active, n), sg.in_t(u, (size_t)n * u_stride), u_stride, seed, lane_offset,
-                 sg.out3(*dir, n), sg.out_t(pdf, n), sg.out_t(dbg, (size_t)n * 4), h->fuse_sample_pdf};
+    SampleLane<false> f{tree_view(h), sg.in3(*pos, n), sg.in_t(active, n), sg.in_t(u, (size_t)n * u_stride), u_stride, seed, lane_offset,
+                        sg.out3(*dir, n), sg.out_t(pdf, n), sg.out_t(dbg, (size_t)n * 4), h->fuse_sample_pdf};
     if (sg.status != SDT_OK) return sg.status;
-    SDT_TRY(launch_wavefront(h, st, n, f, h->query_block, h->query_ctas_per_sm));
+    if (u) {
+        SampleLane<true> fe{f.t, f.pos, f.active, f.u, f.u_stride, f.seed, f.lane_offset, f.dir, f.pdf, f.dbg, f.fuse};
+        SDT_TRY(launch_wavefront(h, st, n, fe, h->query_block, h->query_ctas_per_sm));
+    } else {
+        SDT_TRY(launch_wavefront(h, st, n, f, h->query_block, h->query_ctas_per_sm));
+    }
     return sg.finish(flags);
 }
 
@@ -287,8 +296,13 @@ extern "C" int sdt_guided(sdt_handle h, const sdt_guided_args* a, uint32_t n, ui
         }
     }
     if (sg.status != SDT_OK) return sg.status;
-    GuidedLane f{tree_view(h), d, h->fuse_sample_pdf};
-    SDT_TRY(launch_wavefront(h, st, n, f, h->query_block, h->query_ctas_per_sm));
+    if (d.u) {
+        GuidedLane<true> f{tree_view(h), d, h->fuse_sample_pdf};
+        SDT_TRY(launch_wavefront(h, st, n, f, h->query_block, h->query_ctas_per_sm));
+    } else {
+        GuidedLane<false> f{tree_view(h), d, h->fuse_sample_pdf};
+        SDT_TRY(launch_wavefront(h, st, n, f, h->query_block, h->query_ctas_per_sm));
+    }
     return sg.finish(flags);
 }
 
