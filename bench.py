@@ -34,7 +34,7 @@ if ROOT not in sys.path:
 METRIC = "guided samples/s (sample + pdf + splat per path vertex, synthetic frozen SD-tree)"
 UNIT = "samples/s"
 N_DEFAULT = 1 << 24
-CPU_SAMPLE = 1 << 17
+CPU_SAMPLE = 1 << 21
 
 
 def parse():
@@ -138,12 +138,32 @@ def oracle_tree():
     return cur, prev
 
 
-def oracle_step(cur, prev, pos, dirs, rec, seed):
-    from oracle import sdtree_oracle as so
-    n = pos.shape[0]
-    prev.sample(pos, so.ExplicitSampler(seed=seed, n=n), True)
-    prev.pdf(pos, dirs, True)
-    cur.addDataPropagate(so.SurfaceInteractionRecord(rec['position'], rec['direction'], rec['radiance'], rec['wo_pdf']))
+class CpuPort:
+    """the reference's per-vertex operations in C + OpenMP on all host cores (oracle/sdtree_port.c,
+    checked against the numpy oracle in tests/test_oracle_port.py) on a tree in the npz schema"""
+
+    def __init__(self, tree_arrays):
+        from oracle.port import PortTree
+        self.prev = PortTree(tree_arrays)
+        z = dict(tree_arrays)
+        z['kdtree_vertCount'] = np.zeros_like(np.asarray(tree_arrays['kdtree_vertCount'], np.float32))
+        z['quadtree_irradiance'] = np.zeros_like(np.asarray(tree_arrays['quadtree_irradiance'], np.float32))
+        self.cur = PortTree(z)
+        self.cores = self.prev.threads()
+
+    def step(self, pos, dirs, rec, seed):
+        self.prev.sample(pos, seed)
+        self.prev.pdf(pos, dirs)
+        self.cur.splat(rec['position'], rec['direction'], rec['radiance'], rec['wo_pdf'])
+
+    def timed(self, pos, dirs, rec, min_seconds=10.0, min_reps=2):
+        self.step(pos[:4096], dirs[:4096], {k: v[:4096] for k, v in rec.items()}, 3)
+        t0 = time.perf_counter()
+        reps = 0
+        while reps < min_reps or time.perf_counter() - t0 < min_seconds:
+            self.step(pos, dirs, rec, 3)
+            reps += 1
+        return (time.perf_counter() - t0) / reps, reps
 
 
 def cpu_inputs(m):
@@ -152,27 +172,28 @@ def cpu_inputs(m):
 
 
 def run_reference(args):
-    """reference arm: the CPU restatement of the reference's algorithm (oracle/, numpy --
-    Mitsuba 3 / Dr.Jit are not installable in this image) on the host cores"""
+    """reference arm: the CPU restatement of the reference's algorithm on the host cores -- Mitsuba 3 /
+    Dr.Jit are not installable in this image, so the tree is trained by the numpy
+    oracle (oracle/sdtree_oracle.py) and the per-vertex operations run in its C + OpenMP port"""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    # bounded sample: the whole run (warm-up + steps) stays around 1-2 minutes of CPU work
-    m = int(min(args.cpu_sample, max(8192, args.cpu_sample * 12 // max(1, args.steps + args.warmup))))
+    m = int(min(args.n, args.cpu_sample))
     cur, prev = oracle_tree()
+    port = CpuPort(prev.to_arrays())
     pos, dirs, rec = cpu_inputs(m)
     for _ in range(args.warmup):
-        oracle_step(cur, prev, pos, dirs, rec, 3)
+        port.step(pos, dirs, rec, 3)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        oracle_step(cur, prev, pos, dirs, rec, 3)
+        port.step(pos, dirs, rec, 3)
     dt = (time.perf_counter() - t0) / args.steps
     v = m / dt
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic", "config": workload_config(args.n, args.gpus),
-            "cpu_baseline": {"value": v, "unit": UNIT, "cores": 1, "kind": "port",
-                             "sample": f"{m} of the {args.n} vertices per step (numpy oracle, one process; host has {os.cpu_count()} cores)"},
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": port.cores, "kind": "port",
+                             "sample": f"{m} of the {args.n} vertices per step (C + OpenMP port of the reference's per-vertex operations, {port.cores} threads; tree trained by the numpy oracle)"},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line))
@@ -288,8 +309,17 @@ def run_b200(args):
     peak = float(peaks.get("hbm_gbs", 6650.0))
     achieved = bytes_q[names[dom]] * n / (k_ms[dom] * 1e-3) / 1e9
     l2_gbs = tree.measure_l2(32 << 20, 50)
-    roof = {"bound": "hbm", "kernel": f"k_wavefront<{['SampleLane', 'PdfLane', 'SplatRecordsLane'][dom]}>", "achieved": achieved, "peak": peak,
-            "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+    kname = ['SampleLane', 'PdfLane', 'SplatRecordsLane'][dom]
+    traffic = None
+    try:        # DRAM bytes per launch of this kernel from the committed ncu --set full capture (same 16 Mi-vertex launch)
+        tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        if n == N_DEFAULT:
+            key = [k for k in tj if k.startswith(kname)][0]
+            traffic = tj[key]["dram_bytes_read"] + tj[key]["dram_bytes_write"]
+    except Exception:
+        pass
+    roof = {"bound": "hbm", "kernel": f"k_wavefront<{kname}>", "achieved": achieved, "peak": peak,
+            "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
             "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if "hbm_gbs" in peaks else "fallback 6650",
             "algorithmic_bytes_per_query": bytes_q[names[dom]], "kernel_ms": k_ms[dom],
             "l2": {"measured_read_gbs": l2_gbs, "frac_of_l2": achieved / l2_gbs if l2_gbs else None,
@@ -345,24 +375,11 @@ def run_b200(args):
     # ---- CPU port of the reference, timed beside it (rank 0, N=1)
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        from oracle import sdtree_oracle as so
-        mc = args.cpu_sample
-        prev = so.KDTree()
-        prev.loadFromArrays(tr)
-        cur = so.KDTree()
-        cur.copyFrom(prev)
-        cur.resetTreeVertCount()
-        cur.resetAllQuadTreeIrradiance()
-        pos, dirs, crec = h_pos.numpy()[:mc], h_dir.numpy()[:mc], {k: v.numpy()[:mc] for k, v in h_rec.items()}
-        oracle_step(cur, prev, pos[:4096], dirs[:4096], {k: v[:4096] for k, v in crec.items()}, 3)
-        t0 = time.perf_counter()
-        reps = 0
-        while reps < 2 or time.perf_counter() - t0 < 10.0:
-            oracle_step(cur, prev, pos, dirs, crec, 3)
-            reps += 1
-        dt = (time.perf_counter() - t0) / reps
-        cpu = {"value": mc / dt, "unit": UNIT, "cores": 1, "kind": "port",
-               "sample": f"first {mc} of the {n} vertices per step, {reps} repetitions (numpy oracle, one process; host has {os.cpu_count()} cores)"}
+        mc = int(min(n, args.cpu_sample))
+        port = CpuPort(tr)
+        dt, reps = port.timed(h_pos.numpy()[:mc], h_dir.numpy()[:mc], {k: v.numpy()[:mc] for k, v in h_rec.items()})
+        cpu = {"value": mc / dt, "unit": UNIT, "cores": port.cores, "kind": "port",
+               "sample": f"first {mc} of the {n} vertices per step, {reps} repetitions (C + OpenMP port of the reference's per-vertex operations on the reference's SoA layout, {port.cores} threads; host has {os.cpu_count()} cores)"}
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
