@@ -1,0 +1,173 @@
+"""Parameterised equivalent of the reference's training/render driver (/root/reference/main.py:
+97-416): the same iteration doubling (4, 8, 16, ... spp), 1 spp per pass
+while training and `batch_spp` per pass in the final iteration, the same stop rule (variance
+estimate after `stable_variance_spp_threshold`, hard stop at 1000 cumulative spp), the same
+two-iteration image blending, refine after every training iteration, and the same outputs
+(image, .npz tree, .obj boxes, CSV records) -- with scene, resolution, budget, seed as arguments.
+
+`renderer` is anything with the integrator-side interface the reference script uses:
+render(spp, seed) -> (H,W,3) image, setIteration, resetVarianceCounter, computeVariance,
+computeMSE, refineAndPrepareSDTreeForNextIteration, saveSDTreeToFile, saveSDTreeOBJ
+(`cornell.CornellBox` here; the Mitsuba plugin when Mitsuba is installed).
+"""
+import csv
+import math
+import os
+import time
+
+
+def possible_cumm_spps(budget_spp):
+    """main.py:105-118"""
+    cumm, k, out = 0, 0, []
+    while cumm < budget_spp:
+        cumm += 2 ** (k + 2)
+        out.append(cumm)
+        k += 1
+    return out
+
+
+def train_and_render(renderer, budget_spp, seed=0, batch_spp=4, stable_variance_spp_threshold=256,
+                     ground_truth=None, out_dir=None, scene_name="scene", log=None, on_iteration=None):
+    """-> dict(image, records=[per-iteration dicts], iterations=[(iteration, spp, refined)])"""
+    log = log or (lambda *a: None)
+    cumm_spp = cumm_spp_prev = 0
+    image_spp = 0
+    remaining = budget_spp
+    is_final = False
+    is_train = True
+    is_clear = True
+    it = 0
+    variance_prev = 0.0
+    cumm_time = 0.0
+    prev_iter_image = None
+    image = None
+    records, schedule = [], []
+    if out_dir:
+        for sub in ("image", "tree-data", "obj", "performance"):
+            os.makedirs(os.path.join(out_dir, sub), exist_ok=True)
+    while remaining > 0:
+        t0 = time.perf_counter()
+        if is_clear:
+            renderer.resetVarianceCounter()
+            image_spp = 0
+        curr = None
+        if not is_final:
+            iter_spp = 2 ** (it + 2)                                   # main.py:170
+            if iter_spp == remaining:
+                is_final = True
+        else:
+            iter_spp = remaining
+        renderer.setIteration(it, is_final)
+        spp_per_pass = batch_spp if is_final else 1                   # main.py:192-199
+        passes = math.ceil(iter_spp / spp_per_pass)
+        done = 0
+        for _ in range(passes):
+            s = min(spp_per_pass, iter_spp - done)
+            one = renderer.render(s, seed + cumm_spp)                  # main.py:218
+            w = one * float(s / iter_spp)
+            curr = w if curr is None else curr + w
+            image_spp += s
+            done += s
+            cumm_spp += s
+        if is_final and not is_train and prev_iter_image is not None:   # main.py:287-291
+            image = (curr * iter_spp + prev_iter_image * (image_spp - iter_spp)) / image_spp
+        else:
+            image = curr
+        variance = renderer.computeVariance(image_spp)
+        var_gt = renderer.computeVariance(image_spp, ground_truth) if ground_truth is not None else None
+        mse_gt = renderer.computeMSE(image_spp, ground_truth) if ground_truth is not None else None
+        elapsed = (time.perf_counter() - t0) + cumm_time
+        variance_current = (variance * image_spp) / (budget_spp - cumm_spp_prev)    # main.py:325-326
+        was_final, trained_this = is_final, is_train
+        # next-iteration conditions, main.py:335-377
+        next_spp = 2 ** (it + 3)
+        remaining = budget_spp - cumm_spp
+        stop = (cumm_spp > stable_variance_spp_threshold) and (variance_current > variance_prev)
+        if cumm_spp >= 1000:
+            stop = True
+        if next_spp < remaining:
+            if stop:
+                is_final, is_train, is_clear = True, False, False
+        elif next_spp == remaining:
+            is_final = True
+            if stop:
+                is_train, is_clear = False, False
+        else:
+            is_final, is_train, is_clear = True, False, False
+        refined = False
+        if is_train:
+            renderer.refineAndPrepareSDTreeForNextIteration()          # main.py:382-383
+            refined = True
+        prev_iter_image = image
+        cumm_time += time.perf_counter() - t0
+        rec = dict(iteration=it, iter_spp=iter_spp, spp=image_spp, cumm_spp=cumm_spp, time=elapsed, variance=variance,
+                   variance_groundTruth=var_gt, mse_groundTruth=mse_gt, variance_estimated_final=variance_current,
+                   isFinalIter=was_final, refined=refined)
+        records.append(rec)
+        schedule.append((it, iter_spp, refined))
+        log(f"iteration {it}: spp {iter_spp}, cumm {cumm_spp}, final {was_final}, refined {refined}, variance {variance:.5g}"
+            + (f", mse {mse_gt:.5g}" if mse_gt is not None else ""))
+        if out_dir:
+            renderer.saveSDTreeToFile(os.path.join(out_dir, "tree-data", f"{scene_name}_iter-{it}.npz"))
+            renderer.saveSDTreeOBJ(os.path.join(out_dir, "obj", f"{scene_name}_iter-{it}.obj"))
+            save_image(os.path.join(out_dir, "image", f"{scene_name}_iter-{it}_spp-{image_spp}_cumm_spp-{cumm_spp}"), image)
+        if on_iteration:
+            on_iteration(rec, image)
+        variance_prev = variance_current
+        it += 1
+        cumm_spp_prev = cumm_spp
+    if out_dir:
+        for key in ("variance", "variance_groundTruth", "mse_groundTruth", "variance_estimated_final"):
+            with open(os.path.join(out_dir, "performance", f"{key}_endIter.csv"), "w", newline="") as f:
+                w = csv.writer(f)
+                w.writerow(["time", "spp", "cumm_spp", "iteration", "mse" if key.startswith("mse") else "variance"])
+                for r in records:
+                    w.writerow([r["time"], r["spp"], r["cumm_spp"], r["iteration"], r[key]])
+    return dict(image=image, records=records, iterations=schedule)
+
+
+def save_image(stem, image):
+    import numpy as np
+    a = image.detach().cpu().numpy() if hasattr(image, "detach") else np.asarray(image)
+    np.save(stem + ".npy", a.astype(np.float32))
+    try:
+        os.environ.setdefault("OPENCV_IO_ENABLE_OPENEXR", "1")
+        import cv2
+        cv2.imwrite(stem + ".png", (np.clip(a[..., ::-1], 0, 1) ** (1 / 2.2) * 255).astype(np.uint8))
+    except Exception:
+        pass
+
+
+def main(argv=None):
+    """python -m practical_path_guiding_lab_b200.driver --scene cornell-box --res 256 --budget 64"""
+    import argparse
+    import json
+    import numpy as np
+    import torch
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--scene", default="cornell-box", choices=["cornell-box"])
+    ap.add_argument("--res", type=int, default=256)
+    ap.add_argument("--budget", type=int, default=64)
+    ap.add_argument("--seed", type=int, default=0)
+    ap.add_argument("--max-depth", type=int, default=30)
+    ap.add_argument("--out", default=None)
+    ap.add_argument("--ground-truth", default=None, help=".npy (H,W,3) linear RGB")
+    ap.add_argument("--no-guiding", action="store_true", help="BSDF-only baseline: never refine (tree stays a single leaf)")
+    a = ap.parse_args(argv)
+    from .cornell import CornellBox
+    r = CornellBox(a.res, a.res, max_depth=a.max_depth, device="cuda")
+    r.setup()
+    gt = None
+    if a.ground_truth:
+        gt = torch.from_numpy(np.load(a.ground_truth).astype(np.float32)).cuda()
+    if a.no_guiding:
+        r.refineAndPrepareSDTreeForNextIteration = lambda: None
+    t0 = time.perf_counter()
+    res = train_and_render(r, a.budget, seed=a.seed, ground_truth=gt, out_dir=a.out, scene_name=a.scene, log=print)
+    torch.cuda.synchronize()
+    print(json.dumps(dict(scene=a.scene, res=a.res, budget=a.budget, seconds=time.perf_counter() - t0,
+                          iterations=res["iterations"], final=res["records"][-1], tree=r.core.tree.sizes())))
+
+
+if __name__ == "__main__":
+    main()
