@@ -55,9 +55,13 @@ struct sdt_tree_s {
     cudaEvent_t hdr_event = nullptr;
     bool hdr_pending = false;       // an async header read-back (after refine) is in flight
 
-    // staging for SDT_HOST_PTRS
+    // staging for SDT_HOST_PTRS: one arena; large host calls run as a 2-slot pipeline
+    // (H2D of chunk k+1 | kernel of chunk k | D2H of chunk k-1 on three streams)
     char* stage = nullptr;
     size_t stage_cap = 0, stage_off = 0;
+    cudaStream_t s_in = nullptr, s_out = nullptr;
+    cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_comp[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
+    int host_chunk = 1 << 20;       // lanes per pipeline chunk
 
     // tuning
     int query_block = 512;
@@ -115,36 +119,43 @@ struct Stager {
     cudaStream_t st;
     bool host;
     int status = SDT_OK;
+    int slot = -1;                  // >= 0: pipelined chunk using half `slot` of the arena
+    size_t off = 0, lim = 0;
     struct Out { void* host; void* dev; size_t bytes; };
     std::vector<Out> outs;
-    size_t h2d = 0, d2h = 0;
 
-    Stager(sdt_handle h_, cudaStream_t st_, uint32_t flags) : h(h_), st(st_), host((flags & SDT_HOST_PTRS) != 0) {
-        h->stage_off = 0;
+    Stager(sdt_handle h_, cudaStream_t st_, uint32_t flags, int slot_ = -1)
+        : h(h_), st(st_), host((flags & SDT_HOST_PTRS) != 0), slot(slot_) {
+        if (slot >= 0) {
+            const size_t half = (h->stage_cap / 2) & ~(size_t)255;
+            off = (size_t)slot * half; lim = off + half;
+            // the slot's input buffers are free once the kernels of the chunk that used it have run
+            cudaStreamWaitEvent(h->s_in, h->ev_comp[slot], 0);
+        } else { off = 0; lim = h->stage_cap; }
     }
     // total bytes this call will stage; grows the arena once (pointers stay valid)
     int reserve(size_t bytes) {
         if (!host) return SDT_OK;
         bytes += 4096;
-        if (bytes <= h->stage_cap) return SDT_OK;
-        if (h->stage) { cudaStreamSynchronize(st); cudaFree(h->stage); h->stage = nullptr; h->stage_cap = 0; }
+        if (bytes <= h->stage_cap) { if (slot < 0) lim = h->stage_cap; return SDT_OK; }
+        if (h->stage) { cudaDeviceSynchronize(); cudaFree(h->stage); h->stage = nullptr; h->stage_cap = 0; }
         size_t cap = bytes + bytes / 4;
         if (cudaMalloc((void**)&h->stage, cap) != cudaSuccess) { status = sdt_fail(h, SDT_ERR_CUDA, "staging arena cudaMalloc failed"); return status; }
         h->stage_cap = cap;
+        if (slot < 0) lim = cap;
         return SDT_OK;
     }
     void* alloc(size_t bytes) {
-        size_t off = (h->stage_off + 255) & ~(size_t)255;
-        if (off + bytes > h->stage_cap) { status = sdt_fail(h, SDT_ERR_INVALID, "staging arena overflow (reserve too small)"); return nullptr; }
-        h->stage_off = off + bytes;
-        return h->stage + off;
+        size_t o = (off + 255) & ~(size_t)255;
+        if (o + bytes > lim) { status = sdt_fail(h, SDT_ERR_INVALID, "staging arena overflow (reserve too small)"); return nullptr; }
+        off = o + bytes;
+        return h->stage + o;
     }
     const void* in(const void* p, size_t bytes) {
         if (!host || !p) return p;
         void* d = alloc(bytes);
         if (!d) return nullptr;
-        if (cudaMemcpyAsync(d, p, bytes, cudaMemcpyHostToDevice, st) != cudaSuccess) { status = sdt_fail(h, SDT_ERR_CUDA, "H2D staging copy failed"); return nullptr; }
-        h2d += bytes;
+        if (cudaMemcpyAsync(d, p, bytes, cudaMemcpyHostToDevice, slot >= 0 ? h->s_in : st) != cudaSuccess) { status = sdt_fail(h, SDT_ERR_CUDA, "H2D staging copy failed"); return nullptr; }
         return d;
     }
     void* out(void* p, size_t bytes) {
@@ -153,6 +164,14 @@ struct Stager {
         if (!d) return nullptr;
         outs.push_back(Out{p, d, bytes});
         return d;
+    }
+    // pipelined chunk: the kernels wait for this chunk's inputs and for the D2H of the chunk that
+    // used the slot's output buffers before
+    void before_launch() {
+        if (slot < 0) return;
+        cudaEventRecord(h->ev_in[slot], h->s_in);
+        cudaStreamWaitEvent(st, h->ev_in[slot], 0);
+        cudaStreamWaitEvent(st, h->ev_out[slot], 0);
     }
     template <class T> const T* in_t(const T* p, size_t n) { return (const T*)in(p, n * sizeof(T)); }
     template <class T> T* out_t(T* p, size_t n) { return (T*)out(p, n * sizeof(T)); }
@@ -192,10 +211,18 @@ struct Stager {
     }
     int finish(uint32_t flags) {
         if (status != SDT_OK) return status;
+        if (slot >= 0) {            // pipelined chunk: D2H on the output stream, no synchronisation here
+            cudaEventRecord(h->ev_comp[slot], st);
+            cudaStreamWaitEvent(h->s_out, h->ev_comp[slot], 0);
+            for (const Out& o : outs)
+                if (cudaMemcpyAsync(o.host, o.dev, o.bytes, cudaMemcpyDeviceToHost, h->s_out) != cudaSuccess)
+                    return sdt_fail(h, SDT_ERR_CUDA, "D2H staging copy failed");
+            cudaEventRecord(h->ev_out[slot], h->s_out);
+            return SDT_OK;
+        }
         for (const Out& o : outs) {
             if (cudaMemcpyAsync(o.host, o.dev, o.bytes, cudaMemcpyDeviceToHost, st) != cudaSuccess)
                 return sdt_fail(h, SDT_ERR_CUDA, "D2H staging copy failed");
-            d2h += o.bytes;
         }
         // results in pageable/pinned host memory are only valid after the stream drains
         if ((flags & SDT_SYNC) || (host && !outs.empty())) {
@@ -204,3 +231,53 @@ struct Stager {
         return SDT_OK;
     }
 };
+
+// Runs body(stager, first_lane, lane_count) once (device pointers / small host calls) or as a
+// 2-slot pipeline over chunks of h->host_chunk lanes (large SDT_HOST_PTRS calls): the H2D copy of
+// chunk k+1, the kernels of chunk k and the D2H copy of chunk k-1 overlap on three streams.
+template <class Body>
+static int sdt_run_chunked(sdt_handle h, cudaStream_t st, uint32_t flags, uint32_t n, size_t bytes_per_lane, bool has_outputs, Body body) {
+    const bool host = (flags & SDT_HOST_PTRS) != 0;
+    const uint32_t chunk = (uint32_t)h->host_chunk;
+    if (!host || !h->s_in || n <= chunk + chunk / 2) {
+        Stager sg(h, st, flags);
+        SDT_TRY(sg.reserve((size_t)n * bytes_per_lane + 65536));
+        SDT_TRY(body(sg, 0u, n));
+        return sg.finish(flags);
+    }
+    {
+        Stager probe(h, st, flags);
+        SDT_TRY(probe.reserve(2 * ((size_t)chunk * bytes_per_lane + 65536)));
+    }
+    int k = 0;
+    for (uint32_t off = 0; off < n; off += chunk, ++k) {
+        const uint32_t cnt = n - off < chunk ? n - off : chunk;
+        Stager sg(h, st, flags, k & 1);
+        SDT_TRY(body(sg, off, cnt));
+        SDT_TRY(sg.finish(flags));
+    }
+    // stream order for the caller: everything, D2H included, is complete when `st` drains
+    cudaStreamWaitEvent(st, h->ev_out[0], 0);
+    cudaStreamWaitEvent(st, h->ev_out[1], 0);
+    if ((flags & SDT_SYNC) || has_outputs) {
+        if (cudaStreamSynchronize(st) != cudaSuccess) return sdt_fail(h, SDT_ERR_CUDA, "stream synchronize failed");
+    }
+    return SDT_OK;
+}
+
+static inline sdt_vec3 sdt_off3(const sdt_vec3& v, uint32_t off) {
+    sdt_vec3 r = v;
+    if (v.x) { r.x = v.x + (int64_t)off * v.stride; r.y = v.y + (int64_t)off * v.stride; r.z = v.z + (int64_t)off * v.stride; }
+    return r;
+}
+static inline sdt_vec3_out sdt_off3o(const sdt_vec3_out& v, uint32_t off) {
+    sdt_vec3_out r = v;
+    if (v.x) { r.x = v.x + (int64_t)off * v.stride; r.y = v.y + (int64_t)off * v.stride; r.z = v.z + (int64_t)off * v.stride; }
+    return r;
+}
+static inline sdt_vec2 sdt_off2(const sdt_vec2& v, uint32_t off) {
+    sdt_vec2 r = v;
+    if (v.x) { r.x = v.x + (int64_t)off * v.stride; r.y = v.y + (int64_t)off * v.stride; }
+    return r;
+}
+template <class T> static inline T* sdt_offp(T* p, size_t off) { return p ? p + off : p; }

@@ -18,6 +18,11 @@ static int sdt_free_all(sdt_handle h) {
     }
     if (h->h_hdr) cudaFreeHost(h->h_hdr);
     if (h->hdr_event) cudaEventDestroy(h->hdr_event);
+#ifndef SDT_HOSTEMU
+    for (int k = 0; k < 2; ++k) { if (h->ev_in[k]) cudaEventDestroy(h->ev_in[k]); if (h->ev_comp[k]) cudaEventDestroy(h->ev_comp[k]); if (h->ev_out[k]) cudaEventDestroy(h->ev_out[k]); }
+    if (h->s_in) cudaStreamDestroy(h->s_in);
+    if (h->s_out) cudaStreamDestroy(h->s_out);
+#endif
     return SDT_OK;
 }
 
@@ -74,6 +79,17 @@ extern "C" int sdt_create(const sdt_config* cfg, sdt_handle* out) {
 #undef A
     if (st == SDT_OK && cudaMallocHost((void**)&h->h_hdr, sizeof(DevHeader)) != cudaSuccess) st = sdt_fail(h, SDT_ERR_CUDA, "cudaMallocHost failed");
     if (st == SDT_OK && cudaEventCreate(&h->hdr_event) != cudaSuccess) st = sdt_fail(h, SDT_ERR_CUDA, "cudaEventCreate failed");
+#ifndef SDT_HOSTEMU
+    if (st == SDT_OK) {
+        bool ok = cudaStreamCreateWithFlags(&h->s_in, cudaStreamNonBlocking) == cudaSuccess &&
+                  cudaStreamCreateWithFlags(&h->s_out, cudaStreamNonBlocking) == cudaSuccess;
+        for (int k = 0; k < 2 && ok; ++k)
+            ok = cudaEventCreateWithFlags(&h->ev_in[k], cudaEventDisableTiming) == cudaSuccess &&
+                 cudaEventCreateWithFlags(&h->ev_comp[k], cudaEventDisableTiming) == cudaSuccess &&
+                 cudaEventCreateWithFlags(&h->ev_out[k], cudaEventDisableTiming) == cudaSuccess;
+        if (!ok) st = sdt_fail(h, SDT_ERR_CUDA, "staging pipeline streams/events could not be created");
+    }
+#endif
     if (st == SDT_OK) {
         // initial tree: src/kdtree.py:117-130, src/quadtree.py:350-362
         DevHeader H;
@@ -331,6 +347,7 @@ extern "C" int sdt_set_tuning(sdt_handle h, const char* key, int64_t value) {
     else if (k == "splat_block") { SDT_CHECK(h, value >= 64 && value <= 512 && value % 32 == 0, SDT_ERR_INVALID, "splat_block must be 64..512, multiple of 32"); h->splat_block = (int)value; }
     else if (k == "splat_ctas_per_sm") { SDT_CHECK(h, value >= 1 && value <= 32, SDT_ERR_INVALID, "splat_ctas_per_sm must be 1..32"); h->splat_ctas_per_sm = (int)value; }
     else if (k == "fuse_sample_pdf") h->fuse_sample_pdf = value != 0;
+    else if (k == "host_chunk") { SDT_CHECK(h, value >= 256, SDT_ERR_INVALID, "host_chunk must be >= 256 lanes"); h->host_chunk = (int)value; }
     else return sdt_fail(h, SDT_ERR_INVALID, "sdt_set_tuning: unknown key " + k);
     return SDT_OK;
 }

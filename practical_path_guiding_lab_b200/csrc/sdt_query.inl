@@ -236,18 +236,20 @@ extern "C" int sdt_sample(sdt_handle h, const sdt_vec3* pos, const uint8_t* acti
     SDT_CHECK(h, pos && pos->x && dir && dir->x && pdf, SDT_ERR_INVALID, "sdt_sample: pos / dir / pdf is NULL");
     SDT_CHECK(h, !u || u_stride >= 3, SDT_ERR_INVALID, "sdt_sample: u_stride must be >= 3");
     cudaStream_t st = (cudaStream_t)stream;
-    Stager sg(h, st, flags);
-    SDT_TRY(sg.reserve((size_t)n * (12 + 1 + 12 + 4 + 16 + (u ? 4ull * u_stride : 0)) + 8192));
-    SampleLane<false> f{tree_view(h), sg.in3(*pos, n), sg.in_t(active, n), sg.in_t(u, (size_t)n * u_stride), u_stride, seed, lane_offset,
-                        sg.out3(*dir, n), sg.out_t(pdf, n), sg.out_t(dbg, (size_t)n * 4), h->fuse_sample_pdf};
-    if (sg.status != SDT_OK) return sg.status;
-    if (u) {
-        SampleLane<true> fe{f.t, f.pos, f.active, f.u, f.u_stride, f.seed, f.lane_offset, f.dir, f.pdf, f.dbg, f.fuse};
-        SDT_TRY(launch_wavefront(h, st, n, fe, h->query_block, h->query_ctas_per_sm));
-    } else {
-        SDT_TRY(launch_wavefront(h, st, n, f, h->query_block, h->query_ctas_per_sm));
-    }
-    return sg.finish(flags);
+    const size_t per_lane = 12 + 1 + 12 + 4 + (dbg ? 16 : 0) + (u ? 4ull * u_stride : 0) + 8;
+    return sdt_run_chunked(h, st, flags, n, per_lane, true, [&](Stager& sg, uint32_t off, uint32_t cnt) -> int {
+        SampleLane<false> f{tree_view(h), sg.in3(sdt_off3(*pos, off), cnt), sg.in_t(sdt_offp(active, off), cnt),
+                            sg.in_t(sdt_offp(u, (size_t)off * u_stride), (size_t)cnt * u_stride), u_stride, seed, lane_offset + off,
+                            sg.out3(sdt_off3o(*dir, off), cnt), sg.out_t(sdt_offp(pdf, off), cnt),
+                            sg.out_t(sdt_offp(dbg, (size_t)off * 4), (size_t)cnt * 4), h->fuse_sample_pdf};
+        if (sg.status != SDT_OK) return sg.status;
+        sg.before_launch();
+        if (u) {
+            SampleLane<true> fe{f.t, f.pos, f.active, f.u, f.u_stride, f.seed, f.lane_offset, f.dir, f.pdf, f.dbg, f.fuse};
+            return launch_wavefront(h, st, cnt, fe, h->query_block, h->query_ctas_per_sm);
+        }
+        return launch_wavefront(h, st, cnt, f, h->query_block, h->query_ctas_per_sm);
+    });
 }
 
 extern "C" int sdt_pdf(sdt_handle h, const sdt_vec3* pos, const sdt_vec3* dir, const uint8_t* active,
@@ -255,12 +257,14 @@ extern "C" int sdt_pdf(sdt_handle h, const sdt_vec3* pos, const sdt_vec3* dir, c
     if (!h) return SDT_ERR_INVALID;
     SDT_CHECK(h, pos && pos->x && dir && dir->x && pdf, SDT_ERR_INVALID, "sdt_pdf: pos / dir / pdf is NULL");
     cudaStream_t st = (cudaStream_t)stream;
-    Stager sg(h, st, flags);
-    SDT_TRY(sg.reserve((size_t)n * (24 + 1 + 4 + 12) + 8192));
-    PdfLane f{tree_view(h), sg.in3(*pos, n), sg.in3(*dir, n), sg.in_t(active, n), sg.out_t(pdf, n), sg.out_t(dbg, (size_t)n * 3)};
-    if (sg.status != SDT_OK) return sg.status;
-    SDT_TRY(launch_wavefront(h, st, n, f, h->query_block, h->query_ctas_per_sm));
-    return sg.finish(flags);
+    const size_t per_lane = 24 + 1 + 4 + (dbg ? 12 : 0) + 8;
+    return sdt_run_chunked(h, st, flags, n, per_lane, true, [&](Stager& sg, uint32_t off, uint32_t cnt) -> int {
+        PdfLane f{tree_view(h), sg.in3(sdt_off3(*pos, off), cnt), sg.in3(sdt_off3(*dir, off), cnt), sg.in_t(sdt_offp(active, off), cnt),
+                  sg.out_t(sdt_offp(pdf, off), cnt), sg.out_t(sdt_offp(dbg, (size_t)off * 3), (size_t)cnt * 3)};
+        if (sg.status != SDT_OK) return sg.status;
+        sg.before_launch();
+        return launch_wavefront(h, st, cnt, f, h->query_block, h->query_ctas_per_sm);
+    });
 }
 
 extern "C" int sdt_guided(sdt_handle h, const sdt_guided_args* a, uint32_t n, uint32_t flags, sdt_stream stream) {

@@ -171,20 +171,22 @@ extern "C" int sdt_splat_records(sdt_handle h, const sdt_records* rec, uint32_t 
     if (!h) return SDT_ERR_INVALID;
     SDT_CHECK(h, rec && rec->position.x && rec->direction.x && rec->radiance && rec->wo_pdf, SDT_ERR_INVALID, "sdt_splat_records: missing field");
     cudaStream_t st = (cudaStream_t)stream;
-    Stager sg(h, st, flags);
-    SDT_TRY(sg.reserve((size_t)n * (12 + 8 + 4 + 4 + 12 + 8 + 1) + 16384));
-    sdt_records d = *rec;
-    d.position = sg.in3(rec->position, n);
-    d.direction = sg.in2(rec->direction, n);
-    d.radiance = sg.in_t(rec->radiance, n);
-    d.wo_pdf = sg.in_t(rec->wo_pdf, n);
-    if (h->cfg.store_nee) { d.radiance_nee = sg.in3(rec->radiance_nee, n); d.direction_nee = sg.in2(rec->direction_nee, n); }
-    d.active = sg.in_t(rec->active, n);
-    if (sg.status != SDT_OK) return sg.status;
-    SplatRecordsLane f{tree_view(h), SplatTarget{h->kd_count, h->q_ecur, (uint32_t)(h->cfg.store_nee != 0)}, d};
+    const bool nee = h->cfg.store_nee != 0;
     h->stats_complete = false;
-    SDT_TRY(launch_wavefront(h, st, n, f, h->splat_block, h->splat_ctas_per_sm));
-    return sg.finish(flags);
+    const size_t per_lane = 12 + 8 + 4 + 4 + (nee ? 20 : 0) + 1 + 8;
+    return sdt_run_chunked(h, st, flags, n, per_lane, false, [&](Stager& sg, uint32_t off, uint32_t cnt) -> int {
+        sdt_records d = *rec;
+        d.position = sg.in3(sdt_off3(rec->position, off), cnt);
+        d.direction = sg.in2(sdt_off2(rec->direction, off), cnt);
+        d.radiance = sg.in_t(sdt_offp(rec->radiance, off), cnt);
+        d.wo_pdf = sg.in_t(sdt_offp(rec->wo_pdf, off), cnt);
+        if (nee) { d.radiance_nee = sg.in3(sdt_off3(rec->radiance_nee, off), cnt); d.direction_nee = sg.in2(sdt_off2(rec->direction_nee, off), cnt); }
+        d.active = sg.in_t(sdt_offp(rec->active, off), cnt);
+        if (sg.status != SDT_OK) return sg.status;
+        SplatRecordsLane f{tree_view(h), SplatTarget{h->kd_count, h->q_ecur, (uint32_t)nee}, d};
+        sg.before_launch();
+        return launch_wavefront(h, st, cnt, f, h->splat_block, h->splat_ctas_per_sm);
+    });
 }
 
 extern "C" int sdt_splat_path_data(sdt_handle h, const sdt_path_data* pd, uint32_t flags, sdt_stream stream) {

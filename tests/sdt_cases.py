@@ -245,6 +245,18 @@ def case_fused_equals_two_descents(ctx):
     t.set_tuning("fuse_sample_pdf", 1)
 
 
+def case_host_pipeline_chunks(ctx):
+    """large SDT_HOST_PTRS calls run as a chunked 3-stream pipeline: same results, chunk edges included"""
+    t, cur, prev = train(ctx, iters=3)
+    t.set_tuning("host_chunk", 1000)                  # 9 chunks of 1000 + a ragged tail
+    check_queries(ctx, t, prev, n=9531, explicit=True)
+    check_queries(ctx, t, prev, n=9531, explicit=False)
+    rec = dyadic_records(9531, 77, ((0.3, 0.7, 0.02),))
+    splat(t, ctx, rec)
+    cur.addDataPropagate(rec)
+    assert_tree_equal(t.download(1), cur)
+
+
 def case_splat_float_tolerance(ctx):
     """general fp32 radiance: energies within 1e-4 relative of the exactly-rounded sums;
     conservation root = sum leaves = sum radiance/woPdf (src/quadtree.py:1205-1218)"""
@@ -409,7 +421,7 @@ def case_npz_roundtrip(ctx, tmp_path):
     check_queries(ctx, t2, o, n=1024)
 
 
-ALL_CASES = [case_initial_tree, case_golden_upload_download, case_train_refine_topology,
+ALL_CASES = [case_initial_tree, case_golden_upload_download, case_train_refine_topology, case_host_pipeline_chunks,
              case_train_refine_nee_shallow, case_fused_equals_two_descents, case_splat_float_tolerance,
              case_path_data, case_mis, case_guided_bounce, case_refine_flags_and_frozen_stats,
              case_capacity_error]
