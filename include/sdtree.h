@@ -79,6 +79,7 @@ typedef struct sdt_sizes {
     uint32_t kd_leaves;
     uint32_t error;      /* sticky device-side error flag (0 = none) */
     uint32_t refine_count;
+    uint32_t jump_trees; /* quadtrees covered by the 16x16 jump table over their top 4 levels */
 } sdt_sizes;
 
 /* The reference's on-disk contract: the 23 arrays of KDTree.saveToFile
@@ -258,7 +259,7 @@ int sdt_stat_buffers(sdt_handle h, float** q_energy, uint32_t* n_quad, float** k
 
 /* ---- tuning / introspection --------------------------------------------------- */
 /* key: "query_block", "query_ctas_per_sm", "kd_smem_nodes", "splat_block",
- * "splat_ctas_per_sm", "fuse_sample_pdf", "host_chunk" (lanes per chunk of the pipelined
+ * "splat_ctas_per_sm", "fuse_sample_pdf", "use_jump", "host_chunk" (lanes per chunk of the pipelined
  * SDT_HOST_PTRS staging: H2D of chunk k+1 | kernels of chunk k | D2H of chunk k-1) */
 int sdt_set_tuning(sdt_handle h, const char* key, int64_t value);
 /* number of kernels this handle has launched since creation */

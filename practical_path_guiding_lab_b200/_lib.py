@@ -39,7 +39,7 @@ class Config(C.Structure):
 
 class Sizes(C.Structure):
     _fields_ = [(k, C.c_uint32) for k in ("n_kd", "n_quad", "n_roots", "n_interior", "n_levels",
-                                         "kd_leaves", "error", "refine_count")]
+                                         "kd_leaves", "error", "refine_count", "jump_trees")]
 
 
 class Arrays(C.Structure):

@@ -44,7 +44,8 @@ struct DevHeader {
     uint32_t root_of_node0;                 // quadTreeRootIndex[0] (out-of-box lanes, :224,:482)
     uint32_t kd_max_depth, quad_max_depth, store_nee;
     uint32_t rootrec_of_node0;              // record index of that tree's root (SDT_NONE: single-leaf tree)
-    uint32_t pad0[3];
+    uint32_t jump_trees;                    // trees covered by the 16x16 jump table (0: none)
+    uint32_t pad0[2];
     float bbox_min[3], bbox_max[3];         // spatial root box
     float max_leaf_size;                    // KDTree.maxLeafSize as fp32
     uint32_t pad1;
@@ -70,11 +71,24 @@ enum DevError : uint32_t {
 };
 
 // What the query kernels need (by value).
+// Jump table over the top SDT_JUMP_LEVELS levels of every non-single-leaf quadtree: for each of
+// the 16x16 cells of [0,1]^2 the node a pdf / splat descent reaches after 4 levels (or the leaf /
+// NaN stop it meets earlier) and the pdf product accumulated on the way -- computed with exactly
+// the operations of the level-by-level descent, so the result is bit-identical.  Points on a
+// 1/16 grid line (where the reference's inclusive-box tie rules matter) take the slow path.
+#define SDT_JUMP_LEVELS 4
+#define SDT_JUMP_CELLS 256
+#define SDT_JUMP_LEAF 0x80000000u      // entry.ri = LEAF | node id: a leaf was reached
+#define SDT_JUMP_DEAD 0xC0000000u      // entry.ri = DEAD | node id: the pdf product went NaN at that node
+struct __align__(8) QJump { uint32_t ri; float prod; };
+
 struct TreeView {
     const DevHeader* hdr;
     const uint32_t* kd_word;
     const uint32_t* kd_root;    // per spatial node: quadTreeRootIndex (= canonical node id of the tree's root)
     const QRec* rec;
+    const QJump* jump;          // [root record][cell]
+    uint32_t jump_trees;        // 0: table not in use
 };
 
 // ---------------------------------------------------------------------------
@@ -334,6 +348,13 @@ SDT_HD uint32_t sdt_descend_child(float x, float y, float mx, float my) {
 SDT_HD uint32_t sdt_energy_child(float x, float y, float mx, float my) {
     return (y >= my) ? ((x >= mx) ? 0u : 1u) : ((x <= mx) ? 2u : 3u);
 }
+// (4*childE)/nodeE of pdfQuadTree (:1084).  A +0 child energy over a positive node energy is +0
+// in IEEE arithmetic; answering it directly keeps those lanes (most pdf queries outside the lobes)
+// off the division's slow path, which the hardware check takes for a zero numerator.
+SDT_HD float sdt_pdf_ratio(float child_e, float own) {
+    if (sdt_f2u(child_e) == 0u && own > 0.0f) return 0.0f;
+    return (4.0f * child_e) / own;
+}
 SDT_HD float sdt_pick4(const SdtF4& v, uint32_t c) {
     const float a = (c & 1u) ? v.y : v.x;
     const float b = (c & 1u) ? v.w : v.z;
@@ -343,20 +364,53 @@ SDT_HD float sdt_pick4(const SdtF4& v, uint32_t c) {
 // QuadTree.pdfQuadTree, src/quadtree.py:1001-1101, from canonical position (x,y) in
 // [0,1]^2.  ri = record index of the root (SDT_NONE: single-leaf tree).  One 32-byte record
 // (one L2 sector) per level carries everything: child ids, own energy, child energies.
-SDT_HD float sdt_quad_pdf(const QRec* __restrict__ rec, uint32_t ri, uint32_t root_node,
+SDT_HD QJump sdt_load_jump(const QJump* __restrict__ p) {
+    QJump j;
+#if defined(__CUDA_ARCH__)
+    const uint2 v = __ldg(reinterpret_cast<const uint2*>(p));
+    j.ri = v.x; j.prod = __uint_as_float(v.y);
+#else
+    j = *p;
+#endif
+    return j;
+}
+// cell of a canonical position; false when it lies on a grid line or outside [0,1)
+SDT_HD bool sdt_jump_cell(float x, float y, uint32_t& cx, uint32_t& cy) {
+    const float fx = x * 16.0f, fy = y * 16.0f;          // exact scalings
+    if (!(fx >= 0.0f && fx < 16.0f && fy >= 0.0f && fy < 16.0f)) return false;
+    cx = (uint32_t)fx; cy = (uint32_t)fy;
+    return fx != (float)cx && fy != (float)cy;
+}
+
+SDT_HD float sdt_quad_pdf(const TreeView& t, uint32_t ri, uint32_t root_node,
                           float x, float y, uint32_t& node_out) {
+    const QRec* __restrict__ rec = t.rec;
     float pdf = 1.0f;
     float lox = 0.0f, loy = 0.0f, hix = 1.0f, hiy = 1.0f;
     uint32_t node = root_node;
     bool dead = false;
-    for (int level = 0; level < SDT_MAX_LEVELS; ++level) {
+    int level = 0;
+    uint32_t cx, cy;
+    if (ri < t.jump_trees && sdt_jump_cell(x, y, cx, cy)) {
+        const QJump j = sdt_load_jump(t.jump + (size_t)ri * SDT_JUMP_CELLS + cy * 16u + cx);
+        pdf = j.prod;
+        if (j.ri & SDT_JUMP_LEAF) {
+            node_out = j.ri & 0x3FFFFFFFu;
+            return ((j.ri & SDT_JUMP_DEAD) == SDT_JUMP_DEAD) ? 0.0f : pdf * SDT_INV_FOUR_PI;
+        }
+        ri = j.ri;
+        lox = (float)cx * 0.0625f; hix = (float)(cx + 1u) * 0.0625f;
+        loy = (float)cy * 0.0625f; hiy = (float)(cy + 1u) * 0.0625f;
+        level = SDT_JUMP_LEVELS;
+    }
+    for (; level < SDT_MAX_LEVELS; ++level) {
         if (ri == SDT_NONE) break;
         QHead h; SdtF4 e;
         sdt_load_rec(rec, ri, h, e);
         const float mx = (lox + hix) / 2.0f, my = (loy + hiy) / 2.0f;
         const uint32_t ce = sdt_energy_child(x, y, mx, my);
         const uint32_t cd = sdt_descend_child(x, y, mx, my);
-        pdf = pdf * ((4.0f * sdt_pick4(e, ce)) / h.own);                // :1084
+        pdf = pdf * sdt_pdf_ratio(sdt_pick4(e, ce), h.own);             // :1084
         if (pdf != pdf) { dead = true; break; }                         // :1090-1092
         node = h.child_base + cd;
         sdt_quadrant_m(cd, mx, my, lox, loy, hix, hiy);
@@ -365,6 +419,27 @@ SDT_HD float sdt_quad_pdf(const QRec* __restrict__ rec, uint32_t ri, uint32_t ro
     pdf = dead ? 0.0f : pdf * SDT_INV_FOUR_PI;                          // :1030
     node_out = node;
     return pdf;
+}
+
+// one jump-table entry: the descent of pdfQuadTree for any interior point of cell (cx,cy)
+SDT_HD QJump sdt_build_jump(const QRec* __restrict__ rec, uint32_t root_rec, uint32_t cx, uint32_t cy) {
+    QJump j;
+    float pdf = 1.0f;
+    uint32_t ri = root_rec;
+    uint32_t node = 0;
+    for (int l = 0; l < SDT_JUMP_LEVELS; ++l) {
+        const QRec r = rec[ri];
+        if (l == 0) node = 0;    // (root node id is not needed: a root with a record is never the answer)
+        const uint32_t bx = (cx >> (SDT_JUMP_LEVELS - 1 - l)) & 1u, by = (cy >> (SDT_JUMP_LEVELS - 1 - l)) & 1u;
+        const uint32_t c = by ? (bx ? 0u : 1u) : (bx ? 3u : 2u);         // strict interior: every tie rule agrees
+        pdf = pdf * sdt_pdf_ratio(r.e[c], r.own);
+        if (pdf != pdf) { j.ri = SDT_JUMP_DEAD | (l == 0 ? 0x3FFFFFFFu : node); j.prod = 0.0f; return j; }
+        node = r.child_base + c;
+        ri = sdt_child_rec(r.cinfo, r.interior_base, c);
+        if (ri == SDT_NONE) { j.ri = SDT_JUMP_LEAF | node; j.prod = pdf; return j; }
+    }
+    j.ri = ri; j.prod = pdf;
+    return j;
 }
 
 // QuadTree.sampleQuadTree, src/quadtree.py:931-998.  Consumes 3 uniforms per visited
@@ -405,7 +480,7 @@ SDT_HD QSample sdt_quad_sample(const QRec* __restrict__ rec, uint32_t ri, uint32
         const bool m0 = s < e1, m1 = b1 && (s < e2), m2 = b2 && (s < e3);
         if (!(m0 || m1 || m2 || b3)) { q.stuck = true; break; }
         const uint32_t cu = b3 ? 3u : (m2 ? 2u : (m1 ? 1u : 0u));
-        const float f = q.pdf_path * ((4.0f * sdt_pick4(e, cu)) / h.own);   // :1084
+        const float f = q.pdf_path * ((4.0f * sdt_pick4(e, cu)) / h.own);   // :1084 (the sampled child has energy: no zero shortcut)
         if (!q.pdf_dead) {
             q.pdf_dead = f != f;                                         // :1090-1092
             q.pdf_path = q.pdf_dead ? 0.0f : f;
@@ -441,7 +516,7 @@ SDT_HD GuidedSample sdt_sample_tree(const TreeView& t, uint32_t ri, uint32_t roo
         g.pdf_node = q.node;
     } else {
         uint32_t nd;
-        g.pdf = sdt_quad_pdf(t.rec, ri, root, px, py, nd);
+        g.pdf = sdt_quad_pdf(t, ri, root, px, py, nd);
         g.pdf_node = nd;
     }
     return g;
@@ -449,11 +524,24 @@ SDT_HD GuidedSample sdt_sample_tree(const TreeView& t, uint32_t ri, uint32_t roo
 
 // Leaf reached by QuadTree.addDataPropagate's descent (src/quadtree.py:401-441) for a
 // canonical direction; SDT_NONE when the root box does not contain it (:405).
-SDT_HD uint32_t sdt_quad_leaf(const QRec* __restrict__ rec, uint32_t ri, uint32_t root_node, float x, float y) {
+SDT_HD uint32_t sdt_quad_leaf(const TreeView& t, uint32_t ri, uint32_t root_node, float x, float y) {
     if (!(x >= 0.0f && x <= 1.0f && y >= 0.0f && y <= 1.0f)) return SDT_NONE;
+    const QRec* __restrict__ rec = t.rec;
     float lox = 0.0f, loy = 0.0f, hix = 1.0f, hiy = 1.0f;
     uint32_t node = root_node;
-    for (int level = 0; level < SDT_MAX_LEVELS && ri != SDT_NONE; ++level) {
+    int level = 0;
+    uint32_t cx, cy;
+    if (ri < t.jump_trees && sdt_jump_cell(x, y, cx, cy)) {
+        const QJump j = sdt_load_jump(t.jump + (size_t)ri * SDT_JUMP_CELLS + cy * 16u + cx);
+        if ((j.ri & SDT_JUMP_DEAD) != SDT_JUMP_DEAD) {              // (a NaN stop says nothing about the topology: slow path)
+            if (j.ri & SDT_JUMP_LEAF) return j.ri & 0x3FFFFFFFu;
+            ri = j.ri;
+            lox = (float)cx * 0.0625f; hix = (float)(cx + 1u) * 0.0625f;
+            loy = (float)cy * 0.0625f; hiy = (float)(cy + 1u) * 0.0625f;
+            level = SDT_JUMP_LEVELS;
+        }
+    }
+    for (; level < SDT_MAX_LEVELS && ri != SDT_NONE; ++level) {
         const QHead h = sdt_load_head(rec, ri);      // 16 of the record's 32 bytes
         const float mx = (lox + hix) / 2.0f, my = (loy + hiy) / 2.0f;
         const uint32_t cd = sdt_descend_child(x, y, mx, my);

@@ -12,6 +12,7 @@ struct QuadSet {
     float* thr = nullptr;           // refinementThreshold per node
     uint32_t* iidx = nullptr;       // per node: number of non-leaf nodes before it (= record index if non-leaf)
     QRec* rec = nullptr;
+    QJump* jump = nullptr;          // [root record][16x16 cell] jump table over the top 4 levels
     uint32_t* root_iidx = nullptr;
     DevHeader* hdr = nullptr;
 };
@@ -51,6 +52,9 @@ struct sdt_tree_s {
     cudaStream_t last_stream = nullptr;
     uint64_t launches = 0;
     uint32_t levels_hint = 1;       // upper bound of quadtree levels in use
+    uint32_t jump_cap = 0;          // trees the jump table can hold
+    uint32_t jump_trees_known = 0;  // trees covered, as last seen by the host (0 until known: slow path)
+    int use_jump = 1;
     uint32_t kd_nodes_known = 1;    // last spatial node count seen by the host (sizes the smem staging)
     cudaEvent_t hdr_event = nullptr;
     bool hdr_pending = false;       // an async header read-back (after refine) is in flight
@@ -101,7 +105,7 @@ static inline ExecCtx exec_ctx(sdt_handle h, cudaStream_t st) {
 
 static inline TreeView tree_view(const sdt_tree_s* h) {
     const QuadSet& s = h->set[h->cur];
-    return TreeView{s.hdr, h->kd_word, h->kd_root, s.rec};
+    return TreeView{s.hdr, h->kd_word, h->kd_root, s.rec, s.jump, h->use_jump ? h->jump_trees_known : 0u};
 }
 
 static int sdt_read_header(sdt_handle h, DevHeader& H);

@@ -13,7 +13,7 @@ static int sdt_free_all(sdt_handle h) {
     for (void* p : ptrs) if (p) cudaFree(p);
     for (int k = 0; k < 2; ++k) {
         QuadSet& s = h->set[k];
-        void* q[] = {s.child, s.energy, s.thr, s.iidx, s.rec, s.root_iidx, s.hdr};
+        void* q[] = {s.child, s.energy, s.thr, s.iidx, s.rec, s.jump, s.root_iidx, s.hdr};
         for (void* p : q) if (p) cudaFree(p);
     }
     if (h->h_hdr) cudaFreeHost(h->h_hdr);
@@ -56,6 +56,8 @@ extern "C" int sdt_create(const sdt_config* cfg, sdt_handle* out) {
     if (h->kd_cap < 1) h->kd_cap = 1;
     if (h->quad_cap < 4) h->quad_cap = 4;
     h->rec_cap = h->quad_cap / 4u + 1u;
+    h->jump_cap = h->kd_cap < 65536u ? h->kd_cap : 65536u;
+    if ((uint64_t)h->jump_cap * SDT_JUMP_CELLS > 4ull * h->quad_cap) h->jump_cap = (uint32_t)(4ull * h->quad_cap / SDT_JUMP_CELLS);
 #ifndef SDT_HOSTEMU
     {
         cudaError_t e = cudaSetDevice(cfg->device);
@@ -74,7 +76,7 @@ extern "C" int sdt_create(const sdt_config* cfg, sdt_handle* out) {
     for (int k = 0; k < 2; ++k) {
         QuadSet& s = h->set[k];
         A(s.child, h->quad_cap); A(s.energy, h->quad_cap); A(s.thr, h->quad_cap); A(s.iidx, h->quad_cap);
-        A(s.rec, h->rec_cap); A(s.root_iidx, h->kd_cap); A(s.hdr, 1);
+        A(s.rec, h->rec_cap); A(s.jump, (size_t)h->jump_cap * SDT_JUMP_CELLS); A(s.root_iidx, h->kd_cap); A(s.hdr, 1);
     }
 #undef A
     if (st == SDT_OK && cudaMallocHost((void**)&h->h_hdr, sizeof(DevHeader)) != cudaSuccess) st = sdt_fail(h, SDT_ERR_CUDA, "cudaMallocHost failed");
@@ -126,6 +128,7 @@ static int sdt_read_header(sdt_handle h, DevHeader& H) {
     H = *h->h_hdr;
     h->hdr_pending = false;
     h->kd_nodes_known = H.n_kd;
+    h->jump_trees_known = H.jump_trees;
     return SDT_OK;
 }
 
@@ -134,7 +137,7 @@ extern "C" int sdt_get_sizes(sdt_handle h, sdt_sizes* out) {
     DevHeader H;
     SDT_TRY(sdt_read_header(h, H));
     out->n_kd = H.n_kd; out->n_quad = H.n_quad; out->n_roots = H.n_roots; out->n_interior = H.n_interior;
-    out->n_levels = H.n_levels; out->kd_leaves = H.kd_leaves; out->error = H.error; out->refine_count = H.refine_count;
+    out->n_levels = H.n_levels; out->kd_leaves = H.kd_leaves; out->error = H.error; out->refine_count = H.refine_count; out->jump_trees = H.jump_trees;
     h->levels_hint = H.n_levels > 0 ? H.n_levels : 1;
     return SDT_OK;
 }
@@ -245,6 +248,7 @@ extern "C" int sdt_upload(sdt_handle h, const sdt_arrays* a) {
     h->kd_nodes_known = nk;
     h->hdr_pending = false;
     h->stats_complete = true;
+    { DevHeader H2; SDT_TRY(sdt_read_header(h, H2)); }      // jump_trees of the uploaded tree
     return SDT_OK;
 }
 
@@ -347,6 +351,7 @@ extern "C" int sdt_set_tuning(sdt_handle h, const char* key, int64_t value) {
     else if (k == "splat_block") { SDT_CHECK(h, value >= 64 && value <= 512 && value % 32 == 0, SDT_ERR_INVALID, "splat_block must be 64..512, multiple of 32"); h->splat_block = (int)value; }
     else if (k == "splat_ctas_per_sm") { SDT_CHECK(h, value >= 1 && value <= 32, SDT_ERR_INVALID, "splat_ctas_per_sm must be 1..32"); h->splat_ctas_per_sm = (int)value; }
     else if (k == "fuse_sample_pdf") h->fuse_sample_pdf = value != 0;
+    else if (k == "use_jump") h->use_jump = value != 0;
     else if (k == "host_chunk") { SDT_CHECK(h, value >= 256, SDT_ERR_INVALID, "host_chunk must be >= 256 lanes"); h->host_chunk = (int)value; }
     else return sdt_fail(h, SDT_ERR_INVALID, "sdt_set_tuning: unknown key " + k);
     return SDT_OK;

@@ -32,6 +32,7 @@ static int launch_wavefront(sdt_handle h, cudaStream_t st, uint32_t n, const Lan
     if (h->hdr_pending && cudaEventQuery(h->hdr_event) == cudaSuccess) {
         h->hdr_pending = false;
         h->kd_nodes_known = h->h_hdr->n_kd;
+        h->jump_trees_known = h->h_hdr->jump_trees;
     }
     uint32_t want = h->hdr_pending ? 2u * h->kd_nodes_known + 2u : h->kd_nodes_known;   // a refine at most... unknown: be generous
     uint32_t smem_nodes = (want + 255u) & ~255u;
@@ -62,6 +63,7 @@ static int launch_wavefront(sdt_handle h, cudaStream_t st, uint32_t n, const Lan
 #else
 template <class Lane>
 static int launch_wavefront(sdt_handle h, cudaStream_t st, uint32_t n, const Lane& f, int, int) {
+    if (h->hdr_pending) { h->hdr_pending = false; h->kd_nodes_known = h->h_hdr->n_kd; h->jump_trees_known = h->h_hdr->jump_trees; }
     const KdCtx k = sdt_kd_ctx(f.t.kd_word, 0u, f.t.kd_word, f.t.hdr);
     for (uint32_t i = 0; i < n; ++i) f.template run<false>(k, i);
     ++h->launches;
@@ -131,7 +133,7 @@ struct PdfLane {
             sdt_dir_to_canonical(sdt_ld(dir.x, dir.stride, i), sdt_ld(dir.y, dir.stride, i), sdt_ld(dir.z, dir.stride, i), x, y);
             uint32_t nd;
             const uint32_t root = dbg ? SDT_LDG(t.kd_root + r.leaf) : 0u;
-            p = sdt_quad_pdf(t.rec, r.rootrec, root, x, y, nd);
+            p = sdt_quad_pdf(t, r.rootrec, root, x, y, nd);
             d0 = r.leaf; d1 = root; d2 = nd;
         }
         pdf[i] = p;
@@ -162,7 +164,7 @@ struct GuidedLane {
             float x, y;
             sdt_dir_to_canonical(sdt_ld(a.wo.x, a.wo.stride, i), sdt_ld(a.wo.y, a.wo.stride, i), sdt_ld(a.wo.z, a.wo.stride, i), x, y);
             uint32_t nd;
-            const float p = sdt_quad_pdf(t.rec, r.rootrec, 0u, x, y, nd);
+            const float p = sdt_quad_pdf(t, r.rootrec, 0u, x, y, nd);
             a.sdtree_pdf[i] = p;
             if (a.bsdf_pdf && a.wo_pdf) {
                 const float f = a.bsdf_sampling_fraction;
@@ -219,6 +221,7 @@ struct MisMixtureItem {
 extern "C" int sdt_locate(sdt_handle h, const sdt_vec3* pos, const uint8_t* active, uint32_t n,
                           uint32_t* leaf, uint32_t* root, uint32_t flags, sdt_stream stream) {
     if (!h) return SDT_ERR_INVALID;
+    if (n == 0) return SDT_OK;                          // empty wavefront: nothing to do (pointers may be NULL)
     SDT_CHECK(h, pos && pos->x, SDT_ERR_INVALID, "sdt_locate: pos is NULL");
     cudaStream_t st = (cudaStream_t)stream;
     Stager sg(h, st, flags);
@@ -233,6 +236,7 @@ extern "C" int sdt_sample(sdt_handle h, const sdt_vec3* pos, const uint8_t* acti
                           const float* u, uint32_t u_stride, uint32_t seed, uint32_t lane_offset,
                           const sdt_vec3_out* dir, float* pdf, uint32_t* dbg, uint32_t flags, sdt_stream stream) {
     if (!h) return SDT_ERR_INVALID;
+    if (n == 0) return SDT_OK;                          // empty wavefront: nothing to do (pointers may be NULL)
     SDT_CHECK(h, pos && pos->x && dir && dir->x && pdf, SDT_ERR_INVALID, "sdt_sample: pos / dir / pdf is NULL");
     SDT_CHECK(h, !u || u_stride >= 3, SDT_ERR_INVALID, "sdt_sample: u_stride must be >= 3");
     cudaStream_t st = (cudaStream_t)stream;
@@ -255,6 +259,7 @@ extern "C" int sdt_sample(sdt_handle h, const sdt_vec3* pos, const uint8_t* acti
 extern "C" int sdt_pdf(sdt_handle h, const sdt_vec3* pos, const sdt_vec3* dir, const uint8_t* active,
                        uint32_t n, float* pdf, uint32_t* dbg, uint32_t flags, sdt_stream stream) {
     if (!h) return SDT_ERR_INVALID;
+    if (n == 0) return SDT_OK;                          // empty wavefront: nothing to do (pointers may be NULL)
     SDT_CHECK(h, pos && pos->x && dir && dir->x && pdf, SDT_ERR_INVALID, "sdt_pdf: pos / dir / pdf is NULL");
     cudaStream_t st = (cudaStream_t)stream;
     const size_t per_lane = 24 + 1 + 4 + (dbg ? 12 : 0) + 8;
@@ -269,6 +274,7 @@ extern "C" int sdt_pdf(sdt_handle h, const sdt_vec3* pos, const sdt_vec3* dir, c
 
 extern "C" int sdt_guided(sdt_handle h, const sdt_guided_args* a, uint32_t n, uint32_t flags, sdt_stream stream) {
     if (!h) return SDT_ERR_INVALID;
+    if (n == 0) return SDT_OK;                          // empty wavefront: nothing to do (pointers may be NULL)
     SDT_CHECK(h, a && a->pos.x && a->mode && a->sdtree_pdf && a->dir.x, SDT_ERR_INVALID, "sdt_guided: pos / mode / dir / sdtree_pdf is NULL");
     SDT_CHECK(h, !a->u || a->u_stride >= 3, SDT_ERR_INVALID, "sdt_guided: u_stride must be >= 3");
     cudaStream_t st = (cudaStream_t)stream;
@@ -315,6 +321,7 @@ extern "C" int sdt_mis_nee(sdt_handle h, uint32_t n, const float* bsdf_pdf_em, c
                            const uint8_t* ds_delta, float bsdf_sampling_fraction, int32_t iteration,
                            float* surface_pdf_em, float* mis_em, uint32_t flags, sdt_stream stream) {
     if (!h) return SDT_ERR_INVALID;
+    if (n == 0) return SDT_OK;                          // empty wavefront: nothing to do (pointers may be NULL)
     SDT_CHECK(h, bsdf_pdf_em && (iteration <= 1 || (sdtree_pdf_em && pdf_with_delta && pdf_without_delta)) && (!mis_em || ds_pdf),
               SDT_ERR_INVALID, "sdt_mis_nee: missing input");
     cudaStream_t st = (cudaStream_t)stream;
@@ -333,6 +340,7 @@ extern "C" int sdt_mis_mixture(sdt_handle h, uint32_t n, const float* bsdf_pdf, 
                                const sdt_vec3* bsdf_value, const uint8_t* do_mis, float bsdf_sampling_fraction,
                                float* wo_pdf, const sdt_vec3_out* weight, uint32_t flags, sdt_stream stream) {
     if (!h) return SDT_ERR_INVALID;
+    if (n == 0) return SDT_OK;                          // empty wavefront: nothing to do (pointers may be NULL)
     SDT_CHECK(h, bsdf_pdf && sdtree_pdf, SDT_ERR_INVALID, "sdt_mis_mixture: missing input");
     cudaStream_t st = (cudaStream_t)stream;
     Stager sg(h, st, flags);
@@ -368,6 +376,7 @@ struct CanonicalToDirItem {
 
 extern "C" int sdt_dir_to_canonical(sdt_handle h, const sdt_vec3* dir, uint32_t n, float* out_xy, uint32_t flags, sdt_stream stream) {
     if (!h) return SDT_ERR_INVALID;
+    if (n == 0) return SDT_OK;                          // empty wavefront: nothing to do (pointers may be NULL)
     SDT_CHECK(h, dir && dir->x && out_xy, SDT_ERR_INVALID, "sdt_dir_to_canonical: NULL argument");
     cudaStream_t st = (cudaStream_t)stream;
     Stager sg(h, st, flags);
@@ -381,6 +390,7 @@ extern "C" int sdt_dir_to_canonical(sdt_handle h, const sdt_vec3* dir, uint32_t 
 
 extern "C" int sdt_canonical_to_dir(sdt_handle h, const sdt_vec2* pos, uint32_t n, const sdt_vec3_out* dir, uint32_t flags, sdt_stream stream) {
     if (!h) return SDT_ERR_INVALID;
+    if (n == 0) return SDT_OK;                          // empty wavefront: nothing to do (pointers may be NULL)
     SDT_CHECK(h, pos && pos->x && dir && dir->x, SDT_ERR_INVALID, "sdt_canonical_to_dir: NULL argument");
     cudaStream_t st = (cudaStream_t)stream;
     Stager sg(h, st, flags);

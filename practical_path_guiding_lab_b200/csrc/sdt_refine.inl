@@ -278,10 +278,29 @@ struct KdLeafWordItem {
     }
 };
 
+// jump table: trees with a root record are records 0 .. iidx[n_roots]-1 (records follow node order)
+struct JumpCountItem {
+    DevHeader* H; const uint32_t* iidx; uint32_t cap;
+    SDT_HD void operator()() const {
+        const uint32_t trees = H->n_roots < H->n_quad ? iidx[H->n_roots] : H->n_interior;
+        H->jump_trees = trees <= cap ? trees : 0u;            // does not fit: table off, kernels take the level-by-level path
+        H->lvl_n[0] = H->jump_trees * SDT_JUMP_CELLS;
+    }
+};
+struct JumpBuildItem {
+    const QRec* rec; QJump* jump;
+    SDT_HD void operator()(uint32_t i) const {
+        const uint32_t tr = i / SDT_JUMP_CELLS, cell = i % SDT_JUMP_CELLS;
+        jump[i] = sdt_build_jump(rec, tr, cell & 15u, cell >> 4);
+    }
+};
+
 static void sdt_build_records(sdt_handle h, const ExecCtx& x, QuadSet& s) {
     launch_scan(x, &s.hdr->n_quad, 0, RecFlag{s.child}, RecEmit{s.iidx}, RecFin{s.hdr});
     launch_items(x, &s.hdr->n_quad, 0, RecBuildItem{s.hdr, s.child, s.energy, s.iidx, s.rec, s.root_iidx});
     launch_items(x, &s.hdr->n_kd, 0, KdLeafWordItem{s.hdr, h->kd_word, h->kd_root, s.root_iidx});
+    launch_single(x, JumpCountItem{s.hdr, s.iidx, h->jump_cap});
+    launch_items(x, &s.hdr->lvl_n[0], 0, JumpBuildItem{s.rec, s.jump});
 }
 
 struct KdRollItem {         // prev.vertCount <- current.vertCount; current <- 0 (:141-153, :401-432)
@@ -332,6 +351,7 @@ extern "C" int sdt_refine(sdt_handle h, uint32_t flags, sdt_stream stream) {
     launch_items(x, &c.H1->n_quad, 0, ZeroItem{h->q_ecur});
     SDT_TRY(sdt_post_launch(h, "sdt_refine"));
     h->cur = 1 - h->cur;
+    h->jump_trees_known = 0;
     h->levels_hint = levels_bound;
     h->stats_complete = true;
     // non-blocking read-back of the new sizes (only used to size the smem staging of later launches)

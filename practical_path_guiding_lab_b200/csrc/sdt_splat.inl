@@ -56,13 +56,13 @@ SDT_HD void sdt_splat_one(const TreeView& t, const SplatTarget& tg, const KdCtx&
     if (act && ri == SDT_NONE) root = SDT_LDG(t.kd_root + r.leaf);
     const float irr = (wo_pdf > 0.0f) ? radiance / wo_pdf : 0.0f;                      // src/quadtree.py:451
     uint32_t leaf = SDT_NONE;
-    if (act && irr != 0.0f) leaf = sdt_quad_leaf(t.rec, ri, root, dx, dy);
+    if (act && irr != 0.0f) leaf = sdt_quad_leaf(t, ri, root, dx, dy);
     sdt_splat_add(tg.q_ecur, leaf, irr, leaf != SDT_NONE);
     if (tg.store_nee) {                                                               // :455-464
         const float lum = sdt_luminance(nr, ng, nb);
         const float irr2 = (wo_pdf > 0.0f) ? lum / wo_pdf : 0.0f;
         uint32_t leaf2 = SDT_NONE;
-        if (act && irr2 != 0.0f) leaf2 = sdt_quad_leaf(t.rec, ri, root, ndx, ndy);
+        if (act && irr2 != 0.0f) leaf2 = sdt_quad_leaf(t, ri, root, ndx, ndy);
         sdt_splat_add(tg.q_ecur, leaf2, irr2, leaf2 != SDT_NONE);
     }
 }
@@ -169,6 +169,7 @@ static int sdt_complete_stats(sdt_handle h, cudaStream_t st) {
 // ---------------------------------------------------------------------------- entry points
 extern "C" int sdt_splat_records(sdt_handle h, const sdt_records* rec, uint32_t n, uint32_t flags, sdt_stream stream) {
     if (!h) return SDT_ERR_INVALID;
+    if (n == 0) return SDT_OK;                          // empty wavefront: nothing to do (pointers may be NULL)
     SDT_CHECK(h, rec && rec->position.x && rec->direction.x && rec->radiance && rec->wo_pdf, SDT_ERR_INVALID, "sdt_splat_records: missing field");
     cudaStream_t st = (cudaStream_t)stream;
     const bool nee = h->cfg.store_nee != 0;
@@ -191,6 +192,7 @@ extern "C" int sdt_splat_records(sdt_handle h, const sdt_records* rec, uint32_t 
 
 extern "C" int sdt_splat_path_data(sdt_handle h, const sdt_path_data* pd, uint32_t flags, sdt_stream stream) {
     if (!h) return SDT_ERR_INVALID;
+    if (pd && pd->slots == 0) return SDT_OK;            // empty wavefront: nothing to do (pointers may be NULL)
     SDT_CHECK(h, pd && pd->max_depth > 0 && pd->l_final.x && pd->throughput_radiance.x && pd->throughput_bsdf.x && pd->bsdf.x &&
                      pd->position.x && pd->direction.x && pd->wo_pdf, SDT_ERR_INVALID, "sdt_splat_path_data: missing field");
     cudaStream_t st = (cudaStream_t)stream;

@@ -230,6 +230,34 @@ def case_train_refine_nee_shallow(ctx):
     check_queries(ctx, t, prev, box=100.0)
 
 
+def case_jump_table_equals_descent(ctx):
+    """the 16x16 jump table over the top 4 quadtree levels answers pdf / splat descents with the
+    same bits as the level-by-level descent (grid-line points included: they take the slow path)"""
+    t, cur, prev = train(ctx, iters=4)
+    assert t.sizes()['jump_trees'] > 0
+    rng = np.random.default_rng(17)
+    n = 20000
+    pos = rng.random((n, 3)).astype(F)
+    dirs = rng.standard_normal((n, 3)).astype(F)
+    dirs /= np.linalg.norm(dirs, axis=1, keepdims=True)
+    d2 = rng.random((n, 2)).astype(F)
+    d2[:64] = (rng.integers(0, 17, (64, 2)) / 16.0).astype(F)            # exactly on the 1/16 grid lines
+    d2[64:128, 0] = (rng.integers(0, 17, 64) / 16.0).astype(F)
+    dirs[:128] = dm.canonical_to_dir(d2[:128])
+    out = {}
+    for use in (1, 0):
+        t.set_tuning("use_jump", use)
+        p, dbg = t.pdf(ctx.dev(pos), ctx.dev(dirs), debug=True)
+        t.reset_stats()
+        t.splat_records(ctx.dev(pos), ctx.dev(d2), ctx.dev(np.ones(n, F)), ctx.dev(np.ones(n, F)))
+        out[use] = (ctx.host(p).copy(), ctx.host(dbg).copy(), t.download(1)['quadtree_irradiance'].copy())
+    t.set_tuning("use_jump", 1)
+    t.reset_stats()
+    assert beq(out[1][0], out[0][0]) and np.array_equal(out[1][1], out[0][1]) and np.array_equal(out[1][2], out[0][2])
+    op, odbg = prev.pdf(pos, dirs, True, return_debug=True)
+    assert beq(out[1][0], op) and np.array_equal(out[1][1].view(U)[:, 2], odbg['pdf_node'])
+
+
 def case_fused_equals_two_descents(ctx):
     t, cur, prev = train(ctx, iters=3)
     rng = np.random.default_rng(3)
@@ -407,6 +435,53 @@ def case_capacity_error(ctx):
     assert ctx.host(root).view(U).max() < s['n_roots']
 
 
+def case_edge_inputs_and_errors(ctx):
+    """empty / single / ragged wavefronts, SoA (Dr.Jit-style) component planes, error reporting"""
+    from practical_path_guiding_lab_b200 import SDTreeError
+    t, cur, prev = train(ctx, iters=2)
+    z3 = np.zeros((0, 3), F)
+    d, p = t.sample(ctx.dev(z3), seed=1)
+    assert ctx.host(d).shape == (0, 3) and ctx.host(p).shape == (0,)
+    assert ctx.host(t.pdf(ctx.dev(z3), ctx.dev(z3))).shape == (0,)
+    t.splat_records(ctx.dev(z3), ctx.dev(np.zeros((0, 2), F)), ctx.dev(np.zeros(0, F)), ctx.dev(np.zeros(0, F)))
+    for n in (1, 31, 33, 1025):
+        check_queries(ctx, t, prev, n=max(n, 16), seed=n)
+    # SoA planes (stride 1) == interleaved (stride 3)
+    rng = np.random.default_rng(12)
+    n = 777
+    pos = rng.random((n, 3)).astype(F)
+    planes = tuple(ctx.dev(np.ascontiguousarray(pos[:, k])) for k in range(3))
+    d1, p1 = t.sample(ctx.dev(pos), seed=5)
+    d2, p2 = t.sample(planes, seed=5)
+    assert beq(ctx.host(d1), ctx.host(d2)) and beq(ctx.host(p1), ctx.host(p2))
+    dirs = rng.standard_normal((n, 3)).astype(F)
+    dplanes = tuple(ctx.dev(np.ascontiguousarray(dirs[:, k])) for k in range(3))
+    assert beq(ctx.host(t.pdf(ctx.dev(pos), ctx.dev(dirs))), ctx.host(t.pdf(planes, dplanes)))
+    # errors: negative status + message, the handle stays usable
+    bad = dict(prev.to_arrays())
+    bad['kdtree_child_right_index'] = bad['kdtree_child_right_index'].copy()
+    bad['kdtree_child_right_index'][0] += 1
+    t2 = ctx.make(kd_capacity=1 << 14, quad_capacity=1 << 18)
+    try:
+        t2.upload(bad)
+        raise AssertionError("invalid spatial layout accepted")
+    except SDTreeError as e:
+        assert e.code == -4 and "adjacent" in str(e)
+    small = ctx.make(kd_capacity=4, quad_capacity=16)
+    try:
+        small.upload(prev.to_arrays())
+        raise AssertionError("oversized tree accepted")
+    except SDTreeError as e:
+        assert e.code == -3
+    try:
+        t.set_tuning("no_such_key", 1)
+        raise AssertionError("unknown tuning key accepted")
+    except SDTreeError as e:
+        assert e.code == -1
+    t2.upload(prev.to_arrays())
+    assert_tree_equal(t2.download(0), prev)
+
+
 def case_npz_roundtrip(ctx, tmp_path):
     t, cur, prev = train(ctx, iters=2)
     f = str(tmp_path / "tree.npz")
@@ -421,7 +496,7 @@ def case_npz_roundtrip(ctx, tmp_path):
     check_queries(ctx, t2, o, n=1024)
 
 
-ALL_CASES = [case_initial_tree, case_golden_upload_download, case_train_refine_topology, case_host_pipeline_chunks,
+ALL_CASES = [case_jump_table_equals_descent, case_initial_tree, case_golden_upload_download, case_train_refine_topology, case_host_pipeline_chunks,
              case_train_refine_nee_shallow, case_fused_equals_two_descents, case_splat_float_tolerance,
              case_path_data, case_mis, case_guided_bounce, case_refine_flags_and_frozen_stats,
-             case_capacity_error]
+             case_capacity_error, case_edge_inputs_and_errors]
