@@ -231,12 +231,14 @@ struct KdCtx {
     const uint32_t* kdg;      // full array
     float lo[3], hi[3];       // root box
     uint32_t rootrec0;        // root record of the tree owned by node 0 (out-of-box lanes, :224,:482)
+    float* cnt_s;             // splat kernels: per-CTA shared-memory leaf counters (NULL: count in global memory)
 };
 SDT_HD KdCtx sdt_kd_ctx(const uint32_t* kd, uint32_t n_smem, const uint32_t* kdg, const DevHeader* hdr) {
     KdCtx k;
     k.kd = kd; k.n_smem = n_smem; k.kdg = kdg;
     for (int a = 0; a < 3; ++a) { k.lo[a] = hdr->bbox_min[a]; k.hi[a] = hdr->bbox_max[a]; }
     k.rootrec0 = hdr->rootrec_of_node0;
+    k.cnt_s = nullptr;
     return k;
 }
 

@@ -11,7 +11,15 @@ __global__ void __launch_bounds__(512, 3) k_wavefront(Lane f, uint32_t n, uint32
     const uint32_t n_kd = hdr->n_kd;
     const uint32_t n_smem = n_kd < smem_cap ? n_kd : smem_cap;
     for (uint32_t j = threadIdx.x; j < n_smem; j += blockDim.x) kd_s[j] = __ldg(f.t.kd_word + j);
-    const KdCtx k = sdt_kd_ctx(kd_s, n_smem, f.t.kd_word, hdr);
+    KdCtx k = sdt_kd_ctx(kd_s, n_smem, f.t.kd_word, hdr);
+    // splat kernels with the whole spatial tree staged: leaf counters live in shared memory for the
+    // lifetime of the CTA and are flushed once (16M same-slice L2 atomics become a few per leaf and CTA)
+    float* cnt_s = nullptr;
+    if (Lane::kSmemCounts && n_smem == n_kd) {
+        cnt_s = reinterpret_cast<float*>(kd_s + smem_cap);
+        for (uint32_t j = threadIdx.x; j < n_smem; j += blockDim.x) cnt_s[j] = 0.0f;
+        k.cnt_s = cnt_s;
+    }
     __syncthreads();
     if (n_smem == n_kd) {           // whole spatial tree staged: descent loop without the global path
         for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
@@ -19,6 +27,13 @@ __global__ void __launch_bounds__(512, 3) k_wavefront(Lane f, uint32_t n, uint32
     } else {
         for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
             f.template run<false>(k, i);
+    }
+    if (cnt_s) {
+        __syncthreads();
+        for (uint32_t j = threadIdx.x; j < n_smem; j += blockDim.x) {
+            const float c = cnt_s[j];
+            if (c != 0.0f) f.flush_count(j, c);
+        }
     }
 }
 
@@ -37,7 +52,7 @@ static int launch_wavefront(sdt_handle h, cudaStream_t st, uint32_t n, const Lan
     uint32_t want = h->hdr_pending ? 2u * h->kd_nodes_known + 2u : h->kd_nodes_known;   // a refine at most... unknown: be generous
     uint32_t smem_nodes = (want + 255u) & ~255u;
     if (smem_nodes > (uint32_t)h->kd_smem_nodes) smem_nodes = (uint32_t)h->kd_smem_nodes;
-    const size_t smem = (size_t)smem_nodes * 4u;
+    const size_t smem = (size_t)smem_nodes * 4u * (Lane::kSmemCounts ? 2u : 1u);
     static size_t attr_set = 0;
     if (smem > 48u * 1024u && smem > attr_set) {
         if (cudaFuncSetAttribute(k_wavefront<Lane>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess)
@@ -74,6 +89,8 @@ static int launch_wavefront(sdt_handle h, cudaStream_t st, uint32_t n, const Lan
 
 // ---------------------------------------------------------------------------- lanes
 struct LocateLane {
+    static constexpr bool kSmemCounts = false;
+    SDT_HD void flush_count(uint32_t, float) const {}
     TreeView t;
     sdt_vec3 pos; const uint8_t* active; uint32_t* leaf; uint32_t* root;
     template <bool ALL_SMEM>
@@ -92,6 +109,8 @@ struct LocateLane {
 
 template <bool EXPLICIT_U>
 struct SampleLane {
+    static constexpr bool kSmemCounts = false;
+    SDT_HD void flush_count(uint32_t, float) const {}
     TreeView t;
     sdt_vec3 pos; const uint8_t* active;
     const float* u; uint32_t u_stride, seed, lane_offset;
@@ -119,6 +138,8 @@ struct SampleLane {
 };
 
 struct PdfLane {
+    static constexpr bool kSmemCounts = false;
+    SDT_HD void flush_count(uint32_t, float) const {}
     TreeView t;
     sdt_vec3 pos; sdt_vec3 dir; const uint8_t* active; float* pdf; uint32_t* dbg;
     template <bool ALL_SMEM>
@@ -145,6 +166,8 @@ struct PdfLane {
 // mode 2 = tree pdf of the BSDF-sampled direction (:307) + fused mixture (:310-311)
 template <bool EXPLICIT_U>
 struct GuidedLane {
+    static constexpr bool kSmemCounts = false;
+    SDT_HD void flush_count(uint32_t, float) const {}
     TreeView t;
     sdt_guided_args a; int fuse;
     template <bool ALL_SMEM>

@@ -48,7 +48,13 @@ SDT_HD void sdt_splat_one(const TreeView& t, const SplatTarget& tg, const KdCtx&
     r.leaf = 0; r.rootrec = SDT_NONE; r.inbox = false;
     if (act) r = sdt_kd_descend<ALL_SMEM>(k, px, py, pz);
     // src/kdtree.py:199: +1.0f (fp32 counter; exact below 2^24, then it sticks like the reference's)
-    sdt_splat_add(tg.kd_count, r.leaf, 1.0f, act && r.inbox);
+    if (k.cnt_s) {
+#if defined(__CUDA_ARCH__)
+        if (act && r.inbox) atomicAdd(k.cnt_s + r.leaf, 1.0f);              // shared-memory counter of this CTA
+#endif
+    } else {
+        sdt_splat_add(tg.kd_count, r.leaf, 1.0f, act && r.inbox);
+    }
     // src/kdtree.py:224: the root id is gathered UNMASKED -- out-of-box records go to the tree of node 0
     const uint32_t ri = r.rootrec;
     // a single-leaf tree has no record: its only node is the root, whose id is in kd_root
@@ -68,6 +74,8 @@ SDT_HD void sdt_splat_one(const TreeView& t, const SplatTarget& tg, const KdCtx&
 }
 
 struct SplatRecordsLane {
+    static constexpr bool kSmemCounts = true;
+    SDT_HD void flush_count(uint32_t node, float c) const { sdt_atomic_add_f32(tg.kd_count + node, c); }
     TreeView t; SplatTarget tg; sdt_records r;
     template <bool ALL_SMEM>
     SDT_HD void run(const KdCtx& k, uint32_t i) const {
@@ -92,6 +100,8 @@ SDT_HD float sdt_nan0(float v) { return (v != v) ? 0.0f : v; }
 // processPathData + scatterDataIntoSDTree (src/path_guiding_integrator.py:434-500) fused
 // in front of the splat: no compaction pass, the filter just masks the lane.
 struct SplatPathLane {
+    static constexpr bool kSmemCounts = true;
+    SDT_HD void flush_count(uint32_t node, float c) const { sdt_atomic_add_f32(tg.kd_count + node, c); }
     TreeView t; SplatTarget tg; sdt_path_data p;
     template <bool ALL_SMEM>
     SDT_HD void run(const KdCtx& k, uint32_t i) const {
@@ -146,8 +156,10 @@ struct KdSweepItem {
     const uint32_t* kd_word; const uint32_t* kd_depth; float* cnt; uint32_t depth;
     SDT_HD void operator()(uint32_t i) const {
         const uint32_t w = kd_word[i];
-        if ((w & SDT_KD_LEAF_BIT) || kd_depth[i] != depth) return;
-        const float s = cnt[w] + cnt[w + 1u];
+        if (kd_depth[i] != depth) return;
+        // a leaf counter fed by per-CTA partial sums can pass 2^24, where the reference's chain of
+        // "+1.0f" sticks: clamp leaves and interiors alike
+        const float s = (w & SDT_KD_LEAF_BIT) ? cnt[i] : cnt[w] + cnt[w + 1u];
         cnt[i] = s > 16777216.0f ? 16777216.0f : s;
     }
 };
@@ -159,7 +171,7 @@ static int sdt_complete_stats(sdt_handle h, cudaStream_t st) {
     // level sizes live on the device
     for (int l = (int)h->levels_hint - 1; l >= 0; --l)
         launch_items(x, &s.hdr->level_cnt[l], 0, QuadSweepItem{s.hdr, s.child, h->q_ecur, (uint32_t)l});
-    for (int d = h->cfg.kd_max_depth - 1; d >= 0; --d)
+    for (int d = h->cfg.kd_max_depth; d >= 0; --d)
         launch_items(x, &s.hdr->n_kd, 0, KdSweepItem{h->kd_word, h->kd_depth, h->kd_count, (uint32_t)d});
     SDT_TRY(sdt_post_launch(h, "sdt_complete_stats"));
     h->stats_complete = true;
