@@ -79,6 +79,7 @@ class CornellBox:
         self.bbox_max = pts.max(0).values.cpu().numpy()
         self.sumL = None
         self.sumL2 = None
+        self._gL = self._gL2 = None
 
     # ---- what main.py does before the loop (main.py:45-64) -----------------------------------
     def setup(self, sdTreeMaxDepth=20, quadTreeMaxDepth=20, isStoreNEERadiance=True, bsdfSamplingFraction=0.5):
@@ -90,6 +91,10 @@ class CornellBox:
     def resetVarianceCounter(self):
         self.sumL = torch.zeros(self.W * self.H, 3, device=self.dev)
         self.sumL2 = torch.zeros(self.W * self.H, 3, device=self.dev)
+        self._gL = self._gL2 = None          # all-rank sums (multi-GPU), else the local counters are the totals
+
+    def _sums(self):
+        return (self.sumL, self.sumL2) if self._gL is None else (self._gL, self._gL2)
 
     # buffers handed to the library: torch CUDA tensors, or numpy views of CPU tensors (host emulation in tests)
     def _x(self, t):
@@ -258,16 +263,34 @@ class CornellBox:
         return (x * self.lum).sum(-1)
 
     def computeMSE(self, spp, groundTruth):
-        mse = self._lum((self.sumL / spp - groundTruth.view(-1, 3)) ** 2).clamp_max(10000)
+        sL, _ = self._sums()
+        mse = self._lum((sL / spp - groundTruth.view(-1, 3)) ** 2).clamp_max(10000)
         return float(mse.mean())
 
     def computeVariance(self, spp, groundTruth=None):
+        sL, sL2 = self._sums()
         if groundTruth is not None:
-            v = self._lum(self.sumL2 / spp - groundTruth.view(-1, 3) ** 2).clamp_max(10000)
+            v = self._lum(sL2 / spp - groundTruth.view(-1, 3) ** 2).clamp_max(10000)
             return float(v.mean()) / spp
-        Lm = self.sumL / spp
-        v = float(self._lum(self.sumL2 / spp - Lm * Lm).clamp_max(10000).mean())
+        Lm = sL / spp
+        v = float(self._lum(sL2 / spp - Lm * Lm).clamp_max(10000).mean())
         return v / (spp - 1) if spp > 1 else v
+
+    # ---- multi-GPU (driver.TorchDistRanks) -------------------------------------------------------
+    def zero_image(self):
+        return torch.zeros(self.H, self.W, 3, device=self.dev)
+
+    def comm_init(self, dist):
+        ids = [self.core.tree.comm_unique_id() if dist.get_rank() == 0 else None]
+        dist.broadcast_object_list(ids, src=0)
+        self.core.tree.comm_init(ids[0], dist.get_rank(), dist.get_world_size())
+
+    def allreduce_statistics(self, dist):
+        """one exchange per iteration: SD-tree statistics (sdt_allreduce, NCCL) + variance counters"""
+        self.core.tree.allreduce(torch.cuda.current_stream().cuda_stream)
+        self._gL, self._gL2 = self.sumL.clone(), self.sumL2.clone()      # local counters stay local
+        dist.all_reduce(self._gL)
+        dist.all_reduce(self._gL2)
 
     # forwarded integrator interface used by the driver
     def setIteration(self, iteration, isFinalIter):

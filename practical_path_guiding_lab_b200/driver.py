@@ -26,9 +26,40 @@ def possible_cumm_spps(budget_spp):
     return out
 
 
+class SingleRank:
+    rank, world = 0, 1
+
+    def sum_image(self, x):
+        return x
+
+    def sync_iteration(self, renderer):
+        pass
+
+
+class TorchDistRanks:
+    """One process per GPU: the render passes of an iteration are dealt round-robin to
+    the ranks (pass p -> rank p % world, seed = seed0 + cumm_spp exactly as in the sequential loop);
+    at the end of the iteration the statistics of `current` are combined with ONE sdt_allreduce
+    (NCCL), the variance counters and the image with torch.distributed, and every rank runs the same
+    deterministic refine -> bit-identical trees without a broadcast."""
+
+    def __init__(self):
+        import torch.distributed as dist
+        self.dist = dist
+        self.rank, self.world = dist.get_rank(), dist.get_world_size()
+
+    def sum_image(self, x):
+        self.dist.all_reduce(x)
+        return x
+
+    def sync_iteration(self, renderer):
+        renderer.allreduce_statistics(self.dist)
+
+
 def train_and_render(renderer, budget_spp, seed=0, batch_spp=4, stable_variance_spp_threshold=256,
-                     ground_truth=None, out_dir=None, scene_name="scene", log=None, on_iteration=None):
+                     ground_truth=None, out_dir=None, scene_name="scene", log=None, on_iteration=None, ranks=None):
     """-> dict(image, records=[per-iteration dicts], iterations=[(iteration, spp, refined)])"""
+    ranks = ranks or SingleRank()
     log = log or (lambda *a: None)
     cumm_spp = cumm_spp_prev = 0
     image_spp = 0
@@ -61,14 +92,20 @@ def train_and_render(renderer, budget_spp, seed=0, batch_spp=4, stable_variance_
         spp_per_pass = batch_spp if is_final else 1                   # main.py:192-199
         passes = math.ceil(iter_spp / spp_per_pass)
         done = 0
-        for _ in range(passes):
+        for p_i in range(passes):
             s = min(spp_per_pass, iter_spp - done)
-            one = renderer.render(s, seed + cumm_spp)                  # main.py:218
-            w = one * float(s / iter_spp)
-            curr = w if curr is None else curr + w
+            if p_i % ranks.world == ranks.rank:
+                one = renderer.render(s, seed + cumm_spp)              # main.py:218
+                w = one * float(s / iter_spp)
+                curr = w if curr is None else curr + w
             image_spp += s
             done += s
             cumm_spp += s
+        if ranks.world > 1:
+            if curr is None:
+                curr = renderer.zero_image()
+            curr = ranks.sum_image(curr)
+            ranks.sync_iteration(renderer)                             # one exchange per iteration
         if is_final and not is_train and prev_iter_image is not None:   # main.py:287-291
             image = (curr * iter_spp + prev_iter_image * (image_spp - iter_spp)) / image_spp
         else:
@@ -107,7 +144,7 @@ def train_and_render(renderer, budget_spp, seed=0, batch_spp=4, stable_variance_
         schedule.append((it, iter_spp, refined))
         log(f"iteration {it}: spp {iter_spp}, cumm {cumm_spp}, final {was_final}, refined {refined}, variance {variance:.5g}"
             + (f", mse {mse_gt:.5g}" if mse_gt is not None else ""))
-        if out_dir:
+        if out_dir and ranks.rank == 0:
             renderer.saveSDTreeToFile(os.path.join(out_dir, "tree-data", f"{scene_name}_iter-{it}.npz"))
             renderer.saveSDTreeOBJ(os.path.join(out_dir, "obj", f"{scene_name}_iter-{it}.obj"))
             save_image(os.path.join(out_dir, "image", f"{scene_name}_iter-{it}_spp-{image_spp}_cumm_spp-{cumm_spp}"), image)
@@ -116,7 +153,7 @@ def train_and_render(renderer, budget_spp, seed=0, batch_spp=4, stable_variance_
         variance_prev = variance_current
         it += 1
         cumm_spp_prev = cumm_spp
-    if out_dir:
+    if out_dir and ranks.rank == 0:
         for key in ("variance", "variance_groundTruth", "mse_groundTruth", "variance_estimated_final"):
             with open(os.path.join(out_dir, "performance", f"{key}_endIter.csv"), "w", newline="") as f:
                 w = csv.writer(f)
@@ -155,18 +192,43 @@ def main(argv=None):
     ap.add_argument("--no-guiding", action="store_true", help="BSDF-only baseline: never refine (tree stays a single leaf)")
     a = ap.parse_args(argv)
     from .cornell import CornellBox
-    r = CornellBox(a.res, a.res, max_depth=a.max_depth, device="cuda")
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    ranks = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        ranks = TorchDistRanks()
+    r = CornellBox(a.res, a.res, max_depth=a.max_depth, device=f"cuda:{local}")
     r.setup()
+    if ranks is not None:
+        r.comm_init(ranks.dist)
     gt = None
     if a.ground_truth:
-        gt = torch.from_numpy(np.load(a.ground_truth).astype(np.float32)).cuda()
+        g = np.load(a.ground_truth).astype(np.float32)
+        if g.shape[0] != a.res:                      # box-resample the fixture to the render resolution
+            g = torch.nn.functional.interpolate(torch.from_numpy(g).permute(2, 0, 1)[None], size=(a.res, a.res), mode="area")[0].permute(1, 2, 0).numpy()
+        gt = torch.from_numpy(np.ascontiguousarray(g)).cuda()
     if a.no_guiding:
         r.refineAndPrepareSDTreeForNextIteration = lambda: None
     t0 = time.perf_counter()
-    res = train_and_render(r, a.budget, seed=a.seed, ground_truth=gt, out_dir=a.out, scene_name=a.scene, log=print)
+    rank0 = ranks is None or ranks.rank == 0
+    res = train_and_render(r, a.budget, seed=a.seed, ground_truth=gt, out_dir=a.out, scene_name=a.scene,
+                           log=print if rank0 else None, ranks=ranks)
     torch.cuda.synchronize()
-    print(json.dumps(dict(scene=a.scene, res=a.res, budget=a.budget, seconds=time.perf_counter() - t0,
-                          iterations=res["iterations"], final=res["records"][-1], tree=r.core.tree.sizes())))
+    sizes = r.core.tree.sizes()
+    if ranks is not None:                            # every rank must hold the same tree
+        sig = torch.tensor([sizes["n_kd"], sizes["n_quad"], sizes["n_roots"]], device="cuda", dtype=torch.int64)
+        lo, hi = sig.clone(), sig.clone()
+        ranks.dist.all_reduce(lo, op=ranks.dist.ReduceOp.MIN)
+        ranks.dist.all_reduce(hi, op=ranks.dist.ReduceOp.MAX)
+        assert torch.equal(lo, hi), "trees differ between ranks"
+    if rank0:
+        print(json.dumps(dict(scene=a.scene, res=a.res, budget=a.budget, n_gpus=world, seconds=time.perf_counter() - t0,
+                              iterations=res["iterations"], final=res["records"][-1], tree=sizes)))
+    if ranks is not None:
+        ranks.dist.destroy_process_group()
 
 
 if __name__ == "__main__":
