@@ -232,6 +232,7 @@ struct KdCtx {
     float lo[3], hi[3];       // root box
     uint32_t rootrec0;        // root record of the tree owned by node 0 (out-of-box lanes, :224,:482)
     float* cnt_s;             // splat kernels: per-CTA shared-memory leaf counters (NULL: count in global memory)
+    const uint32_t* grid;     // 16x16x8 cell -> node reached after the first 11 levels (NULL: descend from the root)
 };
 SDT_HD KdCtx sdt_kd_ctx(const uint32_t* kd, uint32_t n_smem, const uint32_t* kdg, const DevHeader* hdr) {
     KdCtx k;
@@ -239,11 +240,44 @@ SDT_HD KdCtx sdt_kd_ctx(const uint32_t* kd, uint32_t n_smem, const uint32_t* kdg
     for (int a = 0; a < 3; ++a) { k.lo[a] = hdr->bbox_min[a]; k.hi[a] = hdr->bbox_max[a]; }
     k.rootrec0 = hdr->rootrec_of_node0;
     k.cnt_s = nullptr;
+    k.grid = nullptr;
     return k;
 }
 
-template <bool ALL_SMEM>
+// The first SDT_GRID_LEVELS = 11 levels split x,y,z,x,y,z,x,y,z,x,y: 4 halvings of x, 4 of y, 3 of z.
+// The split planes of one axis do not depend on the other axes, so the three chains of exact fp32
+// midpoints run independently (no memory access, ILP 3) and give the cell of a 16x16x8 grid; the
+// grid (built per CTA from the staged tree) names the node the level-by-level walk would have
+// reached -- a leaf shallower than 11 levels fills all its cells.
+#define SDT_GRID_LEVELS 11
+#define SDT_GRID_CELLS 2048
+#define SDT_AXIS_STEP(P, LO, HI, C)                                         \
+    {                                                                       \
+        const float mid = (LO + HI) / 2.0f;                                 \
+        const bool right = P >= mid;                                        \
+        LO = right ? mid : LO;                                              \
+        HI = right ? HI : mid;                                              \
+        C = (C << 1) | (right ? 1u : 0u);                                   \
+    }
+// node reached from the root by the path bits of cell (cx 4 bits, cy 4 bits, cz 3 bits)
+SDT_HD uint32_t sdt_kd_grid_node(const uint32_t* __restrict__ kd, uint32_t cell) {
+    const uint32_t cx = cell >> 7, cy = (cell >> 3) & 15u, cz = cell & 7u;
+    uint32_t node = 0;
+    for (uint32_t l = 0; l < SDT_GRID_LEVELS; ++l) {
+        const uint32_t w = kd[node];
+        if (w & SDT_KD_LEAF_BIT) break;
+        const uint32_t a = l % 3u, j = l / 3u;
+        const uint32_t bit = a == 0u ? (cx >> (3u - j)) & 1u : (a == 1u ? (cy >> (3u - j)) & 1u : (cz >> (2u - j)) & 1u);
+        node = w + bit;
+    }
+    return node;
+}
+
+// MODE 0: partly staged tree (global loads beyond the prefix); 1: whole tree staged, walk from the
+// root; 2: whole tree staged + grid over the first 11 levels
+template <int MODE>
 SDT_HD KdResult sdt_kd_descend(const KdCtx& k, float px, float py, float pz) {
+    constexpr bool ALL_SMEM = MODE != 0;
     const uint32_t* __restrict__ kd = k.kd;
     const uint32_t* __restrict__ kdg = k.kdg;
     const uint32_t n_smem = k.n_smem;
@@ -256,12 +290,30 @@ SDT_HD KdResult sdt_kd_descend(const KdCtx& k, float px, float py, float pz) {
     r.rootrec = k.rootrec0;
     if (!r.inbox) return r;
     uint32_t node = 0;
-    uint32_t w = sdt_kd_load<ALL_SMEM>(kd, n_smem, kdg, 0u);
-    if (!(w & SDT_KD_LEAF_BIT)) {
-        for (int guard = 0; guard < SDT_KD_MAX_DEPTH; guard += 3) {   // axis = depth % 3 (:277)
-            SDT_KD_STEP(px, lo0, hi0)
-            SDT_KD_STEP(py, lo1, hi1)
-            SDT_KD_STEP(pz, lo2, hi2)
+    uint32_t w;
+    if (MODE == 2) {
+        uint32_t cx = 0, cy = 0, cz = 0;
+        SDT_AXIS_STEP(px, lo0, hi0, cx) SDT_AXIS_STEP(py, lo1, hi1, cy) SDT_AXIS_STEP(pz, lo2, hi2, cz)
+        SDT_AXIS_STEP(px, lo0, hi0, cx) SDT_AXIS_STEP(py, lo1, hi1, cy) SDT_AXIS_STEP(pz, lo2, hi2, cz)
+        SDT_AXIS_STEP(px, lo0, hi0, cx) SDT_AXIS_STEP(py, lo1, hi1, cy) SDT_AXIS_STEP(pz, lo2, hi2, cz)
+        SDT_AXIS_STEP(px, lo0, hi0, cx) SDT_AXIS_STEP(py, lo1, hi1, cy)
+        node = k.grid[(cx << 7) | (cy << 3) | cz];
+        w = kd[node];
+        if (!(w & SDT_KD_LEAF_BIT)) {
+            for (int guard = SDT_GRID_LEVELS; guard < SDT_KD_MAX_DEPTH; guard += 3) {   // level 11 splits z, then x, y, ...
+                SDT_KD_STEP(pz, lo2, hi2)
+                SDT_KD_STEP(px, lo0, hi0)
+                SDT_KD_STEP(py, lo1, hi1)
+            }
+        }
+    } else {
+        w = sdt_kd_load<ALL_SMEM>(kd, n_smem, kdg, 0u);
+        if (!(w & SDT_KD_LEAF_BIT)) {
+            for (int guard = 0; guard < SDT_KD_MAX_DEPTH; guard += 3) {   // axis = depth % 3 (:277)
+                SDT_KD_STEP(px, lo0, hi0)
+                SDT_KD_STEP(py, lo1, hi1)
+                SDT_KD_STEP(pz, lo2, hi2)
+            }
         }
     }
     r.leaf = node;
@@ -397,7 +449,8 @@ SDT_HD float sdt_quad_pdf(const TreeView& t, uint32_t ri, uint32_t root_node,
         const QJump j = sdt_load_jump(t.jump + (size_t)ri * SDT_JUMP_CELLS + cy * 16u + cx);
         pdf = j.prod;
         if (j.ri & SDT_JUMP_LEAF) {
-            node_out = j.ri & 0x3FFFFFFFu;
+            const uint32_t nd = j.ri & 0x3FFFFFFFu;
+            node_out = nd == 0x3FFFFFFFu ? root_node : nd;       // (a NaN at the root stops on the root)
             return ((j.ri & SDT_JUMP_DEAD) == SDT_JUMP_DEAD) ? 0.0f : pdf * SDT_INV_FOUR_PI;
         }
         ri = j.ri;

@@ -55,6 +55,7 @@ struct sdt_tree_s {
     uint32_t jump_cap = 0;          // trees the jump table can hold
     uint32_t jump_trees_known = 0;  // trees covered, as last seen by the host (0 until known: slow path)
     int use_jump = 1;
+    int use_kd_grid = 1;            // per-CTA 16x16x8 grid over the first 11 spatial levels
     uint32_t kd_nodes_known = 1;    // last spatial node count seen by the host (sizes the smem staging)
     cudaEvent_t hdr_event = nullptr;
     bool hdr_pending = false;       // an async header read-back (after refine) is in flight
@@ -103,7 +104,13 @@ static inline ExecCtx exec_ctx(sdt_handle h, cudaStream_t st) {
     return ExecCtx{st, h->num_sms, h->s_blk, &h->launches};
 }
 
-static inline TreeView tree_view(const sdt_tree_s* h) {
+static inline TreeView tree_view(sdt_tree_s* h) {
+    // a refine leaves a non-blocking read-back of the new sizes in flight: pick it up once it landed
+    if (h->hdr_pending && cudaEventQuery(h->hdr_event) == cudaSuccess) {
+        h->hdr_pending = false;
+        h->kd_nodes_known = h->h_hdr->n_kd;
+        h->jump_trees_known = h->h_hdr->jump_trees;
+    }
     const QuadSet& s = h->set[h->cur];
     return TreeView{s.hdr, h->kd_word, h->kd_root, s.rec, s.jump, h->use_jump ? h->jump_trees_known : 0u};
 }

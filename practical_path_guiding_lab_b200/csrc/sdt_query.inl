@@ -5,7 +5,7 @@
 // ---------------------------------------------------------------------------- launch
 #ifndef SDT_HOSTEMU
 template <class Lane>
-__global__ void __launch_bounds__(512, 3) k_wavefront(Lane f, uint32_t n, uint32_t smem_cap) {
+__global__ void __launch_bounds__(512, 3) k_wavefront(Lane f, uint32_t n, uint32_t smem_cap, uint32_t use_grid) {
     extern __shared__ uint32_t kd_s[];
     const DevHeader* hdr = f.t.hdr;
     const uint32_t n_kd = hdr->n_kd;
@@ -21,12 +21,23 @@ __global__ void __launch_bounds__(512, 3) k_wavefront(Lane f, uint32_t n, uint32
         k.cnt_s = cnt_s;
     }
     __syncthreads();
-    if (n_smem == n_kd) {           // whole spatial tree staged: descent loop without the global path
+    // (measured: the grid pays for the pdf / splat / locate kernels, -7 % / -4 %, not for the sampling
+    // kernels, +3 %, whose long quadtree loop wants the registers)
+    if (Lane::kGrid && use_grid && n_smem == n_kd) {   // 16x16x8 grid over the first 11 levels (see sdt_kd_descend)
+        uint32_t* grid = kd_s + smem_cap * (Lane::kSmemCounts ? 2u : 1u);
+        for (uint32_t c = threadIdx.x; c < SDT_GRID_CELLS; c += blockDim.x) grid[c] = sdt_kd_grid_node(kd_s, c);
+        k.grid = grid;
+        __syncthreads();
+    }
+    if (k.grid) {                   // whole spatial tree staged + grid over its first 11 levels
         for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
-            f.template run<true>(k, i);
+            f.template run<2>(k, i);
+    } else if (n_smem == n_kd) {    // whole spatial tree staged: descent loop without the global path
+        for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+            f.template run<1>(k, i);
     } else {
         for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
-            f.template run<false>(k, i);
+            f.template run<0>(k, i);
     }
     if (cnt_s) {
         __syncthreads();
@@ -44,15 +55,10 @@ __global__ void __launch_bounds__(512, 3) k_wavefront(Lane f, uint32_t n, uint32
 template <class Lane>
 static int launch_wavefront(sdt_handle h, cudaStream_t st, uint32_t n, const Lane& f, int block, int ctas_per_sm) {
     if (n == 0) return SDT_OK;
-    if (h->hdr_pending && cudaEventQuery(h->hdr_event) == cudaSuccess) {
-        h->hdr_pending = false;
-        h->kd_nodes_known = h->h_hdr->n_kd;
-        h->jump_trees_known = h->h_hdr->jump_trees;
-    }
     uint32_t want = h->hdr_pending ? 2u * h->kd_nodes_known + 2u : h->kd_nodes_known;   // a refine at most... unknown: be generous
     uint32_t smem_nodes = (want + 255u) & ~255u;
     if (smem_nodes > (uint32_t)h->kd_smem_nodes) smem_nodes = (uint32_t)h->kd_smem_nodes;
-    const size_t smem = (size_t)smem_nodes * 4u * (Lane::kSmemCounts ? 2u : 1u);
+    const size_t smem = (size_t)smem_nodes * 4u * (Lane::kSmemCounts ? 2u : 1u) + ((Lane::kGrid && h->use_kd_grid) ? SDT_GRID_CELLS * 4u : 0u);
     static size_t attr_set = 0;
     if (smem > 48u * 1024u && smem > attr_set) {
         if (cudaFuncSetAttribute(k_wavefront<Lane>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess)
@@ -70,7 +76,7 @@ static int launch_wavefront(sdt_handle h, cudaStream_t st, uint32_t n, const Lan
     uint32_t grid = (n + (uint32_t)block - 1u) / (uint32_t)block;
     const uint32_t cap = (uint32_t)(h->num_sms * per_sm);
     if (grid > cap) grid = cap;
-    k_wavefront<Lane><<<grid, block, smem, st>>>(f, n, smem_nodes);
+    k_wavefront<Lane><<<grid, block, smem, st>>>(f, n, smem_nodes, (uint32_t)h->use_kd_grid);
     ++h->launches;
     h->last_stream = st;
     return sdt_post_launch(h, "k_wavefront");
@@ -78,9 +84,8 @@ static int launch_wavefront(sdt_handle h, cudaStream_t st, uint32_t n, const Lan
 #else
 template <class Lane>
 static int launch_wavefront(sdt_handle h, cudaStream_t st, uint32_t n, const Lane& f, int, int) {
-    if (h->hdr_pending) { h->hdr_pending = false; h->kd_nodes_known = h->h_hdr->n_kd; h->jump_trees_known = h->h_hdr->jump_trees; }
     const KdCtx k = sdt_kd_ctx(f.t.kd_word, 0u, f.t.kd_word, f.t.hdr);
-    for (uint32_t i = 0; i < n; ++i) f.template run<false>(k, i);
+    for (uint32_t i = 0; i < n; ++i) f.template run<0>(k, i);
     ++h->launches;
     h->last_stream = st;
     return SDT_OK;
@@ -90,15 +95,16 @@ static int launch_wavefront(sdt_handle h, cudaStream_t st, uint32_t n, const Lan
 // ---------------------------------------------------------------------------- lanes
 struct LocateLane {
     static constexpr bool kSmemCounts = false;
+    static constexpr bool kGrid = true;
     SDT_HD void flush_count(uint32_t, float) const {}
     TreeView t;
     sdt_vec3 pos; const uint8_t* active; uint32_t* leaf; uint32_t* root;
-    template <bool ALL_SMEM>
+    template <int MODE>
     SDT_HD void run(const KdCtx& k, uint32_t i) const {
         const bool act = active ? SDT_LDG(active + i) != 0 : true;
         uint32_t lf = 0, rt = 0;                     // inactive: node 0, masked gather -> 0
         if (act) {
-            const KdResult r = sdt_kd_descend<ALL_SMEM>(k, sdt_ld(pos.x, pos.stride, i),
+            const KdResult r = sdt_kd_descend<MODE>(k, sdt_ld(pos.x, pos.stride, i),
                                               sdt_ld(pos.y, pos.stride, i), sdt_ld(pos.z, pos.stride, i));
             lf = r.leaf; rt = SDT_LDG(t.kd_root + r.leaf);
         }
@@ -110,18 +116,19 @@ struct LocateLane {
 template <bool EXPLICIT_U>
 struct SampleLane {
     static constexpr bool kSmemCounts = false;
+    static constexpr bool kGrid = false;
     SDT_HD void flush_count(uint32_t, float) const {}
     TreeView t;
     sdt_vec3 pos; const uint8_t* active;
     const float* u; uint32_t u_stride, seed, lane_offset;
     sdt_vec3_out dir; float* pdf; uint32_t* dbg; int fuse;
-    template <bool ALL_SMEM>
+    template <int MODE>
     SDT_HD void run(const KdCtx& k, uint32_t i) const {
         const bool act = active ? SDT_LDG(active + i) != 0 : true;
         float dx = 0.0f, dy = 0.0f, dz = -1.0f, p = 1.0f;   // inactive lanes: pos (0,0) -> (0,0,-1), pdf 1
         uint32_t d0 = 0, d1 = 0, d2 = 0, d3 = 0;
         if (act) {
-            const KdResult r = sdt_kd_descend<ALL_SMEM>(k, sdt_ld(pos.x, pos.stride, i),
+            const KdResult r = sdt_kd_descend<MODE>(k, sdt_ld(pos.x, pos.stride, i),
                                               sdt_ld(pos.y, pos.stride, i), sdt_ld(pos.z, pos.stride, i));
             const uint32_t root = dbg ? SDT_LDG(t.kd_root + r.leaf) : 0u;
             GuidedSample g;
@@ -139,16 +146,17 @@ struct SampleLane {
 
 struct PdfLane {
     static constexpr bool kSmemCounts = false;
+    static constexpr bool kGrid = true;
     SDT_HD void flush_count(uint32_t, float) const {}
     TreeView t;
     sdt_vec3 pos; sdt_vec3 dir; const uint8_t* active; float* pdf; uint32_t* dbg;
-    template <bool ALL_SMEM>
+    template <int MODE>
     SDT_HD void run(const KdCtx& k, uint32_t i) const {
         const bool act = active ? SDT_LDG(active + i) != 0 : true;
         float p = 1.0f;
         uint32_t d0 = 0, d1 = 0, d2 = 0;
         if (act) {
-            const KdResult r = sdt_kd_descend<ALL_SMEM>(k, sdt_ld(pos.x, pos.stride, i),
+            const KdResult r = sdt_kd_descend<MODE>(k, sdt_ld(pos.x, pos.stride, i),
                                               sdt_ld(pos.y, pos.stride, i), sdt_ld(pos.z, pos.stride, i));
             float x, y;
             sdt_dir_to_canonical(sdt_ld(dir.x, dir.stride, i), sdt_ld(dir.y, dir.stride, i), sdt_ld(dir.z, dir.stride, i), x, y);
@@ -167,14 +175,15 @@ struct PdfLane {
 template <bool EXPLICIT_U>
 struct GuidedLane {
     static constexpr bool kSmemCounts = false;
+    static constexpr bool kGrid = false;
     SDT_HD void flush_count(uint32_t, float) const {}
     TreeView t;
     sdt_guided_args a; int fuse;
-    template <bool ALL_SMEM>
+    template <int MODE>
     SDT_HD void run(const KdCtx& k, uint32_t i) const {
         const uint32_t m = SDT_LDG(a.mode + i);
         if (m != 1u && m != 2u) return;
-        const KdResult r = sdt_kd_descend<ALL_SMEM>(k, sdt_ld(a.pos.x, a.pos.stride, i),
+        const KdResult r = sdt_kd_descend<MODE>(k, sdt_ld(a.pos.x, a.pos.stride, i),
                                           sdt_ld(a.pos.y, a.pos.stride, i), sdt_ld(a.pos.z, a.pos.stride, i));
         if (m == 1u) {
             GuidedSample g;

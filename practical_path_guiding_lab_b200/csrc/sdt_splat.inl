@@ -40,13 +40,13 @@ SDT_HD void sdt_splat_add(float* base, uint32_t idx, float v, bool valid) {
 }
 
 // one record through both trees
-template <bool ALL_SMEM>
+template <int MODE>
 SDT_HD void sdt_splat_one(const TreeView& t, const SplatTarget& tg, const KdCtx& k, bool act,
                           float px, float py, float pz, float dx, float dy, float radiance, float wo_pdf,
                           float nr, float ng, float nb, float ndx, float ndy) {
     KdResult r;
     r.leaf = 0; r.rootrec = SDT_NONE; r.inbox = false;
-    if (act) r = sdt_kd_descend<ALL_SMEM>(k, px, py, pz);
+    if (act) r = sdt_kd_descend<MODE>(k, px, py, pz);
     // src/kdtree.py:199: +1.0f (fp32 counter; exact below 2^24, then it sticks like the reference's)
     if (k.cnt_s) {
 #if defined(__CUDA_ARCH__)
@@ -75,9 +75,10 @@ SDT_HD void sdt_splat_one(const TreeView& t, const SplatTarget& tg, const KdCtx&
 
 struct SplatRecordsLane {
     static constexpr bool kSmemCounts = true;
+    static constexpr bool kGrid = true;
     SDT_HD void flush_count(uint32_t node, float c) const { sdt_atomic_add_f32(tg.kd_count + node, c); }
     TreeView t; SplatTarget tg; sdt_records r;
-    template <bool ALL_SMEM>
+    template <int MODE>
     SDT_HD void run(const KdCtx& k, uint32_t i) const {
         const bool act = r.active ? SDT_LDG(r.active + i) != 0 : true;
         float nr = 0.0f, ng = 0.0f, nb = 0.0f, ndx = 0.0f, ndy = 0.0f;
@@ -88,7 +89,7 @@ struct SplatRecordsLane {
             ndx = sdt_ld(r.direction_nee.x, r.direction_nee.stride, i);
             ndy = sdt_ld(r.direction_nee.y, r.direction_nee.stride, i);
         }
-        sdt_splat_one<ALL_SMEM>(t, tg, k, act,
+        sdt_splat_one<MODE>(t, tg, k, act,
                       sdt_ld(r.position.x, r.position.stride, i), sdt_ld(r.position.y, r.position.stride, i), sdt_ld(r.position.z, r.position.stride, i),
                       sdt_ld(r.direction.x, r.direction.stride, i), sdt_ld(r.direction.y, r.direction.stride, i),
                       SDT_LDG(r.radiance + i), SDT_LDG(r.wo_pdf + i), nr, ng, nb, ndx, ndy);
@@ -101,9 +102,10 @@ SDT_HD float sdt_nan0(float v) { return (v != v) ? 0.0f : v; }
 // in front of the splat: no compaction pass, the filter just masks the lane.
 struct SplatPathLane {
     static constexpr bool kSmemCounts = true;
+    static constexpr bool kGrid = true;
     SDT_HD void flush_count(uint32_t node, float c) const { sdt_atomic_add_f32(tg.kd_count + node, c); }
     TreeView t; SplatTarget tg; sdt_path_data p;
-    template <bool ALL_SMEM>
+    template <int MODE>
     SDT_HD void run(const KdCtx& k, uint32_t i) const {
         const uint32_t ray = i / p.max_depth;                                          // :440
         float inc[3];
@@ -133,7 +135,7 @@ struct SplatPathLane {
         const bool both_zero = (radiance == 0.0f) && (sdt_luminance(nr, ng, nb) == 0.0f);  // :470-472
         bool act = p.active ? SDT_LDG(p.active + i) != 0 : true;
         act = act && !both_zero && !(wo_pdf == 0.0f) && !(wo_pdf != wo_pdf);           // :475-478
-        sdt_splat_one<ALL_SMEM>(t, tg, k, act,
+        sdt_splat_one<MODE>(t, tg, k, act,
                       sdt_ld(p.position.x, p.position.stride, i), sdt_ld(p.position.y, p.position.stride, i), sdt_ld(p.position.z, p.position.stride, i),
                       sdt_ld(p.direction.x, p.direction.stride, i), sdt_ld(p.direction.y, p.direction.stride, i),
                       radiance, wo_pdf, nr, ng, nb, ndx, ndy);

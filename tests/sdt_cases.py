@@ -258,6 +258,24 @@ def case_jump_table_equals_descent(ctx):
     assert beq(out[1][0], op) and np.array_equal(out[1][1].view(U)[:, 2], odbg['pdf_node'])
 
 
+def case_spatial_descent_variants(ctx):
+    """the three spatial-descent code paths of the kernels give the same leaves: grid over the first
+    11 levels + staged tree (default), staged tree walked from the root, partly staged tree (global loads)"""
+    t, cur, prev = train(ctx, iters=3, max_leaf=12, quad_max_depth=7, caps=dict(kd_capacity=1 << 14, quad_capacity=1 << 20))   # deep spatial tree: leaves beyond level 11
+    assert t.sizes()["error"] == 0
+    assert int(prev.kdTreeNode.depth.max()) > 11
+    for key, val in (("use_kd_grid", 1), ("use_kd_grid", 0), ("kd_smem_nodes", 16)):
+        t.set_tuning(key, val)
+        check_queries(ctx, t, prev, n=6000, seed=23)
+    t.set_tuning("kd_smem_nodes", 24576)
+    t.set_tuning("use_kd_grid", 1)
+    # points exactly on split planes of the first levels (the right child wins, src/kdtree.py:462-468)
+    g = np.array([0.0, 0.125, 0.25, 0.375, 0.5, 0.625, 0.75, 0.875, 1.0], F)
+    pos = np.stack(np.meshgrid(g, g, g, indexing="ij"), -1).reshape(-1, 3)
+    leaf, root = t.locate(ctx.dev(pos))
+    assert np.array_equal(ctx.host(leaf).view(U), prev.getLeafNodeIndex(pos))
+
+
 def case_fused_equals_two_descents(ctx):
     t, cur, prev = train(ctx, iters=3)
     rng = np.random.default_rng(3)
@@ -496,7 +514,7 @@ def case_npz_roundtrip(ctx, tmp_path):
     check_queries(ctx, t2, o, n=1024)
 
 
-ALL_CASES = [case_jump_table_equals_descent, case_initial_tree, case_golden_upload_download, case_train_refine_topology, case_host_pipeline_chunks,
+ALL_CASES = [case_jump_table_equals_descent, case_spatial_descent_variants, case_initial_tree, case_golden_upload_download, case_train_refine_topology, case_host_pipeline_chunks,
              case_train_refine_nee_shallow, case_fused_equals_two_descents, case_splat_float_tolerance,
              case_path_data, case_mis, case_guided_bounce, case_refine_flags_and_frozen_stats,
              case_capacity_error, case_edge_inputs_and_errors]
