@@ -342,6 +342,42 @@ def run_b200(args):
     torch.cuda.synchronize()
     per_iter = {"allreduce_ms": e0.elapsed_time(e1) if allreduce else 0.0, "refine_ms": e1.elapsed_time(e2)}
 
+    # ---- extras (not part of the step): the integrator's own entry points on the same vertices
+    extras = {}
+    try:
+        gg = torch.Generator(device=dev).manual_seed(99 + rank)
+        mode = (torch.rand(n, device=dev, generator=gg) * 2.2).to(torch.uint8).clamp_(max=2)      # ~45 % sample, ~45 % pdf+mixture, ~10 % idle
+        bp = torch.rand(n, device=dev, generator=gg)
+        bv = torch.rand(n, 3, device=dev, generator=gg)
+        g_dir = torch.zeros(n, 3, device=dev); g_sp = torch.zeros(n, device=dev); g_wp = torch.zeros(n, device=dev); g_w = torch.zeros(n, 3, device=dev)
+        md = 8
+        rays = n // md
+        lfin = torch.rand(rays, 3, device=dev, generator=gg) * 4
+        tr_ = torch.rand(n, 3, device=dev, generator=gg)
+        tb_ = torch.rand(n, 3, device=dev, generator=gg)
+        bs_ = torch.rand(n, 3, device=dev, generator=gg)
+        act_ = (torch.rand(n, device=dev, generator=gg) < 0.6).to(torch.uint8)
+
+        def timeit(fn, reps=10):
+            for _ in range(3):
+                fn()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            a.record()
+            for _ in range(reps):
+                fn()
+            b.record()
+            torch.cuda.synchronize()
+            return a.elapsed_time(b) / reps
+        ms_g = timeit(lambda: tree.guided(d_pos, mode, wo=d_dir, seed=5, lane_offset=lane0, bsdf_pdf=bp, bsdf_value=bv,
+                                          dir_out=g_dir, sdtree_pdf_out=g_sp, wo_pdf_out=g_wp, weight_out=g_w))
+        ms_p = timeit(lambda: tree.splat_path_data(md, lfin, tr_, tb_, bs_, d_rec['position'], d_rec['direction'], d_rec['wo_pdf'], active=act_))
+        extras = {"sdt_guided": {"ms": ms_g, "lanes_per_s": n / (ms_g * 1e-3), "what": "one bounce: ~45 % lanes sampled, ~45 % pdf + fused mixture, ~10 % idle"},
+                  "sdt_splat_path_data": {"ms": ms_p, "slots_per_s": n / (ms_p * 1e-3), "what": f"processPathData + filter + splat fused, {n} slots (max_depth {md}), 60 % active"}}
+        tree.reset_stats()
+    except Exception as e:            # extras never break the contract line
+        extras = {"error": repr(e)}
+
     # ---- end to end: the same three C-ABI calls on HOST buffers (pinned)
     e2e = None
     if not args.no_e2e:
@@ -387,7 +423,7 @@ def run_b200(args):
                 "data": "synthetic", "config": workload_config(n, world), "clocks": clk.summary(), "e2e": e2e,
                 "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu,
                 "tree": {k: sizes[k] for k in ("n_kd", "kd_leaves", "n_quad", "n_interior", "n_levels")},
-                "tree_build_s": t_build, "per_iteration": per_iter}
+                "tree_build_s": t_build, "per_iteration": per_iter, "extras": extras}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -351,17 +351,6 @@ SDT_HD void sdt_load_rec(const QRec* __restrict__ rec, uint32_t i, QHead& h, Sdt
     e.x = rec[i].e[0]; e.y = rec[i].e[1]; e.z = rec[i].e[2]; e.w = rec[i].e[3];
 #endif
 }
-SDT_HD SdtF4 sdt_load_f4(const float* __restrict__ p) {
-    SdtF4 v;
-#if defined(__CUDA_ARCH__)
-    const float4 a = __ldg(reinterpret_cast<const float4*>(p));
-    v.x = a.x; v.y = a.y; v.z = a.z; v.w = a.w;
-#else
-    v.x = p[0]; v.y = p[1]; v.z = p[2]; v.w = p[3];
-#endif
-    return v;
-}
-
 // cinfo: bits 0..3 = child c is a leaf; bits 8+2c..9+2c = rank of child c among the
 // non-leaf children (its record is interior_base + rank)
 SDT_HD uint32_t sdt_make_cinfo(uint32_t leafmask) {

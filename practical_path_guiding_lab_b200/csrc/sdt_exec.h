@@ -173,10 +173,3 @@ SDT_HD void sdt_atomic_add_f32(float* p, float v) {
     *p += v;
 #endif
 }
-SDT_HD void sdt_atomic_or_u32(uint32_t* p, uint32_t v) {
-#if defined(__CUDA_ARCH__)
-    atomicOr(p, v);
-#else
-    *p |= v;
-#endif
-}

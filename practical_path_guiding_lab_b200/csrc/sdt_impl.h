@@ -75,10 +75,8 @@ struct sdt_tree_s {
     int splat_block = 512;
     int splat_ctas_per_sm = 3;
     int fuse_sample_pdf = 1;
-    int splat_all_levels = 0;       // 1: atomics at every level like the reference (no sweep)
 
     // NCCL
-    void* nccl_lib = nullptr;
     void* nccl_comm = nullptr;
     int rank = 0, nranks = 1;
 };

@@ -27,7 +27,6 @@ static int sdt_free_all(sdt_handle h) {
 }
 
 struct SetLeafSize { DevHeader* H; float v; SDT_HD void operator()() const { H->max_leaf_size = v; } };
-struct SetDepths { DevHeader* H; uint32_t kd, quad; SDT_HD void operator()() const { H->kd_max_depth = kd; H->quad_max_depth = quad; } };
 
 extern "C" const char* sdt_last_error(sdt_handle h) { return h ? h->err.c_str() : g_create_err.c_str(); }
 
@@ -251,8 +250,6 @@ extern "C" int sdt_upload(sdt_handle h, const sdt_arrays* a) {
     { DevHeader H2; SDT_TRY(sdt_read_header(h, H2)); }      // jump_trees of the uploaded tree
     return SDT_OK;
 }
-
-struct CopyF32Item { const float* src; float* dst; SDT_HD void operator()(uint32_t i) const { dst[i] = src[i]; } };
 
 extern "C" int sdt_upload_stats(sdt_handle h, const float* q_irradiance, const float* kd_vert_count) {
     if (!h) return SDT_ERR_INVALID;
