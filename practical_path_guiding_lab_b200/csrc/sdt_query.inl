@@ -29,7 +29,40 @@ __global__ void __launch_bounds__(512, 3) k_wavefront(Lane f, uint32_t n, uint32
         k.grid = grid;
         __syncthreads();
     }
-    if (k.grid) {                   // whole spatial tree staged + grid over its first 11 levels
+    if (Lane::kCompact) {
+        // Mixed wavefront (guided bounce: some lanes sample, some evaluate a pdf, some idle): the lanes of a
+        // 4*blockDim tile are first sorted by mode into two shared-memory lists, then each list is
+        // processed by dense warps -- a warp never runs both code paths.
+        uint16_t* list = reinterpret_cast<uint16_t*>(kd_s + smem_cap * (Lane::kSmemCounts ? 2u : 1u) + ((Lane::kGrid && use_grid) ? SDT_GRID_CELLS : 0u));
+        __shared__ uint32_t s_cnt[2];
+        const uint32_t tile_n = 4u * blockDim.x;
+        const uint32_t lane = threadIdx.x & 31u;
+        for (uint32_t tile = blockIdx.x * tile_n; tile < n; tile += gridDim.x * tile_n) {
+            if (threadIdx.x < 2u) s_cnt[threadIdx.x] = 0u;
+            __syncthreads();
+            for (uint32_t q = 0; q < 4u; ++q) {
+                const uint32_t li = q * blockDim.x + threadIdx.x, i = tile + li;
+                const uint32_t m = i < n ? f.mode_of(i) : 0u;
+                for (uint32_t L = 0; L < 2u; ++L) {
+                    const uint32_t b = __ballot_sync(0xFFFFFFFFu, m == L + 1u);
+                    uint32_t base = 0;
+                    if (lane == 0u && b) base = atomicAdd(&s_cnt[L], (uint32_t)__popc(b));
+                    base = __shfl_sync(0xFFFFFFFFu, base, 0);
+                    if (m == L + 1u) list[L * tile_n + base + __popc(b & ((1u << lane) - 1u))] = (uint16_t)li;
+                }
+            }
+            __syncthreads();
+            for (uint32_t L = 0; L < 2u; ++L) {
+                const uint32_t cnt = s_cnt[L];
+                for (uint32_t j = threadIdx.x; j < cnt; j += blockDim.x) {
+                    const uint32_t i = tile + list[L * tile_n + j];
+                    if (n_smem == n_kd) f.template run_mode<1>(k, i, L + 1u);
+                    else f.template run_mode<0>(k, i, L + 1u);
+                }
+            }
+            __syncthreads();
+        }
+    } else if (k.grid) {            // whole spatial tree staged + grid over its first 11 levels
         for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
             f.template run<2>(k, i);
     } else if (n_smem == n_kd) {    // whole spatial tree staged: descent loop without the global path
@@ -58,7 +91,7 @@ static int launch_wavefront(sdt_handle h, cudaStream_t st, uint32_t n, const Lan
     uint32_t want = h->hdr_pending ? 2u * h->kd_nodes_known + 2u : h->kd_nodes_known;   // a refine at most... unknown: be generous
     uint32_t smem_nodes = (want + 255u) & ~255u;
     if (smem_nodes > (uint32_t)h->kd_smem_nodes) smem_nodes = (uint32_t)h->kd_smem_nodes;
-    const size_t smem = (size_t)smem_nodes * 4u * (Lane::kSmemCounts ? 2u : 1u) + ((Lane::kGrid && h->use_kd_grid) ? SDT_GRID_CELLS * 4u : 0u);
+    const size_t smem = (size_t)smem_nodes * 4u * (Lane::kSmemCounts ? 2u : 1u) + ((Lane::kGrid && h->use_kd_grid) ? SDT_GRID_CELLS * 4u : 0u) + (Lane::kCompact ? (size_t)block * 4u * 2u * 2u : 0u);
     static size_t attr_set = 0;
     if (smem > 48u * 1024u && smem > attr_set) {
         if (cudaFuncSetAttribute(k_wavefront<Lane>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess)
@@ -95,6 +128,9 @@ static int launch_wavefront(sdt_handle h, cudaStream_t st, uint32_t n, const Lan
 // ---------------------------------------------------------------------------- lanes
 struct LocateLane {
     static constexpr bool kSmemCounts = false;
+    static constexpr bool kCompact = false;
+    SDT_HD uint32_t mode_of(uint32_t) const { return 0u; }
+    template <int MODE> SDT_HD void run_mode(const KdCtx&, uint32_t, uint32_t) const {}
     static constexpr bool kGrid = true;
     SDT_HD void flush_count(uint32_t, float) const {}
     TreeView t;
@@ -116,6 +152,9 @@ struct LocateLane {
 template <bool EXPLICIT_U>
 struct SampleLane {
     static constexpr bool kSmemCounts = false;
+    static constexpr bool kCompact = false;
+    SDT_HD uint32_t mode_of(uint32_t) const { return 0u; }
+    template <int MODE> SDT_HD void run_mode(const KdCtx&, uint32_t, uint32_t) const {}
     static constexpr bool kGrid = false;
     SDT_HD void flush_count(uint32_t, float) const {}
     TreeView t;
@@ -146,6 +185,9 @@ struct SampleLane {
 
 struct PdfLane {
     static constexpr bool kSmemCounts = false;
+    static constexpr bool kCompact = false;
+    SDT_HD uint32_t mode_of(uint32_t) const { return 0u; }
+    template <int MODE> SDT_HD void run_mode(const KdCtx&, uint32_t, uint32_t) const {}
     static constexpr bool kGrid = true;
     SDT_HD void flush_count(uint32_t, float) const {}
     TreeView t;
@@ -176,13 +218,18 @@ template <bool EXPLICIT_U>
 struct GuidedLane {
     static constexpr bool kSmemCounts = false;
     static constexpr bool kGrid = false;
+    static constexpr bool kCompact = true;
     SDT_HD void flush_count(uint32_t, float) const {}
     TreeView t;
     sdt_guided_args a; int fuse;
+    SDT_HD uint32_t mode_of(uint32_t i) const { const uint32_t m = SDT_LDG(a.mode + i); return m <= 2u ? m : 0u; }
     template <int MODE>
     SDT_HD void run(const KdCtx& k, uint32_t i) const {
-        const uint32_t m = SDT_LDG(a.mode + i);
-        if (m != 1u && m != 2u) return;
+        const uint32_t m = mode_of(i);
+        if (m) run_mode<MODE>(k, i, m);
+    }
+    template <int MODE>
+    SDT_HD void run_mode(const KdCtx& k, uint32_t i, uint32_t m) const {
         const KdResult r = sdt_kd_descend<MODE>(k, sdt_ld(a.pos.x, a.pos.stride, i),
                                           sdt_ld(a.pos.y, a.pos.stride, i), sdt_ld(a.pos.z, a.pos.stride, i));
         if (m == 1u) {

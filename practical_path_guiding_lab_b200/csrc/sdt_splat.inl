@@ -76,6 +76,9 @@ SDT_HD void sdt_splat_one(const TreeView& t, const SplatTarget& tg, const KdCtx&
 struct SplatRecordsLane {
     static constexpr bool kSmemCounts = true;
     static constexpr bool kGrid = true;
+    static constexpr bool kCompact = false;
+    SDT_HD uint32_t mode_of(uint32_t) const { return 0u; }
+    template <int MODE> SDT_HD void run_mode(const KdCtx&, uint32_t, uint32_t) const {}
     SDT_HD void flush_count(uint32_t node, float c) const { sdt_atomic_add_f32(tg.kd_count + node, c); }
     TreeView t; SplatTarget tg; sdt_records r;
     template <int MODE>
@@ -103,6 +106,9 @@ SDT_HD float sdt_nan0(float v) { return (v != v) ? 0.0f : v; }
 struct SplatPathLane {
     static constexpr bool kSmemCounts = true;
     static constexpr bool kGrid = true;
+    static constexpr bool kCompact = false;
+    SDT_HD uint32_t mode_of(uint32_t) const { return 0u; }
+    template <int MODE> SDT_HD void run_mode(const KdCtx&, uint32_t, uint32_t) const {}
     SDT_HD void flush_count(uint32_t node, float c) const { sdt_atomic_add_f32(tg.kd_count + node, c); }
     TreeView t; SplatTarget tg; sdt_path_data p;
     template <int MODE>
