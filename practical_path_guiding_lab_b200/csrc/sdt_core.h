@@ -71,16 +71,23 @@ enum DevError : uint32_t {
 };
 
 // What the query kernels need (by value).
-// Jump table over the top SDT_JUMP_LEVELS levels of every non-single-leaf quadtree: for each of
-// the 16x16 cells of [0,1]^2 the node a pdf / splat descent reaches after 4 levels (or the leaf /
-// NaN stop it meets earlier) and the pdf product accumulated on the way -- computed with exactly
-// the operations of the level-by-level descent, so the result is bit-identical.  Points on a
-// 1/16 grid line (where the reference's inclusive-box tie rules matter) take the slow path.
+// Per-node pdf product `pp[node]`: pdfQuadTree multiplies, level by level, pdf *= (4*childE)/nodeE
+// along the root->node path (src/quadtree.py:1084) and gives up with 0 when the product goes NaN
+// (:1090-1092).  The path to a node is unique, so that running product is a property of the NODE:
+// it is computed once per refine, top-down, with exactly those operations in exactly that order
+// (NaN is sticky), and a descent only has to find its leaf: pdf = isnan(pp[leaf]) ? 0 : pp[leaf]/(4 pi).
+// No division, multiply or NaN test per level in the query kernels -- and bit-identical results.
+// The one case where the reference's pdf is NOT a function of the reached leaf is a point exactly
+// on a split line (its first-match energy child and last-match descent child differ): those points
+// take the level-by-level path.
+//
+// Jump table over the top SDT_JUMP_LEVELS levels of every non-single-leaf quadtree: for each of the
+// 16x16 cells of [0,1]^2 the node a pdf / splat descent reaches after 4 levels (its record index), or
+// the leaf it meets earlier.  Points on a 1/16 grid line take the level-by-level path.
 #define SDT_JUMP_LEVELS 4
 #define SDT_JUMP_CELLS 256
-#define SDT_JUMP_LEAF 0x80000000u      // entry.ri = LEAF | node id: a leaf was reached
-#define SDT_JUMP_DEAD 0xC0000000u      // entry.ri = DEAD | node id: the pdf product went NaN at that node
-struct __align__(8) QJump { uint32_t ri; float prod; };
+#define SDT_JUMP_LEAF 0x80000000u      // entry = LEAF | node id: a leaf was reached
+typedef uint32_t QJump;
 
 struct TreeView {
     const DevHeader* hdr;
@@ -88,6 +95,7 @@ struct TreeView {
     const uint32_t* kd_root;    // per spatial node: quadTreeRootIndex (= canonical node id of the tree's root)
     const QRec* rec;
     const QJump* jump;          // [root record][cell]
+    const float* pp;            // per node: pdf product of the root->node path (NaN: it went NaN)
     uint32_t jump_trees;        // 0: table not in use
 };
 
@@ -391,32 +399,12 @@ SDT_HD uint32_t sdt_descend_child(float x, float y, float mx, float my) {
 SDT_HD uint32_t sdt_energy_child(float x, float y, float mx, float my) {
     return (y >= my) ? ((x >= mx) ? 0u : 1u) : ((x <= mx) ? 2u : 3u);
 }
-// (4*childE)/nodeE of pdfQuadTree (:1084).  A +0 child energy over a positive node energy is +0
-// in IEEE arithmetic; answering it directly keeps those lanes (most pdf queries outside the lobes)
-// off the division's slow path, which the hardware check takes for a zero numerator.
-SDT_HD float sdt_pdf_ratio(float child_e, float own) {
-    if (sdt_f2u(child_e) == 0u && own > 0.0f) return 0.0f;
-    return (4.0f * child_e) / own;
-}
 SDT_HD float sdt_pick4(const SdtF4& v, uint32_t c) {
     const float a = (c & 1u) ? v.y : v.x;
     const float b = (c & 1u) ? v.w : v.z;
     return (c & 2u) ? b : a;
 }
 
-// QuadTree.pdfQuadTree, src/quadtree.py:1001-1101, from canonical position (x,y) in
-// [0,1]^2.  ri = record index of the root (SDT_NONE: single-leaf tree).  One 32-byte record
-// (one L2 sector) per level carries everything: child ids, own energy, child energies.
-SDT_HD QJump sdt_load_jump(const QJump* __restrict__ p) {
-    QJump j;
-#if defined(__CUDA_ARCH__)
-    const uint2 v = __ldg(reinterpret_cast<const uint2*>(p));
-    j.ri = v.x; j.prod = __uint_as_float(v.y);
-#else
-    j = *p;
-#endif
-    return j;
-}
 // cell of a canonical position; false when it lies on a grid line or outside [0,1)
 SDT_HD bool sdt_jump_cell(float x, float y, uint32_t& cx, uint32_t& cy) {
     const float fx = x * 16.0f, fy = y * 16.0f;          // exact scalings
@@ -425,36 +413,22 @@ SDT_HD bool sdt_jump_cell(float x, float y, uint32_t& cx, uint32_t& cy) {
     return fx != (float)cx && fy != (float)cy;
 }
 
-SDT_HD float sdt_quad_pdf(const TreeView& t, uint32_t ri, uint32_t root_node,
-                          float x, float y, uint32_t& node_out) {
-    const QRec* __restrict__ rec = t.rec;
+// QuadTree.pdfQuadTree, src/quadtree.py:1001-1101, level by level with the reference's own
+// arithmetic: the path for points on split lines, and for naming the node a NaN stop happens at.
+SDT_HD float sdt_quad_pdf_levels(const QRec* __restrict__ rec, uint32_t ri, uint32_t root_node,
+                                 float x, float y, uint32_t& node_out) {
     float pdf = 1.0f;
     float lox = 0.0f, loy = 0.0f, hix = 1.0f, hiy = 1.0f;
     uint32_t node = root_node;
     bool dead = false;
-    int level = 0;
-    uint32_t cx, cy;
-    if (ri < t.jump_trees && sdt_jump_cell(x, y, cx, cy)) {
-        const QJump j = sdt_load_jump(t.jump + (size_t)ri * SDT_JUMP_CELLS + cy * 16u + cx);
-        pdf = j.prod;
-        if (j.ri & SDT_JUMP_LEAF) {
-            const uint32_t nd = j.ri & 0x3FFFFFFFu;
-            node_out = nd == 0x3FFFFFFFu ? root_node : nd;       // (a NaN at the root stops on the root)
-            return ((j.ri & SDT_JUMP_DEAD) == SDT_JUMP_DEAD) ? 0.0f : pdf * SDT_INV_FOUR_PI;
-        }
-        ri = j.ri;
-        lox = (float)cx * 0.0625f; hix = (float)(cx + 1u) * 0.0625f;
-        loy = (float)cy * 0.0625f; hiy = (float)(cy + 1u) * 0.0625f;
-        level = SDT_JUMP_LEVELS;
-    }
-    for (; level < SDT_MAX_LEVELS; ++level) {
+    for (int level = 0; level < SDT_MAX_LEVELS; ++level) {
         if (ri == SDT_NONE) break;
         QHead h; SdtF4 e;
         sdt_load_rec(rec, ri, h, e);
         const float mx = (lox + hix) / 2.0f, my = (loy + hiy) / 2.0f;
         const uint32_t ce = sdt_energy_child(x, y, mx, my);
         const uint32_t cd = sdt_descend_child(x, y, mx, my);
-        pdf = pdf * sdt_pdf_ratio(sdt_pick4(e, ce), h.own);             // :1084
+        pdf = pdf * ((4.0f * sdt_pick4(e, ce)) / h.own);                // :1084
         if (pdf != pdf) { dead = true; break; }                         // :1090-1092
         node = h.child_base + cd;
         sdt_quadrant_m(cd, mx, my, lox, loy, hix, hiy);
@@ -465,25 +439,55 @@ SDT_HD float sdt_quad_pdf(const TreeView& t, uint32_t ri, uint32_t root_node,
     return pdf;
 }
 
-// one jump-table entry: the descent of pdfQuadTree for any interior point of cell (cx,cy)
+// pdfQuadTree from canonical position (x,y) in [0,1]^2.  ri = record index of the root (SDT_NONE:
+// single-leaf tree).  Finds the leaf (jump table, then 16 B of each record per level) and reads its
+// path product; split-line points and NaN stops go through sdt_quad_pdf_levels.
+SDT_HD float sdt_quad_pdf(const TreeView& t, uint32_t ri, uint32_t root_node,
+                          float x, float y, uint32_t& node_out) {
+    if (ri == SDT_NONE) { node_out = root_node; return SDT_INV_FOUR_PI; }     // 1 * 1/(4 pi)
+    const QRec* __restrict__ rec = t.rec;
+    const uint32_t ri0 = ri;
+    float lox = 0.0f, loy = 0.0f, hix = 1.0f, hiy = 1.0f;
+    uint32_t node = root_node;
+    int level = 0;
+    bool tie = false;
+    uint32_t cx, cy;
+    if (ri < t.jump_trees && sdt_jump_cell(x, y, cx, cy)) {
+        const QJump j = SDT_LDG(t.jump + (size_t)ri * SDT_JUMP_CELLS + cy * 16u + cx);
+        if (j & SDT_JUMP_LEAF) { node = j & ~SDT_JUMP_LEAF; ri = SDT_NONE; }
+        else {
+            ri = j;
+            lox = (float)cx * 0.0625f; hix = (float)(cx + 1u) * 0.0625f;
+            loy = (float)cy * 0.0625f; hiy = (float)(cy + 1u) * 0.0625f;
+            level = SDT_JUMP_LEVELS;
+        }
+    }
+    for (; level < SDT_MAX_LEVELS && ri != SDT_NONE; ++level) {
+        const QHead h = sdt_load_head(rec, ri);
+        const float mx = (lox + hix) / 2.0f, my = (loy + hiy) / 2.0f;
+        tie = tie || (x == mx) || (y == my);
+        const uint32_t cd = sdt_descend_child(x, y, mx, my);
+        node = h.child_base + cd;
+        sdt_quadrant_m(cd, mx, my, lox, loy, hix, hiy);
+        ri = sdt_child_rec(h.cinfo, h.interior_base, cd);
+    }
+    const float pp = SDT_LDG(t.pp + node);
+    if (tie || pp != pp) return sdt_quad_pdf_levels(rec, ri0, root_node, x, y, node_out);
+    node_out = node;
+    return pp * SDT_INV_FOUR_PI;
+}
+
+// one jump-table entry: where the descent arrives for any interior point of cell (cx,cy)
 SDT_HD QJump sdt_build_jump(const QRec* __restrict__ rec, uint32_t root_rec, uint32_t cx, uint32_t cy) {
-    QJump j;
-    float pdf = 1.0f;
     uint32_t ri = root_rec;
-    uint32_t node = 0;
     for (int l = 0; l < SDT_JUMP_LEVELS; ++l) {
         const QRec r = rec[ri];
-        if (l == 0) node = 0;    // (root node id is not needed: a root with a record is never the answer)
         const uint32_t bx = (cx >> (SDT_JUMP_LEVELS - 1 - l)) & 1u, by = (cy >> (SDT_JUMP_LEVELS - 1 - l)) & 1u;
         const uint32_t c = by ? (bx ? 0u : 1u) : (bx ? 3u : 2u);         // strict interior: every tie rule agrees
-        pdf = pdf * sdt_pdf_ratio(r.e[c], r.own);
-        if (pdf != pdf) { j.ri = SDT_JUMP_DEAD | (l == 0 ? 0x3FFFFFFFu : node); j.prod = 0.0f; return j; }
-        node = r.child_base + c;
         ri = sdt_child_rec(r.cinfo, r.interior_base, c);
-        if (ri == SDT_NONE) { j.ri = SDT_JUMP_LEAF | node; j.prod = pdf; return j; }
+        if (ri == SDT_NONE) return SDT_JUMP_LEAF | (r.child_base + c);
     }
-    j.ri = ri; j.prod = pdf;
-    return j;
+    return ri;
 }
 
 // QuadTree.sampleQuadTree, src/quadtree.py:931-998.  Consumes 3 uniforms per visited
@@ -496,8 +500,7 @@ SDT_HD QJump sdt_build_jump(const QRec* __restrict__ rec, uint32_t root_rec, uin
 struct QSample {
     float x, y;                 // canonical position
     uint32_t node;              // leaf node reached
-    float pdf_path;             // product of 4*childE/nodeE along the path (0 if it went NaN)
-    bool pdf_dead;              // the product went NaN (-> pdf 0, :1090-1092)
+    bool moved;                 // the tree has a record (node is a real node id)
     bool stuck;                 // NaN child energies: no bin matched (oracle: stop at (0,0))
     float lox, loy, hix, hiy;   // leaf cell
 };
@@ -505,7 +508,7 @@ struct QSample {
 template <class Rng>
 SDT_HD QSample sdt_quad_sample(const QRec* __restrict__ rec, uint32_t ri, uint32_t root_node, const Rng& rng) {
     QSample q;
-    q.x = 0.0f; q.y = 0.0f; q.node = root_node; q.pdf_path = 1.0f; q.pdf_dead = false; q.stuck = false;
+    q.x = 0.0f; q.y = 0.0f; q.node = root_node; q.moved = ri != SDT_NONE; q.stuck = false;
     q.lox = 0.0f; q.loy = 0.0f; q.hix = 1.0f; q.hiy = 1.0f;
     uint32_t level = 0;
     // the loop only descends; the leaf position is drawn after it, where the warp has reconverged
@@ -524,11 +527,6 @@ SDT_HD QSample sdt_quad_sample(const QRec* __restrict__ rec, uint32_t ri, uint32
         const bool m0 = s < e1, m1 = b1 && (s < e2), m2 = b2 && (s < e3);
         if (!(m0 || m1 || m2 || b3)) { q.stuck = true; break; }
         const uint32_t cu = b3 ? 3u : (m2 ? 2u : (m1 ? 1u : 0u));
-        const float f = q.pdf_path * ((4.0f * sdt_pick4(e, cu)) / h.own);   // :1084 (the sampled child has energy: no zero shortcut)
-        if (!q.pdf_dead) {
-            q.pdf_dead = f != f;                                         // :1090-1092
-            q.pdf_path = q.pdf_dead ? 0.0f : f;
-        }
         q.node = h.child_base + cu;
         sdt_quadrant_m(cu, (q.lox + q.hix) / 2.0f, (q.loy + q.hiy) / 2.0f, q.lox, q.loy, q.hix, q.hiy);
         ri = sdt_child_rec(h.cinfo, h.interior_base, cu);
@@ -542,7 +540,10 @@ SDT_HD QSample sdt_quad_sample(const QRec* __restrict__ rec, uint32_t ri, uint32
     return q;
 }
 
-// KDTree.sample after the spatial descent (src/kdtree.py:482-485).
+// KDTree.sample after the spatial descent (src/kdtree.py:482-485).  The pdf of the sampled direction
+// (second descent of the reference, :483-484) is the path product of the sampled leaf whenever the
+// canonical->dir->canonical round trip stays strictly inside the leaf cell -- then both descents
+// arrive at the same leaf and every tie rule is moot; otherwise the pdf descent runs.
 struct GuidedSample { float dx, dy, dz, pdf; uint32_t sample_node, pdf_node; };
 
 // ri = record of the tree's root (from the spatial leaf word); root = its node id, only used for
@@ -555,8 +556,9 @@ SDT_HD GuidedSample sdt_sample_tree(const TreeView& t, uint32_t ri, uint32_t roo
     float px, py;
     sdt_dir_to_canonical(g.dx, g.dy, g.dz, px, py);                      // :1016
     g.sample_node = q.node;
-    if (fuse && !q.stuck && !q.pdf_dead && px > q.lox && px < q.hix && py > q.loy && py < q.hiy) {
-        g.pdf = q.pdf_path * SDT_INV_FOUR_PI;
+    const float pp = q.moved ? SDT_LDG(t.pp + q.node) : 1.0f;
+    if (fuse && !q.stuck && pp == pp && px > q.lox && px < q.hix && py > q.loy && py < q.hiy) {
+        g.pdf = pp * SDT_INV_FOUR_PI;
         g.pdf_node = q.node;
     } else {
         uint32_t nd;
@@ -576,14 +578,12 @@ SDT_HD uint32_t sdt_quad_leaf(const TreeView& t, uint32_t ri, uint32_t root_node
     int level = 0;
     uint32_t cx, cy;
     if (ri < t.jump_trees && sdt_jump_cell(x, y, cx, cy)) {
-        const QJump j = sdt_load_jump(t.jump + (size_t)ri * SDT_JUMP_CELLS + cy * 16u + cx);
-        if ((j.ri & SDT_JUMP_DEAD) != SDT_JUMP_DEAD) {              // (a NaN stop says nothing about the topology: slow path)
-            if (j.ri & SDT_JUMP_LEAF) return j.ri & 0x3FFFFFFFu;
-            ri = j.ri;
-            lox = (float)cx * 0.0625f; hix = (float)(cx + 1u) * 0.0625f;
-            loy = (float)cy * 0.0625f; hiy = (float)(cy + 1u) * 0.0625f;
-            level = SDT_JUMP_LEVELS;
-        }
+        const QJump j = SDT_LDG(t.jump + (size_t)ri * SDT_JUMP_CELLS + cy * 16u + cx);
+        if (j & SDT_JUMP_LEAF) return j & ~SDT_JUMP_LEAF;
+        ri = j;
+        lox = (float)cx * 0.0625f; hix = (float)(cx + 1u) * 0.0625f;
+        loy = (float)cy * 0.0625f; hiy = (float)(cy + 1u) * 0.0625f;
+        level = SDT_JUMP_LEVELS;
     }
     for (; level < SDT_MAX_LEVELS && ri != SDT_NONE; ++level) {
         const QHead h = sdt_load_head(rec, ri);      // 16 of the record's 32 bytes

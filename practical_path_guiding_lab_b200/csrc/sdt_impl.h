@@ -10,6 +10,7 @@ struct QuadSet {
     uint32_t* child = nullptr;      // child_base per canonical node (0 = leaf)
     float* energy = nullptr;        // prev energies per canonical node
     float* thr = nullptr;           // refinementThreshold per node
+    float* pp = nullptr;            // per node: pdf product of the root->node path (see sdt_core.h)
     uint32_t* iidx = nullptr;       // per node: number of non-leaf nodes before it (= record index if non-leaf)
     QRec* rec = nullptr;
     QJump* jump = nullptr;          // [root record][16x16 cell] jump table over the top 4 levels
@@ -110,7 +111,7 @@ static inline TreeView tree_view(sdt_tree_s* h) {
         h->jump_trees_known = h->h_hdr->jump_trees;
     }
     const QuadSet& s = h->set[h->cur];
-    return TreeView{s.hdr, h->kd_word, h->kd_root, s.rec, s.jump, h->use_jump ? h->jump_trees_known : 0u};
+    return TreeView{s.hdr, h->kd_word, h->kd_root, s.rec, s.jump, s.pp, h->use_jump ? h->jump_trees_known : 0u};
 }
 
 static int sdt_read_header(sdt_handle h, DevHeader& H);

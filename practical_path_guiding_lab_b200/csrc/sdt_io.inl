@@ -13,7 +13,7 @@ static int sdt_free_all(sdt_handle h) {
     for (void* p : ptrs) if (p) cudaFree(p);
     for (int k = 0; k < 2; ++k) {
         QuadSet& s = h->set[k];
-        void* q[] = {s.child, s.energy, s.thr, s.iidx, s.rec, s.jump, s.root_iidx, s.hdr};
+        void* q[] = {s.child, s.energy, s.thr, s.pp, s.iidx, s.rec, s.jump, s.root_iidx, s.hdr};
         for (void* p : q) if (p) cudaFree(p);
     }
     if (h->h_hdr) cudaFreeHost(h->h_hdr);
@@ -74,7 +74,7 @@ extern "C" int sdt_create(const sdt_config* cfg, sdt_handle* out) {
     A(h->s_blk, SDT_SCAN_MAX_BLOCKS + 64);
     for (int k = 0; k < 2; ++k) {
         QuadSet& s = h->set[k];
-        A(s.child, h->quad_cap); A(s.energy, h->quad_cap); A(s.thr, h->quad_cap); A(s.iidx, h->quad_cap);
+        A(s.child, h->quad_cap); A(s.energy, h->quad_cap); A(s.thr, h->quad_cap); A(s.pp, h->quad_cap); A(s.iidx, h->quad_cap);
         A(s.rec, h->rec_cap); A(s.jump, (size_t)h->jump_cap * SDT_JUMP_CELLS); A(s.root_iidx, h->kd_cap); A(s.hdr, 1);
     }
 #undef A
@@ -240,6 +240,7 @@ extern "C" int sdt_upload(sdt_handle h, const sdt_arrays* a) {
     SDT_CUDA(h, cudaMemsetAsync(h->kd_count, 0, 4ull * h->kd_cap, nullptr));
     SDT_CUDA(h, cudaMemsetAsync(h->q_ecur, 0, 4ull * h->quad_cap, nullptr));
     const ExecCtx x = exec_ctx(h, nullptr);
+    h->levels_hint = nlev > 0 ? nlev : 1;          // the per-level passes of sdt_build_records cover the uploaded tree
     sdt_build_records(h, x, s);
     SDT_TRY(sdt_post_launch(h, "sdt_upload"));
     SDT_CUDA(h, cudaStreamSynchronize(nullptr));

@@ -278,6 +278,20 @@ struct KdLeafWordItem {
     }
 };
 
+// per-node pdf product, one level per pass, parents before children (see sdt_core.h):
+// pp[root] = 1; pp[child c] = pp[node] * ((4 * E[child c]) / E[node])   (src/quadtree.py:1084)
+struct PpLevelItem {
+    const DevHeader* H; const uint32_t* child; const float* energy; float* pp; uint32_t level;
+    SDT_HD void operator()(uint32_t i) const {
+        const uint32_t id = H->level_off[level] + i;
+        if (level == 0u) pp[id] = 1.0f;
+        const uint32_t cb = child[id];
+        if (!cb) return;
+        const float p = pp[id], own = energy[id];
+        for (uint32_t k = 0; k < 4u; ++k) pp[cb + k] = p * ((4.0f * energy[cb + k]) / own);   // NaN is sticky
+    }
+};
+
 // jump table: trees with a root record are records 0 .. iidx[n_roots]-1 (records follow node order)
 struct JumpCountItem {
     DevHeader* H; const uint32_t* iidx; uint32_t cap;
@@ -299,6 +313,8 @@ static void sdt_build_records(sdt_handle h, const ExecCtx& x, QuadSet& s) {
     launch_scan(x, &s.hdr->n_quad, 0, RecFlag{s.child}, RecEmit{s.iidx}, RecFin{s.hdr});
     launch_items(x, &s.hdr->n_quad, 0, RecBuildItem{s.hdr, s.child, s.energy, s.iidx, s.rec, s.root_iidx});
     launch_items(x, &s.hdr->n_kd, 0, KdLeafWordItem{s.hdr, h->kd_word, h->kd_root, s.root_iidx});
+    for (uint32_t l = 0; l < h->levels_hint && l < SDT_MAX_LEVELS; ++l)
+        launch_items(x, &s.hdr->level_cnt[l], 0, PpLevelItem{s.hdr, s.child, s.energy, s.pp, l});
     launch_single(x, JumpCountItem{s.hdr, s.iidx, h->jump_cap});
     launch_items(x, &s.hdr->lvl_n[0], 0, JumpBuildItem{s.rec, s.jump});
 }
@@ -345,6 +361,7 @@ extern "C" int sdt_refine(sdt_handle h, uint32_t flags, sdt_stream stream) {
     for (uint32_t l = 0; l < levels_bound; ++l)
         launch_scan(x, &c.H1->lvl_n[l & 1u], 0, QLevelFlag{c, l, (uint32_t)(l + 1u == levels_bound)}, QLevelEmit{c, l}, QLevelFin{c, l});
     launch_single(x, QFinalize{c, levels_bound});
+    h->levels_hint = levels_bound;
     sdt_build_records(h, x, s1);
     // prev <- current, then reset current (:582-586)
     launch_items(x, &c.H1->n_kd, 0, KdRollItem{h->kd_count, h->kd_prev_count});
