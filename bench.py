@@ -372,7 +372,17 @@ def run_b200(args):
         ms_g = timeit(lambda: tree.guided(d_pos, mode, wo=d_dir, seed=5, lane_offset=lane0, bsdf_pdf=bp, bsdf_value=bv,
                                           dir_out=g_dir, sdtree_pdf_out=g_sp, wo_pdf_out=g_wp, weight_out=g_w))
         ms_p = timeit(lambda: tree.splat_path_data(md, lfin, tr_, tb_, bs_, d_rec['position'], d_rec['direction'], d_rec['wo_pdf'], active=act_))
-        extras = {"sdt_guided": {"ms": ms_g, "lanes_per_s": n / (ms_g * 1e-3), "what": "one bounce: ~45 % lanes sampled, ~45 % pdf + fused mixture, ~10 % idle"},
+        act15 = (torch.rand(n, device=dev, generator=gg) < 0.15).to(torch.uint8)
+        sparse = {}
+        for comp in (1, 0):
+            tree.set_tuning("use_compaction", comp)
+            key = "compacted" if comp else "masked"
+            sparse[key] = {"splat_path_data_ms": timeit(lambda: tree.splat_path_data(md, lfin, tr_, tb_, bs_, d_rec['position'], d_rec['direction'], d_rec['wo_pdf'], active=act15)),
+                           "pdf_ms": timeit(lambda: tree.pdf(d_pos, d_dir, active=act15, out=o_pdf2)),
+                           "sample_ms": timeit(lambda: tree.sample(d_pos, active=act15, seed=3, out=(o_dir, o_pdf)))}
+        tree.set_tuning("use_compaction", 1)
+        extras = {"sparse_wavefront_15pct_active": dict(sparse, what="same calls with 15 % of the lanes active (late bounces / numRays*max_depth record slots): lanes of a tile sorted into dense warps vs plain masking"),
+                  "sdt_guided": {"ms": ms_g, "lanes_per_s": n / (ms_g * 1e-3), "what": "one bounce: ~45 % lanes sampled, ~45 % pdf + fused mixture, ~10 % idle"},
                   "sdt_splat_path_data": {"ms": ms_p, "slots_per_s": n / (ms_p * 1e-3), "what": f"processPathData + filter + splat fused, {n} slots (max_depth {md}), 60 % active"}}
         tree.reset_stats()
     except Exception as e:            # extras never break the contract line

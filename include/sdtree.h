@@ -259,7 +259,7 @@ int sdt_stat_buffers(sdt_handle h, float** q_energy, uint32_t* n_quad, float** k
 
 /* ---- tuning / introspection --------------------------------------------------- */
 /* key: "query_block", "query_ctas_per_sm", "kd_smem_nodes", "splat_block",
- * "splat_ctas_per_sm", "fuse_sample_pdf", "use_jump", "use_kd_grid", "host_chunk" (lanes per chunk of the pipelined
+ * "splat_ctas_per_sm", "fuse_sample_pdf", "use_jump", "use_kd_grid", "use_compaction", "host_chunk" (lanes per chunk of the pipelined
  * SDT_HOST_PTRS staging: H2D of chunk k+1 | kernels of chunk k | D2H of chunk k-1) */
 int sdt_set_tuning(sdt_handle h, const char* key, int64_t value);
 /* number of kernels this handle has launched since creation */

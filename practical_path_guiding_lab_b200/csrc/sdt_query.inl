@@ -3,8 +3,25 @@
 // tree is staged in shared memory by every CTA, the quadtree records stay L2-resident.
 
 // ---------------------------------------------------------------------------- launch
+// A lane functor provides
+//   kModes             1 (active / idle) or 2 (guided bounce: sample / pdf / idle)
+//   mode_of(i)         0 = idle lane, 1..kModes = what the lane does
+//   idle(i)            outputs of an idle lane
+//   run_mode<KD>(k,i,m) the work of a non-idle lane; KD = spatial-descent variant (sdt_kd_descend)
+//   kGrid, kSmemCounts, flush_count   see k_wavefront
+template <class Lane, int KD>
+SDT_HD void sdt_lane(const Lane& f, const KdCtx& k, uint32_t i) {
+    const uint32_t m = f.mode_of(i);
+    if (m) f.template run_mode<KD>(k, i, m);
+    else f.idle(i);
+}
+
 #ifndef SDT_HOSTEMU
-template <class Lane>
+// COMPACT: the wavefront has idle lanes or lanes of different kinds.  The lanes of a 4*blockDim tile
+// are first sorted by mode into shared-memory lists, then every list is processed by dense warps:
+// a warp never runs two code paths, and idle lanes (dead paths, masked-out vertices, filtered records)
+// cost a classification, not a share of a descent.
+template <class Lane, bool COMPACT>
 __global__ void __launch_bounds__(512, 3) k_wavefront(Lane f, uint32_t n, uint32_t smem_cap, uint32_t use_grid) {
     extern __shared__ uint32_t kd_s[];
     const DevHeader* hdr = f.t.hdr;
@@ -12,28 +29,32 @@ __global__ void __launch_bounds__(512, 3) k_wavefront(Lane f, uint32_t n, uint32
     const uint32_t n_smem = n_kd < smem_cap ? n_kd : smem_cap;
     for (uint32_t j = threadIdx.x; j < n_smem; j += blockDim.x) kd_s[j] = __ldg(f.t.kd_word + j);
     KdCtx k = sdt_kd_ctx(kd_s, n_smem, f.t.kd_word, hdr);
+    uint32_t* smem_next = kd_s + smem_cap;
     // splat kernels with the whole spatial tree staged: leaf counters live in shared memory for the
     // lifetime of the CTA and are flushed once (16M same-slice L2 atomics become a few per leaf and CTA)
     float* cnt_s = nullptr;
-    if (Lane::kSmemCounts && n_smem == n_kd) {
-        cnt_s = reinterpret_cast<float*>(kd_s + smem_cap);
-        for (uint32_t j = threadIdx.x; j < n_smem; j += blockDim.x) cnt_s[j] = 0.0f;
-        k.cnt_s = cnt_s;
+    if (Lane::kSmemCounts) {
+        if (n_smem == n_kd) {
+            cnt_s = reinterpret_cast<float*>(smem_next);
+            for (uint32_t j = threadIdx.x; j < n_smem; j += blockDim.x) cnt_s[j] = 0.0f;
+            k.cnt_s = cnt_s;
+        }
+        smem_next += smem_cap;
     }
     __syncthreads();
     // (measured: the grid pays for the pdf / splat / locate kernels, -7 % / -4 %, not for the sampling
     // kernels, +3 %, whose long quadtree loop wants the registers)
-    if (Lane::kGrid && use_grid && n_smem == n_kd) {   // 16x16x8 grid over the first 11 levels (see sdt_kd_descend)
-        uint32_t* grid = kd_s + smem_cap * (Lane::kSmemCounts ? 2u : 1u);
-        for (uint32_t c = threadIdx.x; c < SDT_GRID_CELLS; c += blockDim.x) grid[c] = sdt_kd_grid_node(kd_s, c);
-        k.grid = grid;
+    if (Lane::kGrid && use_grid) {               // 16x16x8 grid over the first 11 levels (see sdt_kd_descend)
+        if (n_smem == n_kd) {
+            for (uint32_t c = threadIdx.x; c < SDT_GRID_CELLS; c += blockDim.x) smem_next[c] = sdt_kd_grid_node(kd_s, c);
+            k.grid = smem_next;
+        }
+        smem_next += SDT_GRID_CELLS;
         __syncthreads();
     }
-    if (Lane::kCompact) {
-        // Mixed wavefront (guided bounce: some lanes sample, some evaluate a pdf, some idle): the lanes of a
-        // 4*blockDim tile are first sorted by mode into two shared-memory lists, then each list is
-        // processed by dense warps -- a warp never runs both code paths.
-        uint16_t* list = reinterpret_cast<uint16_t*>(kd_s + smem_cap * (Lane::kSmemCounts ? 2u : 1u) + ((Lane::kGrid && use_grid) ? SDT_GRID_CELLS : 0u));
+    const int kd_mode = k.grid ? 2 : (n_smem == n_kd ? 1 : 0);
+    if (COMPACT) {
+        uint16_t* list = reinterpret_cast<uint16_t*>(smem_next);
         __shared__ uint32_t s_cnt[2];
         const uint32_t tile_n = 4u * blockDim.x;
         const uint32_t lane = threadIdx.x & 31u;
@@ -42,8 +63,10 @@ __global__ void __launch_bounds__(512, 3) k_wavefront(Lane f, uint32_t n, uint32
             __syncthreads();
             for (uint32_t q = 0; q < 4u; ++q) {
                 const uint32_t li = q * blockDim.x + threadIdx.x, i = tile + li;
-                const uint32_t m = i < n ? f.mode_of(i) : 0u;
-                for (uint32_t L = 0; L < 2u; ++L) {
+                uint32_t m = 0;
+                if (i < n) { m = f.mode_of(i); if (!m) f.idle(i); }
+#pragma unroll
+                for (uint32_t L = 0; L < (uint32_t)Lane::kModes; ++L) {
                     const uint32_t b = __ballot_sync(0xFFFFFFFFu, m == L + 1u);
                     uint32_t base = 0;
                     if (lane == 0u && b) base = atomicAdd(&s_cnt[L], (uint32_t)__popc(b));
@@ -52,25 +75,24 @@ __global__ void __launch_bounds__(512, 3) k_wavefront(Lane f, uint32_t n, uint32
                 }
             }
             __syncthreads();
-            for (uint32_t L = 0; L < 2u; ++L) {
+#pragma unroll
+            for (uint32_t L = 0; L < (uint32_t)Lane::kModes; ++L) {
                 const uint32_t cnt = s_cnt[L];
                 for (uint32_t j = threadIdx.x; j < cnt; j += blockDim.x) {
                     const uint32_t i = tile + list[L * tile_n + j];
-                    if (n_smem == n_kd) f.template run_mode<1>(k, i, L + 1u);
+                    if (kd_mode == 2) f.template run_mode<2>(k, i, L + 1u);
+                    else if (kd_mode == 1) f.template run_mode<1>(k, i, L + 1u);
                     else f.template run_mode<0>(k, i, L + 1u);
                 }
             }
             __syncthreads();
         }
-    } else if (k.grid) {            // whole spatial tree staged + grid over its first 11 levels
-        for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
-            f.template run<2>(k, i);
-    } else if (n_smem == n_kd) {    // whole spatial tree staged: descent loop without the global path
-        for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
-            f.template run<1>(k, i);
+    } else if (kd_mode == 2) {      // whole spatial tree staged + grid over its first 11 levels
+        for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) sdt_lane<Lane, 2>(f, k, i);
+    } else if (kd_mode == 1) {      // whole spatial tree staged: descent loop without the global path
+        for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) sdt_lane<Lane, 1>(f, k, i);
     } else {
-        for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
-            f.template run<0>(k, i);
+        for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) sdt_lane<Lane, 0>(f, k, i);
     }
     if (cnt_s) {
         __syncthreads();
@@ -85,40 +107,48 @@ __global__ void __launch_bounds__(512, 3) k_wavefront(Lane f, uint32_t n, uint32
 // host last saw (exact after upload / get_sizes; after a refine a non-blocking header read-back
 // refreshes it), capped by the "kd_smem_nodes" tuning; a larger tree falls back to global loads
 // for the nodes beyond the staged prefix.
-template <class Lane>
-static int launch_wavefront(sdt_handle h, cudaStream_t st, uint32_t n, const Lane& f, int block, int ctas_per_sm) {
+template <class Lane, bool COMPACT>
+static int launch_wavefront_c(sdt_handle h, cudaStream_t st, uint32_t n, const Lane& f, int block, int ctas_per_sm) {
     if (n == 0) return SDT_OK;
-    uint32_t want = h->hdr_pending ? 2u * h->kd_nodes_known + 2u : h->kd_nodes_known;   // a refine at most... unknown: be generous
+    uint32_t want = h->hdr_pending ? 2u * h->kd_nodes_known + 2u : h->kd_nodes_known;   // a refine is in flight: be generous
     uint32_t smem_nodes = (want + 255u) & ~255u;
     if (smem_nodes > (uint32_t)h->kd_smem_nodes) smem_nodes = (uint32_t)h->kd_smem_nodes;
-    const size_t smem = (size_t)smem_nodes * 4u * (Lane::kSmemCounts ? 2u : 1u) + ((Lane::kGrid && h->use_kd_grid) ? SDT_GRID_CELLS * 4u : 0u) + (Lane::kCompact ? (size_t)block * 4u * 2u * 2u : 0u);
+    const size_t smem = (size_t)smem_nodes * 4u * (Lane::kSmemCounts ? 2u : 1u) + ((Lane::kGrid && h->use_kd_grid) ? SDT_GRID_CELLS * 4u : 0u) +
+                        (COMPACT ? (size_t)block * 4u * 2u * (size_t)Lane::kModes : 0u);
     static size_t attr_set = 0;
     if (smem > 48u * 1024u && smem > attr_set) {
-        if (cudaFuncSetAttribute(k_wavefront<Lane>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess)
+        if (cudaFuncSetAttribute(k_wavefront<Lane, COMPACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess)
             return sdt_fail(h, SDT_ERR_CUDA, "cudaFuncSetAttribute(MaxDynamicSharedMemorySize) failed");
         attr_set = 200 * 1024;
     }
     static int occ_cache = 0, occ_block = 0;
     static size_t occ_smem = ~(size_t)0;
     if (occ_smem != smem || occ_block != block) {
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_cache, k_wavefront<Lane>, block, smem) != cudaSuccess || occ_cache < 1) occ_cache = 1;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_cache, k_wavefront<Lane, COMPACT>, block, smem) != cudaSuccess || occ_cache < 1) occ_cache = 1;
         occ_smem = smem; occ_block = block;
     }
     int per_sm = ctas_per_sm < occ_cache ? ctas_per_sm : occ_cache;
     if (per_sm < 1) per_sm = 1;
-    uint32_t grid = (n + (uint32_t)block - 1u) / (uint32_t)block;
+    const uint32_t per_cta = (uint32_t)block * (COMPACT ? 4u : 1u);
+    uint32_t grid = (n + per_cta - 1u) / per_cta;
     const uint32_t cap = (uint32_t)(h->num_sms * per_sm);
     if (grid > cap) grid = cap;
-    k_wavefront<Lane><<<grid, block, smem, st>>>(f, n, smem_nodes, (uint32_t)h->use_kd_grid);
+    k_wavefront<Lane, COMPACT><<<grid, block, smem, st>>>(f, n, smem_nodes, (uint32_t)h->use_kd_grid);
     ++h->launches;
     h->last_stream = st;
     return sdt_post_launch(h, "k_wavefront");
 }
+// compact = the wavefront may contain idle lanes / several kinds of lanes
+template <class Lane>
+static int launch_wavefront(sdt_handle h, cudaStream_t st, uint32_t n, const Lane& f, int block, int ctas_per_sm, bool compact) {
+    if (compact && h->use_compaction) return launch_wavefront_c<Lane, true>(h, st, n, f, block, ctas_per_sm);
+    return launch_wavefront_c<Lane, false>(h, st, n, f, block, ctas_per_sm);
+}
 #else
 template <class Lane>
-static int launch_wavefront(sdt_handle h, cudaStream_t st, uint32_t n, const Lane& f, int, int) {
+static int launch_wavefront(sdt_handle h, cudaStream_t st, uint32_t n, const Lane& f, int, int, bool) {
     const KdCtx k = sdt_kd_ctx(f.t.kd_word, 0u, f.t.kd_word, f.t.hdr);
-    for (uint32_t i = 0; i < n; ++i) f.template run<0>(k, i);
+    for (uint32_t i = 0; i < n; ++i) sdt_lane<Lane, 0>(f, k, i);
     ++h->launches;
     h->last_stream = st;
     return SDT_OK;
@@ -127,88 +157,74 @@ static int launch_wavefront(sdt_handle h, cudaStream_t st, uint32_t n, const Lan
 
 // ---------------------------------------------------------------------------- lanes
 struct LocateLane {
-    static constexpr bool kSmemCounts = false;
-    static constexpr bool kCompact = false;
-    SDT_HD uint32_t mode_of(uint32_t) const { return 0u; }
-    template <int MODE> SDT_HD void run_mode(const KdCtx&, uint32_t, uint32_t) const {}
-    static constexpr bool kGrid = true;
+    static constexpr bool kSmemCounts = false, kGrid = true;
+    static constexpr int kModes = 1;
     SDT_HD void flush_count(uint32_t, float) const {}
     TreeView t;
     sdt_vec3 pos; const uint8_t* active; uint32_t* leaf; uint32_t* root;
-    template <int MODE>
-    SDT_HD void run(const KdCtx& k, uint32_t i) const {
-        const bool act = active ? SDT_LDG(active + i) != 0 : true;
-        uint32_t lf = 0, rt = 0;                     // inactive: node 0, masked gather -> 0
-        if (act) {
-            const KdResult r = sdt_kd_descend<MODE>(k, sdt_ld(pos.x, pos.stride, i),
-                                              sdt_ld(pos.y, pos.stride, i), sdt_ld(pos.z, pos.stride, i));
-            lf = r.leaf; rt = SDT_LDG(t.kd_root + r.leaf);
-        }
-        if (leaf) leaf[i] = lf;
-        if (root) root[i] = rt;
+    SDT_HD uint32_t mode_of(uint32_t i) const { return active ? (SDT_LDG(active + i) != 0 ? 1u : 0u) : 1u; }
+    SDT_HD void idle(uint32_t i) const {                 // inactive: node 0, masked gather -> 0
+        if (leaf) leaf[i] = 0u;
+        if (root) root[i] = 0u;
+    }
+    template <int KD>
+    SDT_HD void run_mode(const KdCtx& k, uint32_t i, uint32_t) const {
+        const KdResult r = sdt_kd_descend<KD>(k, sdt_ld(pos.x, pos.stride, i), sdt_ld(pos.y, pos.stride, i), sdt_ld(pos.z, pos.stride, i));
+        if (leaf) leaf[i] = r.leaf;
+        if (root) root[i] = SDT_LDG(t.kd_root + r.leaf);
     }
 };
 
 template <bool EXPLICIT_U>
 struct SampleLane {
-    static constexpr bool kSmemCounts = false;
-    static constexpr bool kCompact = false;
-    SDT_HD uint32_t mode_of(uint32_t) const { return 0u; }
-    template <int MODE> SDT_HD void run_mode(const KdCtx&, uint32_t, uint32_t) const {}
-    static constexpr bool kGrid = false;
+    static constexpr bool kSmemCounts = false, kGrid = false;
+    static constexpr int kModes = 1;
     SDT_HD void flush_count(uint32_t, float) const {}
     TreeView t;
     sdt_vec3 pos; const uint8_t* active;
     const float* u; uint32_t u_stride, seed, lane_offset;
     sdt_vec3_out dir; float* pdf; uint32_t* dbg; int fuse;
-    template <int MODE>
-    SDT_HD void run(const KdCtx& k, uint32_t i) const {
-        const bool act = active ? SDT_LDG(active + i) != 0 : true;
-        float dx = 0.0f, dy = 0.0f, dz = -1.0f, p = 1.0f;   // inactive lanes: pos (0,0) -> (0,0,-1), pdf 1
-        uint32_t d0 = 0, d1 = 0, d2 = 0, d3 = 0;
-        if (act) {
-            const KdResult r = sdt_kd_descend<MODE>(k, sdt_ld(pos.x, pos.stride, i),
-                                              sdt_ld(pos.y, pos.stride, i), sdt_ld(pos.z, pos.stride, i));
-            const uint32_t root = dbg ? SDT_LDG(t.kd_root + r.leaf) : 0u;
-            GuidedSample g;
-            if (EXPLICIT_U) g = sdt_sample_tree(t, r.rootrec, root, ExplicitRng(u, u_stride, i), fuse != 0);
-            else g = sdt_sample_tree(t, r.rootrec, root, CounterRng(seed, lane_offset + i), fuse != 0);
-            dx = g.dx; dy = g.dy; dz = g.dz; p = g.pdf;
-            d0 = r.leaf; d1 = root; d2 = g.sample_node; d3 = g.pdf_node;
-        }
+    SDT_HD uint32_t mode_of(uint32_t i) const { return active ? (SDT_LDG(active + i) != 0 ? 1u : 0u) : 1u; }
+    SDT_HD void idle(uint32_t i) const {                 // inactive lanes: pos (0,0) -> (0,0,-1), pdf 1
         const int64_t o = (int64_t)i * dir.stride;
-        dir.x[o] = dx; dir.y[o] = dy; dir.z[o] = dz;
-        pdf[i] = p;
-        if (dbg) { dbg[4u * i] = d0; dbg[4u * i + 1u] = d1; dbg[4u * i + 2u] = d2; dbg[4u * i + 3u] = d3; }
+        dir.x[o] = 0.0f; dir.y[o] = 0.0f; dir.z[o] = -1.0f;
+        pdf[i] = 1.0f;
+        if (dbg) { dbg[4u * i] = 0u; dbg[4u * i + 1u] = 0u; dbg[4u * i + 2u] = 0u; dbg[4u * i + 3u] = 0u; }
+    }
+    template <int KD>
+    SDT_HD void run_mode(const KdCtx& k, uint32_t i, uint32_t) const {
+        const KdResult r = sdt_kd_descend<KD>(k, sdt_ld(pos.x, pos.stride, i), sdt_ld(pos.y, pos.stride, i), sdt_ld(pos.z, pos.stride, i));
+        const uint32_t root = dbg ? SDT_LDG(t.kd_root + r.leaf) : 0u;
+        GuidedSample g;
+        if (EXPLICIT_U) g = sdt_sample_tree(t, r.rootrec, root, ExplicitRng(u, u_stride, i), fuse != 0);
+        else g = sdt_sample_tree(t, r.rootrec, root, CounterRng(seed, lane_offset + i), fuse != 0);
+        const int64_t o = (int64_t)i * dir.stride;
+        dir.x[o] = g.dx; dir.y[o] = g.dy; dir.z[o] = g.dz;
+        pdf[i] = g.pdf;
+        if (dbg) { dbg[4u * i] = r.leaf; dbg[4u * i + 1u] = root; dbg[4u * i + 2u] = g.sample_node; dbg[4u * i + 3u] = g.pdf_node; }
     }
 };
 
 struct PdfLane {
-    static constexpr bool kSmemCounts = false;
-    static constexpr bool kCompact = false;
-    SDT_HD uint32_t mode_of(uint32_t) const { return 0u; }
-    template <int MODE> SDT_HD void run_mode(const KdCtx&, uint32_t, uint32_t) const {}
-    static constexpr bool kGrid = true;
+    static constexpr bool kSmemCounts = false, kGrid = true;
+    static constexpr int kModes = 1;
     SDT_HD void flush_count(uint32_t, float) const {}
     TreeView t;
     sdt_vec3 pos; sdt_vec3 dir; const uint8_t* active; float* pdf; uint32_t* dbg;
-    template <int MODE>
-    SDT_HD void run(const KdCtx& k, uint32_t i) const {
-        const bool act = active ? SDT_LDG(active + i) != 0 : true;
-        float p = 1.0f;
-        uint32_t d0 = 0, d1 = 0, d2 = 0;
-        if (act) {
-            const KdResult r = sdt_kd_descend<MODE>(k, sdt_ld(pos.x, pos.stride, i),
-                                              sdt_ld(pos.y, pos.stride, i), sdt_ld(pos.z, pos.stride, i));
-            float x, y;
-            sdt_dir_to_canonical(sdt_ld(dir.x, dir.stride, i), sdt_ld(dir.y, dir.stride, i), sdt_ld(dir.z, dir.stride, i), x, y);
-            uint32_t nd;
-            const uint32_t root = dbg ? SDT_LDG(t.kd_root + r.leaf) : 0u;
-            p = sdt_quad_pdf(t, r.rootrec, root, x, y, nd);
-            d0 = r.leaf; d1 = root; d2 = nd;
-        }
-        pdf[i] = p;
-        if (dbg) { dbg[3u * i] = d0; dbg[3u * i + 1u] = d1; dbg[3u * i + 2u] = d2; }
+    SDT_HD uint32_t mode_of(uint32_t i) const { return active ? (SDT_LDG(active + i) != 0 ? 1u : 0u) : 1u; }
+    SDT_HD void idle(uint32_t i) const {
+        pdf[i] = 1.0f;
+        if (dbg) { dbg[3u * i] = 0u; dbg[3u * i + 1u] = 0u; dbg[3u * i + 2u] = 0u; }
+    }
+    template <int KD>
+    SDT_HD void run_mode(const KdCtx& k, uint32_t i, uint32_t) const {
+        const KdResult r = sdt_kd_descend<KD>(k, sdt_ld(pos.x, pos.stride, i), sdt_ld(pos.y, pos.stride, i), sdt_ld(pos.z, pos.stride, i));
+        float x, y;
+        sdt_dir_to_canonical(sdt_ld(dir.x, dir.stride, i), sdt_ld(dir.y, dir.stride, i), sdt_ld(dir.z, dir.stride, i), x, y);
+        uint32_t nd;
+        const uint32_t root = dbg ? SDT_LDG(t.kd_root + r.leaf) : 0u;
+        pdf[i] = sdt_quad_pdf(t, r.rootrec, root, x, y, nd);
+        if (dbg) { dbg[3u * i] = r.leaf; dbg[3u * i + 1u] = root; dbg[3u * i + 2u] = nd; }
     }
 };
 
@@ -216,22 +232,16 @@ struct PdfLane {
 // mode 2 = tree pdf of the BSDF-sampled direction (:307) + fused mixture (:310-311)
 template <bool EXPLICIT_U>
 struct GuidedLane {
-    static constexpr bool kSmemCounts = false;
-    static constexpr bool kGrid = false;
-    static constexpr bool kCompact = true;
+    static constexpr bool kSmemCounts = false, kGrid = false;
+    static constexpr int kModes = 2;
     SDT_HD void flush_count(uint32_t, float) const {}
     TreeView t;
     sdt_guided_args a; int fuse;
     SDT_HD uint32_t mode_of(uint32_t i) const { const uint32_t m = SDT_LDG(a.mode + i); return m <= 2u ? m : 0u; }
-    template <int MODE>
-    SDT_HD void run(const KdCtx& k, uint32_t i) const {
-        const uint32_t m = mode_of(i);
-        if (m) run_mode<MODE>(k, i, m);
-    }
-    template <int MODE>
+    SDT_HD void idle(uint32_t) const {}
+    template <int KD>
     SDT_HD void run_mode(const KdCtx& k, uint32_t i, uint32_t m) const {
-        const KdResult r = sdt_kd_descend<MODE>(k, sdt_ld(a.pos.x, a.pos.stride, i),
-                                          sdt_ld(a.pos.y, a.pos.stride, i), sdt_ld(a.pos.z, a.pos.stride, i));
+        const KdResult r = sdt_kd_descend<KD>(k, sdt_ld(a.pos.x, a.pos.stride, i), sdt_ld(a.pos.y, a.pos.stride, i), sdt_ld(a.pos.z, a.pos.stride, i));
         if (m == 1u) {
             GuidedSample g;
             if (EXPLICIT_U) g = sdt_sample_tree(t, r.rootrec, 0u, ExplicitRng(a.u, a.u_stride, i), fuse != 0);
@@ -307,7 +317,7 @@ extern "C" int sdt_locate(sdt_handle h, const sdt_vec3* pos, const uint8_t* acti
     SDT_TRY(sg.reserve((size_t)n * (12 + 1 + 8) + 4096));
     LocateLane f{tree_view(h), sg.in3(*pos, n), sg.in_t(active, n), sg.out_t(leaf, n), sg.out_t(root, n)};
     if (sg.status != SDT_OK) return sg.status;
-    SDT_TRY(launch_wavefront(h, st, n, f, h->query_block, h->query_ctas_per_sm));
+    SDT_TRY(launch_wavefront(h, st, n, f, h->query_block, h->query_ctas_per_sm, false));
     return sg.finish(flags);
 }
 
@@ -329,9 +339,9 @@ extern "C" int sdt_sample(sdt_handle h, const sdt_vec3* pos, const uint8_t* acti
         sg.before_launch();
         if (u) {
             SampleLane<true> fe{f.t, f.pos, f.active, f.u, f.u_stride, f.seed, f.lane_offset, f.dir, f.pdf, f.dbg, f.fuse};
-            return launch_wavefront(h, st, cnt, fe, h->query_block, h->query_ctas_per_sm);
+            return launch_wavefront(h, st, cnt, fe, h->query_block, h->query_ctas_per_sm, active != nullptr);
         }
-        return launch_wavefront(h, st, cnt, f, h->query_block, h->query_ctas_per_sm);
+        return launch_wavefront(h, st, cnt, f, h->query_block, h->query_ctas_per_sm, active != nullptr);
     });
 }
 
@@ -347,7 +357,7 @@ extern "C" int sdt_pdf(sdt_handle h, const sdt_vec3* pos, const sdt_vec3* dir, c
                   sg.out_t(sdt_offp(pdf, off), cnt), sg.out_t(sdt_offp(dbg, (size_t)off * 3), (size_t)cnt * 3)};
         if (sg.status != SDT_OK) return sg.status;
         sg.before_launch();
-        return launch_wavefront(h, st, cnt, f, h->query_block, h->query_ctas_per_sm);
+        return launch_wavefront(h, st, cnt, f, h->query_block, h->query_ctas_per_sm, active != nullptr);
     });
 }
 
@@ -387,10 +397,10 @@ extern "C" int sdt_guided(sdt_handle h, const sdt_guided_args* a, uint32_t n, ui
     if (sg.status != SDT_OK) return sg.status;
     if (d.u) {
         GuidedLane<true> f{tree_view(h), d, h->fuse_sample_pdf};
-        SDT_TRY(launch_wavefront(h, st, n, f, h->query_block, h->query_ctas_per_sm));
+        SDT_TRY(launch_wavefront(h, st, n, f, h->query_block, h->query_ctas_per_sm, true));
     } else {
         GuidedLane<false> f{tree_view(h), d, h->fuse_sample_pdf};
-        SDT_TRY(launch_wavefront(h, st, n, f, h->query_block, h->query_ctas_per_sm));
+        SDT_TRY(launch_wavefront(h, st, n, f, h->query_block, h->query_ctas_per_sm, true));
     }
     return sg.finish(flags);
 }

@@ -39,51 +39,47 @@ SDT_HD void sdt_splat_add(float* base, uint32_t idx, float v, bool valid) {
 #endif
 }
 
-// one record through both trees
-template <int MODE>
-SDT_HD void sdt_splat_one(const TreeView& t, const SplatTarget& tg, const KdCtx& k, bool act,
+// one ACTIVE record through both trees
+template <int KD>
+SDT_HD void sdt_splat_one(const TreeView& t, const SplatTarget& tg, const KdCtx& k,
                           float px, float py, float pz, float dx, float dy, float radiance, float wo_pdf,
                           float nr, float ng, float nb, float ndx, float ndy) {
-    KdResult r;
-    r.leaf = 0; r.rootrec = SDT_NONE; r.inbox = false;
-    if (act) r = sdt_kd_descend<MODE>(k, px, py, pz);
-    // src/kdtree.py:199: +1.0f (fp32 counter; exact below 2^24, then it sticks like the reference's)
+    const KdResult r = sdt_kd_descend<KD>(k, px, py, pz);
+    // src/kdtree.py:199: +1.0f (fp32 counter; exact below 2^24, clamped there by the sweep like the reference's sticks)
     if (k.cnt_s) {
 #if defined(__CUDA_ARCH__)
-        if (act && r.inbox) atomicAdd(k.cnt_s + r.leaf, 1.0f);              // shared-memory counter of this CTA
+        if (r.inbox) atomicAdd(k.cnt_s + r.leaf, 1.0f);                    // shared-memory counter of this CTA
 #endif
     } else {
-        sdt_splat_add(tg.kd_count, r.leaf, 1.0f, act && r.inbox);
+        sdt_splat_add(tg.kd_count, r.leaf, 1.0f, r.inbox);
     }
     // src/kdtree.py:224: the root id is gathered UNMASKED -- out-of-box records go to the tree of node 0
     const uint32_t ri = r.rootrec;
     // a single-leaf tree has no record: its only node is the root, whose id is in kd_root
     uint32_t root = 0;
-    if (act && ri == SDT_NONE) root = SDT_LDG(t.kd_root + r.leaf);
+    if (ri == SDT_NONE) root = SDT_LDG(t.kd_root + r.leaf);
     const float irr = (wo_pdf > 0.0f) ? radiance / wo_pdf : 0.0f;                      // src/quadtree.py:451
     uint32_t leaf = SDT_NONE;
-    if (act && irr != 0.0f) leaf = sdt_quad_leaf(t, ri, root, dx, dy);
+    if (irr != 0.0f) leaf = sdt_quad_leaf(t, ri, root, dx, dy);
     sdt_splat_add(tg.q_ecur, leaf, irr, leaf != SDT_NONE);
     if (tg.store_nee) {                                                               // :455-464
         const float lum = sdt_luminance(nr, ng, nb);
         const float irr2 = (wo_pdf > 0.0f) ? lum / wo_pdf : 0.0f;
         uint32_t leaf2 = SDT_NONE;
-        if (act && irr2 != 0.0f) leaf2 = sdt_quad_leaf(t, ri, root, ndx, ndy);
+        if (irr2 != 0.0f) leaf2 = sdt_quad_leaf(t, ri, root, ndx, ndy);
         sdt_splat_add(tg.q_ecur, leaf2, irr2, leaf2 != SDT_NONE);
     }
 }
 
 struct SplatRecordsLane {
-    static constexpr bool kSmemCounts = true;
-    static constexpr bool kGrid = true;
-    static constexpr bool kCompact = false;
-    SDT_HD uint32_t mode_of(uint32_t) const { return 0u; }
-    template <int MODE> SDT_HD void run_mode(const KdCtx&, uint32_t, uint32_t) const {}
+    static constexpr bool kSmemCounts = true, kGrid = true;
+    static constexpr int kModes = 1;
     SDT_HD void flush_count(uint32_t node, float c) const { sdt_atomic_add_f32(tg.kd_count + node, c); }
     TreeView t; SplatTarget tg; sdt_records r;
-    template <int MODE>
-    SDT_HD void run(const KdCtx& k, uint32_t i) const {
-        const bool act = r.active ? SDT_LDG(r.active + i) != 0 : true;
+    SDT_HD uint32_t mode_of(uint32_t i) const { return r.active ? (SDT_LDG(r.active + i) != 0 ? 1u : 0u) : 1u; }
+    SDT_HD void idle(uint32_t) const {}
+    template <int KD>
+    SDT_HD void run_mode(const KdCtx& k, uint32_t i, uint32_t) const {
         float nr = 0.0f, ng = 0.0f, nb = 0.0f, ndx = 0.0f, ndy = 0.0f;
         if (tg.store_nee && r.radiance_nee.x && r.direction_nee.x) {
             nr = sdt_ld(r.radiance_nee.x, r.radiance_nee.stride, i);
@@ -92,27 +88,26 @@ struct SplatRecordsLane {
             ndx = sdt_ld(r.direction_nee.x, r.direction_nee.stride, i);
             ndy = sdt_ld(r.direction_nee.y, r.direction_nee.stride, i);
         }
-        sdt_splat_one<MODE>(t, tg, k, act,
-                      sdt_ld(r.position.x, r.position.stride, i), sdt_ld(r.position.y, r.position.stride, i), sdt_ld(r.position.z, r.position.stride, i),
-                      sdt_ld(r.direction.x, r.direction.stride, i), sdt_ld(r.direction.y, r.direction.stride, i),
-                      SDT_LDG(r.radiance + i), SDT_LDG(r.wo_pdf + i), nr, ng, nb, ndx, ndy);
+        sdt_splat_one<KD>(t, tg, k,
+                          sdt_ld(r.position.x, r.position.stride, i), sdt_ld(r.position.y, r.position.stride, i), sdt_ld(r.position.z, r.position.stride, i),
+                          sdt_ld(r.direction.x, r.direction.stride, i), sdt_ld(r.direction.y, r.direction.stride, i),
+                          SDT_LDG(r.radiance + i), SDT_LDG(r.wo_pdf + i), nr, ng, nb, ndx, ndy);
     }
 };
 
 SDT_HD float sdt_nan0(float v) { return (v != v) ? 0.0f : v; }
 
-// processPathData + scatterDataIntoSDTree (src/path_guiding_integrator.py:434-500) fused
-// in front of the splat: no compaction pass, the filter just masks the lane.
+// processPathData + scatterDataIntoSDTree (src/path_guiding_integrator.py:434-500) fused in front
+// of the splat.  The reference compacts the surviving records (dr.compress + 9 gathers + a host
+// sync); here the slots of a tile are classified (mode_of: radiance back-propagation + filter) and
+// the survivors are splatted by dense warps -- a pass has numRays*max_depth slots, most of them idle.
 struct SplatPathLane {
-    static constexpr bool kSmemCounts = true;
-    static constexpr bool kGrid = true;
-    static constexpr bool kCompact = false;
-    SDT_HD uint32_t mode_of(uint32_t) const { return 0u; }
-    template <int MODE> SDT_HD void run_mode(const KdCtx&, uint32_t, uint32_t) const {}
+    static constexpr bool kSmemCounts = true, kGrid = true;
+    static constexpr int kModes = 1;
     SDT_HD void flush_count(uint32_t node, float c) const { sdt_atomic_add_f32(tg.kd_count + node, c); }
     TreeView t; SplatTarget tg; sdt_path_data p;
-    template <int MODE>
-    SDT_HD void run(const KdCtx& k, uint32_t i) const {
+    struct Vals { float radiance, wo_pdf, nr, ng, nb; };
+    SDT_HD bool prepare(uint32_t i, Vals& v) const {
         const uint32_t ray = i / p.max_depth;                                          // :440
         float inc[3];
         const float* lf[3] = {p.l_final.x, p.l_final.y, p.l_final.z};
@@ -125,26 +120,38 @@ struct SplatPathLane {
             out = sdt_nan0(out);                                                       // :444
             inc[c] = sdt_nan0(out / sdt_ld(bs[c], p.bsdf.stride, i));                  // :448-449
         }
-        const float radiance = sdt_nan0(sdt_luminance(inc[0], inc[1], inc[2]));       // :452, :466
-        if (p.radiance_out) p.radiance_out[i] = radiance;
-        float nr = 0.0f, ng = 0.0f, nb = 0.0f, ndx = 0.0f, ndy = 0.0f;
+        v.radiance = sdt_nan0(sdt_luminance(inc[0], inc[1], inc[2]));                 // :452, :466
+        v.nr = v.ng = v.nb = 0.0f;
         if (p.radiance_nee.x) {
-            nr = sdt_nan0(sdt_ld(p.radiance_nee.x, p.radiance_nee.stride, i));         // :467
-            ng = sdt_nan0(sdt_ld(p.radiance_nee.y, p.radiance_nee.stride, i));
-            nb = sdt_nan0(sdt_ld(p.radiance_nee.z, p.radiance_nee.stride, i));
+            v.nr = sdt_nan0(sdt_ld(p.radiance_nee.x, p.radiance_nee.stride, i));       // :467
+            v.ng = sdt_nan0(sdt_ld(p.radiance_nee.y, p.radiance_nee.stride, i));
+            v.nb = sdt_nan0(sdt_ld(p.radiance_nee.z, p.radiance_nee.stride, i));
         }
+        v.wo_pdf = SDT_LDG(p.wo_pdf + i);
+        const bool both_zero = (v.radiance == 0.0f) && (sdt_luminance(v.nr, v.ng, v.nb) == 0.0f);  // :470-472
+        const bool act = p.active ? SDT_LDG(p.active + i) != 0 : true;
+        return act && !both_zero && !(v.wo_pdf == 0.0f) && !(v.wo_pdf != v.wo_pdf);    // :475-478
+    }
+    SDT_HD uint32_t mode_of(uint32_t i) const {
+        Vals v;
+        const bool keep = prepare(i, v);
+        if (p.radiance_out) p.radiance_out[i] = v.radiance;       // SurfaceInteractionRecord.radiance, every slot
+        return keep ? 1u : 0u;
+    }
+    SDT_HD void idle(uint32_t) const {}
+    template <int KD>
+    SDT_HD void run_mode(const KdCtx& k, uint32_t i, uint32_t) const {
+        Vals v;
+        prepare(i, v);
+        float ndx = 0.0f, ndy = 0.0f;
         if (p.direction_nee.x) {
             ndx = sdt_ld(p.direction_nee.x, p.direction_nee.stride, i);
             ndy = sdt_ld(p.direction_nee.y, p.direction_nee.stride, i);
         }
-        const float wo_pdf = SDT_LDG(p.wo_pdf + i);
-        const bool both_zero = (radiance == 0.0f) && (sdt_luminance(nr, ng, nb) == 0.0f);  // :470-472
-        bool act = p.active ? SDT_LDG(p.active + i) != 0 : true;
-        act = act && !both_zero && !(wo_pdf == 0.0f) && !(wo_pdf != wo_pdf);           // :475-478
-        sdt_splat_one<MODE>(t, tg, k, act,
-                      sdt_ld(p.position.x, p.position.stride, i), sdt_ld(p.position.y, p.position.stride, i), sdt_ld(p.position.z, p.position.stride, i),
-                      sdt_ld(p.direction.x, p.direction.stride, i), sdt_ld(p.direction.y, p.direction.stride, i),
-                      radiance, wo_pdf, nr, ng, nb, ndx, ndy);
+        sdt_splat_one<KD>(t, tg, k,
+                          sdt_ld(p.position.x, p.position.stride, i), sdt_ld(p.position.y, p.position.stride, i), sdt_ld(p.position.z, p.position.stride, i),
+                          sdt_ld(p.direction.x, p.direction.stride, i), sdt_ld(p.direction.y, p.direction.stride, i),
+                          v.radiance, v.wo_pdf, v.nr, v.ng, v.nb, ndx, ndy);
     }
 };
 
@@ -206,7 +213,7 @@ extern "C" int sdt_splat_records(sdt_handle h, const sdt_records* rec, uint32_t 
         if (sg.status != SDT_OK) return sg.status;
         SplatRecordsLane f{tree_view(h), SplatTarget{h->kd_count, h->q_ecur, (uint32_t)nee}, d};
         sg.before_launch();
-        return launch_wavefront(h, st, cnt, f, h->splat_block, h->splat_ctas_per_sm);
+        return launch_wavefront(h, st, cnt, f, h->splat_block, h->splat_ctas_per_sm, rec->active != nullptr);
     });
 }
 
@@ -235,6 +242,6 @@ extern "C" int sdt_splat_path_data(sdt_handle h, const sdt_path_data* pd, uint32
     if (sg.status != SDT_OK) return sg.status;
     SplatPathLane f{tree_view(h), SplatTarget{h->kd_count, h->q_ecur, (uint32_t)(h->cfg.store_nee != 0)}, d};
     h->stats_complete = false;
-    SDT_TRY(launch_wavefront(h, st, n, f, h->splat_block, h->splat_ctas_per_sm));
+    SDT_TRY(launch_wavefront(h, st, n, f, h->splat_block, h->splat_ctas_per_sm, true));
     return sg.finish(flags);
 }
