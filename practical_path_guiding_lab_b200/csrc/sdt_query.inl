@@ -9,6 +9,7 @@
 //   idle(i)            outputs of an idle lane
 //   run_mode<KD>(k,i,m) the work of a non-idle lane; KD = spatial-descent variant (sdt_kd_descend)
 //   kGrid, kSmemCounts, flush_count   see k_wavefront
+#define SDT_TILE_MUL 4u       // lanes per thread and tile in the compacting kernel
 template <class Lane, int KD>
 SDT_HD void sdt_lane(const Lane& f, const KdCtx& k, uint32_t i) {
     const uint32_t m = f.mode_of(i);
@@ -56,15 +57,19 @@ __global__ void __launch_bounds__(512, 3) k_wavefront(Lane f, uint32_t n, uint32
     if (COMPACT) {
         uint16_t* list = reinterpret_cast<uint16_t*>(smem_next);
         __shared__ uint32_t s_cnt[2];
-        const uint32_t tile_n = 4u * blockDim.x;
+        constexpr uint32_t TM = SDT_TILE_MUL;
+        const uint32_t tile_n = TM * blockDim.x;
         const uint32_t lane = threadIdx.x & 31u;
         for (uint32_t tile = blockIdx.x * tile_n; tile < n; tile += gridDim.x * tile_n) {
             if (threadIdx.x < 2u) s_cnt[threadIdx.x] = 0u;
             __syncthreads();
-            for (uint32_t q = 0; q < 4u; ++q) {
+            uint32_t mq = 0;                 // modes of this thread's lanes, 2 bits each
+#pragma unroll
+            for (uint32_t q = 0; q < TM; ++q) {
                 const uint32_t li = q * blockDim.x + threadIdx.x, i = tile + li;
                 uint32_t m = 0;
                 if (i < n) { m = f.mode_of(i); if (!m) f.idle(i); }
+                mq |= m << (2u * q);
 #pragma unroll
                 for (uint32_t L = 0; L < (uint32_t)Lane::kModes; ++L) {
                     const uint32_t b = __ballot_sync(0xFFFFFFFFu, m == L + 1u);
@@ -75,14 +80,26 @@ __global__ void __launch_bounds__(512, 3) k_wavefront(Lane f, uint32_t n, uint32
                 }
             }
             __syncthreads();
+            if (Lane::kModes == 1 && s_cnt[0] * 2u > tile_n) {
+                // a dense tile gains nothing from the indirection: every thread runs its own lanes in place (coalesced)
 #pragma unroll
-            for (uint32_t L = 0; L < (uint32_t)Lane::kModes; ++L) {
-                const uint32_t cnt = s_cnt[L];
-                for (uint32_t j = threadIdx.x; j < cnt; j += blockDim.x) {
-                    const uint32_t i = tile + list[L * tile_n + j];
-                    if (kd_mode == 2) f.template run_mode<2>(k, i, L + 1u);
-                    else if (kd_mode == 1) f.template run_mode<1>(k, i, L + 1u);
-                    else f.template run_mode<0>(k, i, L + 1u);
+                for (uint32_t q = 0; q < TM; ++q) {
+                    if (!((mq >> (2u * q)) & 3u)) continue;
+                    const uint32_t i = tile + q * blockDim.x + threadIdx.x;
+                    if (kd_mode == 2) f.template run_mode<2>(k, i, 1u);
+                    else if (kd_mode == 1) f.template run_mode<1>(k, i, 1u);
+                    else f.template run_mode<0>(k, i, 1u);
+                }
+            } else {
+#pragma unroll
+                for (uint32_t L = 0; L < (uint32_t)Lane::kModes; ++L) {
+                    const uint32_t cnt = s_cnt[L];
+                    for (uint32_t j = threadIdx.x; j < cnt; j += blockDim.x) {
+                        const uint32_t i = tile + list[L * tile_n + j];
+                        if (kd_mode == 2) f.template run_mode<2>(k, i, L + 1u);
+                        else if (kd_mode == 1) f.template run_mode<1>(k, i, L + 1u);
+                        else f.template run_mode<0>(k, i, L + 1u);
+                    }
                 }
             }
             __syncthreads();
@@ -114,7 +131,7 @@ static int launch_wavefront_c(sdt_handle h, cudaStream_t st, uint32_t n, const L
     uint32_t smem_nodes = (want + 255u) & ~255u;
     if (smem_nodes > (uint32_t)h->kd_smem_nodes) smem_nodes = (uint32_t)h->kd_smem_nodes;
     const size_t smem = (size_t)smem_nodes * 4u * (Lane::kSmemCounts ? 2u : 1u) + ((Lane::kGrid && h->use_kd_grid) ? SDT_GRID_CELLS * 4u : 0u) +
-                        (COMPACT ? (size_t)block * 4u * 2u * (size_t)Lane::kModes : 0u);
+                        (COMPACT ? (size_t)block * SDT_TILE_MUL * 2u * (size_t)Lane::kModes : 0u);
     static size_t attr_set = 0;
     if (smem > 48u * 1024u && smem > attr_set) {
         if (cudaFuncSetAttribute(k_wavefront<Lane, COMPACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess)
@@ -129,7 +146,7 @@ static int launch_wavefront_c(sdt_handle h, cudaStream_t st, uint32_t n, const L
     }
     int per_sm = ctas_per_sm < occ_cache ? ctas_per_sm : occ_cache;
     if (per_sm < 1) per_sm = 1;
-    const uint32_t per_cta = (uint32_t)block * (COMPACT ? 4u : 1u);
+    const uint32_t per_cta = (uint32_t)block * (COMPACT ? SDT_TILE_MUL : 1u);
     uint32_t grid = (n + per_cta - 1u) / per_cta;
     const uint32_t cap = (uint32_t)(h->num_sms * per_sm);
     if (grid > cap) grid = cap;
