@@ -9,6 +9,9 @@
 //   idle(i)            outputs of an idle lane
 //   run_mode<KD>(k,i,m) the work of a non-idle lane; KD = spatial-descent variant (sdt_kd_descend)
 //   kGrid, kSmemCounts, flush_count   see k_wavefront
+#ifndef SDT_MIN_CTAS
+#define SDT_MIN_CTAS 3
+#endif
 #define SDT_TILE_MUL 4u       // lanes per thread and tile in the compacting kernel
 template <class Lane, int KD>
 SDT_HD void sdt_lane(const Lane& f, const KdCtx& k, uint32_t i) {
@@ -23,7 +26,7 @@ SDT_HD void sdt_lane(const Lane& f, const KdCtx& k, uint32_t i) {
 // a warp never runs two code paths, and idle lanes (dead paths, masked-out vertices, filtered records)
 // cost a classification, not a share of a descent.
 template <class Lane, bool COMPACT>
-__global__ void __launch_bounds__(512, 3) k_wavefront(Lane f, uint32_t n, uint32_t smem_cap, uint32_t use_grid) {
+__global__ void __launch_bounds__(512, SDT_MIN_CTAS) k_wavefront(Lane f, uint32_t n, uint32_t smem_cap, uint32_t use_grid) {
     extern __shared__ uint32_t kd_s[];
     const DevHeader* hdr = f.t.hdr;
     const uint32_t n_kd = hdr->n_kd;
