@@ -336,7 +336,7 @@ if _HAVE_MITSUBA:                                      # pragma: no cover
                     if not rec_ready:
                         core.resetRayPathData(p_t)
                         rec_ready = True
-                    core.store_vertex(_t(ray_index).long(), _t(depth).long(), _t(store).bool(), p_t, _t(wo_world), _t(bsdf_weight),
+                    core.store_vertex(_t(mi.Int32(ray_index)).long(), _t(mi.Int32(depth)).long(), _t(store).bool(), p_t, _t(wo_world), _t(bsdf_weight),
                                       _t(throughput), _t(L), _t(Lr_dir / throughput), _t(ds.d), _t(woPdf))
                 ray = si.spawn_ray(wo_world)
                 ior *= bsdf_sample.eta
