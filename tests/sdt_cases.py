@@ -500,6 +500,32 @@ def case_edge_inputs_and_errors(ctx):
     assert_tree_equal(t2.download(0), prev)
 
 
+def case_golden_fixture(ctx):
+    """the committed golden file (tests/golden/sdtree_golden.npz, written by make_sdtree_golden.py with
+    the oracle): upload its tree, replay its queries and records, compare with its stored answers"""
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "sdtree_golden.npz"))
+    tree = {k[5:]: g[k] for k in g.files if k.startswith("tree_")}
+    t = ctx.make(kd_capacity=1 << 12, quad_capacity=1 << 17)
+    t.upload(tree)
+    a = g['active']
+    act = ctx.dev(a.astype(np.uint8))
+    leaf, root = t.locate(ctx.dev(g['pos']), act)
+    assert np.array_equal(ctx.host(leaf).view(U), g['leaf']) and np.array_equal(ctx.host(root).view(U)[a], g['root'][a])
+    d, p, dbg = t.sample(ctx.dev(g['pos']), act, u=ctx.dev(g['u']), debug=True)
+    dbg = ctx.host(dbg).view(U)
+    assert np.array_equal(dbg[a, 2], g['sample_node'][a]) and np.array_equal(dbg[a, 3], g['pdf_node'][a])
+    assert beq(ctx.host(d), g['sample_dir']) and beq(ctx.host(p), g['sample_pdf'])
+    np.testing.assert_allclose(ctx.host(p), g['sample_pdf'], rtol=1e-5)              # the north_star tolerance
+    d, p = t.sample(ctx.dev(g['pos']), act, seed=77, lane_offset=3)
+    assert beq(ctx.host(d), g['counter_dir']) and beq(ctx.host(p), g['counter_pdf'])
+    pp, pdbg = t.pdf(ctx.dev(g['pos']), ctx.dev(g['dirs']), act, debug=True)
+    assert beq(ctx.host(pp), g['pdf']) and np.array_equal(ctx.host(pdbg).view(U)[a, 2], g['pdf_query_node'][a])
+    t.splat_records(ctx.dev(g['rec_position']), ctx.dev(g['rec_direction']), ctx.dev(g['rec_radiance']), ctx.dev(g['rec_wo_pdf']))
+    cur = t.download(1)
+    assert np.array_equal(cur['kdtree_vertCount'], g['splat_vert_count']) and beq(cur['quadtree_irradiance'], g['splat_irradiance'])
+
+
 def case_npz_roundtrip(ctx, tmp_path):
     t, cur, prev = train(ctx, iters=2)
     f = str(tmp_path / "tree.npz")
@@ -514,7 +540,7 @@ def case_npz_roundtrip(ctx, tmp_path):
     check_queries(ctx, t2, o, n=1024)
 
 
-ALL_CASES = [case_jump_table_equals_descent, case_spatial_descent_variants, case_initial_tree, case_golden_upload_download, case_train_refine_topology, case_host_pipeline_chunks,
+ALL_CASES = [case_golden_fixture, case_jump_table_equals_descent, case_spatial_descent_variants, case_initial_tree, case_golden_upload_download, case_train_refine_topology, case_host_pipeline_chunks,
              case_train_refine_nee_shallow, case_fused_equals_two_descents, case_splat_float_tolerance,
              case_path_data, case_mis, case_guided_bounce, case_refine_flags_and_frozen_stats,
              case_capacity_error, case_edge_inputs_and_errors]

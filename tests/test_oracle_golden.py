@@ -252,3 +252,19 @@ def test_npz_roundtrip(tmp_path):
         if k == 'kdtree_maxLeafSize':
             continue
         assert np.array_equal(np.asarray(v), np.asarray(t2.to_arrays()[k])), k
+
+
+def test_oracle_reproduces_committed_golden_file():
+    """tests/golden/sdtree_golden.npz (made by tests/golden/make_sdtree_golden.py): the oracle, reloaded
+    from the stored tree arrays, gives the stored answers -- any later change of the oracle is caught"""
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "sdtree_golden.npz"))
+    t = so.KDTree()
+    t.loadFromArrays({k[5:]: g[k] for k in g.files if k.startswith("tree_")})
+    a = g['active']
+    assert np.array_equal(t.getLeafNodeIndex(g['pos'], a), g['leaf'])
+    d, p, dbg = t.sample(g['pos'], so.ExplicitSampler(u=g['u']), a, return_debug=True)
+    assert np.array_equal(dbg['sample_node'][a], g['sample_node'][a])
+    assert np.array_equal(d.view(U), g['sample_dir'].view(U)) and np.array_equal(p.view(U), g['sample_pdf'].view(U))
+    pp = t.pdf(g['pos'], g['dirs'], a)
+    assert np.array_equal(np.isnan(pp), np.isnan(g['pdf'])) and np.array_equal(pp[~np.isnan(pp)], g['pdf'][~np.isnan(pp)])
