@@ -93,6 +93,7 @@ struct TreeView {
     const DevHeader* hdr;
     const uint32_t* kd_word;
     const uint32_t* kd_root;    // per spatial node: quadTreeRootIndex (= canonical node id of the tree's root)
+    const uint32_t* kd_grid;    // SDT_GRID_CELLS cells -> spatial node after the first 11 levels
     const QRec* rec;
     const QJump* jump;          // [root record][cell]
     const float* pp;            // per node: pdf product of the root->node path (NaN: it went NaN)
@@ -281,11 +282,12 @@ SDT_HD uint32_t sdt_kd_grid_node(const uint32_t* __restrict__ kd, uint32_t cell)
     return node;
 }
 
-// MODE 0: partly staged tree (global loads beyond the prefix); 1: whole tree staged, walk from the
-// root; 2: whole tree staged + grid over the first 11 levels
+// MODE 0: partly staged tree (global loads beyond the prefix), walk from the root; 1: whole tree
+// staged, walk from the root; 2: whole tree staged + grid over the first 11 levels; 3: grid + partly
+// staged tree (large trees: 11 levels by arithmetic, the few levels below through L1/L2)
 template <int MODE>
 SDT_HD KdResult sdt_kd_descend(const KdCtx& k, float px, float py, float pz) {
-    constexpr bool ALL_SMEM = MODE != 0;
+    constexpr bool ALL_SMEM = MODE == 1 || MODE == 2;
     const uint32_t* __restrict__ kd = k.kd;
     const uint32_t* __restrict__ kdg = k.kdg;
     const uint32_t n_smem = k.n_smem;
@@ -299,14 +301,14 @@ SDT_HD KdResult sdt_kd_descend(const KdCtx& k, float px, float py, float pz) {
     if (!r.inbox) return r;
     uint32_t node = 0;
     uint32_t w;
-    if (MODE == 2) {
+    if (MODE >= 2) {
         uint32_t cx = 0, cy = 0, cz = 0;
         SDT_AXIS_STEP(px, lo0, hi0, cx) SDT_AXIS_STEP(py, lo1, hi1, cy) SDT_AXIS_STEP(pz, lo2, hi2, cz)
         SDT_AXIS_STEP(px, lo0, hi0, cx) SDT_AXIS_STEP(py, lo1, hi1, cy) SDT_AXIS_STEP(pz, lo2, hi2, cz)
         SDT_AXIS_STEP(px, lo0, hi0, cx) SDT_AXIS_STEP(py, lo1, hi1, cy) SDT_AXIS_STEP(pz, lo2, hi2, cz)
         SDT_AXIS_STEP(px, lo0, hi0, cx) SDT_AXIS_STEP(py, lo1, hi1, cy)
         node = k.grid[(cx << 7) | (cy << 3) | cz];
-        w = kd[node];
+        w = sdt_kd_load<ALL_SMEM>(kd, n_smem, kdg, node);
         if (!(w & SDT_KD_LEAF_BIT)) {
             for (int guard = SDT_GRID_LEVELS; guard < SDT_KD_MAX_DEPTH; guard += 3) {   // level 11 splits z, then x, y, ...
                 SDT_KD_STEP(pz, lo2, hi2)

@@ -37,6 +37,7 @@ struct sdt_tree_s {
     uint32_t* kd_sel = nullptr;     // round: selected old leaves in ascending id
     uint32_t* kd_rank[2] = {nullptr, nullptr};  // round: rank of an old leaf among the selected
     uint32_t* root_src = nullptr;   // new root id -> root id whose tree it copies
+    uint32_t* kd_grid = nullptr;    // 16x16x8 cells -> node reached after the first 11 levels (rebuilt with the records)
 
     QuadSet set[2];
     int cur = 0;                    // set[cur] = topology + prev energies in use
@@ -112,7 +113,7 @@ static inline TreeView tree_view(sdt_tree_s* h) {
         h->jump_trees_known = h->h_hdr->jump_trees;
     }
     const QuadSet& s = h->set[h->cur];
-    return TreeView{s.hdr, h->kd_word, h->kd_root, s.rec, s.jump, s.pp, h->use_jump ? h->jump_trees_known : 0u};
+    return TreeView{s.hdr, h->kd_word, h->kd_root, h->kd_grid, s.rec, s.jump, s.pp, h->use_jump ? h->jump_trees_known : 0u};
 }
 
 static int sdt_read_header(sdt_handle h, DevHeader& H);

@@ -9,7 +9,7 @@ static int dev_alloc(sdt_handle h, T** p, size_t n) {
 
 static int sdt_free_all(sdt_handle h) {
     void* ptrs[] = {h->kd_word, h->kd_count, h->kd_depth, h->kd_root, h->kd_bmin, h->kd_bmax, h->kd_prev_count, h->kd_s,
-                    h->kd_sel, h->kd_rank[0], h->kd_rank[1], h->root_src, h->q_ecur, h->s_src, h->s_kind, h->s_srem, h->s_blk, h->stage};
+                    h->kd_sel, h->kd_rank[0], h->kd_rank[1], h->root_src, h->kd_grid, h->q_ecur, h->s_src, h->s_kind, h->s_srem, h->s_blk, h->stage};
     for (void* p : ptrs) if (p) cudaFree(p);
     for (int k = 0; k < 2; ++k) {
         QuadSet& s = h->set[k];
@@ -69,7 +69,7 @@ extern "C" int sdt_create(const sdt_config* cfg, sdt_handle* out) {
 #define A(p, n) if (st == SDT_OK) st = dev_alloc(h, &(p), (size_t)(n))
     A(h->kd_word, h->kd_cap); A(h->kd_count, h->kd_cap); A(h->kd_depth, h->kd_cap); A(h->kd_root, h->kd_cap);
     A(h->kd_bmin, 3ull * h->kd_cap); A(h->kd_bmax, 3ull * h->kd_cap); A(h->kd_prev_count, h->kd_cap); A(h->kd_s, h->kd_cap);
-    A(h->kd_sel, h->kd_cap); A(h->kd_rank[0], h->kd_cap); A(h->kd_rank[1], h->kd_cap); A(h->root_src, h->kd_cap);
+    A(h->kd_sel, h->kd_cap); A(h->kd_rank[0], h->kd_cap); A(h->kd_rank[1], h->kd_cap); A(h->root_src, h->kd_cap); A(h->kd_grid, SDT_GRID_CELLS);
     A(h->q_ecur, h->quad_cap); A(h->s_src, h->quad_cap); A(h->s_kind, h->quad_cap); A(h->s_srem, h->quad_cap);
     A(h->s_blk, SDT_SCAN_MAX_BLOCKS + 64);
     for (int k = 0; k < 2; ++k) {

@@ -46,17 +46,23 @@ __global__ void __launch_bounds__(512, SDT_MIN_CTAS) k_wavefront(Lane f, uint32_
         smem_next += smem_cap;
     }
     __syncthreads();
-    // (measured: the grid pays for the pdf / splat / locate kernels, -7 % / -4 %, not for the sampling
-    // kernels, +3 %, whose long quadtree loop wants the registers)
-    if (Lane::kGrid && use_grid) {               // 16x16x8 grid over the first 11 levels (see sdt_kd_descend)
-        if (n_smem == n_kd) {
-            for (uint32_t c = threadIdx.x; c < SDT_GRID_CELLS; c += blockDim.x) smem_next[c] = sdt_kd_grid_node(kd_s, c);
-            k.grid = smem_next;
-        }
-        smem_next += SDT_GRID_CELLS;
-        __syncthreads();
+    // 16x16x8 grid over the first 11 spatial levels (built with the records, see sdt_kd_descend).  With
+    // the whole tree staged it pays for the pdf / splat / locate kernels (measured -7 % / -4 %) but not
+    // for the sampling kernels (+3 %: their long quadtree loop wants the registers); when the tree does
+    // not fit in shared memory every kernel uses it, and only the levels below 11 go through L1/L2.
+    const bool staged = n_smem == n_kd;
+    if (use_grid && (Lane::kGrid || !staged)) {
+        for (uint32_t c = threadIdx.x; c < SDT_GRID_CELLS; c += blockDim.x) smem_next[c] = __ldg(f.t.kd_grid + c);
+        k.grid = smem_next;
     }
-    const int kd_mode = k.grid ? 2 : (n_smem == n_kd ? 1 : 0);
+    smem_next += SDT_GRID_CELLS;
+    __syncthreads();
+    const int kd_mode = k.grid ? (staged ? 2 : 3) : (staged ? 1 : 0);
+#define SDT_KD_DISPATCH(...)                                              \
+    if (kd_mode == 2) { constexpr int KD = 2; __VA_ARGS__; }                \
+    else if (kd_mode == 1) { constexpr int KD = 1; __VA_ARGS__; }           \
+    else if (kd_mode == 3) { constexpr int KD = 3; __VA_ARGS__; }           \
+    else { constexpr int KD = 0; __VA_ARGS__; }
     if (COMPACT) {
         uint16_t* list = reinterpret_cast<uint16_t*>(smem_next);
         __shared__ uint32_t s_cnt[2];
@@ -89,9 +95,7 @@ __global__ void __launch_bounds__(512, SDT_MIN_CTAS) k_wavefront(Lane f, uint32_
                 for (uint32_t q = 0; q < TM; ++q) {
                     if (!((mq >> (2u * q)) & 3u)) continue;
                     const uint32_t i = tile + q * blockDim.x + threadIdx.x;
-                    if (kd_mode == 2) f.template run_mode<2>(k, i, 1u);
-                    else if (kd_mode == 1) f.template run_mode<1>(k, i, 1u);
-                    else f.template run_mode<0>(k, i, 1u);
+                    SDT_KD_DISPATCH(f.template run_mode<KD>(k, i, 1u))
                 }
             } else {
 #pragma unroll
@@ -99,21 +103,16 @@ __global__ void __launch_bounds__(512, SDT_MIN_CTAS) k_wavefront(Lane f, uint32_
                     const uint32_t cnt = s_cnt[L];
                     for (uint32_t j = threadIdx.x; j < cnt; j += blockDim.x) {
                         const uint32_t i = tile + list[L * tile_n + j];
-                        if (kd_mode == 2) f.template run_mode<2>(k, i, L + 1u);
-                        else if (kd_mode == 1) f.template run_mode<1>(k, i, L + 1u);
-                        else f.template run_mode<0>(k, i, L + 1u);
+                        SDT_KD_DISPATCH(f.template run_mode<KD>(k, i, L + 1u))
                     }
                 }
             }
             __syncthreads();
         }
-    } else if (kd_mode == 2) {      // whole spatial tree staged + grid over its first 11 levels
-        for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) sdt_lane<Lane, 2>(f, k, i);
-    } else if (kd_mode == 1) {      // whole spatial tree staged: descent loop without the global path
-        for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) sdt_lane<Lane, 1>(f, k, i);
     } else {
-        for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) sdt_lane<Lane, 0>(f, k, i);
+        SDT_KD_DISPATCH(for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) sdt_lane<Lane, KD>(f, k, i))
     }
+#undef SDT_KD_DISPATCH
     if (cnt_s) {
         __syncthreads();
         for (uint32_t j = threadIdx.x; j < n_smem; j += blockDim.x) {
@@ -133,7 +132,7 @@ static int launch_wavefront_c(sdt_handle h, cudaStream_t st, uint32_t n, const L
     uint32_t want = h->hdr_pending ? 2u * h->kd_nodes_known + 2u : h->kd_nodes_known;   // a refine is in flight: be generous
     uint32_t smem_nodes = (want + 255u) & ~255u;
     if (smem_nodes > (uint32_t)h->kd_smem_nodes) smem_nodes = (uint32_t)h->kd_smem_nodes;
-    const size_t smem = (size_t)smem_nodes * 4u * (Lane::kSmemCounts ? 2u : 1u) + ((Lane::kGrid && h->use_kd_grid) ? SDT_GRID_CELLS * 4u : 0u) +
+    const size_t smem = (size_t)smem_nodes * 4u * (Lane::kSmemCounts ? 2u : 1u) + SDT_GRID_CELLS * 4u +
                         (COMPACT ? (size_t)block * SDT_TILE_MUL * 2u * (size_t)Lane::kModes : 0u);
     static size_t attr_set = 0;
     if (smem > 48u * 1024u && smem > attr_set) {

@@ -309,10 +309,13 @@ struct JumpBuildItem {
     }
 };
 
+struct KdGridItem { const uint32_t* kd_word; uint32_t* grid; SDT_HD void operator()(uint32_t c) const { grid[c] = sdt_kd_grid_node(kd_word, c); } };
+
 static void sdt_build_records(sdt_handle h, const ExecCtx& x, QuadSet& s) {
     launch_scan(x, &s.hdr->n_quad, 0, RecFlag{s.child}, RecEmit{s.iidx}, RecFin{s.hdr});
     launch_items(x, &s.hdr->n_quad, 0, RecBuildItem{s.hdr, s.child, s.energy, s.iidx, s.rec, s.root_iidx});
     launch_items(x, &s.hdr->n_kd, 0, KdLeafWordItem{s.hdr, h->kd_word, h->kd_root, s.root_iidx});
+    launch_items(x, nullptr, SDT_GRID_CELLS, KdGridItem{h->kd_word, h->kd_grid});
     for (uint32_t l = 0; l < h->levels_hint && l < SDT_MAX_LEVELS; ++l)
         launch_items(x, &s.hdr->level_cnt[l], 0, PpLevelItem{s.hdr, s.child, s.energy, s.pp, l});
     launch_single(x, JumpCountItem{s.hdr, s.iidx, h->jump_cap});

@@ -264,9 +264,16 @@ def case_spatial_descent_variants(ctx):
     t, cur, prev = train(ctx, iters=3, max_leaf=12, quad_max_depth=7, caps=dict(kd_capacity=1 << 14, quad_capacity=1 << 20))   # deep spatial tree: leaves beyond level 11
     assert t.sizes()["error"] == 0
     assert int(prev.kdTreeNode.depth.max()) > 11
-    for key, val in (("use_kd_grid", 1), ("use_kd_grid", 0), ("kd_smem_nodes", 16)):
-        t.set_tuning(key, val)
+    for grid, smem in ((1, 24576), (0, 24576), (1, 16), (0, 16)):     # kernel modes 2, 1, 3, 0 of sdt_kd_descend
+        t.set_tuning("use_kd_grid", grid)
+        t.set_tuning("kd_smem_nodes", smem)
         check_queries(ctx, t, prev, n=6000, seed=23)
+        rec = dyadic_records(4000, 31, ((0.3, 0.7, 0.02),))
+        t.reset_stats()
+        splat(t, ctx, rec)
+        cur.resetTreeVertCount(); cur.resetAllQuadTreeIrradiance()
+        cur.addDataPropagate(rec)
+        assert_tree_equal(t.download(1), cur)
     t.set_tuning("kd_smem_nodes", 24576)
     t.set_tuning("use_kd_grid", 1)
     # points exactly on split planes of the first levels (the right child wins, src/kdtree.py:462-468)
