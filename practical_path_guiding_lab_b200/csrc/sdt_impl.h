@@ -261,6 +261,10 @@ static int sdt_run_chunked(sdt_handle h, cudaStream_t st, uint32_t flags, uint32
         Stager probe(h, st, flags);
         SDT_TRY(probe.reserve(2 * ((size_t)chunk * bytes_per_lane + 65536)));
     }
+    // earlier work on `st` may still read the arena (a small host call stages through it on `st`
+    // itself): the input stream starts after it
+    cudaEventRecord(h->ev_in[0], st);
+    cudaStreamWaitEvent(h->s_in, h->ev_in[0], 0);
     int k = 0;
     for (uint32_t off = 0; off < n; off += chunk, ++k) {
         const uint32_t cnt = n - off < chunk ? n - off : chunk;

@@ -254,6 +254,7 @@ extern "C" int sdt_upload(sdt_handle h, const sdt_arrays* a) {
 
 extern "C" int sdt_upload_stats(sdt_handle h, const float* q_irradiance, const float* kd_vert_count) {
     if (!h) return SDT_ERR_INVALID;
+    SDT_TRY(sdt_complete_stats(h, h->last_stream));       // whatever is not overwritten below stays consistent
     DevHeader H;
     SDT_TRY(sdt_read_header(h, H));
     if (q_irradiance) SDT_CUDA(h, cudaMemcpy(h->q_ecur, q_irradiance, 4ull * H.n_quad, cudaMemcpyHostToDevice));
