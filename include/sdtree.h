@@ -123,8 +123,10 @@ const char* sdt_last_error(sdt_handle h);
 /* ---- tree exchange in the reference schema --------------------------------- */
 /* loadSDTreeFromFile (src/path_guiding_integrator.py:597-608 -> KDTree.loadFromFile
  * src/kdtree.py:156-170): prev <- arrays; current <- same topology, zero statistics.
- * Quadtree nodes must have adjacent children; a non-canonical node order is
- * re-labelled to the canonical layout of clearTreeUnusedNode (src/quadtree.py:844-851). */
+ * Spatial children must be adjacent and follow their parent (the reference's split appends them
+ * so, src/kdtree.py:243-245); quadtree nodes may come in any order and are re-labelled to the
+ * canonical layout of clearTreeUnusedNode (src/quadtree.py:844-851), which is also the numbering
+ * of every node id the library reports. */
 int sdt_upload(sdt_handle h, const sdt_arrays* host);
 /* Overwrite the statistics of `current` with frozen buffers (all nodes, interior
  * included; same node numbering as the last upload / refine): q_irradiance[n_quad],
