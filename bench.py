@@ -97,6 +97,12 @@ class ClockSampler:
         return self
 
     def __exit__(self, *a):
+        if self.nv is not None:
+            try:        # one reading taken with the work still queued / just drained, whatever the thread managed
+                self.sm.append(float(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM)))
+                self.reasons |= int(self.nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+            except Exception:
+                pass
         self.stop = True
         if self.th is not None:
             self.th.join(timeout=10)

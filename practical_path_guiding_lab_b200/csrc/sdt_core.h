@@ -98,6 +98,7 @@ struct TreeView {
     const QJump* jump;          // [root record][cell]
     const float* pp;            // per node: pdf product of the root->node path (NaN: it went NaN)
     uint32_t jump_trees;        // 0: table not in use
+    uint32_t int_cell;          // quadtrees no deeper than 23 levels: integer cell tracking in the sampler
 };
 
 // ---------------------------------------------------------------------------
@@ -507,12 +508,16 @@ struct QSample {
     float lox, loy, hix, hiy;   // leaf cell
 };
 
-template <class Rng>
+// INT_CELL: track the cell as integer coordinates (ix, iy, level) instead of four floats and build
+// the box once at the leaf.  Cell corners k/2^level are exact in fp32 up to level 23, where the
+// reference's repeated (min+max)/2 is exact too, so the box is bit-identical; deeper trees
+// (QuadTree.maxDepth > 23) use the float tracking that reproduces the reference's rounding.
+template <class Rng, bool INT_CELL>
 SDT_HD QSample sdt_quad_sample(const QRec* __restrict__ rec, uint32_t ri, uint32_t root_node, const Rng& rng) {
     QSample q;
     q.x = 0.0f; q.y = 0.0f; q.node = root_node; q.moved = ri != SDT_NONE; q.stuck = false;
     q.lox = 0.0f; q.loy = 0.0f; q.hix = 1.0f; q.hiy = 1.0f;
-    uint32_t level = 0;
+    uint32_t level = 0, ix = 0, iy = 0;
     // the loop only descends; the leaf position is drawn after it, where the warp has reconverged
     for (; level < SDT_MAX_LEVELS; ++level) {
         if (ri == SDT_NONE) break;
@@ -530,10 +535,20 @@ SDT_HD QSample sdt_quad_sample(const QRec* __restrict__ rec, uint32_t ri, uint32
         if (!(m0 || m1 || m2 || b3)) { q.stuck = true; break; }
         const uint32_t cu = b3 ? 3u : (m2 ? 2u : (m1 ? 1u : 0u));
         q.node = h.child_base + cu;
-        sdt_quadrant_m(cu, (q.lox + q.hix) / 2.0f, (q.loy + q.hiy) / 2.0f, q.lox, q.loy, q.hix, q.hiy);
+        if (INT_CELL) {
+            ix = 2u * ix + (((cu + 1u) >> 1) & 1u ^ 1u);                 // c1, c4 are the right half (:153-175)
+            iy = 2u * iy + ((cu >> 1) ^ 1u);                             // c1, c2 are the upper half
+        } else {
+            sdt_quadrant_m(cu, (q.lox + q.hix) / 2.0f, (q.loy + q.hiy) / 2.0f, q.lox, q.loy, q.hix, q.hiy);
+        }
         ri = sdt_child_rec(h.cinfo, h.interior_base, cu);
     }
     if (level >= SDT_MAX_LEVELS) q.stuck = true;   // deeper than SDT_MAX_LEVELS: impossible for a valid tree
+    if (INT_CELL) {
+        const float sc = sdt_u2f((127u - level) << 23);                  // 2^-level
+        q.lox = (float)ix * sc; q.hix = (float)(ix + 1u) * sc;
+        q.loy = (float)iy * sc; q.hiy = (float)(iy + 1u) * sc;
+    }
     if (!q.stuck) {
         const float ux = rng.get(3u * level), uy = rng.get(3u * level + 1u);
         q.x = q.lox + ux * (q.hix - q.lox);                              // :960-962
@@ -553,7 +568,7 @@ struct GuidedSample { float dx, dy, dz, pdf; uint32_t sample_node, pdf_node; };
 template <class Rng>
 SDT_HD GuidedSample sdt_sample_tree(const TreeView& t, uint32_t ri, uint32_t root, const Rng& rng, bool fuse) {
     GuidedSample g;
-    const QSample q = sdt_quad_sample(t.rec, ri, root, rng);
+    const QSample q = t.int_cell ? sdt_quad_sample<Rng, true>(t.rec, ri, root, rng) : sdt_quad_sample<Rng, false>(t.rec, ri, root, rng);
     sdt_canonical_to_dir(q.x, q.y, g.dx, g.dy, g.dz);                    // :996
     float px, py;
     sdt_dir_to_canonical(g.dx, g.dy, g.dz, px, py);                      // :1016

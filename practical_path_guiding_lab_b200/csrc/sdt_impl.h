@@ -57,6 +57,7 @@ struct sdt_tree_s {
     uint32_t jump_cap = 0;          // trees the jump table can hold
     uint32_t jump_trees_known = 0;  // trees covered, as last seen by the host (0 until known: slow path)
     int use_jump = 1;
+    int use_int_cell = 1;
     int use_compaction = 1;         // sort the lanes of a tile by mode when a wavefront has idle / mixed lanes
     int use_kd_grid = 1;            // per-CTA 16x16x8 grid over the first 11 spatial levels
     uint32_t kd_nodes_known = 1;    // last spatial node count seen by the host (sizes the smem staging)
@@ -113,7 +114,8 @@ static inline TreeView tree_view(sdt_tree_s* h) {
         h->jump_trees_known = h->h_hdr->jump_trees;
     }
     const QuadSet& s = h->set[h->cur];
-    return TreeView{s.hdr, h->kd_word, h->kd_root, h->kd_grid, s.rec, s.jump, s.pp, h->use_jump ? h->jump_trees_known : 0u};
+    return TreeView{s.hdr, h->kd_word, h->kd_root, h->kd_grid, s.rec, s.jump, s.pp, h->use_jump ? h->jump_trees_known : 0u,
+                    (uint32_t)(h->use_int_cell && h->cfg.quad_max_depth <= 23 && h->levels_hint <= 24u)};
 }
 
 static int sdt_read_header(sdt_handle h, DevHeader& H);
