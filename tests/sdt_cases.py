@@ -283,6 +283,35 @@ def case_spatial_descent_variants(ctx):
     assert np.array_equal(ctx.host(leaf).view(U), prev.getLeafNodeIndex(pos))
 
 
+def case_deep_quadtree_beyond_fp32_grid(ctx):
+    """QuadTree.maxDepth 28: every record has the same direction, so the tree is a chain down to level 28,
+    past the level (23) where cell corners stop being exact in fp32 -- the sampler falls back to float
+    cell tracking and must reproduce the reference's rounding of (min+max)/2"""
+    t = ctx.make(kd_capacity=64, quad_capacity=1 << 12, kd_max_depth=4, quad_max_depth=28, store_nee=False)
+    cur, prev = oracle_pair(kd_max_depth=4, quad_max_depth=28)
+    rng = np.random.default_rng(3)
+    n = 4000
+    for it in range(8):
+        rec = so.SurfaceInteractionRecord(rng.random((n, 3)).astype(F), np.tile(np.array([[0.3, 0.7]], F), (n, 1)),
+                                          np.ones(n, F), np.ones(n, F))
+        rec.direction[: n // 8] = rng.random((n // 8, 2)).astype(F)       # a little energy elsewhere
+        splat(t, ctx, rec)
+        cur.addDataPropagate(rec)
+        t.set_max_leaf_size(1e9)
+        t.refine()
+        oracle_refine(cur, prev, 1e9)
+    assert int(prev.quadTree.quadTreeNode.depth.max()) == 28 and t.sizes()['error'] == 0
+    assert_tree_equal(t.download(0), prev)
+    check_queries(ctx, t, prev, n=3000, seed=5, explicit=True)
+    check_queries(ctx, t, prev, n=3000, seed=6, explicit=False)
+    # pdf exactly at / next to the chain's direction
+    d = dm.canonical_to_dir(np.array([[0.3, 0.7], [np.nextafter(F(0.3), F(1)), 0.7], [0.3, np.nextafter(F(0.7), F(0))]], F))
+    pos = np.full((3, 3), 0.5, F)
+    p, dbg = t.pdf(ctx.dev(pos), ctx.dev(d), debug=True)
+    op, odbg = prev.pdf(pos, d, True, return_debug=True)
+    assert beq(ctx.host(p), op) and np.array_equal(ctx.host(dbg).view(U)[:, 2], odbg['pdf_node'])
+
+
 def case_fused_equals_two_descents(ctx):
     t, cur, prev = train(ctx, iters=3)
     rng = np.random.default_rng(3)
@@ -547,7 +576,7 @@ def case_npz_roundtrip(ctx, tmp_path):
     check_queries(ctx, t2, o, n=1024)
 
 
-ALL_CASES = [case_golden_fixture, case_jump_table_equals_descent, case_spatial_descent_variants, case_initial_tree, case_golden_upload_download, case_train_refine_topology, case_host_pipeline_chunks,
+ALL_CASES = [case_golden_fixture, case_deep_quadtree_beyond_fp32_grid, case_jump_table_equals_descent, case_spatial_descent_variants, case_initial_tree, case_golden_upload_download, case_train_refine_topology, case_host_pipeline_chunks,
              case_train_refine_nee_shallow, case_fused_equals_two_descents, case_splat_float_tolerance,
              case_path_data, case_mis, case_guided_bounce, case_refine_flags_and_frozen_stats,
              case_capacity_error, case_edge_inputs_and_errors]
