@@ -163,6 +163,36 @@ def train_and_render(renderer, budget_spp, seed=0, batch_spp=4, stable_variance_
     return dict(image=image, records=records, iterations=schedule)
 
 
+def render_fixed_trees(renderer, tree_files, iter_spp=1024, batch_spp=4, seed=0, ground_truth=None, log=None):
+    """The fixed-tree study of the reference's repeat_high_spp_renderer.py:69-160: for iteration k the
+    tree saved after iteration k-1 is loaded (`loadSDTreeFromFile`; iteration 0 renders unguided), the
+    integrator is put in final mode (`setIteration(k, True)`: nothing is recorded) and `iter_spp`
+    samples are rendered in `batch_spp` passes; variance / MSE are recorded per iteration.
+    tree_files[k-1] = npz of the tree to use in iteration k."""
+    log = log or (lambda *a: None)
+    records = []
+    cumm_spp = 0
+    for it in range(len(tree_files) + 1):
+        renderer.resetVarianceCounter()
+        renderer.setIteration(it, True)
+        if it > 0:
+            renderer.loadSDTreeFromFile(tree_files[it - 1])
+        t0 = time.perf_counter()
+        image, done = None, 0
+        for _ in range(math.ceil(iter_spp / batch_spp)):
+            s = min(batch_spp, iter_spp - done)
+            one = renderer.render(s, seed + cumm_spp) * float(s / iter_spp)
+            image = one if image is None else image + one
+            done += s
+            cumm_spp += s
+        rec = dict(iteration=it, spp=iter_spp, time=time.perf_counter() - t0, variance=renderer.computeVariance(iter_spp),
+                   variance_groundTruth=renderer.computeVariance(iter_spp, ground_truth) if ground_truth is not None else None,
+                   mse_groundTruth=renderer.computeMSE(iter_spp, ground_truth) if ground_truth is not None else None)
+        records.append(rec)
+        log(f"fixed tree, iteration {it}: {iter_spp} spp, variance {rec['variance']:.5g}")
+    return records
+
+
 def save_image(stem, image):
     import numpy as np
     a = image.detach().cpu().numpy() if hasattr(image, "detach") else np.asarray(image)

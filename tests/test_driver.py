@@ -65,3 +65,19 @@ def test_cornell_box_loop_on_host_emulation(tmp_path):
     # energy reached the tree: the first refine saw non-zero statistics
     d = r.core.tree.download(0)
     assert d["quadtree_irradiance"].sum() > 0
+
+
+def test_fixed_tree_rerender_flow(tmp_path):
+    """repeat_high_spp_renderer.py flow: trees saved by a training run are reloaded and rendered in
+    final mode (no recording, guided from iteration 2)"""
+    from hostemu.build_hostemu import build as build_hostemu
+    from practical_path_guiding_lab_b200.cornell import CornellBox
+    r = CornellBox(16, 16, max_depth=5, device="cpu", lib_path=build_hostemu(), kd_capacity=1 << 12, quad_capacity=1 << 16)
+    r.setup()
+    driver.train_and_render(r, 28, seed=2, out_dir=str(tmp_path), scene_name="cb")
+    files = [str(tmp_path / "tree-data" / f"cb_iter-{k}.npz") for k in range(3)]
+    before = r.core.tree.kernel_launches()
+    recs = driver.render_fixed_trees(r, files, iter_spp=8, batch_spp=4, seed=9)
+    assert [x["iteration"] for x in recs] == [0, 1, 2, 3] and all(np.isfinite(x["variance"]) for x in recs)
+    assert r.core.tree.kernel_launches() > before            # iterations 2, 3 query the loaded trees
+    assert r.core.tree.download(1)["quadtree_irradiance"].sum() == 0      # final mode: nothing splatted
