@@ -67,7 +67,7 @@ typedef struct sdt_config {
     int32_t store_nee;       /* QuadTree.isStoreNEERadiance                    */
     int32_t device;          /* CUDA ordinal                                   */
     uint32_t kd_capacity;    /* spatial-node arena (0 = 1<<21)                 */
-    uint32_t quad_capacity;  /* quadtree-node arena per buffer (0 = 1<<24)     */
+    uint32_t quad_capacity;  /* quadtree-node arena per buffer (0 = 1<<26)     */
 } sdt_config;
 
 typedef struct sdt_sizes {

@@ -51,11 +51,11 @@ extern "C" int sdt_create(const sdt_config* cfg, sdt_handle* out) {
     sdt_handle h = new sdt_tree_s();
     h->cfg = *cfg;
     h->kd_cap = cfg->kd_capacity ? cfg->kd_capacity : (1u << 21);
-    h->quad_cap = cfg->quad_capacity ? cfg->quad_capacity : (1u << 24);
+    h->quad_cap = cfg->quad_capacity ? cfg->quad_capacity : (1u << 26);      // ~4.5 GB of the B200's 180 GB: room for 3840x2160-scale forests
     if (h->kd_cap < 1) h->kd_cap = 1;
     if (h->quad_cap < 4) h->quad_cap = 4;
     h->rec_cap = h->quad_cap / 4u + 1u;
-    h->jump_cap = h->kd_cap < 65536u ? h->kd_cap : 65536u;
+    h->jump_cap = h->kd_cap / 2u + 1u < 262144u ? h->kd_cap / 2u + 1u : 262144u;   // one table per tree = per spatial leaf
     if ((uint64_t)h->jump_cap * SDT_JUMP_CELLS > 4ull * h->quad_cap) h->jump_cap = (uint32_t)(4ull * h->quad_cap / SDT_JUMP_CELLS);
 #ifndef SDT_HOSTEMU
     {
