@@ -12,7 +12,9 @@
 #ifndef SDT_MIN_CTAS
 #define SDT_MIN_CTAS 3
 #endif
-#define SDT_TILE_MUL 4u       // lanes per thread and tile in the compacting kernel
+#ifndef SDT_TILE_MUL
+#define SDT_TILE_MUL 8u       // lanes per thread and warp tile in the compacting kernel (tile = 256 lanes per warp)
+#endif
 template <class Lane, int KD>
 SDT_HD void sdt_lane(const Lane& f, const KdCtx& k, uint32_t i) {
     const uint32_t m = f.mode_of(i);
@@ -21,12 +23,12 @@ SDT_HD void sdt_lane(const Lane& f, const KdCtx& k, uint32_t i) {
 }
 
 #ifndef SDT_HOSTEMU
-// COMPACT: the wavefront has idle lanes or lanes of different kinds.  The lanes of a 4*blockDim tile
-// are first sorted by mode into shared-memory lists, then every list is processed by dense warps:
-// a warp never runs two code paths, and idle lanes (dead paths, masked-out vertices, filtered records)
-// cost a classification, not a share of a descent.
+// COMPACT: the wavefront has idle lanes or lanes of different kinds.  Each warp sorts the lanes of its
+// 256-lane tile by mode into shared-memory lists and then works through every list with all 32 threads:
+// a warp never runs two code paths, and idle lanes (dead paths, masked-out vertices, inactive record
+// slots) cost a classification, not a share of a descent.
 template <class Lane, bool COMPACT>
-__global__ void __launch_bounds__(512, SDT_MIN_CTAS) k_wavefront(Lane f, uint32_t n, uint32_t smem_cap, uint32_t use_grid) {
+__global__ void __launch_bounds__(768, 2) k_wavefront(Lane f, uint32_t n, uint32_t smem_cap, uint32_t use_grid) {
     extern __shared__ uint32_t kd_s[];
     const DevHeader* hdr = f.t.hdr;
     const uint32_t n_kd = hdr->n_kd;
@@ -64,50 +66,50 @@ __global__ void __launch_bounds__(512, SDT_MIN_CTAS) k_wavefront(Lane f, uint32_
     else if (kd_mode == 3) { constexpr int KD = 3; __VA_ARGS__; }           \
     else { constexpr int KD = 0; __VA_ARGS__; }
     if (COMPACT) {
-        uint16_t* list = reinterpret_cast<uint16_t*>(smem_next);
-        __shared__ uint32_t s_cnt[2];
+        // warp-local: every warp sorts its own tile of 32*SDT_TILE_MUL lanes into its slice of the
+        // shared-memory lists (no CTA barrier: a warp never waits for the deepest descent of another warp)
         constexpr uint32_t TM = SDT_TILE_MUL;
-        const uint32_t tile_n = TM * blockDim.x;
-        const uint32_t lane = threadIdx.x & 31u;
-        for (uint32_t tile = blockIdx.x * tile_n; tile < n; tile += gridDim.x * tile_n) {
-            if (threadIdx.x < 2u) s_cnt[threadIdx.x] = 0u;
-            __syncthreads();
+        constexpr uint32_t tile_w = 32u * TM;
+        const uint32_t lane = threadIdx.x & 31u, wib = threadIdx.x >> 5;
+        uint16_t* list = reinterpret_cast<uint16_t*>(smem_next) + wib * tile_w * (uint32_t)Lane::kModes;
+        const uint32_t warps_total = gridDim.x * (blockDim.x >> 5);
+        const uint32_t warp_id = blockIdx.x * (blockDim.x >> 5) + wib;
+        for (uint64_t tile64 = (uint64_t)warp_id * tile_w; tile64 < n; tile64 += (uint64_t)warps_total * tile_w) {
+            const uint32_t tile = (uint32_t)tile64;
+            uint32_t cnt[2] = {0u, 0u};
             uint32_t mq = 0;                 // modes of this thread's lanes, 2 bits each
 #pragma unroll
             for (uint32_t q = 0; q < TM; ++q) {
-                const uint32_t li = q * blockDim.x + threadIdx.x, i = tile + li;
+                const uint32_t li = q * 32u + lane, i = tile + li;
                 uint32_t m = 0;
                 if (i < n) { m = f.mode_of(i); if (!m) f.idle(i); }
                 mq |= m << (2u * q);
 #pragma unroll
                 for (uint32_t L = 0; L < (uint32_t)Lane::kModes; ++L) {
                     const uint32_t b = __ballot_sync(0xFFFFFFFFu, m == L + 1u);
-                    uint32_t base = 0;
-                    if (lane == 0u && b) base = atomicAdd(&s_cnt[L], (uint32_t)__popc(b));
-                    base = __shfl_sync(0xFFFFFFFFu, base, 0);
-                    if (m == L + 1u) list[L * tile_n + base + __popc(b & ((1u << lane) - 1u))] = (uint16_t)li;
+                    if (m == L + 1u) list[L * tile_w + cnt[L] + __popc(b & ((1u << lane) - 1u))] = (uint16_t)li;
+                    cnt[L] += (uint32_t)__popc(b);
                 }
             }
-            __syncthreads();
-            if (Lane::kModes == 1 && s_cnt[0] * 2u > tile_n) {
+            __syncwarp();
+            if (Lane::kModes == 1 && cnt[0] * 2u > tile_w) {
                 // a dense tile gains nothing from the indirection: every thread runs its own lanes in place (coalesced)
 #pragma unroll
                 for (uint32_t q = 0; q < TM; ++q) {
                     if (!((mq >> (2u * q)) & 3u)) continue;
-                    const uint32_t i = tile + q * blockDim.x + threadIdx.x;
+                    const uint32_t i = tile + q * 32u + lane;
                     SDT_KD_DISPATCH(f.template run_mode<KD>(k, i, 1u))
                 }
             } else {
 #pragma unroll
                 for (uint32_t L = 0; L < (uint32_t)Lane::kModes; ++L) {
-                    const uint32_t cnt = s_cnt[L];
-                    for (uint32_t j = threadIdx.x; j < cnt; j += blockDim.x) {
-                        const uint32_t i = tile + list[L * tile_n + j];
+                    for (uint32_t j = lane; j < cnt[L]; j += 32u) {
+                        const uint32_t i = tile + list[L * tile_w + j];
                         SDT_KD_DISPATCH(f.template run_mode<KD>(k, i, L + 1u))
                     }
                 }
             }
-            __syncthreads();
+            __syncwarp();
         }
     } else {
         SDT_KD_DISPATCH(for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) sdt_lane<Lane, KD>(f, k, i))
@@ -133,7 +135,7 @@ static int launch_wavefront_c(sdt_handle h, cudaStream_t st, uint32_t n, const L
     uint32_t smem_nodes = (want + 255u) & ~255u;
     if (smem_nodes > (uint32_t)h->kd_smem_nodes) smem_nodes = (uint32_t)h->kd_smem_nodes;
     const size_t smem = (size_t)smem_nodes * 4u * (Lane::kSmemCounts ? 2u : 1u) + SDT_GRID_CELLS * 4u +
-                        (COMPACT ? (size_t)block * SDT_TILE_MUL * 2u * (size_t)Lane::kModes : 0u);
+                        (COMPACT ? (size_t)block * SDT_TILE_MUL * 2u * (size_t)Lane::kModes : 0u);   // uint16 lists: 32*TM entries per warp and mode
     static size_t attr_set = 0;
     if (smem > 48u * 1024u && smem > attr_set) {
         if (cudaFuncSetAttribute(k_wavefront<Lane, COMPACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess)

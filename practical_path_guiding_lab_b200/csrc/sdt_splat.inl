@@ -99,7 +99,7 @@ SDT_HD float sdt_nan0(float v) { return (v != v) ? 0.0f : v; }
 
 // processPathData + scatterDataIntoSDTree (src/path_guiding_integrator.py:434-500) fused in front
 // of the splat.  The reference compacts the surviving records (dr.compress + 9 gathers + a host
-// sync); here the filter just masks the lane.
+// sync); here the slots of a tile are sorted by their `active` flag and the filter masks the rest.
 struct SplatPathLane {
     static constexpr bool kSmemCounts = true, kGrid = true;
     static constexpr int kModes = 1;
@@ -131,10 +131,17 @@ struct SplatPathLane {
         const bool act = p.active ? SDT_LDG(p.active + i) != 0 : true;
         return act && !both_zero && !(v.wo_pdf == 0.0f) && !(v.wo_pdf != v.wo_pdf);    // :475-478
     }
-    // (always launched without compaction: the 93 B/slot prologue dominates this kernel and would run
-    //  twice; measured 0.61 ms masked vs 0.78 ms compacted at 60 % active, 0.63 vs 0.50 ms at 15 %)
-    SDT_HD uint32_t mode_of(uint32_t) const { return 1u; }
-    SDT_HD void idle(uint32_t) const {}
+    // Lanes are classified by the `active` flag alone (one byte per slot): a pass has numRays*max_depth
+    // slots and most of them lie beyond the end of their path, so idle slots cost that byte and nothing
+    // else (unless the caller wants SurfaceInteractionRecord.radiance for every slot); the radiance
+    // back-propagation and the reference's filter run once, on the active slots.
+    SDT_HD uint32_t mode_of(uint32_t i) const { return p.active ? (SDT_LDG(p.active + i) != 0 ? 1u : 0u) : 1u; }
+    SDT_HD void idle(uint32_t i) const {
+        if (!p.radiance_out) return;
+        Vals v;
+        prepare(i, v);
+        p.radiance_out[i] = v.radiance;
+    }
     template <int KD>
     SDT_HD void run_mode(const KdCtx& k, uint32_t i, uint32_t) const {
         Vals v;
@@ -240,6 +247,6 @@ extern "C" int sdt_splat_path_data(sdt_handle h, const sdt_path_data* pd, uint32
     if (sg.status != SDT_OK) return sg.status;
     SplatPathLane f{tree_view(h), SplatTarget{h->kd_count, h->q_ecur, (uint32_t)(h->cfg.store_nee != 0)}, d};
     h->stats_complete = false;
-    SDT_TRY(launch_wavefront(h, st, n, f, h->splat_block, h->splat_ctas_per_sm, false));
+    SDT_TRY(launch_wavefront(h, st, n, f, h->splat_block, h->splat_ctas_per_sm, pd->active != nullptr));
     return sg.finish(flags);
 }
