@@ -75,6 +75,8 @@ struct sdt_tree_s {
     // tuning
     int query_block = 768;          // 2 CTAs x 768 threads per SM: same 1536 threads as 3 x 512 but one staged copy
     int query_ctas_per_sm = 2;      // of the spatial tree less -> ~75 KB more L1 for the quadtree records (measured)
+    int splat_stage_words = 1;
+    int kd_smem_count_nodes = 24576; // cap of the shared-memory leaf counters of the splat kernels
     int kd_smem_nodes = 24576;      // cap of the smem-staged prefix of the spatial tree (96 KB)
     int splat_block = 768;
     int splat_ctas_per_sm = 2;

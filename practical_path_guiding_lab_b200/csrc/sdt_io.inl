@@ -347,6 +347,8 @@ extern "C" int sdt_set_tuning(sdt_handle h, const char* key, int64_t value) {
     if (k == "query_block") { SDT_CHECK(h, value >= 64 && value <= 768 && value % 32 == 0, SDT_ERR_INVALID, "query_block must be 64..768, multiple of 32"); h->query_block = (int)value; }
     else if (k == "query_ctas_per_sm") { SDT_CHECK(h, value >= 1 && value <= 32, SDT_ERR_INVALID, "query_ctas_per_sm must be 1..32"); h->query_ctas_per_sm = (int)value; }
     else if (k == "kd_smem_nodes") { SDT_CHECK(h, value >= 0 && value <= 49152, SDT_ERR_INVALID, "kd_smem_nodes must be 0..49152"); h->kd_smem_nodes = (int)value; }
+    else if (k == "splat_stage_words") h->splat_stage_words = value != 0;
+    else if (k == "kd_smem_count_nodes") { SDT_CHECK(h, value >= 0 && value <= 49152, SDT_ERR_INVALID, "kd_smem_count_nodes must be 0..49152"); h->kd_smem_count_nodes = (int)value; }
     else if (k == "splat_block") { SDT_CHECK(h, value >= 64 && value <= 768 && value % 32 == 0, SDT_ERR_INVALID, "splat_block must be 64..768, multiple of 32"); h->splat_block = (int)value; }
     else if (k == "splat_ctas_per_sm") { SDT_CHECK(h, value >= 1 && value <= 32, SDT_ERR_INVALID, "splat_ctas_per_sm must be 1..32"); h->splat_ctas_per_sm = (int)value; }
     else if (k == "fuse_sample_pdf") h->fuse_sample_pdf = value != 0;

@@ -28,7 +28,7 @@ SDT_HD void sdt_lane(const Lane& f, const KdCtx& k, uint32_t i) {
 // a warp never runs two code paths, and idle lanes (dead paths, masked-out vertices, inactive record
 // slots) cost a classification, not a share of a descent.
 template <class Lane, bool COMPACT>
-__global__ void __launch_bounds__(768, 2) k_wavefront(Lane f, uint32_t n, uint32_t smem_cap, uint32_t use_grid) {
+__global__ void __launch_bounds__(768, 2) k_wavefront(Lane f, uint32_t n, uint32_t smem_cap, uint32_t cnt_cap, uint32_t use_grid) {
     extern __shared__ uint32_t kd_s[];
     const DevHeader* hdr = f.t.hdr;
     const uint32_t n_kd = hdr->n_kd;
@@ -40,12 +40,12 @@ __global__ void __launch_bounds__(768, 2) k_wavefront(Lane f, uint32_t n, uint32
     // lifetime of the CTA and are flushed once (16M same-slice L2 atomics become a few per leaf and CTA)
     float* cnt_s = nullptr;
     if (Lane::kSmemCounts) {
-        if (n_smem == n_kd) {
+        if (n_kd <= cnt_cap) {               // (independent of whether the words are staged)
             cnt_s = reinterpret_cast<float*>(smem_next);
-            for (uint32_t j = threadIdx.x; j < n_smem; j += blockDim.x) cnt_s[j] = 0.0f;
+            for (uint32_t j = threadIdx.x; j < n_kd; j += blockDim.x) cnt_s[j] = 0.0f;
             k.cnt_s = cnt_s;
         }
-        smem_next += smem_cap;
+        smem_next += cnt_cap;
     }
     __syncthreads();
     // 16x16x8 grid over the first 11 spatial levels (built with the records, see sdt_kd_descend).  With
@@ -117,7 +117,7 @@ __global__ void __launch_bounds__(768, 2) k_wavefront(Lane f, uint32_t n, uint32
 #undef SDT_KD_DISPATCH
     if (cnt_s) {
         __syncthreads();
-        for (uint32_t j = threadIdx.x; j < n_smem; j += blockDim.x) {
+        for (uint32_t j = threadIdx.x; j < n_kd; j += blockDim.x) {
             const float c = cnt_s[j];
             if (c != 0.0f) f.flush_count(j, c);
         }
@@ -134,7 +134,13 @@ static int launch_wavefront_c(sdt_handle h, cudaStream_t st, uint32_t n, const L
     uint32_t want = h->hdr_pending ? 2u * h->kd_nodes_known + 2u : h->kd_nodes_known;   // a refine is in flight: be generous
     uint32_t smem_nodes = (want + 255u) & ~255u;
     if (smem_nodes > (uint32_t)h->kd_smem_nodes) smem_nodes = (uint32_t)h->kd_smem_nodes;
-    const size_t smem = (size_t)smem_nodes * 4u * (Lane::kSmemCounts ? 2u : 1u) + SDT_GRID_CELLS * 4u +
+    if (Lane::kSmemCounts && !h->splat_stage_words) smem_nodes = 0;     // splat: counters + grid only, words through L1/L2
+    uint32_t cnt_nodes = 0;                  // shared-memory leaf counters of the splat kernels
+    if (Lane::kSmemCounts) {
+        cnt_nodes = (want + 255u) & ~255u;
+        if (cnt_nodes > (uint32_t)h->kd_smem_count_nodes) cnt_nodes = (uint32_t)h->kd_smem_count_nodes;
+    }
+    const size_t smem = (size_t)smem_nodes * 4u + (size_t)cnt_nodes * 4u + SDT_GRID_CELLS * 4u +
                         (COMPACT ? (size_t)block * SDT_TILE_MUL * 2u * (size_t)Lane::kModes : 0u);   // uint16 lists: 32*TM entries per warp and mode
     static size_t attr_set = 0;
     if (smem > 48u * 1024u && smem > attr_set) {
@@ -154,7 +160,7 @@ static int launch_wavefront_c(sdt_handle h, cudaStream_t st, uint32_t n, const L
     uint32_t grid = (n + per_cta - 1u) / per_cta;
     const uint32_t cap = (uint32_t)(h->num_sms * per_sm);
     if (grid > cap) grid = cap;
-    k_wavefront<Lane, COMPACT><<<grid, block, smem, st>>>(f, n, smem_nodes, (uint32_t)h->use_kd_grid);
+    k_wavefront<Lane, COMPACT><<<grid, block, smem, st>>>(f, n, smem_nodes, cnt_nodes, (uint32_t)h->use_kd_grid);
     ++h->launches;
     h->last_stream = st;
     return sdt_post_launch(h, "k_wavefront");
