@@ -37,6 +37,11 @@ from . import drjit_math as dm
 F = np.float32
 U = np.uint32
 
+# Open uncertainty: a Dr.Jit build may lower `irradiance / 100` (src/quadtree.py:519)
+# to a multiplication by the fp32 reciprocal.  False = IEEE fp32 division (the default everywhere);
+# tests flip it together with the library's "quad_thr_reciprocal" switch.
+QUAD_THR_RECIPROCAL = False
+
 
 # --------------------------------------------------------------------------- helpers
 def gather(src, idx, active=None):
@@ -337,7 +342,8 @@ class QuadTree:
     def setRefinementThreshold(self, rootIndex, total_flux_prev_quadtree):
         q = self.quadTreeNode
         with np.errstate(all='ignore'):
-            thr = (np.asarray(total_flux_prev_quadtree, dtype=F) / F(100)).astype(F)     # :519
+            e = np.asarray(total_flux_prev_quadtree, dtype=F)
+            thr = (e * F(1.0 / 100) if QUAD_THR_RECIPROCAL else e / F(100)).astype(F)      # :519
         nodeIndex = q.rootNodeIndex[rootIndex]
         active = nodeIndex.shape[0] > 0
         while active:

@@ -58,6 +58,7 @@ struct sdt_tree_s {
     uint32_t jump_trees_known = 0;  // trees covered, as last seen by the host (0 until known: slow path)
     int use_jump = 1;
     int use_int_cell = 1;
+    int quad_thr_reciprocal = 0;    // semantics switch, see sdt_set_tuning in sdtree.h
     int use_compaction = 1;         // sort the lanes of a tile by mode when a wavefront has idle / mixed lanes
     int use_kd_grid = 1;            // per-CTA 16x16x8 grid over the first 11 spatial levels
     uint32_t kd_nodes_known = 1;    // last spatial node count seen by the host (sizes the smem staging)

@@ -30,6 +30,7 @@ struct RefineCtx {
     uint32_t* child1; float* energy1; float* thr1; uint32_t* iidx1; QRec* rec1; uint32_t* root_iidx1;
     uint32_t* s_src; uint8_t* s_kind; uint8_t* s_srem;
     uint32_t no_quad;
+    uint32_t thr_recip;   // threshold = E * fp32(1/100) instead of E / 100 (how Dr.Jit may lower the literal division)
 };
 
 struct RefineInit {
@@ -143,7 +144,7 @@ struct QRootItem {          // level 0: tree r copies the tree of root_src[r]; t
         c.s_kind[r] = SDT_KIND_REACHED;
         const float e = c.e_cur[src];
         c.energy1[r] = e;
-        c.thr1[r] = c.no_quad ? c.thr0[src] : e / 100.0f;
+        c.thr1[r] = c.no_quad ? c.thr0[src] : (c.thr_recip ? e * 0.01f : e / 100.0f);
     }
 };
 
@@ -344,6 +345,7 @@ extern "C" int sdt_refine(sdt_handle h, uint32_t flags, sdt_stream stream) {
     c.child1 = s1.child; c.energy1 = s1.energy; c.thr1 = s1.thr; c.iidx1 = s1.iidx; c.rec1 = s1.rec; c.root_iidx1 = s1.root_iidx;
     c.s_src = h->s_src; c.s_kind = h->s_kind; c.s_srem = h->s_srem;
     c.no_quad = (flags & SDT_REFINE_NO_QUAD) ? 1u : 0u;
+    c.thr_recip = h->quad_thr_reciprocal ? 1u : 0u;
 
     launch_single(x, RefineInit{c});
     launch_items(x, &c.H1->n_roots_old, 0, RootIdentityItem{h->root_src});

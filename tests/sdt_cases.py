@@ -102,11 +102,13 @@ def assert_tree_equal(got, want_tree, exact_energy=True, rtol=1e-4):
             assert np.array_equal(g, w), k
 
 
-def train(ctx, iters=4, n=20000, max_leaf=600, kd_max_depth=20, quad_max_depth=20, store_nee=False, box=1.0, caps=None):
+def train(ctx, iters=4, n=20000, max_leaf=600, kd_max_depth=20, quad_max_depth=20, store_nee=False, box=1.0, caps=None, tuning=()):
     """identical splat+refine loop on the library and on the oracle; returns both"""
     caps = caps or dict(kd_capacity=1 << 14, quad_capacity=1 << 18)
     t = ctx.make(bbox_min=(0, 0, 0), bbox_max=(box, box, box), kd_max_depth=kd_max_depth, quad_max_depth=quad_max_depth,
                  store_nee=store_nee, **caps)
+    for k, v in tuning:
+        t.set_tuning(k, v)
     cur, prev = oracle_pair((0, 0, 0), (box, box, box), kd_max_depth, quad_max_depth, store_nee)
     lobes = [((0.3, 0.7, 0.02),), ((0.3, 0.7, 0.004), (0.8, 0.2, 0.05)), ((0.8, 0.2, 0.01),), ((0.55, 0.5, 0.001), (0.1, 0.1, 0.1))]
     for it in range(iters):
@@ -220,6 +222,21 @@ def case_train_refine_topology(ctx):
     assert prev.validateTreeNodeBBox() and prev.quadTree.validateQuadTreeNodeBBox()
     check_queries(ctx, t, prev, explicit=True)
     check_queries(ctx, t, prev, explicit=False)
+
+
+def case_threshold_reciprocal_variant(ctx):
+    """semantics switch "quad_thr_reciprocal" (E * fp32(0.01) instead of E / 100): library and
+    oracle agree bit for bit in that mode too, and the mode really changes some thresholds"""
+    base = train(ctx, iters=3)[2].quadTree.quadTreeNode.refinementThreshold.copy()
+    so.QUAD_THR_RECIPROCAL = True
+    try:
+        t, cur, prev = train(ctx, iters=3, tuning=(("quad_thr_reciprocal", 1),))
+    finally:
+        so.QUAD_THR_RECIPROCAL = False
+    assert_tree_equal(t.download(0), prev)
+    assert_tree_equal(t.download(1), cur)
+    thr = prev.quadTree.quadTreeNode.refinementThreshold
+    assert thr.shape != base.shape or not np.array_equal(thr, base)
 
 
 def case_train_refine_nee_shallow(ctx):
@@ -576,7 +593,7 @@ def case_npz_roundtrip(ctx, tmp_path):
     check_queries(ctx, t2, o, n=1024)
 
 
-ALL_CASES = [case_golden_fixture, case_deep_quadtree_beyond_fp32_grid, case_jump_table_equals_descent, case_spatial_descent_variants, case_initial_tree, case_golden_upload_download, case_train_refine_topology, case_host_pipeline_chunks,
+ALL_CASES = [case_golden_fixture, case_deep_quadtree_beyond_fp32_grid, case_jump_table_equals_descent, case_spatial_descent_variants, case_initial_tree, case_golden_upload_download, case_train_refine_topology, case_threshold_reciprocal_variant, case_host_pipeline_chunks,
              case_train_refine_nee_shallow, case_fused_equals_two_descents, case_splat_float_tolerance,
              case_path_data, case_mis, case_guided_bounce, case_refine_flags_and_frozen_stats,
              case_capacity_error, case_edge_inputs_and_errors]
