@@ -10,6 +10,7 @@ import pytest
 
 sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 import sdt_cases as cases  # noqa: E402
+import fuzz_cases  # noqa: E402
 
 pytestmark = pytest.mark.gpu
 
@@ -46,7 +47,7 @@ def ctx(request):
     return _ctx(request.param)
 
 
-@pytest.mark.parametrize("case", cases.ALL_CASES, ids=lambda c: c.__name__)
+@pytest.mark.parametrize("case", cases.ALL_CASES + fuzz_cases.SUITE_CASES, ids=lambda c: c.__name__)
 def test_case(ctx, case):
     case(ctx)
 

@@ -9,6 +9,7 @@ import pytest
 
 sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 import sdt_cases as cases  # noqa: E402
+import fuzz_cases  # noqa: E402
 from hostemu.build_hostemu import build as build_hostemu  # noqa: E402
 
 from practical_path_guiding_lab_b200 import SDTree  # noqa: E402
@@ -20,7 +21,7 @@ def ctx():
     return cases.Ctx(make=lambda **kw: SDTree(lib_path=lib, **kw))
 
 
-@pytest.mark.parametrize("case", cases.ALL_CASES, ids=lambda c: c.__name__)
+@pytest.mark.parametrize("case", cases.ALL_CASES + fuzz_cases.SUITE_CASES, ids=lambda c: c.__name__)
 def test_case(ctx, case):
     case(ctx)
 
