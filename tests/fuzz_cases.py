@@ -85,8 +85,9 @@ def fuzz_one(ctx, seed, verbose=False):
     cur, prev = cases.oracle_pair(lo, hi, kd_max_depth, quad_max_depth, store_nee)
     peak = 0
     for it in range(iters):
-        # a tree whose total energy is negative has a negative threshold: every leaf then splits down to the depth
-        # cap (4^depth nodes per tree, in the reference too) -- only affordable with shallow caps
+        # negative radiance can cancel a tree's total to exactly 0 -> threshold 0 -> every leaf with positive energy splits
+        # down to the depth cap (up to 4^depth nodes per tree, in the reference too; sdt_cases.case_zero_total_energy) --
+        # only affordable with shallow caps
         rec, active = random_records(rng, n, lo, hi, store_nee, negative=quad_max_depth <= 4 and kd_max_depth <= 8)
         cases.splat(t, ctx, rec, active)
         cur.addDataPropagate(_compress(rec, active))

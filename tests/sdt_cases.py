@@ -506,6 +506,40 @@ def case_capacity_error(ctx):
     assert ctx.host(root).view(U).max() < s['n_roots']
 
 
+def case_zero_total_energy(ctx):
+    """negative radiance can cancel a tree's total energy to exactly 0: the threshold E_root/100 is then 0 and every
+    leaf that holds any positive energy splits down to the depth cap, in the reference too (src/quadtree.py:519,
+    615-637).  Moderate cap: bit for bit like the oracle; deep cap: arena exhaustion reported (error bit 2) and the
+    handle stays usable"""
+    n = 4000
+    rng = np.random.default_rng(3)
+    pos = rng.random((n, 3)).astype(F)
+    first = so.SurfaceInteractionRecord(pos, rng.random((n, 2)).astype(F), np.ones(n, F), np.ones(n, F))
+    spot = np.tile(np.array([[0.40625, 0.40625]], F), (n, 1))           # all the negative energy in one cell
+    second = so.SurfaceInteractionRecord(np.concatenate([pos, pos]), np.concatenate([first.direction, spot]),
+                                         np.concatenate([np.ones(n, F), -np.ones(n, F)]), np.ones(2 * n, F))
+    for qd, cap in ((6, 1 << 15), (20, 1 << 12)):
+        t = ctx.make(kd_max_depth=2, quad_max_depth=qd, store_nee=False, kd_capacity=64, quad_capacity=cap)
+        cur, prev = oracle_pair((0, 0, 0), (1, 1, 1), 2, qd, False)
+        for rec in (first, second):
+            splat(t, ctx, rec)
+            t.set_max_leaf_size(1e9)                                    # one spatial leaf: the tree's total is exactly 0
+            t.refine()
+            if qd == 6:
+                cur.addDataPropagate(rec)
+                oracle_refine(cur, prev, 1e9)
+        s = t.sizes()
+        if qd == 6:
+            assert prev.quadTree.quadTreeNode.refinementThreshold[0] == 0 and s['error'] == 0
+            assert int(prev.quadTree.quadTreeNode.depth.max()) == 6 and s['n_quad'] > 3000       # nearly the full 4^6 tree
+            assert_tree_equal(t.download(0), prev)
+            check_queries(ctx, t, prev, n=512)
+        else:
+            assert s['error'] == 2 and s['n_quad'] <= cap
+            dd, p = t.sample(ctx.dev(pos), seed=1)
+            assert ctx.host(p).shape == (n,)
+
+
 def case_edge_inputs_and_errors(ctx):
     """empty / single / ragged wavefronts, SoA (Dr.Jit-style) component planes, error reporting"""
     from practical_path_guiding_lab_b200 import SDTreeError
@@ -593,7 +627,7 @@ def case_npz_roundtrip(ctx, tmp_path):
     check_queries(ctx, t2, o, n=1024)
 
 
-ALL_CASES = [case_golden_fixture, case_deep_quadtree_beyond_fp32_grid, case_jump_table_equals_descent, case_spatial_descent_variants, case_initial_tree, case_golden_upload_download, case_train_refine_topology, case_threshold_reciprocal_variant, case_host_pipeline_chunks,
+ALL_CASES = [case_golden_fixture, case_deep_quadtree_beyond_fp32_grid, case_jump_table_equals_descent, case_spatial_descent_variants, case_initial_tree, case_golden_upload_download, case_train_refine_topology, case_threshold_reciprocal_variant, case_zero_total_energy, case_host_pipeline_chunks,
              case_train_refine_nee_shallow, case_fused_equals_two_descents, case_splat_float_tolerance,
              case_path_data, case_mis, case_guided_bounce, case_refine_flags_and_frozen_stats,
              case_capacity_error, case_edge_inputs_and_errors]
