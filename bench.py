@@ -408,21 +408,46 @@ def run_b200(args):
             tree2.sample(hp, seed=3, lane_offset=lane0, out=(ho_dir, ho_pdf))
             tree2.pdf(hp, hd, out=ho_pdf2)
             tree2.splat_records(hr['position'], hr['direction'], hr['radiance'], hr['wo_pdf'])
+            tree2.synchronize()                         # every output of the step is in host memory here
             torch.cuda.synchronize()
         ke = max(1, min(args.steps, 5))
-        for _ in range(2):
-            step_host()
-        barrier()
+
+        def timed_host():
+            for _ in range(2):
+                step_host()
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(ke):
+                step_host()
+            barrier()
+            dt = torch.tensor([(time.perf_counter() - t0) / ke], device=dev)
+            if world > 1:
+                dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+            return float(dt.item())
+        tree2.host_wait = True                          # each call returns with its outputs on the host
+        dt_e2e = timed_host()
+        tree2.host_wait = False                         # SDT_NO_WAIT: the three calls overlap, one synchronize per step
+        dt_nowait = timed_host()
+        tree2.host_wait = True
+        # what the link gives a plain pinned copy of the same size (context for the number above)
+        big = torch.empty(256 << 20, dtype=torch.uint8).pin_memory()
+        dbig = torch.empty_like(big, device=dev)
+        dbig.copy_(big, non_blocking=True)
+        torch.cuda.synchronize()
         t0 = time.perf_counter()
-        for _ in range(ke):
-            step_host()
-        barrier()
-        dt = torch.tensor([(time.perf_counter() - t0) / ke], device=dev)
-        if world > 1:
-            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
-        e2e = {"value": n * world / float(dt.item()), "unit": UNIT, "ms_per_step": float(dt.item()) * 1e3,
+        for _ in range(4):
+            dbig.copy_(big, non_blocking=True)
+        torch.cuda.synchronize()
+        h2d_gbs = 4 * big.numel() / (time.perf_counter() - t0) / 1e9
+        del big, dbig
+        e2e = {"value": n * world / dt_e2e, "unit": UNIT, "ms_per_step": dt_e2e * 1e3,
                "h2d_bytes_per_step": n * (12 + 24 + 28), "d2h_bytes_per_step": n * (16 + 4),
-               "how": "sdt_sample + sdt_pdf + sdt_splat_records with SDT_HOST_PTRS on pinned host arrays; staging copies inside the calls"}
+               "ms_per_step_no_wait": dt_nowait * 1e3, "pinned_h2d_copy_gbs": h2d_gbs,
+               "h2d_gbs_in_step": n * (12 + 24 + 28) / dt_e2e / 1e9,
+               "how": "sdt_sample + sdt_pdf + sdt_splat_records with SDT_HOST_PTRS on pinned host arrays, each call returning "
+                      "with its outputs on the host; staging copies inside the calls.  ms_per_step_no_wait: the same calls "
+                      "with SDT_NO_WAIT and one sdt_synchronize per step; pinned_h2d_copy_gbs: a plain pinned H2D copy on "
+                      "this box -- the step is bound by the host link (h2d_gbs_in_step, with the D2H traffic beside it)"}
 
     # ---- CPU port of the reference, timed beside it (rank 0, N=1)
     cpu = None

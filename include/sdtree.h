@@ -18,7 +18,8 @@
  *    unless SDT_SYNC is given.
  *  - query / record buffers belong to the caller.  They are DEVICE pointers unless
  *    SDT_HOST_PTRS is given, in which case they are host pointers (pinned for speed)
- *    and the library stages them through its own device buffers inside the call.
+ *    and the library stages them through its own device buffers inside the call;
+ *    such a call returns when its host outputs are complete, unless SDT_NO_WAIT.
  *  - vectors are strided component views (sdt_vec3 / sdt_vec2): Dr.Jit's SoA
  *    Vector3f is {x,y,z,stride=1}; a C-contiguous (n,3) array is {p,p+1,p+2,stride=3}.
  *  - no torch / Dr.Jit / Mitsuba type appears in any signature.
@@ -52,6 +53,10 @@ typedef enum sdt_status {
 #define SDT_SYNC 2u          /* cudaStreamSynchronize(stream) before returning */
 #define SDT_REFINE_NO_KD 4u   /* sdt_refine: skip the spatial split (KDTree.refine) */
 #define SDT_REFINE_NO_QUAD 8u /* sdt_refine: skip threshold + merge/split of the quadtrees */
+#define SDT_NO_WAIT 16u      /* with SDT_HOST_PTRS: return once everything is enqueued instead of waiting for the
+                              * host outputs; they are valid (and the host inputs may be reused) after the caller
+                              * synchronises `stream`.  Back-to-back calls then overlap: the D2H tail of one call
+                              * runs under the H2D head of the next */
 
 typedef struct sdt_vec3 { const float* x; const float* y; const float* z; int64_t stride; } sdt_vec3;
 typedef struct sdt_vec2 { const float* x; const float* y; int64_t stride; } sdt_vec2;
@@ -268,6 +273,9 @@ int sdt_stat_buffers(sdt_handle h, float** q_energy, uint32_t* n_quad, float** k
  * form a Dr.Jit build that lowers division by a literal to a reciprocal multiply would
  * produce (first uncertainty); default 0 = IEEE fp32 division. */
 int sdt_set_tuning(sdt_handle h, const char* key, int64_t value);
+/* cudaStreamSynchronize(stream) on the handle's device: completes SDT_NO_WAIT calls for callers
+ * that have no CUDA runtime of their own (ctypes / cgo hosts) */
+int sdt_synchronize(sdt_handle h, sdt_stream stream);
 /* number of kernels this handle has launched since creation */
 uint64_t sdt_kernel_launches(sdt_handle h);
 /* L2-resident read bandwidth probe (GB/s): `bytes` working set read `passes` times */

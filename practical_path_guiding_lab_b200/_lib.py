@@ -12,6 +12,7 @@ DEFAULT_LIB = os.path.join(_HERE, "libsdtree.so")
 SDT_OK = 0
 SDT_HOST_PTRS = 1
 SDT_SYNC = 2
+SDT_NO_WAIT = 16
 SDT_REFINE_NO_KD = 4
 SDT_REFINE_NO_QUAD = 8
 SDT_TREE_PREV = 0
@@ -109,6 +110,7 @@ SYMBOLS = {
     "sdt_stat_buffers": (C.c_int, [_H, C.POINTER(C.c_void_p), C.POINTER(C.c_uint32), C.POINTER(C.c_void_p),
                                    C.POINTER(C.c_uint32)]),
     "sdt_set_tuning": (C.c_int, [_H, C.c_char_p, C.c_int64]),
+    "sdt_synchronize": (C.c_int, [_H, C.c_void_p]),
     "sdt_kernel_launches": (C.c_uint64, [_H]),
     "sdt_measure_l2": (C.c_int, [_H, C.c_uint64, C.c_uint32, C.POINTER(C.c_float), _S]),
 }

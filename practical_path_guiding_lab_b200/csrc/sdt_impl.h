@@ -72,6 +72,8 @@ struct sdt_tree_s {
     cudaStream_t s_in = nullptr, s_out = nullptr;
     cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_comp[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
     int host_chunk = 1 << 20;       // lanes per pipeline chunk
+    bool arena_on_st = false;       // a non-pipelined host call staged through the arena on `arena_stream`
+    cudaStream_t arena_stream = nullptr;
 
     // tuning
     int query_block = 768;          // 2 CTAs x 768 threads per SM: same 1536 threads as 3 x 512 but one staged copy
@@ -148,7 +150,14 @@ struct Stager {
             off = (size_t)slot * half; lim = off + half;
             // the slot's input buffers are free once the kernels of the chunk that used it have run
             cudaStreamWaitEvent(h->s_in, h->ev_comp[slot], 0);
-        } else { off = 0; lim = h->stage_cap; }
+        } else {
+            off = 0; lim = h->stage_cap;
+            if (host && h->s_in) {
+                // whole-arena call: chunks of an earlier pipelined call (possibly SDT_NO_WAIT, possibly on another
+                // stream) may still be reading / writing their slots
+                for (int k = 0; k < 2; ++k) { cudaStreamWaitEvent(st, h->ev_comp[k], 0); cudaStreamWaitEvent(st, h->ev_out[k], 0); }
+            }
+        }
     }
     // total bytes this call will stage; grows the arena once (pointers stay valid)
     int reserve(size_t bytes) {
@@ -166,6 +175,7 @@ struct Stager {
         size_t o = (off + 255) & ~(size_t)255;
         if (o + bytes > lim) { status = sdt_fail(h, SDT_ERR_INVALID, "staging arena overflow (reserve too small)"); return nullptr; }
         off = o + bytes;
+        if (slot < 0) { h->arena_on_st = true; h->arena_stream = st; }
         return h->stage + o;
     }
     const void* in(const void* p, size_t bytes) {
@@ -242,7 +252,7 @@ struct Stager {
                 return sdt_fail(h, SDT_ERR_CUDA, "D2H staging copy failed");
         }
         // results in pageable/pinned host memory are only valid after the stream drains
-        if ((flags & SDT_SYNC) || (host && !outs.empty())) {
+        if ((flags & SDT_SYNC) || (host && !outs.empty() && !(flags & SDT_NO_WAIT))) {
             if (cudaStreamSynchronize(st) != cudaSuccess) return sdt_fail(h, SDT_ERR_CUDA, "stream synchronize failed");
         }
         return SDT_OK;
@@ -266,10 +276,17 @@ static int sdt_run_chunked(sdt_handle h, cudaStream_t st, uint32_t flags, uint32
         Stager probe(h, st, flags);
         SDT_TRY(probe.reserve(2 * ((size_t)chunk * bytes_per_lane + 65536)));
     }
-    // earlier work on `st` may still read the arena (a small host call stages through it on `st`
-    // itself): the input stream starts after it
-    cudaEventRecord(h->ev_in[0], st);
-    cudaStreamWaitEvent(h->s_in, h->ev_in[0], 0);
+    // a small host call stages through the whole arena on its own stream: the input stream starts after it.
+    // Chunks of an earlier pipelined call are covered slot by slot: ev_comp (Stager) frees the slot's inputs,
+    // ev_out its outputs -- the layouts of two calls differ, so the first two chunks wait for both; everything
+    // else of the earlier call (its D2H tail in particular) overlaps with this call's H2D.
+    if (h->arena_on_st) {
+        cudaEventRecord(h->ev_in[0], h->arena_stream);
+        cudaStreamWaitEvent(h->s_in, h->ev_in[0], 0);
+        h->arena_on_st = false;
+    }
+    cudaStreamWaitEvent(h->s_in, h->ev_out[0], 0);
+    cudaStreamWaitEvent(h->s_in, h->ev_out[1], 0);
     int k = 0;
     for (uint32_t off = 0; off < n; off += chunk, ++k) {
         const uint32_t cnt = n - off < chunk ? n - off : chunk;
@@ -280,7 +297,7 @@ static int sdt_run_chunked(sdt_handle h, cudaStream_t st, uint32_t flags, uint32
     // stream order for the caller: everything, D2H included, is complete when `st` drains
     cudaStreamWaitEvent(st, h->ev_out[0], 0);
     cudaStreamWaitEvent(st, h->ev_out[1], 0);
-    if ((flags & SDT_SYNC) || has_outputs) {
+    if ((flags & SDT_SYNC) || (has_outputs && !(flags & SDT_NO_WAIT))) {
         if (cudaStreamSynchronize(st) != cudaSuccess) return sdt_fail(h, SDT_ERR_CUDA, "stream synchronize failed");
     }
     return SDT_OK;

@@ -362,6 +362,12 @@ extern "C" int sdt_set_tuning(sdt_handle h, const char* key, int64_t value) {
     return SDT_OK;
 }
 
+extern "C" int sdt_synchronize(sdt_handle h, sdt_stream stream) {
+    if (!h) return SDT_ERR_INVALID;
+    SDT_CUDA(h, cudaStreamSynchronize((cudaStream_t)stream));
+    return SDT_OK;
+}
+
 extern "C" uint64_t sdt_kernel_launches(sdt_handle h) { return h ? h->launches : 0; }
 
 // ---------------------------------------------------------------------------- L2 probe

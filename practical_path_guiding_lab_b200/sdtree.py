@@ -140,6 +140,7 @@ class SDTree:
         if rc != 0:
             raise SDTreeError(rc, (self._lib.sdt_last_error(None) or b"").decode())
         self._h = h
+        self.host_wait = True       # False: host-pointer calls pass SDT_NO_WAIT; call synchronize() before reading outputs
         self.store_nee = bool(store_nee)
         self.device = int(device)
 
@@ -154,6 +155,14 @@ class SDTree:
             self.close()
         except Exception:
             pass
+
+    def _flags(self, b, extra=0):
+        """flags of one call; host-pointer calls return before their outputs landed when host_wait is False"""
+        return b.flags(extra) | (L.SDT_NO_WAIT if (b.host and not self.host_wait) else 0)
+
+    def synchronize(self, stream=None):
+        """completes every call enqueued so far (needed after host-pointer calls made with host_wait = False)"""
+        self._ck(self._lib.sdt_synchronize(self._h, stream))
 
     def _ck(self, rc):
         if rc != 0:
@@ -184,7 +193,7 @@ class SDTree:
         a = b.arr(active, np.uint8)
         leaf, lp = b.new((n,), np.uint32)
         root, rp = b.new((n,), np.uint32)
-        self._ck(self._lib.sdt_locate(self._h, C.byref(p), a, n, lp, rp, b.flags(L.SDT_SYNC if sync and b.host else 0), b.stream()))
+        self._ck(self._lib.sdt_locate(self._h, C.byref(p), a, n, lp, rp, self._flags(b, L.SDT_SYNC if sync and b.host else 0), b.stream()))
         return leaf, root
 
     def sample(self, pos, active=None, u=None, seed=0, lane_offset=0, debug=False, out=None):
@@ -207,7 +216,7 @@ class SDTree:
             pdf, pp = b.new((n,), np.float32)
         dbg, gp = (b.new((n, 4), np.uint32) if debug else (None, None))
         self._ck(self._lib.sdt_sample(self._h, C.byref(p), a, n, up, us, int(seed) & 0xFFFFFFFF, int(lane_offset),
-                                      C.byref(dv), pp, gp, b.flags(), b.stream()))
+                                      C.byref(dv), pp, gp, self._flags(b), b.stream()))
         return (d, pdf, dbg) if debug else (d, pdf)
 
     def pdf(self, pos, direction, active=None, debug=False, out=None):
@@ -223,7 +232,7 @@ class SDTree:
         else:
             pdf, pp = b.new((n,), np.float32)
         dbg, gp = (b.new((n, 3), np.uint32) if debug else (None, None))
-        self._ck(self._lib.sdt_pdf(self._h, C.byref(p), C.byref(dv), a, n, pp, gp, b.flags(), b.stream()))
+        self._ck(self._lib.sdt_pdf(self._h, C.byref(p), C.byref(dv), a, n, pp, gp, self._flags(b), b.stream()))
         return (pdf, dbg) if debug else pdf
 
     def guided(self, pos, mode, wo=None, u=None, seed=0, lane_offset=0, bsdf_pdf=None, bsdf_value=None,
@@ -276,7 +285,7 @@ class SDTree:
                 g.wo_pdf = wp.data_ptr()
             if wt is not None:
                 g.weight = L.Vec3(wt.data_ptr(), wt.data_ptr() + 4, wt.data_ptr() + 8, 3)
-        self._ck(self._lib.sdt_guided(self._h, C.byref(g), n, b.flags(), b.stream()))
+        self._ck(self._lib.sdt_guided(self._h, C.byref(g), n, self._flags(b), b.stream()))
         return d, sp, wp, wt
 
     def mis_nee(self, bsdf_pdf_em, sdtree_pdf_em, pdf_with_delta, pdf_without_delta, ds_pdf, ds_delta,
@@ -288,7 +297,7 @@ class SDTree:
         s, sp = b.new((n,), np.float32)
         m, mp = b.new((n,), np.float32)
         self._ck(self._lib.sdt_mis_nee(self._h, n, *ins, dl, float(bsdf_sampling_fraction), int(iteration), sp, mp,
-                                       b.flags(), b.stream()))
+                                       self._flags(b), b.stream()))
         return s, m
 
     def mis_mixture(self, bsdf_pdf, sdtree_pdf, bsdf_value, do_mis, bsdf_sampling_fraction):
@@ -302,7 +311,7 @@ class SDTree:
         w, wp = b.new((n, 3), np.float32)
         wv = L.Vec3(wp, wp + 4, wp + 8, 3)
         self._ck(self._lib.sdt_mis_mixture(self._h, n, bp, sp, C.byref(bv), dm, float(bsdf_sampling_fraction), wop,
-                                           C.byref(wv), b.flags(), b.stream()))
+                                           C.byref(wv), self._flags(b), b.stream()))
         return wo, w
 
     def dir_to_canonical(self, direction):
@@ -311,7 +320,7 @@ class SDTree:
         n = _n_of(direction)
         dv = b.vec(direction, 3)
         o, op = b.new((n, 2), np.float32)
-        self._ck(self._lib.sdt_dir_to_canonical(self._h, C.byref(dv), n, op, b.flags(), b.stream()))
+        self._ck(self._lib.sdt_dir_to_canonical(self._h, C.byref(dv), n, op, self._flags(b), b.stream()))
         return o
 
     def canonical_to_dir(self, pos2):
@@ -321,7 +330,7 @@ class SDTree:
         pv = b.vec(pos2, 2)
         o, op = b.new((n, 3), np.float32)
         ov = L.Vec3(op, op + 4, op + 8, 3)
-        self._ck(self._lib.sdt_canonical_to_dir(self._h, C.byref(pv), n, C.byref(ov), b.flags(), b.stream()))
+        self._ck(self._lib.sdt_canonical_to_dir(self._h, C.byref(pv), n, C.byref(ov), self._flags(b), b.stream()))
         return o
 
     # ---- splat into current -----------------------------------------------------------
@@ -337,7 +346,7 @@ class SDTree:
         r.radiance_nee = b.vec(radiance_nee, 3)
         r.direction_nee = b.vec(direction_nee, 2)
         r.active = b.arr(active, np.uint8)
-        self._ck(self._lib.sdt_splat_records(self._h, C.byref(r), n, b.flags(), b.stream()))
+        self._ck(self._lib.sdt_splat_records(self._h, C.byref(r), n, self._flags(b), b.stream()))
 
     def splat_path_data(self, max_depth, l_final, throughput_radiance, throughput_bsdf, bsdf, position, direction,
                         wo_pdf, radiance_nee=None, direction_nee=None, active=None, want_radiance=False):
@@ -361,7 +370,7 @@ class SDTree:
         if want_radiance:
             rad, rp = b.new((n,), np.float32)
             p.radiance_out = rp
-        self._ck(self._lib.sdt_splat_path_data(self._h, C.byref(p), b.flags(), b.stream()))
+        self._ck(self._lib.sdt_splat_path_data(self._h, C.byref(p), self._flags(b), b.stream()))
         return rad
 
     # ---- refine -------------------------------------------------------------------------

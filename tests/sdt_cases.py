@@ -356,6 +356,38 @@ def case_host_pipeline_chunks(ctx):
     assert_tree_equal(t.download(1), cur)
 
 
+def case_host_calls_no_wait(ctx):
+    """SDT_NO_WAIT: back-to-back host-pointer calls (pipelined and small ones mixed, different buffer layouts) return
+    before their outputs landed and overlap on the device; after one synchronize the results are those of the
+    waiting calls.  (Host buffers only: with device buffers the flag does nothing.)"""
+    t, cur, prev = train(ctx, iters=3)
+    rng = np.random.default_rng(5)
+    n = 20000
+    pos = rng.random((n, 3)).astype(F)
+    dirs = rng.standard_normal((n, 3)).astype(F)
+    dirs /= np.linalg.norm(dirs, axis=1, keepdims=True)
+    rec = dyadic_records(n, 78, ((0.3, 0.7, 0.02),))
+    want_d, want_p = prev.sample(pos, so.ExplicitSampler(seed=7, n=n, lane_offset=0), np.ones(n, bool))
+    want_q = prev.pdf(pos, dirs, np.ones(n, bool))
+    t.set_tuning("host_chunk", 1500)
+    for rep in range(2):
+        t.host_wait = False
+        outs = []
+        for k in range(3):                              # 3 rounds in flight: 13 chunks + ragged tail each, then a small call
+            d, p = t.sample(pos, seed=7)
+            q = t.pdf(pos, dirs)
+            qs = t.pdf(pos[:500], dirs[:500])           # small call: whole-arena staging on the call's stream
+            splat(t, Ctx(make=None), rec)
+            outs.append((d, p, q, qs))
+        t.synchronize()
+        t.host_wait = True
+        for d, p, q, qs in outs:
+            assert beq(d, want_d) and beq(p, want_p) and beq(q, want_q) and beq(qs, want_q[:500])
+    for _ in range(6):                                  # 120 k dyadic records: the fp32 sums stay exact
+        cur.addDataPropagate(rec)
+    assert_tree_equal(t.download(1), cur)
+
+
 def case_splat_float_tolerance(ctx):
     """general fp32 radiance: energies within 1e-4 relative of the exactly-rounded sums;
     conservation root = sum leaves = sum radiance/woPdf (src/quadtree.py:1205-1218)"""
@@ -627,7 +659,7 @@ def case_npz_roundtrip(ctx, tmp_path):
     check_queries(ctx, t2, o, n=1024)
 
 
-ALL_CASES = [case_golden_fixture, case_deep_quadtree_beyond_fp32_grid, case_jump_table_equals_descent, case_spatial_descent_variants, case_initial_tree, case_golden_upload_download, case_train_refine_topology, case_threshold_reciprocal_variant, case_zero_total_energy, case_host_pipeline_chunks,
+ALL_CASES = [case_golden_fixture, case_deep_quadtree_beyond_fp32_grid, case_jump_table_equals_descent, case_spatial_descent_variants, case_initial_tree, case_golden_upload_download, case_train_refine_topology, case_threshold_reciprocal_variant, case_zero_total_energy, case_host_pipeline_chunks, case_host_calls_no_wait,
              case_train_refine_nee_shallow, case_fused_equals_two_descents, case_splat_float_tolerance,
              case_path_data, case_mis, case_guided_bounce, case_refine_flags_and_frozen_stats,
              case_capacity_error, case_edge_inputs_and_errors]
