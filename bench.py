@@ -425,9 +425,9 @@ def run_b200(args):
                 dist.all_reduce(dt, op=dist.ReduceOp.MAX)
             return float(dt.item())
         tree2.host_wait = True                          # each call returns with its outputs on the host
-        dt_e2e = timed_host()
+        dt_wait = timed_host()
         tree2.host_wait = False                         # SDT_NO_WAIT: the three calls overlap, one synchronize per step
-        dt_nowait = timed_host()
+        dt_e2e = timed_host()
         tree2.host_wait = True
         # what the link gives a plain pinned copy of the same size (context for the number above)
         big = torch.empty(256 << 20, dtype=torch.uint8).pin_memory()
@@ -442,12 +442,13 @@ def run_b200(args):
         del big, dbig
         e2e = {"value": n * world / dt_e2e, "unit": UNIT, "ms_per_step": dt_e2e * 1e3,
                "h2d_bytes_per_step": n * (12 + 24 + 28), "d2h_bytes_per_step": n * (16 + 4),
-               "ms_per_step_no_wait": dt_nowait * 1e3, "pinned_h2d_copy_gbs": h2d_gbs,
+               "ms_per_step_waiting_calls": dt_wait * 1e3, "pinned_h2d_copy_gbs": h2d_gbs,
                "h2d_gbs_in_step": n * (12 + 24 + 28) / dt_e2e / 1e9,
-               "how": "sdt_sample + sdt_pdf + sdt_splat_records with SDT_HOST_PTRS on pinned host arrays, each call returning "
-                      "with its outputs on the host; staging copies inside the calls.  ms_per_step_no_wait: the same calls "
-                      "with SDT_NO_WAIT and one sdt_synchronize per step; pinned_h2d_copy_gbs: a plain pinned H2D copy on "
-                      "this box -- the step is bound by the host link (h2d_gbs_in_step, with the D2H traffic beside it)"}
+               "how": "sdt_sample + sdt_pdf + sdt_splat_records with SDT_HOST_PTRS | SDT_NO_WAIT on pinned host arrays and one "
+                      "sdt_synchronize per step (all outputs on the host); staging copies inside the calls.  "
+                      "ms_per_step_waiting_calls: the same without SDT_NO_WAIT, every call returning with its outputs on the "
+                      "host; pinned_h2d_copy_gbs: a plain pinned H2D copy on this box -- the step is bound by the host link "
+                      "(h2d_gbs_in_step, with the D2H traffic beside it)"}
 
     # ---- CPU port of the reference, timed beside it (rank 0, N=1)
     cpu = None

@@ -66,8 +66,10 @@ struct sdt_tree_s {
     bool hdr_pending = false;       // an async header read-back (after refine) is in flight
 
     // staging for SDT_HOST_PTRS: one arena; large host calls run as a 2-slot pipeline
-    // (H2D of chunk k+1 | kernel of chunk k | D2H of chunk k-1 on three streams)
+    // (H2D of chunk k+1 | kernel of chunk k | D2H of chunk k-1 on three streams) whose outputs
+    // live in a second arena of the same size, so that H2D never has to wait for a D2H
     char* stage = nullptr;
+    char* stage_o = nullptr;
     size_t stage_cap = 0, stage_off = 0;
     cudaStream_t s_in = nullptr, s_out = nullptr;
     cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_comp[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
@@ -140,6 +142,7 @@ struct Stager {
     int status = SDT_OK;
     int slot = -1;                  // >= 0: pipelined chunk using half `slot` of the arena
     size_t off = 0, lim = 0;
+    size_t off_o = 0, lim_o = 0;    // pipelined chunks: outputs in the second arena
     struct Out { void* host; void* dev; size_t bytes; };
     std::vector<Out> outs;
 
@@ -148,6 +151,7 @@ struct Stager {
         if (slot >= 0) {
             const size_t half = (h->stage_cap / 2) & ~(size_t)255;
             off = (size_t)slot * half; lim = off + half;
+            off_o = off; lim_o = lim;
             // the slot's input buffers are free once the kernels of the chunk that used it have run
             cudaStreamWaitEvent(h->s_in, h->ev_comp[slot], 0);
         } else {
@@ -164,9 +168,12 @@ struct Stager {
         if (!host) return SDT_OK;
         bytes += 4096;
         if (bytes <= h->stage_cap) { if (slot < 0) lim = h->stage_cap; return SDT_OK; }
-        if (h->stage) { cudaDeviceSynchronize(); cudaFree(h->stage); h->stage = nullptr; h->stage_cap = 0; }
+        if (h->stage) { cudaDeviceSynchronize(); cudaFree(h->stage); cudaFree(h->stage_o); h->stage = h->stage_o = nullptr; h->stage_cap = 0; }
         size_t cap = bytes + bytes / 4;
-        if (cudaMalloc((void**)&h->stage, cap) != cudaSuccess) { status = sdt_fail(h, SDT_ERR_CUDA, "staging arena cudaMalloc failed"); return status; }
+        if (cudaMalloc((void**)&h->stage, cap) != cudaSuccess || (h->s_in && cudaMalloc((void**)&h->stage_o, cap) != cudaSuccess)) {
+            if (h->stage) { cudaFree(h->stage); h->stage = nullptr; }
+            status = sdt_fail(h, SDT_ERR_CUDA, "staging arena cudaMalloc failed"); return status;
+        }
         h->stage_cap = cap;
         if (slot < 0) lim = cap;
         return SDT_OK;
@@ -187,7 +194,13 @@ struct Stager {
     }
     void* out(void* p, size_t bytes) {
         if (!host || !p) return p;
-        void* d = alloc(bytes);
+        void* d;
+        if (slot >= 0) {
+            const size_t o = (off_o + 255) & ~(size_t)255;
+            if (o + bytes > lim_o) { status = sdt_fail(h, SDT_ERR_INVALID, "staging arena overflow (reserve too small)"); return nullptr; }
+            off_o = o + bytes;
+            d = h->stage_o + o;
+        } else d = alloc(bytes);
         if (!d) return nullptr;
         outs.push_back(Out{p, d, bytes});
         return d;
@@ -277,16 +290,14 @@ static int sdt_run_chunked(sdt_handle h, cudaStream_t st, uint32_t flags, uint32
         SDT_TRY(probe.reserve(2 * ((size_t)chunk * bytes_per_lane + 65536)));
     }
     // a small host call stages through the whole arena on its own stream: the input stream starts after it.
-    // Chunks of an earlier pipelined call are covered slot by slot: ev_comp (Stager) frees the slot's inputs,
-    // ev_out its outputs -- the layouts of two calls differ, so the first two chunks wait for both; everything
-    // else of the earlier call (its D2H tail in particular) overlaps with this call's H2D.
+    // Chunks of an earlier pipelined call (SDT_NO_WAIT) are covered slot by slot: ev_comp (Stager) frees the slot's
+    // inputs for the H2D, ev_out (before_launch) its outputs for the kernels; inputs and outputs live in separate
+    // arenas, so the D2H tail of the earlier call runs under this call's H2D head.
     if (h->arena_on_st) {
         cudaEventRecord(h->ev_in[0], h->arena_stream);
         cudaStreamWaitEvent(h->s_in, h->ev_in[0], 0);
         h->arena_on_st = false;
     }
-    cudaStreamWaitEvent(h->s_in, h->ev_out[0], 0);
-    cudaStreamWaitEvent(h->s_in, h->ev_out[1], 0);
     int k = 0;
     for (uint32_t off = 0; off < n; off += chunk, ++k) {
         const uint32_t cnt = n - off < chunk ? n - off : chunk;

@@ -9,7 +9,7 @@ static int dev_alloc(sdt_handle h, T** p, size_t n) {
 
 static int sdt_free_all(sdt_handle h) {
     void* ptrs[] = {h->kd_word, h->kd_count, h->kd_depth, h->kd_root, h->kd_bmin, h->kd_bmax, h->kd_prev_count, h->kd_s,
-                    h->kd_sel, h->kd_rank[0], h->kd_rank[1], h->root_src, h->kd_grid, h->q_ecur, h->s_src, h->s_kind, h->s_srem, h->s_blk, h->stage};
+                    h->kd_sel, h->kd_rank[0], h->kd_rank[1], h->root_src, h->kd_grid, h->q_ecur, h->s_src, h->s_kind, h->s_srem, h->s_blk, h->stage, h->stage_o};
     for (void* p : ptrs) if (p) cudaFree(p);
     for (int k = 0; k < 2; ++k) {
         QuadSet& s = h->set[k];
