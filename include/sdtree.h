@@ -266,7 +266,7 @@ int sdt_stat_buffers(sdt_handle h, float** q_energy, uint32_t* n_quad, float** k
 
 /* ---- tuning / introspection --------------------------------------------------- */
 /* key: "query_block", "query_ctas_per_sm", "kd_smem_nodes", "splat_block",
- * "splat_ctas_per_sm", "fuse_sample_pdf", "use_jump", "use_kd_grid", "use_compaction", "host_chunk" (lanes per chunk of the pipelined
+ * "splat_ctas_per_sm", "fuse_sample_pdf", "use_jump", "use_kd_grid", "use_compaction", "use_pdl", "host_chunk" (lanes per chunk of the pipelined
  * SDT_HOST_PTRS staging: H2D of chunk k+1 | kernels of chunk k | D2H of chunk k-1).
  * One key switches semantics rather than speed: "quad_thr_reciprocal" = 1 computes the
  * quadtree refinement threshold (src/quadtree.py:519, `E / 100`) as E * fp32(0.01), the

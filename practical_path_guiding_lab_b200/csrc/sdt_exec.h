@@ -14,12 +14,36 @@ struct ExecCtx {
     int num_sms;
     uint32_t* blk;        // SDT_SCAN_MAX_BLOCKS words of device scratch for the scans
     uint64_t* launches;   // kernel launch counter of the handle
+    bool pdl;             // programmatic dependent launch for the helper kernels (see sdt_launch)
 };
 
 #ifndef SDT_HOSTEMU
 // ---------------------------------------------------------------------------- CUDA
+// The refine is a chain of ~200 tiny dependent kernels: launch latency is all it costs.  Every helper
+// kernel therefore starts with sdt_grid_dep(): it lets the NEXT kernel of the stream be scheduled right
+// away (griddepcontrol.launch_dependents) and then waits until the PREVIOUS one has completed and
+// flushed (griddepcontrol.wait) -- the dependency is kept, the launch latencies overlap.  Both are no-ops
+// for a kernel launched without the programmatic-serialization attribute.
+__device__ __forceinline__ void sdt_grid_dep() {
+    asm volatile("griddepcontrol.launch_dependents;");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+
+template <class... KArgs, class... Args>
+static inline void sdt_launch(const ExecCtx& x, void (*kernel)(KArgs...), uint32_t grid, uint32_t block, Args... args) {
+    if (!x.pdl) { kernel<<<grid, block, 0, x.st>>>(args...); return; }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(block); cfg.dynamicSmemBytes = 0; cfg.stream = x.st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 template <class F>
 __global__ void __launch_bounds__(256) k_items(F f, const uint32_t* n_ptr, uint32_t n_imm) {
+    sdt_grid_dep();
     const uint32_t n = n_ptr ? *n_ptr : n_imm;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) f(i);
 }
@@ -35,7 +59,7 @@ static inline void launch_items(const ExecCtx& x, const uint32_t* n_ptr, uint32_
         const uint32_t cap = (uint32_t)x.num_sms * 8u;
         if (grid > cap) grid = cap;
     }
-    k_items<F><<<grid, 256, 0, x.st>>>(f, n_ptr, n_imm);
+    sdt_launch(x, k_items<F>, grid, 256u, f, n_ptr, n_imm);
     ++*x.launches;
 }
 
@@ -79,6 +103,7 @@ __device__ __forceinline__ void sdt_chunk(uint32_t n, uint32_t& lo, uint32_t& hi
 template <class Flag>
 __global__ void __launch_bounds__(256) k_scan_reduce(Flag flag, const uint32_t* n_ptr, uint32_t n_imm, uint32_t* blk) {
     __shared__ uint32_t ws[33];
+    sdt_grid_dep();
     const uint32_t n = n_ptr ? *n_ptr : n_imm;
     uint32_t lo, hi;
     sdt_chunk(n, lo, hi);
@@ -92,6 +117,7 @@ __global__ void __launch_bounds__(256) k_scan_reduce(Flag flag, const uint32_t* 
 template <class Fin>
 __global__ void __launch_bounds__(SDT_SCAN_MAX_BLOCKS) k_scan_blocks(uint32_t* blk, uint32_t nblk, Fin fin) {
     __shared__ uint32_t ws[33];
+    sdt_grid_dep();
     const uint32_t v = threadIdx.x < nblk ? blk[threadIdx.x] : 0u;
     uint32_t tot;
     const uint32_t ex = sdt_block_excl_scan(v, ws, tot);
@@ -102,6 +128,7 @@ __global__ void __launch_bounds__(SDT_SCAN_MAX_BLOCKS) k_scan_blocks(uint32_t* b
 template <class Flag, class Emit>
 __global__ void __launch_bounds__(256) k_scan_emit(Flag flag, Emit emit, const uint32_t* n_ptr, uint32_t n_imm, const uint32_t* blk) {
     __shared__ uint32_t ws[33];
+    sdt_grid_dep();
     const uint32_t n = n_ptr ? *n_ptr : n_imm;
     uint32_t lo, hi;
     sdt_chunk(n, lo, hi);
@@ -126,17 +153,17 @@ static inline void launch_scan(const ExecCtx& x, const uint32_t* n_ptr, uint32_t
         const uint32_t g = (n_imm + 255u) / 256u;
         if (g < grid) grid = g ? g : 1u;
     }
-    k_scan_reduce<Flag><<<grid, 256, 0, x.st>>>(flag, n_ptr, n_imm, x.blk);
-    k_scan_blocks<Fin><<<1, SDT_SCAN_MAX_BLOCKS, 0, x.st>>>(x.blk, grid, fin);
-    k_scan_emit<Flag, Emit><<<grid, 256, 0, x.st>>>(flag, emit, n_ptr, n_imm, x.blk);
+    sdt_launch(x, k_scan_reduce<Flag>, grid, 256u, flag, n_ptr, n_imm, x.blk);
+    sdt_launch(x, k_scan_blocks<Fin>, 1u, (uint32_t)SDT_SCAN_MAX_BLOCKS, x.blk, grid, fin);
+    sdt_launch(x, k_scan_emit<Flag, Emit>, grid, 256u, flag, emit, n_ptr, n_imm, (const uint32_t*)x.blk);
     *x.launches += 3;
 }
 
 template <class F>
-__global__ void k_single(F f) { f(); }
+__global__ void k_single(F f) { sdt_grid_dep(); f(); }
 template <class F>
 static inline void launch_single(const ExecCtx& x, F f) {
-    k_single<F><<<1, 1, 0, x.st>>>(f);
+    sdt_launch(x, k_single<F>, 1u, 1u, f);
     ++*x.launches;
 }
 

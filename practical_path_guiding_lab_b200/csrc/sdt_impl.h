@@ -58,6 +58,7 @@ struct sdt_tree_s {
     uint32_t jump_trees_known = 0;  // trees covered, as last seen by the host (0 until known: slow path)
     int use_jump = 1;
     int use_int_cell = 1;
+    int use_pdl = 1;                // programmatic dependent launch for the refine / sweep helper kernels
     int quad_thr_reciprocal = 0;    // semantics switch, see sdt_set_tuning in sdtree.h
     int use_compaction = 1;         // sort the lanes of a tile by mode when a wavefront has idle / mixed lanes
     int use_kd_grid = 1;            // per-CTA 16x16x8 grid over the first 11 spatial levels
@@ -110,7 +111,7 @@ static int sdt_fail(sdt_handle h, int code, const std::string& msg) {
 
 static inline ExecCtx exec_ctx(sdt_handle h, cudaStream_t st) {
     h->last_stream = st;
-    return ExecCtx{st, h->num_sms, h->s_blk, &h->launches};
+    return ExecCtx{st, h->num_sms, h->s_blk, &h->launches, h->use_pdl != 0};
 }
 
 static inline TreeView tree_view(sdt_tree_s* h) {

@@ -356,6 +356,7 @@ extern "C" int sdt_set_tuning(sdt_handle h, const char* key, int64_t value) {
     else if (k == "use_kd_grid") h->use_kd_grid = value != 0;
     else if (k == "use_int_cell") h->use_int_cell = value != 0;
     else if (k == "quad_thr_reciprocal") h->quad_thr_reciprocal = value != 0;
+    else if (k == "use_pdl") h->use_pdl = value != 0;
     else if (k == "use_compaction") h->use_compaction = value != 0;
     else if (k == "host_chunk") { SDT_CHECK(h, value >= 256, SDT_ERR_INVALID, "host_chunk must be >= 256 lanes"); h->host_chunk = (int)value; }
     else return sdt_fail(h, SDT_ERR_INVALID, "sdt_set_tuning: unknown key " + k);
