@@ -279,7 +279,9 @@ if _HAVE_MITSUBA:                                      # pragma: no cover
             it = 0
             while dr.any(active) and (self.max_depth < 0 or it < self.max_depth):
                 it += 1
-                si = scene.ray_intersect(ray, ray_flags=mi.RayFlags.All, coherent=dr.eq(depth, 0))
+                # the reference's recorded mi.Loop masks every state update by `active`; this unrolled wavefront loop
+                # masks what a finished lane could still change: its intersection and its radiance
+                si = scene.ray_intersect(ray, ray_flags=mi.RayFlags.All, coherent=dr.eq(depth, 0), active=active)
                 bsdf = si.bsdf()
                 ds_direct = mi.DirectionSample3f(scene, si=si, ref=prev_si)
                 emitter_pdf = scene.pdf_emitter_direction(prev_si, ds_direct, ~prev_bsdf_delta)
@@ -304,7 +306,7 @@ if _HAVE_MITSUBA:                                      # pragma: no cover
                 torch.cuda.current_stream().synchronize()
                 mis_em = mi.Float(mis_em_t)
                 Lr_dir = throughput * mis_em * bsdf_value_em * em_weight
-                L += Le + Lr_dir
+                L = dr.select(active, L + Le + Lr_dir, L)
                 # continuation
                 bsdf_sample, bsdf_weight = bsdf.sample(bsdf_ctx, si, sampler.next_1d(active_next), sampler.next_2d(active_next), active_next)
                 bsdf_pdf = mi.Float(bsdf_sample.pdf)
