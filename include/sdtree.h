@@ -153,7 +153,10 @@ int sdt_locate(sdt_handle h, const sdt_vec3* pos, const uint8_t* active, uint32_
  * (src/quadtree.py:931-998) -> QuadTree.pdfQuadTree of the sampled direction
  * (:1001-1101).  Uniforms: if `u` != NULL lane i uses u[i*u_stride + 3*level + k],
  * k = 0,1,2 = (u_x, u_y, u_select), consumed as the reference consumes its sampler;
- * else a counter-based generator keyed (seed, lane_offset + i, 3*level + k).
+ * else the library's own generator keyed (seed, lane_offset + i, 3*level + k): a murmur3
+ * finaliser of (seed, lane) starts the lane; the per-level u_select is the top 24 bits of a
+ * 32-bit LCG stream from that key, the leaf position (u_x, u_y) a second hash round
+ * (csrc/sdt_core.h CounterRng; restated in oracle/sdtree_oracle.py counter_uniform).
  * dbg (optional, 4*n uint32): per lane {kd leaf, quadtree root id, quadtree node
  * reached by the sample, quadtree node reached by the pdf}. */
 int sdt_sample(sdt_handle h, const sdt_vec3* pos, const uint8_t* active, uint32_t n,

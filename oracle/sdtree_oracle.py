@@ -81,10 +81,15 @@ def bbox_contains(bmin, bmax, p):
         return np.all((p >= bmin) & (p <= bmax), axis=-1)
 
 
+LCG_M, LCG_C = 747796405, 2891336453
+
+
 def counter_uniform(seed, lane, idx):
-    """Counter-based uniform in [0,1) keyed (seed, lane, idx): two rounds of the
-    murmur3 32-bit finaliser.  Stated identically in the CUDA library (perf mode
-    RNG; the reference's PCG32 state is not reachable from Python)."""
+    """Perf-mode uniform in [0,1) keyed (seed, lane, idx), stated identically in the CUDA library
+    (the reference's PCG32 state is not reachable from Python).  h0 = murmur3 finaliser of
+    (seed, lane).  idx = 3*level + k as QuadTree.sampleQuadTree consumes them: k == 2 (child selection)
+    is the top 24 bits of the 32-bit LCG stream t_{level+1} = t_level*M + C started at t_0 = h0;
+    k in (0, 1) (leaf position) is a second finaliser round of h0 ^ f(idx)."""
     def fmix(h):
         h = h ^ (h >> U(16))
         h = (h * U(0x85EBCA6B)).astype(U)
@@ -95,8 +100,16 @@ def counter_uniform(seed, lane, idx):
     with np.errstate(over='ignore'):
         lane = np.asarray(lane, dtype=U)
         idx = np.asarray(idx, dtype=U)
-        h = fmix((U(seed) + lane * U(0x9E3779B1)).astype(U))
-        h = fmix((h ^ (idx * U(0x85EBCA77) + U(0x165667B1)).astype(U)).astype(U))
+        h0 = fmix((U(seed) + lane * U(0x9E3779B1)).astype(U))
+        h = fmix((h0 ^ (idx * U(0x85EBCA77) + U(0x165667B1)).astype(U)).astype(U))
+        sel = np.broadcast_to((idx % U(3)) == U(2), np.broadcast(h0, idx).shape)
+        if sel.any():
+            steps = np.broadcast_to(idx // U(3) + U(1), sel.shape)
+            t = np.broadcast_to(h0, sel.shape).copy()
+            for k in range(int(steps[sel].max())):
+                go = sel & (steps > k)
+                t[go] = (t[go].astype(np.uint64) * np.uint64(LCG_M) + np.uint64(LCG_C)).astype(U)
+            h = np.where(sel, t, h)
     return ((h >> U(8)).astype(F) * F(2.0 ** -24)).astype(F)
 
 

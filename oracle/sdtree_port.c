@@ -108,9 +108,10 @@ static uint32_t kd_leaf_of(const port_tree* t, const float* p, int active, int* 
 }
 
 static uint32_t fmix(uint32_t h) { h ^= h >> 16; h *= 0x85EBCA6Bu; h ^= h >> 13; h *= 0xC2B2AE35u; h ^= h >> 16; return h; }
-static float counter_uniform(uint32_t seed, uint32_t lane, uint32_t idx) {
-    uint32_t h = fmix(seed + lane * 0x9E3779B1u);
-    h = fmix(h ^ (idx * 0x85EBCA77u + 0x165667B1u));
+/* the library's perf-mode generator (sdt_core.h CounterRng, oracle counter_uniform): position
+ * uniforms by hash, the selection uniform of level L = top 24 bits of the (L+1)-th LCG state */
+static float counter_pos(uint32_t h0, uint32_t idx) {
+    uint32_t h = fmix(h0 ^ (idx * 0x85EBCA77u + 0x165667B1u));
     return (float)(h >> 8) * 5.9604644775390625e-08f;
 }
 
@@ -151,9 +152,11 @@ void port_sample(const port_tree* t, uint32_t n, const float* pos, const uint8_t
             leaf = kd_leaf_of(t, pos + 3 * i, 1, 0);
             root = t->kd_root[leaf];
             node = t->q_rootnode[root];
+            const uint32_t h0 = fmix(seed + (lane_offset + (uint32_t)i) * 0x9E3779B1u);
+            uint32_t lcg = h0;
             for (uint32_t level = 0; level < 64; ++level) {
-                float ux = counter_uniform(seed, lane_offset + (uint32_t)i, 3 * level);
-                float uy = counter_uniform(seed, lane_offset + (uint32_t)i, 3 * level + 1);
+                float ux = counter_pos(h0, 3 * level);       /* drawn at every level like the reference (:956) */
+                float uy = counter_pos(h0, 3 * level + 1);
                 if (t->q_leaf[node]) {
                     const float* mn = t->q_bmin + 2 * node; const float* mx = t->q_bmax + 2 * node;
                     px = mn[0] + ux * (mx[0] - mn[0]);
@@ -166,7 +169,8 @@ void port_sample(const port_tree* t, uint32_t n, const float* pos, const uint8_t
                 float e2 = t->q_energy[c[1]] + e1;
                 float e3 = t->q_energy[c[2]] + e2;
                 float e4 = t->q_energy[c[3]] + e3;
-                float s = counter_uniform(seed, lane_offset + (uint32_t)i, 3 * level + 2) * e4;
+                lcg = lcg * 747796405u + 2891336453u;
+                float s = ((float)(lcg >> 8) * 5.9604644775390625e-08f) * e4;
                 int pick = -1;
                 if (s < e1) pick = 0;
                 if (e1 <= s && s < e2) pick = 1;

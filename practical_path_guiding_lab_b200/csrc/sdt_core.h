@@ -180,31 +180,36 @@ SDT_HD float sdt_luminance(float r, float g, float b) {
     return (r * 0.212671f + g * 0.715160f) + b * 0.072169f;
 }
 
-// counter-based uniform in [0,1): two murmur3 finaliser rounds (oracle: counter_uniform)
+// Perf-mode uniforms in [0,1), keyed (seed, lane, idx) and restated identically in the oracle
+// (counter_uniform).  The lane key h0 is a murmur3 finaliser of (seed, lane).  idx = 3*level + {0,1,2}
+// as the reference consumes them (src/quadtree.py:956,980):
+//   idx % 3 == 2 (the child-selection uniform, one per visited level -- the hot one): the top 24 bits of
+//                a 32-bit LCG stream started at h0, t_{level+1} = t_level * M + C, so that a descent
+//                pays one multiply-add per level instead of a hash;
+//   idx % 3 != 2 (the leaf position, used once per sample): a second finaliser round of h0 ^ f(idx).
+// M, C: the 32-bit multiplier / an odd increment of the PCG family (full period 2^32).
+#define SDT_LCG_M 747796405u
+#define SDT_LCG_C 2891336453u
 SDT_HD uint32_t sdt_fmix(uint32_t h) {
     h ^= h >> 16; h *= 0x85EBCA6Bu; h ^= h >> 13; h *= 0xC2B2AE35u; h ^= h >> 16;
     return h;
 }
-SDT_HD float sdt_uniform(uint32_t seed, uint32_t lane, uint32_t idx) {
-    uint32_t h = sdt_fmix(seed + lane * 0x9E3779B1u);
-    h = sdt_fmix(h ^ (idx * 0x85EBCA77u + 0x165667B1u));
-    return (float)(h >> 8) * 5.9604644775390625e-08f;
-}
+SDT_HD float sdt_u24(uint32_t h) { return (float)(h >> 8) * 5.9604644775390625e-08f; }
 
-// Uniform stream of one lane.  CounterRng: the counter generator (the lane hash is computed
-// once).  ExplicitRng: u[lane*stride + idx], clamped like the oracle's ExplicitSampler.
+// Uniform stream of one lane.  select(level) must be called for level = 0, 1, 2, ... in turn (a descent
+// does); pos(idx) is random access.  ExplicitRng: u[lane*stride + idx], clamped like the oracle's
+// ExplicitSampler.
 struct CounterRng {
-    uint32_t h0;
-    SDT_HD CounterRng(uint32_t seed, uint32_t lane_id) : h0(sdt_fmix(seed + lane_id * 0x9E3779B1u)) {}
-    SDT_HD float get(uint32_t idx) const {
-        const uint32_t h = sdt_fmix(h0 ^ (idx * 0x85EBCA77u + 0x165667B1u));
-        return (float)(h >> 8) * 5.9604644775390625e-08f;
-    }
+    uint32_t h0, t;
+    SDT_HD CounterRng(uint32_t seed, uint32_t lane_id) : h0(sdt_fmix(seed + lane_id * 0x9E3779B1u)), t(h0) {}
+    SDT_HD float select(uint32_t) { t = t * SDT_LCG_M + SDT_LCG_C; return sdt_u24(t); }
+    SDT_HD float pos(uint32_t idx) const { return sdt_u24(sdt_fmix(h0 ^ (idx * 0x85EBCA77u + 0x165667B1u))); }
 };
 struct ExplicitRng {
     const float* row; uint32_t u_stride;
     SDT_HD ExplicitRng(const float* u, uint32_t stride, uint32_t lane_index) : row(u + (size_t)lane_index * stride), u_stride(stride) {}
-    SDT_HD float get(uint32_t idx) const { return SDT_LDG(row + (idx < u_stride ? idx : u_stride - 1u)); }
+    SDT_HD float pos(uint32_t idx) const { return SDT_LDG(row + (idx < u_stride ? idx : u_stride - 1u)); }
+    SDT_HD float select(uint32_t level) const { return pos(3u * level + 2u); }
 };
 
 SDT_HD float sdt_ld(const float* p, int64_t stride, uint32_t i) { return SDT_LDG(p + (int64_t)i * stride); }
@@ -513,7 +518,7 @@ struct QSample {
 // reference's repeated (min+max)/2 is exact too, so the box is bit-identical; deeper trees
 // (QuadTree.maxDepth > 23) use the float tracking that reproduces the reference's rounding.
 template <class Rng, bool INT_CELL>
-SDT_HD QSample sdt_quad_sample(const QRec* __restrict__ rec, uint32_t ri, uint32_t root_node, const Rng& rng) {
+SDT_HD QSample sdt_quad_sample(const QRec* __restrict__ rec, uint32_t ri, uint32_t root_node, Rng rng) {
     QSample q;
     q.x = 0.0f; q.y = 0.0f; q.node = root_node; q.moved = ri != SDT_NONE; q.stuck = false;
     q.lox = 0.0f; q.loy = 0.0f; q.hix = 1.0f; q.hiy = 1.0f;
@@ -527,7 +532,7 @@ SDT_HD QSample sdt_quad_sample(const QRec* __restrict__ rec, uint32_t ri, uint32
         const float e2 = e.y + e1;                                       // :975-977
         const float e3 = e.z + e2;
         const float e4 = e.w + e3;
-        const float s = rng.get(3u * level + 2u) * e4;                   // :980
+        const float s = rng.select(level) * e4;                          // :980
         // :983-991: four masked assignments in turn, a later bin overrides an earlier one
         // (they only overlap for negative energies); no bin (NaN) -> the lane is stuck
         const bool b1 = e1 <= s, b2 = e2 <= s, b3 = e3 <= s;
@@ -550,7 +555,7 @@ SDT_HD QSample sdt_quad_sample(const QRec* __restrict__ rec, uint32_t ri, uint32
         q.loy = (float)iy * sc; q.hiy = (float)(iy + 1u) * sc;
     }
     if (!q.stuck) {
-        const float ux = rng.get(3u * level), uy = rng.get(3u * level + 1u);
+        const float ux = rng.pos(3u * level), uy = rng.pos(3u * level + 1u);
         q.x = q.lox + ux * (q.hix - q.lox);                              // :960-962
         q.y = q.loy + uy * (q.hiy - q.loy);
     }

@@ -619,6 +619,59 @@ def case_edge_inputs_and_errors(ctx):
     assert_tree_equal(t2.download(0), prev)
 
 
+def case_counter_generator_statistics(ctx):
+    """the perf-mode generator (hash for the lane key and the leaf position, an LCG stream for the per-level child
+    selection) must sample the tree's distribution: leaf frequencies of 2^18 draws against prod(E_child / sum of
+    siblings) (chi-square over all levels jointly), the position inside the leaves uniform, and the mean of
+    1 / (4 pi pdf) equal to the fraction of the sphere that has energy (the estimator the integrator relies on)"""
+    t, cur, prev = train(ctx, iters=4)
+    q = prev.quadTree.quadTreeNode
+    n = 1 << 18
+    for point, seed in (((0.3, 0.3, 0.3), 11), ((0.8, 0.6, 0.1), 4242)):
+        pos = np.tile(np.array([point], F), (n, 1))
+        d, p, dbg = t.sample(ctx.dev(pos), seed=seed, debug=True)
+        dbg = ctx.host(dbg).view(U)
+        node = dbg[:, 2]
+        root = int(q.rootNodeIndex[dbg[0, 1]])
+        prob = {root: 1.0}
+        stack = [root]
+        leaves = []
+        while stack:
+            v = stack.pop()
+            if q.isLeaf[v]:
+                leaves.append(v)
+                continue
+            ch = [int(c[v]) for c in (q.child_1_index, q.child_2_index, q.child_3_index, q.child_4_index)]
+            e = np.array([q.irradiance[c] for c in ch], np.float64)
+            for c, w in zip(ch, e / e.sum()):
+                prob[c] = prob[v] * w
+                stack.append(c)
+        assert len(leaves) > 20
+        obs = np.bincount(node, minlength=q.getWidth())[leaves].astype(np.float64)
+        exp = np.array([prob[v] for v in leaves]) * n
+        assert obs.sum() == n
+        big = exp >= 8
+        chi2 = float((((obs - exp) ** 2) / np.maximum(exp, 1e-300))[big].sum())
+        df = int(big.sum()) - 1
+        assert abs(chi2 - df) < 5.0 * np.sqrt(2.0 * df) + 5.0, (chi2, df)
+        pdf = ctx.host(p).astype(np.float64)
+        est = (1.0 / (4.0 * np.pi * pdf)).mean()                        # = integral of 1/(4 pi) over the sampled support
+        sd = (1.0 / (4.0 * np.pi * pdf)).std() / np.sqrt(n)
+        support = sum(float(np.prod(q.bbox_max[v] - q.bbox_min[v])) for v in leaves if prob[v] > 0)   # zero-energy leaves are never sampled
+        assert abs(est - support) < 5.0 * sd + 1e-3, (est, support, sd)
+        # position inside the most frequent leaf: both canonical coordinates uniform over the cell
+        v = leaves[int(np.argmax(obs))]
+        sel = node == v
+        c2 = dm.dir_to_canonical(ctx.host(d)[sel])
+        lo, hi = q.bbox_min[v], q.bbox_max[v]
+        uu = (c2 - lo) / (hi - lo)
+        m = int(sel.sum())
+        for k in range(2):
+            h = np.bincount(np.clip((uu[:, k] * 16).astype(int), 0, 15), minlength=16).astype(np.float64)
+            c = float(((h - m / 16.0) ** 2 / (m / 16.0)).sum())
+            assert c < 15 + 5.0 * np.sqrt(30.0) + 5.0, (k, c)
+
+
 def case_golden_fixture(ctx):
     """the committed golden file (tests/golden/sdtree_golden.npz, written by make_sdtree_golden.py with
     the oracle): upload its tree, replay its queries and records, compare with its stored answers"""
@@ -659,7 +712,7 @@ def case_npz_roundtrip(ctx, tmp_path):
     check_queries(ctx, t2, o, n=1024)
 
 
-ALL_CASES = [case_golden_fixture, case_deep_quadtree_beyond_fp32_grid, case_jump_table_equals_descent, case_spatial_descent_variants, case_initial_tree, case_golden_upload_download, case_train_refine_topology, case_threshold_reciprocal_variant, case_zero_total_energy, case_host_pipeline_chunks, case_host_calls_no_wait,
+ALL_CASES = [case_golden_fixture, case_counter_generator_statistics, case_deep_quadtree_beyond_fp32_grid, case_jump_table_equals_descent, case_spatial_descent_variants, case_initial_tree, case_golden_upload_download, case_train_refine_topology, case_threshold_reciprocal_variant, case_zero_total_energy, case_host_pipeline_chunks, case_host_calls_no_wait,
              case_train_refine_nee_shallow, case_fused_equals_two_descents, case_splat_float_tolerance,
              case_path_data, case_mis, case_guided_bounce, case_refine_flags_and_frozen_stats,
              case_capacity_error, case_edge_inputs_and_errors]
