@@ -67,5 +67,6 @@ with open(f'profiles/{tag}_summary.md', 'w') as f:
     ref = sum(v for n, (c, v) in agg.items() if 'k_wavefront' not in n and 'k_l2_read' not in n)
     cnt = sum(c for n, (c, v) in agg.items() if 'k_wavefront' not in n and 'k_l2_read' not in n)
     f.write(f"Refine + sweeps (all `k_scan_*`, `k_items<...>`, `k_single<...>` launches): {cnt} launches, {ref / 1e3:.2f} ms of kernel time over the 7 refines "
-            f"of the bench run (6 tree-build iterations + 1 timed), ~{ref / 7 / 1e3:.2f} ms each; ~1.0 ms wall per refine (launch-latency bound).\n")
+            f"of the bench run (6 tree-build iterations + 1 timed), ~{ref / 7 / 1e3:.2f} ms each when serialised by ncu; the wall time of one refine is `per_iteration.refine_ms` of the bench line "
+            f"({json.load(open(f'profiles/{tag}_bench_n1.json'))['per_iteration']['refine_ms']:.2f} ms: launch-latency bound, the helper kernels overlap their launches by programmatic dependent launch).\n")
 print(open(f'profiles/{tag}_summary.md').read())
