@@ -85,10 +85,22 @@ class PathGuidingCore:
         """the scatters of :318-346 at globalIndex = ray_index*max_depth + depth"""
         if self.isFinalIter:
             return
-        m = store_flag
+        m = store_flag != 0                             # uint8 / bool, numpy or torch -> boolean mask
         if not bool(m.any()):
             return
+        if _is_torch(ray_index):
+            ray_index, depth = ray_index.long(), depth.long()
+        else:
+            ray_index, depth = np.asarray(ray_index, np.int64), np.asarray(depth, np.int64)
         gi = (ray_index * self.max_depth + depth)[m]
+        n = m.shape[0]
+
+        def wide(x):        # Dr.Jit literals (e.g. the initial throughput Spectrum(1)) have width 1: dr.scatter broadcasts them
+            if x.shape[0] == n:
+                return x
+            return x.expand(n, *x.shape[1:]) if _is_torch(x) else np.broadcast_to(x, (n,) + tuple(x.shape[1:]))
+        position, wo_world, bsdf_weight, throughput_weight, L, radiance_nee, nee_dir_world, woPdf = (
+            wide(x) for x in (position, wo_world, bsdf_weight, throughput_weight, L, radiance_nee, nee_dir_world, woPdf))
         r = self.record
         r['position'][gi] = position[m]
         r['direction'][gi] = self.tree.dir_to_canonical(wo_world[m])
@@ -120,6 +132,7 @@ class PathGuidingCore:
         """:283-307: lanes with choose_u > bsdfSamplingFraction (and do_mis) are sampled from the
         tree, the other do_mis lanes get the tree pdf of the BSDF-sampled direction.
         -> (mode, sdtree_dir, sdtree_pdf); mode 1 = guided sample, 2 = BSDF sample with MIS, 0 = no MIS"""
+        do_mis = do_mis != 0
         guided = (choose_u > self.bsdfSamplingFraction) & do_mis
         mode = guided.astype(np.uint8) if not _is_torch(guided) else guided.to(dtype=__import__("torch").uint8)
         bs = do_mis & ~guided
@@ -197,6 +210,12 @@ if _HAVE_MITSUBA:                                      # pragma: no cover
         dr.sync_thread()
         t = x.torch()
         return t
+
+    def _sync():
+        """the library ran on torch's current stream, Dr.Jit reads on its own: drain before handing results over"""
+        import torch
+        if torch.cuda.is_available():
+            torch.cuda.current_stream().synchronize()
 
     class PathGuidingIntegrator(mi.SamplingIntegrator):
         """Same constructor props, methods and plugin name as the reference class
@@ -303,7 +322,7 @@ if _HAVE_MITSUBA:                                      # pragma: no cover
                 p_t = _t(si.p)
                 mis_em_t = core.nee_mis(p_t, _t(ds.d), _t(act_sd_em), _t(bsdf_pdf_em), _t(pdf_with_delta),
                                         _t(pdf_without_delta), _t(ds.pdf), _t(ds.delta))
-                torch.cuda.current_stream().synchronize()
+                _sync()
                 mis_em = mi.Float(mis_em_t)
                 Lr_dir = throughput * mis_em * bsdf_value_em * em_weight
                 L = dr.select(active, L + Le + Lr_dir, L)
@@ -318,9 +337,9 @@ if _HAVE_MITSUBA:                                      # pragma: no cover
                 do_mis = active_next & ~delta & (core.iteration > 1)
                 choose_u = sampler.next_1d(active_next)
                 if core.iteration > 1:
-                    mode_t, sd_dir_t, sd_pdf_t = core.choose_and_sample(p_t, _t(wo_world), _t(do_mis).bool(), _t(choose_u),
+                    mode_t, sd_dir_t, sd_pdf_t = core.choose_and_sample(p_t, _t(wo_world), _t(do_mis), _t(choose_u),
                                                                         seed=core._pass_seed * 1315423911 + it)
-                    torch.cuda.current_stream().synchronize()
+                    _sync()
                     guided = mi.Bool(mode_t == 1)
                     sd_dir = dr.unravel(mi.Vector3f, mi.Float(sd_dir_t.reshape(-1)))
                     wo_world[guided] = sd_dir
@@ -329,7 +348,7 @@ if _HAVE_MITSUBA:                                      # pragma: no cover
                     bsdf_value[guided] = v2
                     bsdf_pdf[guided] = p2
                     woPdf_t, w_t = core.mixture(_t(bsdf_pdf), sd_pdf_t, _t(bsdf_value), _t(do_mis))
-                    torch.cuda.current_stream().synchronize()
+                    _sync()
                     woPdf[do_mis] = mi.Float(woPdf_t)
                     bsdf_weight[do_mis] = dr.unravel(mi.Spectrum, mi.Float(w_t.reshape(-1)))
                 # record (:318-346)
@@ -338,7 +357,7 @@ if _HAVE_MITSUBA:                                      # pragma: no cover
                     if not rec_ready:
                         core.resetRayPathData(p_t)
                         rec_ready = True
-                    core.store_vertex(_t(mi.Int32(ray_index)).long(), _t(mi.Int32(depth)).long(), _t(store).bool(), p_t, _t(wo_world), _t(bsdf_weight),
+                    core.store_vertex(_t(mi.Int32(ray_index)), _t(mi.Int32(depth)), _t(store), p_t, _t(wo_world), _t(bsdf_weight),
                                       _t(throughput), _t(L), _t(Lr_dir / throughput), _t(ds.d), _t(woPdf))
                 ray = si.spawn_ray(wo_world)
                 ior *= bsdf_sample.eta
