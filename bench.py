@@ -48,6 +48,7 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--tune", action="append", default=[], help="key=value passed to sdt_set_tuning (repeatable)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--lib", default=None, help="path of an alternative build of libsdtree.so (kernel experiments)")
     return ap.parse_args()
 
 
@@ -222,7 +223,7 @@ def run_b200(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     n = args.n
-    tree = SDTree(device=local, kd_max_depth=20, quad_max_depth=20, store_nee=False)
+    tree = SDTree(device=local, kd_max_depth=20, quad_max_depth=20, store_nee=False, lib_path=args.lib)
     for kv in args.tune:
         key, val = kv.split("=")
         tree.set_tuning(key, int(val))

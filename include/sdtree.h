@@ -84,7 +84,7 @@ typedef struct sdt_sizes {
     uint32_t kd_leaves;
     uint32_t error;      /* sticky device-side error flag (0 = none) */
     uint32_t refine_count;
-    uint32_t jump_trees; /* quadtrees covered by the 16x16 jump table over their top 4 levels */
+    uint32_t jump_trees; /* quadtrees covered by the 32x32 jump table over their top 5 levels */
 } sdt_sizes;
 
 /* The reference's on-disk contract: the 23 arrays of KDTree.saveToFile

@@ -44,7 +44,7 @@ struct DevHeader {
     uint32_t root_of_node0;                 // quadTreeRootIndex[0] (out-of-box lanes, :224,:482)
     uint32_t kd_max_depth, quad_max_depth, store_nee;
     uint32_t rootrec_of_node0;              // record index of that tree's root (SDT_NONE: single-leaf tree)
-    uint32_t jump_trees;                    // trees covered by the 16x16 jump table (0: none)
+    uint32_t jump_trees;                    // trees covered by the jump table (0: none)
     uint32_t pad0[2];
     float bbox_min[3], bbox_max[3];         // spatial root box
     float max_leaf_size;                    // KDTree.maxLeafSize as fp32
@@ -82,10 +82,17 @@ enum DevError : uint32_t {
 // take the level-by-level path.
 //
 // Jump table over the top SDT_JUMP_LEVELS levels of every non-single-leaf quadtree: for each of the
-// 16x16 cells of [0,1]^2 the node a pdf / splat descent reaches after 4 levels (its record index), or
-// the leaf it meets earlier.  Points on a 1/16 grid line take the level-by-level path.
-#define SDT_JUMP_LEVELS 4
-#define SDT_JUMP_CELLS 256
+// SIDE x SIDE cells of [0,1]^2 the node a pdf / splat descent reaches after that many levels (its record
+// index), or the leaf it meets earlier.  Points on a 1/SIDE grid line take the level-by-level path.
+// (measured on the config-2 tree: 4 levels / 16x16 cells: pdf 0.273, splat 0.412 ms; 5 / 32x32: 0.257, 0.386; 6 / 64x64:
+// 0.265, 0.368 at 16 KB per tree -- 5 is the default)
+#ifndef SDT_JUMP_LEVELS
+#define SDT_JUMP_LEVELS 5
+#endif
+#define SDT_JUMP_SIDE (1u << SDT_JUMP_LEVELS)                  // 32
+#define SDT_JUMP_CELLS (SDT_JUMP_SIDE * SDT_JUMP_SIDE)         // 1024
+#define SDT_JUMP_SIDE_F ((float)SDT_JUMP_SIDE)
+#define SDT_JUMP_INV_F (1.0f / (float)SDT_JUMP_SIDE)           // exact: a power of two
 #define SDT_JUMP_LEAF 0x80000000u      // entry = LEAF | node id: a leaf was reached
 typedef uint32_t QJump;
 
@@ -415,8 +422,8 @@ SDT_HD float sdt_pick4(const SdtF4& v, uint32_t c) {
 
 // cell of a canonical position; false when it lies on a grid line or outside [0,1)
 SDT_HD bool sdt_jump_cell(float x, float y, uint32_t& cx, uint32_t& cy) {
-    const float fx = x * 16.0f, fy = y * 16.0f;          // exact scalings
-    if (!(fx >= 0.0f && fx < 16.0f && fy >= 0.0f && fy < 16.0f)) return false;
+    const float fx = x * SDT_JUMP_SIDE_F, fy = y * SDT_JUMP_SIDE_F;          // exact scalings
+    if (!(fx >= 0.0f && fx < SDT_JUMP_SIDE_F && fy >= 0.0f && fy < SDT_JUMP_SIDE_F)) return false;
     cx = (uint32_t)fx; cy = (uint32_t)fy;
     return fx != (float)cx && fy != (float)cy;
 }
@@ -461,12 +468,12 @@ SDT_HD float sdt_quad_pdf(const TreeView& t, uint32_t ri, uint32_t root_node,
     bool tie = false;
     uint32_t cx, cy;
     if (ri < t.jump_trees && sdt_jump_cell(x, y, cx, cy)) {
-        const QJump j = SDT_LDG(t.jump + (size_t)ri * SDT_JUMP_CELLS + cy * 16u + cx);
+        const QJump j = SDT_LDG(t.jump + (size_t)ri * SDT_JUMP_CELLS + cy * SDT_JUMP_SIDE + cx);
         if (j & SDT_JUMP_LEAF) { node = j & ~SDT_JUMP_LEAF; ri = SDT_NONE; }
         else {
             ri = j;
-            lox = (float)cx * 0.0625f; hix = (float)(cx + 1u) * 0.0625f;
-            loy = (float)cy * 0.0625f; hiy = (float)(cy + 1u) * 0.0625f;
+            lox = (float)cx * SDT_JUMP_INV_F; hix = (float)(cx + 1u) * SDT_JUMP_INV_F;
+            loy = (float)cy * SDT_JUMP_INV_F; hiy = (float)(cy + 1u) * SDT_JUMP_INV_F;
             level = SDT_JUMP_LEVELS;
         }
     }
@@ -600,11 +607,11 @@ SDT_HD uint32_t sdt_quad_leaf(const TreeView& t, uint32_t ri, uint32_t root_node
     int level = 0;
     uint32_t cx, cy;
     if (ri < t.jump_trees && sdt_jump_cell(x, y, cx, cy)) {
-        const QJump j = SDT_LDG(t.jump + (size_t)ri * SDT_JUMP_CELLS + cy * 16u + cx);
+        const QJump j = SDT_LDG(t.jump + (size_t)ri * SDT_JUMP_CELLS + cy * SDT_JUMP_SIDE + cx);
         if (j & SDT_JUMP_LEAF) return j & ~SDT_JUMP_LEAF;
         ri = j;
-        lox = (float)cx * 0.0625f; hix = (float)(cx + 1u) * 0.0625f;
-        loy = (float)cy * 0.0625f; hiy = (float)(cy + 1u) * 0.0625f;
+        lox = (float)cx * SDT_JUMP_INV_F; hix = (float)(cx + 1u) * SDT_JUMP_INV_F;
+        loy = (float)cy * SDT_JUMP_INV_F; hiy = (float)(cy + 1u) * SDT_JUMP_INV_F;
         level = SDT_JUMP_LEVELS;
     }
     for (; level < SDT_MAX_LEVELS && ri != SDT_NONE; ++level) {

@@ -13,7 +13,7 @@ struct QuadSet {
     float* pp = nullptr;            // per node: pdf product of the root->node path (see sdt_core.h)
     uint32_t* iidx = nullptr;       // per node: number of non-leaf nodes before it (= record index if non-leaf)
     QRec* rec = nullptr;
-    QJump* jump = nullptr;          // [root record][16x16 cell] jump table over the top 4 levels
+    QJump* jump = nullptr;          // [root record][cell] jump table over the top SDT_JUMP_LEVELS levels
     uint32_t* root_iidx = nullptr;
     DevHeader* hdr = nullptr;
 };

@@ -306,7 +306,7 @@ struct JumpBuildItem {
     const QRec* rec; QJump* jump;
     SDT_HD void operator()(uint32_t i) const {
         const uint32_t tr = i / SDT_JUMP_CELLS, cell = i % SDT_JUMP_CELLS;
-        jump[i] = sdt_build_jump(rec, tr, cell & 15u, cell >> 4);
+        jump[i] = sdt_build_jump(rec, tr, cell & (SDT_JUMP_SIDE - 1u), cell >> SDT_JUMP_LEVELS);
     }
 };
 

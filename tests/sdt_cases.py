@@ -248,7 +248,7 @@ def case_train_refine_nee_shallow(ctx):
 
 
 def case_jump_table_equals_descent(ctx):
-    """the 16x16 jump table over the top 4 quadtree levels answers pdf / splat descents with the
+    """the 32x32 jump table over the top 5 quadtree levels answers pdf / splat descents with the
     same bits as the level-by-level descent (grid-line points included: they take the slow path)"""
     t, cur, prev = train(ctx, iters=4)
     assert t.sizes()['jump_trees'] > 0
@@ -258,8 +258,8 @@ def case_jump_table_equals_descent(ctx):
     dirs = rng.standard_normal((n, 3)).astype(F)
     dirs /= np.linalg.norm(dirs, axis=1, keepdims=True)
     d2 = rng.random((n, 2)).astype(F)
-    d2[:64] = (rng.integers(0, 17, (64, 2)) / 16.0).astype(F)            # exactly on the 1/16 grid lines
-    d2[64:128, 0] = (rng.integers(0, 17, 64) / 16.0).astype(F)
+    d2[:64] = (rng.integers(0, 33, (64, 2)) / 32.0).astype(F)            # exactly on the 1/32 grid lines
+    d2[64:128, 0] = (rng.integers(0, 33, 64) / 32.0).astype(F)
     dirs[:128] = dm.canonical_to_dir(d2[:128])
     out = {}
     for use in (1, 0):
