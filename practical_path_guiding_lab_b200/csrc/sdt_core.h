@@ -271,8 +271,16 @@ SDT_HD KdCtx sdt_kd_ctx(const uint32_t* kd, uint32_t n_smem, const uint32_t* kdg
 // midpoints run independently (no memory access, ILP 3) and give the cell of a 16x16x8 grid; the
 // grid (built per CTA from the staged tree) names the node the level-by-level walk would have
 // reached -- a leaf shallower than 11 levels fills all its cells.
+// (measured, config-2 tree: 12 levels / 16 KB: pdf -1.5 %, splat -0.5 %, guided +2 %; 13 levels / 32 KB: splat +33 % --
+// the shared-memory footprint eats the L1; 11 stays)
+#ifndef SDT_GRID_LEVELS
 #define SDT_GRID_LEVELS 11
-#define SDT_GRID_CELLS 2048
+#endif
+#define SDT_GRID_NX ((SDT_GRID_LEVELS + 2) / 3)       // halvings of x, y, z among the first SDT_GRID_LEVELS levels
+#define SDT_GRID_NY ((SDT_GRID_LEVELS + 1) / 3)
+#define SDT_GRID_NZ (SDT_GRID_LEVELS / 3)
+#define SDT_GRID_CELLS (1u << SDT_GRID_LEVELS)
+#define SDT_GRID_CELL(cx, cy, cz) (((cx) << (SDT_GRID_NY + SDT_GRID_NZ)) | ((cy) << SDT_GRID_NZ) | (cz))
 #define SDT_AXIS_STEP(P, LO, HI, C)                                         \
     {                                                                       \
         const float mid = (LO + HI) / 2.0f;                                 \
@@ -281,15 +289,15 @@ SDT_HD KdCtx sdt_kd_ctx(const uint32_t* kd, uint32_t n_smem, const uint32_t* kdg
         HI = right ? HI : mid;                                              \
         C = (C << 1) | (right ? 1u : 0u);                                   \
     }
-// node reached from the root by the path bits of cell (cx 4 bits, cy 4 bits, cz 3 bits)
+// node reached from the root by the path bits of cell (cx NX bits, cy NY bits, cz NZ bits)
 SDT_HD uint32_t sdt_kd_grid_node(const uint32_t* __restrict__ kd, uint32_t cell) {
-    const uint32_t cx = cell >> 7, cy = (cell >> 3) & 15u, cz = cell & 7u;
+    const uint32_t cx = cell >> (SDT_GRID_NY + SDT_GRID_NZ), cy = (cell >> SDT_GRID_NZ) & ((1u << SDT_GRID_NY) - 1u), cz = cell & ((1u << SDT_GRID_NZ) - 1u);
     uint32_t node = 0;
     for (uint32_t l = 0; l < SDT_GRID_LEVELS; ++l) {
         const uint32_t w = kd[node];
         if (w & SDT_KD_LEAF_BIT) break;
         const uint32_t a = l % 3u, j = l / 3u;
-        const uint32_t bit = a == 0u ? (cx >> (3u - j)) & 1u : (a == 1u ? (cy >> (3u - j)) & 1u : (cz >> (2u - j)) & 1u);
+        const uint32_t bit = a == 0u ? (cx >> (SDT_GRID_NX - 1u - j)) & 1u : (a == 1u ? (cy >> (SDT_GRID_NY - 1u - j)) & 1u : (cz >> (SDT_GRID_NZ - 1u - j)) & 1u);
         node = w + bit;
     }
     return node;
@@ -316,17 +324,29 @@ SDT_HD KdResult sdt_kd_descend(const KdCtx& k, float px, float py, float pz) {
     uint32_t w;
     if (MODE >= 2) {
         uint32_t cx = 0, cy = 0, cz = 0;
-        SDT_AXIS_STEP(px, lo0, hi0, cx) SDT_AXIS_STEP(py, lo1, hi1, cy) SDT_AXIS_STEP(pz, lo2, hi2, cz)
-        SDT_AXIS_STEP(px, lo0, hi0, cx) SDT_AXIS_STEP(py, lo1, hi1, cy) SDT_AXIS_STEP(pz, lo2, hi2, cz)
-        SDT_AXIS_STEP(px, lo0, hi0, cx) SDT_AXIS_STEP(py, lo1, hi1, cy) SDT_AXIS_STEP(pz, lo2, hi2, cz)
-        SDT_AXIS_STEP(px, lo0, hi0, cx) SDT_AXIS_STEP(py, lo1, hi1, cy)
-        node = k.grid[(cx << 7) | (cy << 3) | cz];
+#pragma unroll
+        for (int l = 0; l < SDT_GRID_LEVELS; ++l) {          // fully unrolled: three independent chains
+            if (l % 3 == 0) SDT_AXIS_STEP(px, lo0, hi0, cx)
+            else if (l % 3 == 1) SDT_AXIS_STEP(py, lo1, hi1, cy)
+            else SDT_AXIS_STEP(pz, lo2, hi2, cz)
+        }
+        node = k.grid[SDT_GRID_CELL(cx, cy, cz)];
         w = sdt_kd_load<ALL_SMEM>(kd, n_smem, kdg, node);
         if (!(w & SDT_KD_LEAF_BIT)) {
-            for (int guard = SDT_GRID_LEVELS; guard < SDT_KD_MAX_DEPTH; guard += 3) {   // level 11 splits z, then x, y, ...
+            for (int guard = SDT_GRID_LEVELS; guard < SDT_KD_MAX_DEPTH; guard += 3) {   // level SDT_GRID_LEVELS splits axis LEVELS % 3, ...
+#if SDT_GRID_LEVELS % 3 == 2
                 SDT_KD_STEP(pz, lo2, hi2)
                 SDT_KD_STEP(px, lo0, hi0)
                 SDT_KD_STEP(py, lo1, hi1)
+#elif SDT_GRID_LEVELS % 3 == 0
+                SDT_KD_STEP(px, lo0, hi0)
+                SDT_KD_STEP(py, lo1, hi1)
+                SDT_KD_STEP(pz, lo2, hi2)
+#else
+                SDT_KD_STEP(py, lo1, hi1)
+                SDT_KD_STEP(pz, lo2, hi2)
+                SDT_KD_STEP(px, lo0, hi0)
+#endif
             }
         }
     } else {

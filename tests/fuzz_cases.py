@@ -167,9 +167,10 @@ if __name__ == "__main__":
     ap.add_argument("--seeds", type=int, default=100)
     ap.add_argument("--start", type=int, default=0)
     ap.add_argument("--gpu", action="store_true", help="run on libsdtree.so / cuda:0 (host-pointer calls) instead of the host emulation")
+    ap.add_argument("--lib", default=None, help="with --gpu: an alternative build of libsdtree.so")
     a = ap.parse_args()
     if a.gpu:
-        ctx = cases.Ctx(make=lambda **kw: SDTree(device=0, **kw))
+        ctx = cases.Ctx(make=lambda **kw: SDTree(device=0, lib_path=a.lib, **kw))
     else:
         lib = build_hostemu()
         ctx = cases.Ctx(make=lambda **kw: SDTree(lib_path=lib, **kw))
