@@ -172,10 +172,22 @@ static int launch_wavefront(sdt_handle h, cudaStream_t st, uint32_t n, const Lan
     return launch_wavefront_c<Lane, false>(h, st, n, f, block, ctas_per_sm);
 }
 #else
+// host emulation: serial lanes, but the same choice of spatial-descent variant as the kernel makes
+// ("staged" prefix = kd_smem_nodes, grid on / off), so that all four variants run on the CPU too
 template <class Lane>
 static int launch_wavefront(sdt_handle h, cudaStream_t st, uint32_t n, const Lane& f, int, int, bool) {
-    const KdCtx k = sdt_kd_ctx(f.t.kd_word, 0u, f.t.kd_word, f.t.hdr);
-    for (uint32_t i = 0; i < n; ++i) sdt_lane<Lane, 0>(f, k, i);
+    const uint32_t n_kd = f.t.hdr->n_kd;
+    const uint32_t n_smem = n_kd < (uint32_t)h->kd_smem_nodes ? n_kd : (uint32_t)h->kd_smem_nodes;
+    KdCtx k = sdt_kd_ctx(f.t.kd_word, n_smem, f.t.kd_word, f.t.hdr);
+    const bool staged = n_smem == n_kd;
+    if (h->use_kd_grid && (Lane::kGrid || !staged)) k.grid = f.t.kd_grid;
+    const int kd_mode = k.grid ? (staged ? 2 : 3) : (staged ? 1 : 0);
+    for (uint32_t i = 0; i < n; ++i) {
+        if (kd_mode == 2) sdt_lane<Lane, 2>(f, k, i);
+        else if (kd_mode == 1) sdt_lane<Lane, 1>(f, k, i);
+        else if (kd_mode == 3) sdt_lane<Lane, 3>(f, k, i);
+        else sdt_lane<Lane, 0>(f, k, i);
+    }
     ++h->launches;
     h->last_stream = st;
     return SDT_OK;
