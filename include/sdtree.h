@@ -182,7 +182,8 @@ typedef struct sdt_guided_args {
     const float* u; uint32_t u_stride; uint32_t seed; uint32_t lane_offset;
     const float* bsdf_pdf;     /* optional */
     sdt_vec3 bsdf_value;       /* optional (x == NULL -> none) */
-    float bsdf_sampling_fraction;
+    double bsdf_sampling_fraction; /* the reference's Python float: the library uses fp32(f) and fp32(1 - f), the
+                                    * two constants Dr.Jit sees (1 - f is formed in double, src/path_guiding_integrator.py:247,310) */
     sdt_vec3_out dir;          /* in: unused; out: sampled dir on mode 1 lanes */
     float* sdtree_pdf;
     float* wo_pdf;             /* optional */
@@ -194,11 +195,11 @@ int sdt_guided(sdt_handle h, const sdt_guided_args* a, uint32_t n, uint32_t flag
  * iteration <= 1 -> surface_pdf_em = bsdf_pdf_em.  Outputs may be NULL. */
 int sdt_mis_nee(sdt_handle h, uint32_t n, const float* bsdf_pdf_em, const float* sdtree_pdf_em,
                 const float* pdf_with_delta, const float* pdf_without_delta, const float* ds_pdf,
-                const uint8_t* ds_delta, float bsdf_sampling_fraction, int32_t iteration,
+                const uint8_t* ds_delta, double bsdf_sampling_fraction, int32_t iteration,
                 float* surface_pdf_em, float* mis_em, uint32_t flags, sdt_stream stream);
 /* one-sample mixture (src/path_guiding_integrator.py:310-311) on lanes with do_mis != 0 */
 int sdt_mis_mixture(sdt_handle h, uint32_t n, const float* bsdf_pdf, const float* sdtree_pdf,
-                    const sdt_vec3* bsdf_value, const uint8_t* do_mis, float bsdf_sampling_fraction,
+                    const sdt_vec3* bsdf_value, const uint8_t* do_mis, double bsdf_sampling_fraction,
                     float* wo_pdf, const sdt_vec3_out* weight, uint32_t flags, sdt_stream stream);
 
 /* dirToCanonical / canonicalToDir (src/common.py:100-158) on n vectors: what the integrator

@@ -58,7 +58,7 @@ class Arrays(C.Structure):
 class GuidedArgs(C.Structure):
     _fields_ = [("pos", Vec3), ("wo", Vec3), ("mode", C.c_void_p),
                 ("u", C.c_void_p), ("u_stride", C.c_uint32), ("seed", C.c_uint32), ("lane_offset", C.c_uint32),
-                ("bsdf_pdf", C.c_void_p), ("bsdf_value", Vec3), ("bsdf_sampling_fraction", C.c_float),
+                ("bsdf_pdf", C.c_void_p), ("bsdf_value", Vec3), ("bsdf_sampling_fraction", C.c_double),
                 ("dir", Vec3), ("sdtree_pdf", C.c_void_p), ("wo_pdf", C.c_void_p), ("weight", Vec3)]
 
 
@@ -93,8 +93,8 @@ SYMBOLS = {
                           C.c_uint32, _S]),
     "sdt_guided": (C.c_int, [_H, C.POINTER(GuidedArgs), C.c_uint32, C.c_uint32, _S]),
     "sdt_mis_nee": (C.c_int, [_H, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
-                              C.c_float, C.c_int32, C.c_void_p, C.c_void_p, C.c_uint32, _S]),
-    "sdt_mis_mixture": (C.c_int, [_H, C.c_uint32, C.c_void_p, C.c_void_p, C.POINTER(Vec3), C.c_void_p, C.c_float,
+                              C.c_double, C.c_int32, C.c_void_p, C.c_void_p, C.c_uint32, _S]),
+    "sdt_mis_mixture": (C.c_int, [_H, C.c_uint32, C.c_void_p, C.c_void_p, C.POINTER(Vec3), C.c_void_p, C.c_double,
                                   C.c_void_p, C.POINTER(Vec3), C.c_uint32, _S]),
     "sdt_dir_to_canonical": (C.c_int, [_H, C.POINTER(Vec3), C.c_uint32, C.c_void_p, C.c_uint32, _S]),
     "sdt_canonical_to_dir": (C.c_int, [_H, C.POINTER(Vec2), C.c_uint32, C.POINTER(Vec3), C.c_uint32, _S]),

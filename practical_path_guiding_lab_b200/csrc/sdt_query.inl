@@ -276,6 +276,7 @@ struct GuidedLane {
     SDT_HD void flush_count(uint32_t, float) const {}
     TreeView t;
     sdt_guided_args a; int fuse;
+    float f, omf;           // fp32(bsdfSamplingFraction), fp32(1 - bsdfSamplingFraction) with the difference formed in double
     SDT_HD uint32_t mode_of(uint32_t i) const { const uint32_t m = SDT_LDG(a.mode + i); return m <= 2u ? m : 0u; }
     SDT_HD void idle(uint32_t) const {}
     template <int KD>
@@ -295,8 +296,7 @@ struct GuidedLane {
             const float p = sdt_quad_pdf(t, r.rootrec, 0u, x, y, nd);
             a.sdtree_pdf[i] = p;
             if (a.bsdf_pdf && a.wo_pdf) {
-                const float f = a.bsdf_sampling_fraction;
-                const float wp = (f * SDT_LDG(a.bsdf_pdf + i)) + (1.0f - f) * p;       // :310
+                const float wp = (f * SDT_LDG(a.bsdf_pdf + i)) + omf * p;              // :310
                 a.wo_pdf[i] = wp;
                 if (a.bsdf_value.x && a.weight.x) {
                     const int64_t o = (int64_t)i * a.weight.stride;
@@ -311,14 +311,14 @@ struct GuidedLane {
 
 struct MisNeeItem {
     const float* bsdf_pdf_em; const float* sdtree_pdf_em; const float* pdf_with_delta; const float* pdf_without_delta;
-    const float* ds_pdf; const uint8_t* ds_delta; float f; int32_t iteration; float* surface_pdf_em; float* mis_em;
+    const float* ds_pdf; const uint8_t* ds_delta; float f, omf; int32_t iteration; float* surface_pdf_em; float* mis_em;
     SDT_HD void operator()(uint32_t i) const {
         const float bp = SDT_LDG(bsdf_pdf_em + i);
         float surface = bp;
         if (iteration > 1) {                                                            // :250
             const float eps = 0.00001f;
             const float pdf_diffuse = (SDT_LDG(pdf_with_delta + i) + eps) / (SDT_LDG(pdf_without_delta + i) + eps);   // :241
-            surface = f * bp + ((1.0f - f) * SDT_LDG(sdtree_pdf_em + i)) * pdf_diffuse;    // :247
+            surface = f * bp + (omf * SDT_LDG(sdtree_pdf_em + i)) * pdf_diffuse;           // :247
         }
         if (surface_pdf_em) surface_pdf_em[i] = surface;
         if (mis_em) {
@@ -329,12 +329,12 @@ struct MisNeeItem {
 };
 
 struct MisMixtureItem {
-    const float* bsdf_pdf; const float* sdtree_pdf; sdt_vec3 bsdf_value; const uint8_t* do_mis; float f;
+    const float* bsdf_pdf; const float* sdtree_pdf; sdt_vec3 bsdf_value; const uint8_t* do_mis; float f, omf;
     float* wo_pdf; sdt_vec3_out weight;
     SDT_HD void operator()(uint32_t i) const {
         const float bp = SDT_LDG(bsdf_pdf + i);
         const bool mis = do_mis ? SDT_LDG(do_mis + i) != 0 : true;
-        const float wp = mis ? (f * bp) + (1.0f - f) * SDT_LDG(sdtree_pdf + i) : bp;
+        const float wp = mis ? (f * bp) + omf * SDT_LDG(sdtree_pdf + i) : bp;
         if (wo_pdf) wo_pdf[i] = wp;
         if (weight.x && bsdf_value.x) {
             const int64_t o = (int64_t)i * weight.stride;
@@ -435,10 +435,10 @@ extern "C" int sdt_guided(sdt_handle h, const sdt_guided_args* a, uint32_t n, ui
     }
     if (sg.status != SDT_OK) return sg.status;
     if (d.u) {
-        GuidedLane<true> f{tree_view(h), d, h->fuse_sample_pdf};
+        GuidedLane<true> f{tree_view(h), d, h->fuse_sample_pdf, (float)a->bsdf_sampling_fraction, (float)(1.0 - a->bsdf_sampling_fraction)};
         SDT_TRY(launch_wavefront(h, st, n, f, h->query_block, h->query_ctas_per_sm, true));
     } else {
-        GuidedLane<false> f{tree_view(h), d, h->fuse_sample_pdf};
+        GuidedLane<false> f{tree_view(h), d, h->fuse_sample_pdf, (float)a->bsdf_sampling_fraction, (float)(1.0 - a->bsdf_sampling_fraction)};
         SDT_TRY(launch_wavefront(h, st, n, f, h->query_block, h->query_ctas_per_sm, true));
     }
     return sg.finish(flags);
@@ -446,7 +446,7 @@ extern "C" int sdt_guided(sdt_handle h, const sdt_guided_args* a, uint32_t n, ui
 
 extern "C" int sdt_mis_nee(sdt_handle h, uint32_t n, const float* bsdf_pdf_em, const float* sdtree_pdf_em,
                            const float* pdf_with_delta, const float* pdf_without_delta, const float* ds_pdf,
-                           const uint8_t* ds_delta, float bsdf_sampling_fraction, int32_t iteration,
+                           const uint8_t* ds_delta, double bsdf_sampling_fraction, int32_t iteration,
                            float* surface_pdf_em, float* mis_em, uint32_t flags, sdt_stream stream) {
     if (!h) return SDT_ERR_INVALID;
     if (n == 0) return SDT_OK;                          // empty wavefront: nothing to do (pointers may be NULL)
@@ -456,7 +456,7 @@ extern "C" int sdt_mis_nee(sdt_handle h, uint32_t n, const float* bsdf_pdf_em, c
     Stager sg(h, st, flags);
     SDT_TRY(sg.reserve((size_t)n * 32 + 16384));
     MisNeeItem f{sg.in_t(bsdf_pdf_em, n), sg.in_t(sdtree_pdf_em, n), sg.in_t(pdf_with_delta, n), sg.in_t(pdf_without_delta, n),
-                 sg.in_t(ds_pdf, n), sg.in_t(ds_delta, n), bsdf_sampling_fraction, iteration,
+                 sg.in_t(ds_pdf, n), sg.in_t(ds_delta, n), (float)bsdf_sampling_fraction, (float)(1.0 - bsdf_sampling_fraction), iteration,
                  sg.out_t(surface_pdf_em, n), sg.out_t(mis_em, n)};
     if (sg.status != SDT_OK) return sg.status;
     launch_items(exec_ctx(h, st), nullptr, n, f);
@@ -465,7 +465,7 @@ extern "C" int sdt_mis_nee(sdt_handle h, uint32_t n, const float* bsdf_pdf_em, c
 }
 
 extern "C" int sdt_mis_mixture(sdt_handle h, uint32_t n, const float* bsdf_pdf, const float* sdtree_pdf,
-                               const sdt_vec3* bsdf_value, const uint8_t* do_mis, float bsdf_sampling_fraction,
+                               const sdt_vec3* bsdf_value, const uint8_t* do_mis, double bsdf_sampling_fraction,
                                float* wo_pdf, const sdt_vec3_out* weight, uint32_t flags, sdt_stream stream) {
     if (!h) return SDT_ERR_INVALID;
     if (n == 0) return SDT_OK;                          // empty wavefront: nothing to do (pointers may be NULL)
@@ -477,7 +477,7 @@ extern "C" int sdt_mis_mixture(sdt_handle h, uint32_t n, const float* bsdf_pdf, 
     sdt_vec3_out wv{nullptr, nullptr, nullptr, 0};
     if (bsdf_value) bv = sg.in3(*bsdf_value, n);
     if (weight) wv = sg.out3(*weight, n);
-    MisMixtureItem f{sg.in_t(bsdf_pdf, n), sg.in_t(sdtree_pdf, n), bv, sg.in_t(do_mis, n), bsdf_sampling_fraction, sg.out_t(wo_pdf, n), wv};
+    MisMixtureItem f{sg.in_t(bsdf_pdf, n), sg.in_t(sdtree_pdf, n), bv, sg.in_t(do_mis, n), (float)bsdf_sampling_fraction, (float)(1.0 - bsdf_sampling_fraction), sg.out_t(wo_pdf, n), wv};
     if (sg.status != SDT_OK) return sg.status;
     launch_items(exec_ctx(h, st), nullptr, n, f);
     SDT_TRY(sdt_post_launch(h, "sdt_mis_mixture"));

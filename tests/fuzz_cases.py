@@ -2,8 +2,10 @@
 boxes with negative corners, depth caps from 0 up, tiny leaf sizes, NEE on/off), a few
 splat + refine iterations on records salted with the inputs the reference's masks exist for
 (positions outside the box / NaN, directions outside [0,1]^2 / NaN, negative, NaN and infinite
-radiance, zero / negative / NaN woPdf, inactive lanes), then every query -- all held against the
-oracle bit for bit through the same C ABI the other cases use.
+radiance, zero / negative / NaN woPdf, inactive lanes), then every query, one guided bounce
+(sdt_guided with a random bsdfSamplingFraction), the NEE MIS weights and the fused path-data splat on
+salted inputs -- all held against the oracle bit for bit (general fp32 energies: 2e-4) through the
+same C ABI the other cases use.
 
 Energies stay multiples of 1/8 (see sdt_cases.dyadic_records) so the fp32 sums do not depend
 on the order of the atomics.  Run many seeds by hand with
@@ -105,6 +107,7 @@ def fuzz_one(ctx, seed, verbose=False):
     cases.assert_tree_equal(t.download(0), prev)
     cases.assert_tree_equal(t.download(1), cur)
     _queries(ctx, t, prev, rng, lo, hi)
+    _bounce_and_path_data(ctx, t, cur, prev, rng, lo, hi, store_nee)
 
 
 def _compress(rec, active):
@@ -145,6 +148,77 @@ def _queries(ctx, t, prev, rng, lo, hi, n=1500):
     opp, opdbg = prev.pdf(pos, dirs, active, return_debug=True)
     assert np.array_equal(ctx.host(pdbg).view(U)[active, 2], opdbg['pdf_node'][active])
     assert cases.beq(ctx.host(pp), opp)
+
+
+def _salt(rng, a, frac=0.02):
+    """in place: a few zeros, negatives, NaNs and infinities"""
+    flat = a.reshape(-1)
+    for v in (0.0, -1.0, np.nan, np.inf):
+        flat[rng.random(flat.shape[0]) < frac / 4] = v
+    return a
+
+
+def _bounce_and_path_data(ctx, t, cur, prev, rng, lo, hi, store_nee, n=1200):
+    """one guided bounce (sdt_guided: sample / pdf + mixture / idle lanes), the NEE MIS weights, and the fused
+    processPathData + filter + splat call, all on salted inputs, against the oracle's separate steps"""
+    ext = hi - lo
+    pos = (lo - 0.01 * ext + rng.random((n, 3)) * ext * 1.02).astype(F)
+    mode = rng.integers(0, 3, n).astype(np.uint8)
+    wo = rng.standard_normal((n, 3)).astype(F)
+    wo /= np.linalg.norm(wo, axis=1, keepdims=True)
+    wo[:3] = np.array([[0, 0, 1], [np.nan, 0, 0], [0, 0, 0]], F)
+    bp = _salt(rng, (rng.random(n) * 2).astype(F))
+    bv = _salt(rng, rng.random((n, 3)).astype(F))
+    frac = float(rng.choice([0.5, 0.25, 0.9]))
+    d, sp, wp, wt = t.guided(ctx.dev(pos), ctx.dev(mode), wo=ctx.dev(wo), seed=5, lane_offset=11, bsdf_pdf=ctx.dev(bp),
+                             bsdf_value=ctx.dev(bv), bsdf_sampling_fraction=frac)
+    d, sp, wp, wt = ctx.host(d), ctx.host(sp), ctx.host(wp), ctx.host(wt)
+    m1, m2 = mode == 1, mode == 2
+    od, op = prev.sample(pos, so.ExplicitSampler(seed=5, n=n, lane_offset=11), m1)
+    assert cases.beq(d[m1], od[m1]) and cases.beq(sp[m1], op[m1])
+    op2 = prev.pdf(pos, wo, m2)
+    assert cases.beq(sp[m2], op2[m2])
+    owo, ow = so.mixture(bp, op2, bv, m2, frac)
+    assert cases.beq(wp[m2], owo[m2]) and cases.beq(wt[m2], ow[m2])
+    # NEE MIS weight (src/path_guiding_integrator.py:241-253), learning and guiding iterations
+    a = [_salt(rng, (rng.random(n) * 3).astype(F)) for _ in range(5)]
+    delta = rng.random(n) < 0.2
+    for it in (1, 2):
+        s, m = t.mis_nee(ctx.dev(a[0]), ctx.dev(a[1]), ctx.dev(a[2]), ctx.dev(a[3]), ctx.dev(a[4]), ctx.dev(delta.astype(np.uint8)), frac, it)
+        os_, om = so.nee_mis(a[0], a[1], a[2], a[3], a[4], delta, frac, it)
+        assert cases.beq(ctx.host(s), os_) and cases.beq(ctx.host(m), om)
+    # fused path-data splat on top of whatever `current` holds (general fp32 values: tolerance on the energies)
+    md = int(rng.integers(1, 6))
+    rays = n // md
+    slots = rays * md
+    Lf = _salt(rng, (rng.random((rays, 3)) * 4).astype(F), 0.01)
+    tr = _salt(rng, (rng.random((slots, 3)) * 2).astype(F))
+    tb = _salt(rng, rng.random((slots, 3)).astype(F))
+    bsdf = _salt(rng, rng.random((slots, 3)).astype(F))
+    p2 = pos[:slots]
+    d2 = _salt(rng, rng.random((slots, 2)).astype(F), 0.01)
+    wop = _salt(rng, (rng.random(slots) * 2).astype(F))
+    nee = _salt(rng, (rng.random((slots, 3)) * (rng.random((slots, 1)) < 0.5)).astype(F), 0.01)
+    dnee = rng.random((slots, 2)).astype(F)
+    active = rng.random(slots) < 0.7
+    before = t.download(1)
+    rad = t.splat_path_data(md, ctx.dev(Lf), ctx.dev(tr), ctx.dev(tb), ctx.dev(bsdf), ctx.dev(p2), ctx.dev(d2), ctx.dev(wop),
+                            ctx.dev(nee), ctx.dev(dnee), ctx.dev(active.astype(np.uint8)), want_radiance=True)
+    _, orad = so.process_path_data(Lf, tr, tb, bsdf, md)
+    keep, orad2, onee = so.filter_records(active, orad, nee, wop)
+    assert cases.beq(ctx.host(rad), orad2)
+    sub = so.SurfaceInteractionRecord(p2[keep], d2[keep], orad2[keep], wop[keep], onee[keep], dnee[keep])
+    fresh = so.KDTree(maxDepth=cur.maxDepth)
+    fresh.copyFrom(cur)
+    fresh.resetTreeVertCount()
+    fresh.resetAllQuadTreeIrradiance()
+    fresh.addDataPropagate(sub, exact=True)
+    got = t.download(1)
+    np.testing.assert_array_equal(got['kdtree_vertCount'] - before['kdtree_vertCount'], fresh.kdTreeNode.vertCount)
+    e = fresh.quadTree.quadTreeNode.irradiance.astype(np.float64) + before['quadtree_irradiance'].astype(np.float64)
+    with np.errstate(invalid='ignore'):
+        fin = np.isfinite(e) & np.isfinite(before['quadtree_irradiance'])
+    np.testing.assert_allclose(got['quadtree_irradiance'][fin], e[fin], rtol=2e-4, atol=1e-5)
 
 
 def make_case(seed):
