@@ -269,9 +269,12 @@ int sdt_allreduce(sdt_handle h, sdt_stream stream);
 int sdt_stat_buffers(sdt_handle h, float** q_energy, uint32_t* n_quad, float** kd_count, uint32_t* n_kd);
 
 /* ---- tuning / introspection --------------------------------------------------- */
-/* key: "query_block", "query_ctas_per_sm", "kd_smem_nodes", "splat_block",
- * "splat_ctas_per_sm", "fuse_sample_pdf", "use_jump", "use_kd_grid", "use_compaction", "use_pdl", "host_chunk" (lanes per chunk of the pipelined
- * SDT_HOST_PTRS staging: H2D of chunk k+1 | kernels of chunk k | D2H of chunk k-1).
+/* Speed keys (results do not depend on them):
+ *   "query_block", "query_ctas_per_sm", "splat_block", "splat_ctas_per_sm"   CTA shape of the wavefront kernels
+ *   "kd_smem_nodes", "kd_smem_count_nodes", "splat_stage_words"              what of the spatial tree is staged in shared memory
+ *   "use_kd_grid", "use_jump", "use_int_cell", "fuse_sample_pdf", "use_compaction"   fast paths on / off (each has an exact slow path)
+ *   "use_pdl"                                                                programmatic dependent launch of the helper kernels
+ *   "host_chunk"   lanes per chunk of the pipelined SDT_HOST_PTRS staging (H2D of chunk k+1 | kernels of chunk k | D2H of chunk k-1).
  * One key switches semantics rather than speed: "quad_thr_reciprocal" = 1 computes the
  * quadtree refinement threshold (src/quadtree.py:519, `E / 100`) as E * fp32(0.01), the
  * form a Dr.Jit build that lowers division by a literal to a reciprocal multiply would
