@@ -411,7 +411,7 @@ def run_b200(args):
             tree2.splat_records(hr['position'], hr['direction'], hr['radiance'], hr['wo_pdf'])
             tree2.synchronize()                         # every output of the step is in host memory here
             torch.cuda.synchronize()
-        ke = max(1, min(args.steps, 5))
+        ke = max(1, min(args.steps, 10))
 
         def timed_host():
             for _ in range(2):
