@@ -197,6 +197,51 @@ def test_sample_and_pdf_semantics():
     assert np.all(q.pdfQuadTree(np.zeros(4, U), d) == 0)
 
 
+def test_pdf_integrates_to_one_and_sampling_matches_it():
+    """Standard anchors the reference does not test (SURVEY 8c iv): on a trained tree the pdf is a density
+    on the sphere -- sum over the leaves of pdf(leaf centre) x solid angle(leaf) = 1 -- and the sampler draws
+    leaves with probability pdf x solid angle (chi-square on 2^17 draws with explicit uniforms)."""
+    rng = np.random.default_rng(5)
+    n = 30000
+    d2 = np.clip(np.stack([0.3 + 0.05 * rng.standard_normal(n), 0.6 + 0.1 * rng.standard_normal(n)], 1), 0, 1).astype(F)
+    d2[: n // 3] = rng.random((n // 3, 2)).astype(F)
+    rec = so.SurfaceInteractionRecord(rng.random((n, 3)).astype(F), d2, (rng.integers(1, 17, n) / 8.0).astype(F),
+                                      rng.choice(np.array([0.25, 0.5, 1.0, 2.0], F), n).astype(F))
+    cur = so.KDTree(maxDepth=20)
+    cur.setup([0, 0, 0], [1, 1, 1])
+    prev = so.KDTree(maxDepth=20)
+    prev.copyFrom(cur)
+    for _ in range(2):
+        cur.addDataPropagate(rec)
+        cur.maxLeafSize = 1e9                       # one spatial leaf: a single quadtree
+        cur.refine()
+        cur.setQuadTreeRefinementThreshold()
+        cur.refineAllQuadTree()
+        cur.cleanUnusedQuadTree()
+        prev.copyFrom(cur)
+        cur.resetTreeVertCount()
+        cur.resetAllQuadTreeIrradiance()
+    q = prev.quadTree.quadTreeNode
+    leaves = np.nonzero(q.isLeaf)[0]
+    assert len(leaves) > 50
+    centre = ((q.bbox_min[leaves] + q.bbox_max[leaves]) / F(2)).astype(F)
+    area = np.prod((q.bbox_max[leaves] - q.bbox_min[leaves]).astype(np.float64), axis=1)
+    pos = np.full((len(leaves), 3), 0.5, F)
+    pdf = prev.pdf(pos, dm.canonical_to_dir(centre), np.ones(len(leaves), bool)).astype(np.float64)
+    prob = pdf * 4 * np.pi * area                   # canonical area x 4 pi = solid angle (equal-area map, src/common.py:100-129)
+    assert abs(prob.sum() - 1.0) < 1e-5
+    m = 1 << 17
+    u = rng.random((m, 3 * 22)).astype(F)
+    _, _, dbg = prev.sample(np.full((m, 3), 0.5, F), so.ExplicitSampler(u=u), np.ones(m, bool), return_debug=True)
+    obs = np.bincount(dbg['sample_node'], minlength=q.getWidth())[leaves].astype(np.float64)
+    exp = prob * m
+    big = exp >= 8
+    chi2 = float(((obs - exp) ** 2 / np.maximum(exp, 1e-300))[big].sum())
+    df = int(big.sum()) - 1
+    assert abs(chi2 - df) < 5 * np.sqrt(2 * df) + 5, (chi2, df)
+    assert obs[exp == 0].sum() == 0
+
+
 def test_pdf_tie_rules():
     """src/quadtree.py:1063-1075 (energy: first match) vs :1095-1098 (descent: last match)."""
     q = so.QuadTree()
