@@ -57,7 +57,8 @@ class TorchDistRanks:
 
 
 def train_and_render(renderer, budget_spp, seed=0, batch_spp=4, stable_variance_spp_threshold=256,
-                     ground_truth=None, out_dir=None, scene_name="scene", log=None, on_iteration=None, ranks=None):
+                     ground_truth=None, out_dir=None, scene_name="scene", log=None, on_iteration=None, ranks=None,
+                     record_in_iteration=False):
     """-> dict(image, records=[per-iteration dicts], iterations=[(iteration, spp, refined)])"""
     ranks = ranks or SingleRank()
     log = log or (lambda *a: None)
@@ -72,7 +73,7 @@ def train_and_render(renderer, budget_spp, seed=0, batch_spp=4, stable_variance_
     cumm_time = 0.0
     prev_iter_image = None
     image = None
-    records, schedule = [], []
+    records, schedule, in_iter = [], [], []
     if out_dir:
         for sub in ("image", "tree-data", "obj", "performance"):
             os.makedirs(os.path.join(out_dir, sub), exist_ok=True)
@@ -101,6 +102,11 @@ def train_and_render(renderer, budget_spp, seed=0, batch_spp=4, stable_variance_
             image_spp += s
             done += s
             cumm_spp += s
+            if record_in_iteration and ranks.world == 1:               # main.py:245-265 (isRecordPerformanceInIteration)
+                in_iter.append(dict(time=(time.perf_counter() - t0) + cumm_time, spp=image_spp, cumm_spp=cumm_spp, iteration=it,
+                                    variance=renderer.computeVariance(image_spp),
+                                    variance_groundTruth=renderer.computeVariance(image_spp, ground_truth) if ground_truth is not None else 0,
+                                    mse_groundTruth=renderer.computeMSE(image_spp, ground_truth) if ground_truth is not None else 0))
         if ranks.world > 1:
             if curr is None:
                 curr = renderer.zero_image()
@@ -154,12 +160,20 @@ def train_and_render(renderer, budget_spp, seed=0, batch_spp=4, stable_variance_
         it += 1
         cumm_spp_prev = cumm_spp
     if out_dir and ranks.rank == 0:
-        for key in ("variance", "variance_groundTruth", "mse_groundTruth", "variance_estimated_final"):
-            with open(os.path.join(out_dir, "performance", f"{key}_endIter.csv"), "w", newline="") as f:
+        # PerformanceData.saveToFile (src/common.py:86-97): six columns, the unused one of variance / mse stays 0;
+        # file names of main.py:425-429
+        files = [(records, "variance", "variance_endIter.csv"), (records, "variance_groundTruth", "variance_groundTruth_endIter.csv"),
+                 (records, "mse_groundTruth", "mse_groundTruth_endIter.csv"), (records, "variance_estimated_final", "variance_estimated_final.csv")]
+        if in_iter:                                                    # main.py:420-423
+            files += [(in_iter, "variance", "variance_inIter.csv"), (in_iter, "variance_groundTruth", "variance_groundTruth_inIter.csv"),
+                      (in_iter, "mse_groundTruth", "mse_groundTruth_inIter.csv")]
+        for rows, key, name in files:
+            with open(os.path.join(out_dir, "performance", name), "w", newline="") as f:
                 w = csv.writer(f)
-                w.writerow(["time", "spp", "cumm_spp", "iteration", "mse" if key.startswith("mse") else "variance"])
-                for r in records:
-                    w.writerow([r["time"], r["spp"], r["cumm_spp"], r["iteration"], r[key]])
+                w.writerow(["time", "spp", "cumm_spp", "iteration", "variance", "mse"])
+                for r in rows:
+                    v = 0 if r[key] is None else r[key]
+                    w.writerow([r["time"], r["spp"], r["cumm_spp"], r["iteration"]] + ([0, v] if key.startswith("mse") else [v, 0]))
     return dict(image=image, records=records, iterations=schedule)
 
 
@@ -220,6 +234,7 @@ def main(argv=None):
     ap.add_argument("--out", default=None)
     ap.add_argument("--ground-truth", default=None, help=".npy (H,W,3) linear RGB")
     ap.add_argument("--no-guiding", action="store_true", help="BSDF-only baseline: never refine (tree stays a single leaf)")
+    ap.add_argument("--record-in-iteration", action="store_true", help="variance / MSE after every pass (main.py isRecordPerformanceInIteration; one GPU)")
     a = ap.parse_args(argv)
     from .cornell import CornellBox
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -245,7 +260,7 @@ def main(argv=None):
     t0 = time.perf_counter()
     rank0 = ranks is None or ranks.rank == 0
     res = train_and_render(r, a.budget, seed=a.seed, ground_truth=gt, out_dir=a.out, scene_name=a.scene,
-                           log=print if rank0 else None, ranks=ranks)
+                           log=print if rank0 else None, ranks=ranks, record_in_iteration=a.record_in_iteration)
     torch.cuda.synchronize()
     sizes = r.core.tree.sizes()
     if ranks is not None:                            # every rank must hold the same tree

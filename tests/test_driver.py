@@ -54,14 +54,19 @@ def test_cornell_box_loop_on_host_emulation(tmp_path):
     r = CornellBox(24, 24, max_depth=6, device="cpu", lib_path=build_hostemu(), kd_capacity=1 << 12, quad_capacity=1 << 16)
     r.setup(sdTreeMaxDepth=20, quadTreeMaxDepth=20)
     gt = None
-    res = driver.train_and_render(r, 28, seed=1, out_dir=str(tmp_path), scene_name="cornell-box")
+    res = driver.train_and_render(r, 28, seed=1, out_dir=str(tmp_path), scene_name="cornell-box", record_in_iteration=True)
     assert [s for _, s, _ in res["iterations"]] == [4, 8, 16]
     img = res["image"].numpy()
     assert img.shape == (24, 24, 3) and np.isfinite(img).all() and img.mean() > 0.01
     s = r.core.tree.sizes()
     assert s["error"] == 0 and s["refine_count"] == 2
     assert os.path.exists(tmp_path / "tree-data" / "cornell-box_iter-2.npz")
-    assert os.path.exists(tmp_path / "performance" / "variance_endIter.csv")
+    import csv
+    # the reference's CSV contract (src/common.py:86-97, main.py:420-429): names and the six columns
+    for name, rows in (("variance_endIter.csv", 3), ("variance_groundTruth_endIter.csv", 3), ("mse_groundTruth_endIter.csv", 3),
+                       ("variance_estimated_final.csv", 3), ("variance_inIter.csv", 4 + 8 + 4), ("mse_groundTruth_inIter.csv", 4 + 8 + 4)):
+        got = list(csv.reader(open(tmp_path / "performance" / name)))
+        assert got[0] == ['time', 'spp', 'cumm_spp', 'iteration', 'variance', 'mse'] and len(got) == rows + 1, (name, len(got))
     # energy reached the tree: the first refine saw non-zero statistics
     d = r.core.tree.download(0)
     assert d["quadtree_irradiance"].sum() > 0
