@@ -120,29 +120,11 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------ CPU port (oracle) arm
-def oracle_tree():
-    """the frozen tree, built by the oracle itself (numpy restatement of the reference)"""
-    from oracle import sdtree_oracle as so
-    from practical_path_guiding_lab_b200 import synthetic as syn
-    cur = so.KDTree(maxDepth=20)
-    cur.setup([0, 0, 0], [1, 1, 1])
-    cur.quadTree.maxDepth = 20
-    cur.quadTree.isStoreNEERadiance = False
-    prev = so.KDTree(maxDepth=20)
-    prev.copyFrom(cur)
-    scene = syn.Scene()
-    for it in syn.build_schedule():
-        r = scene.records(it['seed'], it['n'])
-        cur.addDataPropagate(so.SurfaceInteractionRecord(r['position'], r['direction'], r['radiance'], r['wo_pdf']))
-        cur.maxLeafSize = it['max_leaf_size']
-        cur.refine()
-        cur.setQuadTreeRefinementThreshold()
-        cur.refineAllQuadTree()
-        cur.cleanUnusedQuadTree()
-        prev.copyFrom(cur)
-        cur.resetTreeVertCount()
-        cur.resetAllQuadTreeIrradiance()
-    return cur, prev
+def frozen_tree():
+    """the frozen benchmark tree (npz schema), built once by the numpy oracle and used as INPUT DATA by both arms
+    (oracle/bench_tree.py; cached in the temp directory so the two arms of one run build it once)"""
+    from oracle import bench_tree
+    return bench_tree.frozen_tree_arrays()
 
 
 class CpuPort:
@@ -156,7 +138,10 @@ class CpuPort:
         z['kdtree_vertCount'] = np.zeros_like(np.asarray(tree_arrays['kdtree_vertCount'], np.float32))
         z['quadtree_irradiance'] = np.zeros_like(np.asarray(tree_arrays['quadtree_irradiance'], np.float32))
         self.cur = PortTree(z)
-        self.cores = self.prev.threads()
+        # torchrun exports OMP_NUM_THREADS=1 to its workers: ask for every core this process may run on
+        want = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+        self.cores = self.prev.set_threads(want)
+        self.cur.set_threads(want)
 
     def step(self, pos, dirs, rec, seed):
         self.prev.sample(pos, seed)
@@ -186,8 +171,7 @@ def run_reference(args):
     if rank != 0:
         return
     m = int(min(args.n, args.cpu_sample))
-    cur, prev = oracle_tree()
-    port = CpuPort(prev.to_arrays())
+    port = CpuPort(frozen_tree())
     pos, dirs, rec = cpu_inputs(m)
     for _ in range(args.warmup):
         port.step(pos, dirs, rec, 3)
@@ -200,7 +184,7 @@ def run_reference(args):
             "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic", "config": workload_config(args.n, args.gpus),
             "cpu_baseline": {"value": v, "unit": UNIT, "cores": port.cores, "kind": "port",
-                             "sample": f"{m} of the {args.n} vertices per step (C + OpenMP port of the reference's per-vertex operations, {port.cores} threads; tree trained by the numpy oracle)"},
+                             "sample": f"{m} of the {args.n} vertices per step (C + OpenMP port of the reference's per-vertex operations, {port.cores} threads of {os.cpu_count()} host cores; the same frozen tree as the B200 arm, built by the numpy oracle)"},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line))
@@ -237,9 +221,14 @@ def run_b200(args):
     t_build0 = time.perf_counter()
     syn.build_tree(tree, to_dev=to_dev, rank=rank, world=world, allreduce=allreduce)
     torch.cuda.synchronize()
-    sizes = tree.sizes()
+    sizes_trained = tree.sizes()
     t_build = time.perf_counter() - t_build0
-    assert sizes["error"] == 0, sizes
+    assert sizes_trained["error"] == 0, sizes_trained
+    # the timed region runs on the SAME frozen tree as the reference arm: the oracle-built one, uploaded in the
+    # reference's npz schema (the device-trained tree above differs from it by a few quadtree nodes: fp32 atomics)
+    tree.upload(frozen_tree())
+    sizes = tree.sizes()
+    assert sizes["error"] == 0 and sizes["n_kd"] == sizes_trained["n_kd"], (sizes, sizes_trained)
 
     # inputs of this rank's shard (host, pinned for the e2e arm) and their device copies
     scene = syn.Scene()
@@ -313,9 +302,12 @@ def run_b200(args):
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception:
         pass
-    peak = float(peaks.get("hbm_gbs", 6650.0))
-    achieved = bytes_q[names[dom]] * n / (k_ms[dom] * 1e-3) / 1e9
-    l2_gbs = tree.measure_l2(32 << 20, 50)
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    l2_gbs = tree.measure_l2(32 << 20, 50)                    # sequential sweep of an L2-resident set (ld.global.cg)
+    gather_gbs = tree.measure_gather(16 << 20, 200, True)     # random 32 B sectors of an L2-resident set, through L1 (the descents' pattern)
+    gather_cg_gbs = tree.measure_gather(16 << 20, 200, False)
+    stream_b = {"sample": 28.0, "pdf": 28.0, "splat": 28.0}  # query / record bytes streamed from and to HBM
+    tree_b = {k: bytes_q[k] - stream_b[k] for k in names}     # tree bytes: served by shared memory / L1 / L2
     kname = ['SampleLane', 'PdfLane', 'SplatRecordsLane'][dom]
     traffic = None
     try:        # DRAM bytes per launch of this kernel from the committed ncu --set full capture (same 16 Mi-vertex launch)
@@ -325,15 +317,32 @@ def run_b200(args):
             traffic = tj[key]["dram_bytes_read"] + tj[key]["dram_bytes_write"]
     except Exception:
         pass
-    roof = {"bound": "hbm", "kernel": f"k_wavefront<{kname}>", "achieved": achieved, "peak": peak,
-            "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-            "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if "hbm_gbs" in peaks else "fallback 6650",
+
+    def per_kernel(j):
+        k = names[j]
+        sec = k_ms[j] * 1e-3
+        tree_gbs, stream_gbs = tree_b[k] * n / sec / 1e9, stream_b[k] * n / sec / 1e9
+        return {"ms": k_ms[j], "bytes_per_query": bytes_q[k], "tree_bytes_per_query": tree_b[k], "stream_bytes_per_query": stream_b[k],
+                "tree_gbs": tree_gbs, "frac_of_l2": tree_gbs / l2_gbs if l2_gbs else None,
+                "frac_of_gather_roof": tree_gbs / gather_gbs if gather_gbs else None,
+                "stream_gbs": stream_gbs, "frac_of_hbm": stream_gbs / hbm_peak, "queries_per_s": n / sec}
+    pk = {names[j]: per_kernel(j) for j in range(3)}
+    d = pk[names[dom]]
+    roof = {"bound": "l2", "kernel": f"k_wavefront<{kname}>", "achieved": d["tree_gbs"], "peak": l2_gbs, "unit": "GB/s",
+            "frac": d["frac_of_l2"], "traffic": traffic,
+            "peak_source": "measured in this run by sdt_measure_l2 (32 MiB resident set, 50 passes, ld.global.cg; an L2 figure is not in "
+                           "MEASURED_PEAKS.json): the friendliest access pattern there is.  The descents read ONE unrelated 32 B sector per "
+                           "lane and level; that pattern's own roof is gather_roof below",
+            "what": "achieved = algorithmic TREE bytes of the dominant kernel (4 B per spatial level + 4 B root id + 20 B per quadtree "
+                    "level [+4 B path product / +8 B leaf update], SURVEY 8d) x queries / its launch time (CUDA events); the 28 B per "
+                    "query streamed from / to HBM are accounted separately (hbm)",
             "algorithmic_bytes_per_query": bytes_q[names[dom]], "kernel_ms": k_ms[dom],
-            "l2": {"measured_read_gbs": l2_gbs, "frac_of_l2": achieved / l2_gbs if l2_gbs else None,
-                   "how": "sdt_measure_l2: 32 MiB resident set, 50 passes, ld.global.cg"},
-            "per_kernel": {names[j]: {"ms": k_ms[j], "bytes_per_query": bytes_q[names[j]],
-                                      "achieved_gbs": bytes_q[names[j]] * n / (k_ms[j] * 1e-3) / 1e9,
-                                      "queries_per_s": n / (k_ms[j] * 1e-3)} for j in range(3)},
+            "gather_roof": {"gbs_via_l1": gather_gbs, "gbs_l2_only": gather_cg_gbs,
+                            "how": "sdt_measure_gather: 16 MiB resident set, every lane loads one random 32 B sector per 256-bit load, 8 independent loads in flight per lane",
+                            "frac": d["frac_of_gather_roof"]},
+            "hbm": {"achieved": d["stream_gbs"], "peak": hbm_peak, "frac": d["frac_of_hbm"],
+                    "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if "hbm_gbs" in peaks else "fallback 6650"},
+            "per_kernel": pk,
             "mean_depths": {"spatial": ds, "quad_sample": dq_s, "quad_pdf": dq_p, "sample_redescend_frac": redescend}}
 
     # ---- refine + allreduce wall time (per training iteration, not part of a step)
@@ -466,6 +475,10 @@ def run_b200(args):
                 "data": "synthetic", "config": workload_config(n, world), "clocks": clk.summary(), "e2e": e2e,
                 "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu,
                 "tree": {k: sizes[k] for k in ("n_kd", "kd_leaves", "n_quad", "n_interior", "n_levels")},
+                "tree_device_trained": dict({k: sizes_trained[k] for k in ("n_kd", "kd_leaves", "n_quad", "n_interior", "n_levels")},
+                                            build_s=t_build, what="the same schedule trained by the library (splat + allreduce + device refine); the timed region uses the oracle-built tree above, like the reference arm"),
+                "allreduce_ms": per_iter["allreduce_ms"], "refine_ms": per_iter["refine_ms"],
+                "e2e_per_gpu": (e2e["value"] / world if e2e else None),
                 "tree_build_s": t_build, "per_iteration": per_iter, "extras": extras}
         print(json.dumps(line))
     if world > 1:

@@ -287,6 +287,10 @@ int sdt_synchronize(sdt_handle h, sdt_stream stream);
 uint64_t sdt_kernel_launches(sdt_handle h);
 /* L2-resident read bandwidth probe (GB/s): `bytes` working set read `passes` times */
 int sdt_measure_l2(sdt_handle h, uint64_t bytes, uint32_t passes, float* gbps, sdt_stream stream);
+/* random 32-byte-sector gather probe (GB/s of sectors delivered): every lane of a warp reads one unrelated sector of an
+ * L2-resident set of `bytes` per load, 8 independent 256-bit loads per lane and iteration -- the access pattern of a
+ * divergent quadtree descent; via_l1 != 0: ld.global.nc (through L1, the kernels' path), 0: ld.global.cg (L2 only) */
+int sdt_measure_gather(sdt_handle h, uint64_t bytes, uint32_t iters, int32_t via_l1, float* gbps, sdt_stream stream);
 
 #ifdef __cplusplus
 }

@@ -54,6 +54,11 @@ class PortTree:
     def threads(self):
         return int(self.lib.port_max_threads())
 
+    def set_threads(self, n):
+        """OpenMP team size for the following calls (torchrun sets OMP_NUM_THREADS=1 in every worker)"""
+        self.lib.port_set_threads(C.c_int(int(n)))
+        return self.threads()
+
     def sample(self, pos, seed, lane_offset=0, active=None, debug=False):
         pos = np.ascontiguousarray(pos, np.float32)
         n = pos.shape[0]

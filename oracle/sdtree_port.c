@@ -249,6 +249,16 @@ void port_splat(port_tree* t, uint32_t n, const float* pos, const float* dir2, c
     }
 }
 
+/* torchrun exports OMP_NUM_THREADS=1 to every worker: the reference arm of bench.py asks for the host's cores explicitly */
+void port_set_threads(int n) {
+#ifdef _OPENMP
+    extern void omp_set_num_threads(int);
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
 int port_max_threads(void) {
 #ifdef _OPENMP
     extern int omp_get_max_threads(void);

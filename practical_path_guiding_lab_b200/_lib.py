@@ -113,6 +113,7 @@ SYMBOLS = {
     "sdt_synchronize": (C.c_int, [_H, C.c_void_p]),
     "sdt_kernel_launches": (C.c_uint64, [_H]),
     "sdt_measure_l2": (C.c_int, [_H, C.c_uint64, C.c_uint32, C.POINTER(C.c_float), _S]),
+    "sdt_measure_gather": (C.c_int, [_H, C.c_uint64, C.c_uint32, C.c_int32, C.POINTER(C.c_float), _S]),
 }
 
 _cache = {}

@@ -1,6 +1,7 @@
 // Host-side handle of libsdtree and small helpers shared by the .inl sections.
 #pragma once
 
+#include <map>
 #include <string>
 #include <vector>
 
@@ -64,6 +65,8 @@ struct sdt_tree_s {
     int use_kd_grid = 1;            // per-CTA 16x16x8 grid over the first 11 spatial levels
     uint32_t kd_nodes_known = 1;    // last spatial node count seen by the host (sizes the smem staging)
     cudaEvent_t hdr_event = nullptr;
+    cudaEvent_t order_event = nullptr;   // orders a call on a new stream after the work enqueued on last_stream
+    uint32_t n_quad_known = 1;      // quadtree node count as last seen by the host
     bool hdr_pending = false;       // an async header read-back (after refine) is in flight
 
     // staging for SDT_HOST_PTRS: one arena; large host calls run as a 2-slot pipeline
@@ -88,6 +91,12 @@ struct sdt_tree_s {
     int splat_ctas_per_sm = 2;
     int fuse_sample_pdf = 1;
 
+    // per-HANDLE (= per device) launch state of the wavefront kernels: the >48 KB dynamic shared-memory opt-in is a
+    // per-device function attribute and the occupancy answer depends on the device, so neither may be cached per process
+    struct LaunchCache { size_t attr_smem = 0; int occ = 0, occ_block = 0; size_t occ_smem = ~(size_t)0; };
+    std::map<const void*, LaunchCache> launch_cache;
+    uint32_t dev_error_seen = 0;    // DevHeader.error as last read back (sticky device-side flag, see sdt_get_sizes)
+
     // NCCL
     void* nccl_comm = nullptr;
     int rank = 0, nranks = 1;
@@ -106,6 +115,18 @@ static int sdt_fail(sdt_handle h, int code, const std::string& msg) {
         if (_e != cudaSuccess)                                                              \
             return sdt_fail(h, SDT_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e)); \
     } while (0)
+// Every entry point runs on the handle's device, whatever device the calling thread had current.
+static inline int sdt_enter(sdt_handle h) {
+#ifndef SDT_HOSTEMU
+    int cur = -1;
+    if (cudaGetDevice(&cur) != cudaSuccess || cur != h->cfg.device) {
+        cudaError_t e = cudaSetDevice(h->cfg.device);
+        if (e != cudaSuccess) return sdt_fail(h, SDT_ERR_CUDA, std::string("cudaSetDevice: ") + cudaGetErrorString(e));
+    }
+#endif
+    return SDT_OK;
+}
+#define SDT_ENTER(h) do { if (!(h)) return SDT_ERR_INVALID; int _d = sdt_enter(h); if (_d != SDT_OK) return _d; } while (0)
 #define SDT_CHECK(h, cond, code, msg) do { if (!(cond)) return sdt_fail(h, code, msg); } while (0)
 #define SDT_TRY(expr) do { int _s = (expr); if (_s != SDT_OK) return _s; } while (0)
 
@@ -119,7 +140,9 @@ static inline TreeView tree_view(sdt_tree_s* h) {
     if (h->hdr_pending && cudaEventQuery(h->hdr_event) == cudaSuccess) {
         h->hdr_pending = false;
         h->kd_nodes_known = h->h_hdr->n_kd;
+        h->n_quad_known = h->h_hdr->n_quad;
         h->jump_trees_known = h->h_hdr->jump_trees;
+        h->dev_error_seen = h->h_hdr->error;
     }
     const QuadSet& s = h->set[h->cur];
     return TreeView{s.hdr, h->kd_word, h->kd_root, h->kd_grid, s.rec, s.jump, s.pp, h->use_jump ? h->jump_trees_known : 0u,
@@ -127,6 +150,18 @@ static inline TreeView tree_view(sdt_tree_s* h) {
 }
 
 static int sdt_read_header(sdt_handle h, DevHeader& H);
+
+// refine / allreduce / reset / download work on the statistics the splats wrote: when the caller hands a different
+// stream than the one the last work was enqueued on, order the new stream after it (an event, no host wait)
+static inline void sdt_order_after_last(sdt_handle h, cudaStream_t st) {
+#ifndef SDT_HOSTEMU
+    if (h->last_stream != st && h->order_event) {
+        if (cudaEventRecord(h->order_event, h->last_stream) == cudaSuccess) cudaStreamWaitEvent(st, h->order_event, 0);
+    }
+#else
+    (void)h; (void)st;
+#endif
+}
 
 static inline int sdt_post_launch(sdt_handle h, const char* what) {
     cudaError_t e = cudaGetLastError();
@@ -265,8 +300,9 @@ struct Stager {
             if (cudaMemcpyAsync(o.host, o.dev, o.bytes, cudaMemcpyDeviceToHost, st) != cudaSuccess)
                 return sdt_fail(h, SDT_ERR_CUDA, "D2H staging copy failed");
         }
-        // results in pageable/pinned host memory are only valid after the stream drains
-        if ((flags & SDT_SYNC) || (host && !outs.empty() && !(flags & SDT_NO_WAIT))) {
+        // results in pageable/pinned host memory are only valid after the stream drains; a host-pointer call without
+        // outputs (a splat) waits too, so that the caller may reuse its input arrays as soon as the call returns
+        if ((flags & SDT_SYNC) || (host && !(flags & SDT_NO_WAIT))) {
             if (cudaStreamSynchronize(st) != cudaSuccess) return sdt_fail(h, SDT_ERR_CUDA, "stream synchronize failed");
         }
         return SDT_OK;
@@ -311,6 +347,9 @@ static int sdt_run_chunked(sdt_handle h, cudaStream_t st, uint32_t flags, uint32
     cudaStreamWaitEvent(st, h->ev_out[1], 0);
     if ((flags & SDT_SYNC) || (has_outputs && !(flags & SDT_NO_WAIT))) {
         if (cudaStreamSynchronize(st) != cudaSuccess) return sdt_fail(h, SDT_ERR_CUDA, "stream synchronize failed");
+    } else if (!(flags & SDT_NO_WAIT)) {
+        // no outputs (a splat): the caller may reuse its host arrays once the last H2D copy has been issued AND has run
+        if (cudaStreamSynchronize(h->s_in) != cudaSuccess) return sdt_fail(h, SDT_ERR_CUDA, "input stream synchronize failed");
     }
     return SDT_OK;
 }

@@ -19,6 +19,9 @@ static int sdt_free_all(sdt_handle h) {
     if (h->h_hdr) cudaFreeHost(h->h_hdr);
     if (h->hdr_event) cudaEventDestroy(h->hdr_event);
 #ifndef SDT_HOSTEMU
+    if (h->order_event) cudaEventDestroy(h->order_event);
+#endif
+#ifndef SDT_HOSTEMU
     for (int k = 0; k < 2; ++k) { if (h->ev_in[k]) cudaEventDestroy(h->ev_in[k]); if (h->ev_comp[k]) cudaEventDestroy(h->ev_comp[k]); if (h->ev_out[k]) cudaEventDestroy(h->ev_out[k]); }
     if (h->s_in) cudaStreamDestroy(h->s_in);
     if (h->s_out) cudaStreamDestroy(h->s_out);
@@ -88,6 +91,7 @@ extern "C" int sdt_create(const sdt_config* cfg, sdt_handle* out) {
             ok = cudaEventCreateWithFlags(&h->ev_in[k], cudaEventDisableTiming) == cudaSuccess &&
                  cudaEventCreateWithFlags(&h->ev_comp[k], cudaEventDisableTiming) == cudaSuccess &&
                  cudaEventCreateWithFlags(&h->ev_out[k], cudaEventDisableTiming) == cudaSuccess;
+        ok = ok && cudaEventCreateWithFlags(&h->order_event, cudaEventDisableTiming) == cudaSuccess;
         if (!ok) st = sdt_fail(h, SDT_ERR_CUDA, "staging pipeline streams/events could not be created");
     }
 #endif
@@ -113,7 +117,7 @@ extern "C" int sdt_create(const sdt_config* cfg, sdt_handle* out) {
 }
 
 extern "C" int sdt_destroy(sdt_handle h) {
-    if (!h) return SDT_ERR_INVALID;
+    SDT_ENTER(h);
     cudaDeviceSynchronize();
     sdt_nccl_destroy(h);
     sdt_free_all(h);
@@ -127,12 +131,15 @@ static int sdt_read_header(sdt_handle h, DevHeader& H) {
     H = *h->h_hdr;
     h->hdr_pending = false;
     h->kd_nodes_known = H.n_kd;
+    h->n_quad_known = H.n_quad;
     h->jump_trees_known = H.jump_trees;
+    h->dev_error_seen = H.error;
     return SDT_OK;
 }
 
 extern "C" int sdt_get_sizes(sdt_handle h, sdt_sizes* out) {
     if (!h || !out) return SDT_ERR_INVALID;
+    SDT_ENTER(h);
     DevHeader H;
     SDT_TRY(sdt_read_header(h, H));
     out->n_kd = H.n_kd; out->n_quad = H.n_quad; out->n_roots = H.n_roots; out->n_interior = H.n_interior;
@@ -144,6 +151,7 @@ extern "C" int sdt_get_sizes(sdt_handle h, sdt_sizes* out) {
 // ---------------------------------------------------------------------------- upload
 extern "C" int sdt_upload(sdt_handle h, const sdt_arrays* a) {
     if (!h || !a) return SDT_ERR_INVALID;
+    SDT_ENTER(h);
     SDT_CHECK(h, a->n_kd >= 1 && a->n_quad >= 1 && a->n_roots >= 1, SDT_ERR_LAYOUT, "sdt_upload: empty tree");
     SDT_CHECK(h, a->n_kd <= h->kd_cap && a->n_roots <= h->kd_cap, SDT_ERR_CAPACITY, "sdt_upload: spatial arena too small");
     SDT_CHECK(h, a->n_quad <= h->quad_cap, SDT_ERR_CAPACITY, "sdt_upload: quadtree arena too small");
@@ -166,6 +174,18 @@ extern "C" int sdt_upload(sdt_handle h, const sdt_arrays* a) {
             const uint32_t l = a->kd_child_left[i], r = a->kd_child_right[i];
             SDT_CHECK(h, r == l + 1u && r < nk && l > i, SDT_ERR_LAYOUT, "sdt_upload: spatial children must be adjacent and after their parent");
             SDT_CHECK(h, a->kd_depth[l] == a->kd_depth[i] + 1u && a->kd_depth[r] == a->kd_depth[i] + 1u, SDT_ERR_LAYOUT, "sdt_upload: spatial depth array inconsistent");
+            // the descent recomputes the split planes instead of reading child boxes: the stored boxes must be what
+            // KDTree.split writes (src/kdtree.py:268-304) -- axis depth % 3 halved at fp32 (min + max) / 2
+            const uint32_t ax = a->kd_depth[i] % 3u;
+            const float* pmin = a->kd_bbox_min + 3ull * i; const float* pmax = a->kd_bbox_max + 3ull * i;
+            const float mid = (pmin[ax] + pmax[ax]) / 2.0f;
+            bool ok = true;
+            for (uint32_t k = 0; k < 3u; ++k) {
+                const float lmax = k == ax ? mid : pmax[k], rmin = k == ax ? mid : pmin[k];
+                ok = ok && a->kd_bbox_min[3ull * l + k] == pmin[k] && a->kd_bbox_max[3ull * l + k] == lmax &&
+                     a->kd_bbox_min[3ull * r + k] == rmin && a->kd_bbox_max[3ull * r + k] == pmax[k];
+            }
+            SDT_CHECK(h, ok, SDT_ERR_LAYOUT, "sdt_upload: spatial child boxes are not the midpoint split of their parent on axis depth % 3");
             word[i] = l;
         }
     }
@@ -253,7 +273,7 @@ extern "C" int sdt_upload(sdt_handle h, const sdt_arrays* a) {
 }
 
 extern "C" int sdt_upload_stats(sdt_handle h, const float* q_irradiance, const float* kd_vert_count) {
-    if (!h) return SDT_ERR_INVALID;
+    SDT_ENTER(h);
     SDT_TRY(sdt_complete_stats(h, h->last_stream));       // whatever is not overwritten below stays consistent
     DevHeader H;
     SDT_TRY(sdt_read_header(h, H));
@@ -266,6 +286,7 @@ extern "C" int sdt_upload_stats(sdt_handle h, const float* q_irradiance, const f
 // ---------------------------------------------------------------------------- download
 extern "C" int sdt_download(sdt_handle h, int which, sdt_arrays* out) {
     if (!h || !out) return SDT_ERR_INVALID;
+    SDT_ENTER(h);
     SDT_CHECK(h, which == SDT_TREE_PREV || which == SDT_TREE_CURRENT, SDT_ERR_INVALID, "sdt_download: which must be 0 or 1");
     if (which == SDT_TREE_CURRENT) SDT_TRY(sdt_complete_stats(h, h->last_stream));
     DevHeader H;
@@ -318,7 +339,7 @@ extern "C" int sdt_download(sdt_handle h, int which, sdt_arrays* out) {
 
 // ---------------------------------------------------------------------------- thresholds
 extern "C" int sdt_set_max_leaf_size(sdt_handle h, float max_leaf_size) {
-    if (!h) return SDT_ERR_INVALID;
+    SDT_ENTER(h);
     launch_single(exec_ctx(h, h->last_stream), SetLeafSize{h->set[h->cur].hdr, max_leaf_size});
     return sdt_post_launch(h, "sdt_set_max_leaf_size");
 }
@@ -330,7 +351,7 @@ extern "C" int sdt_set_iteration_threshold(sdt_handle h, int32_t iteration) {
 }
 
 extern "C" int sdt_stat_buffers(sdt_handle h, float** q_energy, uint32_t* n_quad, float** kd_count, uint32_t* n_kd) {
-    if (!h) return SDT_ERR_INVALID;
+    SDT_ENTER(h);
     DevHeader H;
     SDT_TRY(sdt_read_header(h, H));
     if (q_energy) *q_energy = h->q_ecur;
@@ -343,6 +364,7 @@ extern "C" int sdt_stat_buffers(sdt_handle h, float** q_energy, uint32_t* n_quad
 
 extern "C" int sdt_set_tuning(sdt_handle h, const char* key, int64_t value) {
     if (!h || !key) return SDT_ERR_INVALID;
+    SDT_ENTER(h);
     const std::string k(key);
     if (k == "query_block") { SDT_CHECK(h, value >= 64 && value <= 768 && value % 32 == 0, SDT_ERR_INVALID, "query_block must be 64..768, multiple of 32"); h->query_block = (int)value; }
     else if (k == "query_ctas_per_sm") { SDT_CHECK(h, value >= 1 && value <= 32, SDT_ERR_INVALID, "query_ctas_per_sm must be 1..32"); h->query_ctas_per_sm = (int)value; }
@@ -364,7 +386,7 @@ extern "C" int sdt_set_tuning(sdt_handle h, const char* key, int64_t value) {
 }
 
 extern "C" int sdt_synchronize(sdt_handle h, sdt_stream stream) {
-    if (!h) return SDT_ERR_INVALID;
+    SDT_ENTER(h);
     SDT_CUDA(h, cudaStreamSynchronize((cudaStream_t)stream));
     return SDT_OK;
 }
@@ -385,8 +407,77 @@ __global__ void __launch_bounds__(256) k_l2_read(const uint4* __restrict__ p, ui
 }
 #endif
 
+#ifndef SDT_HOSTEMU
+// What the descents actually do to the memory system: every lane of a warp reads ONE 32-byte sector at an unrelated
+// address of an L2-resident set (the quadtree records), with one 256-bit load.  BATCH independent loads per lane and
+// iteration, so the probe measures throughput, not latency.  via_l1 = ld.global.nc (the kernels' path), else ld.global.cg.
+template <int BATCH, bool VIA_L1>
+__global__ void __launch_bounds__(512) k_gather32(const char* __restrict__ p, uint32_t sectors_mask, uint32_t iters, uint32_t* sink) {
+    uint32_t acc = 0;
+    uint32_t s = (blockIdx.x * blockDim.x + threadIdx.x) * 0x9E3779B1u + 0x7F4A7C15u;
+    for (uint32_t it = 0; it < iters; ++it) {
+        uint32_t v[BATCH][8];
+#pragma unroll
+        for (int b = 0; b < BATCH; ++b) {
+            s = s * 747796405u + 2891336453u;
+            const uint32_t sec = ((s >> 9) ^ (s << 7)) & sectors_mask;
+            const char* q = p + (size_t)sec * 32u;
+            if (VIA_L1) asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];" : "=r"(v[b][0]), "=r"(v[b][1]), "=r"(v[b][2]), "=r"(v[b][3]), "=r"(v[b][4]), "=r"(v[b][5]), "=r"(v[b][6]), "=r"(v[b][7]) : "l"(q));
+            else asm volatile("ld.global.cg.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];" : "=r"(v[b][0]), "=r"(v[b][1]), "=r"(v[b][2]), "=r"(v[b][3]), "=r"(v[b][4]), "=r"(v[b][5]), "=r"(v[b][6]), "=r"(v[b][7]) : "l"(q));
+        }
+#pragma unroll
+        for (int b = 0; b < BATCH; ++b) acc += v[b][0] ^ v[b][3] ^ v[b][7];
+    }
+    if (acc == 0x12345678u) *sink = acc;
+}
+#endif
+
+// Random 32-byte-sector gather bandwidth (GB/s of sectors delivered to the lanes) over an L2-resident set of `bytes`
+// (rounded down to a power of two): the roof of a divergent tree descent, next to the sequential sweep of sdt_measure_l2.
+extern "C" int sdt_measure_gather(sdt_handle h, uint64_t bytes, uint32_t iters, int32_t via_l1, float* gbps, sdt_stream stream) {
+    if (!h || !gbps) return SDT_ERR_INVALID;
+    SDT_ENTER(h);
+#ifndef SDT_HOSTEMU
+    cudaStream_t st = (cudaStream_t)stream;
+    uint64_t sectors = 1;
+    while (sectors * 2 * 32 <= bytes) sectors *= 2;
+    SDT_CHECK(h, sectors >= 1024 && sectors <= (1ull << 31) && iters > 0, SDT_ERR_INVALID, "sdt_measure_gather: bytes must be 32 KiB .. 64 GiB, iters > 0");
+    char* buf = nullptr;
+    SDT_CUDA(h, cudaMalloc((void**)&buf, sectors * 32));
+    SDT_CUDA(h, cudaMemsetAsync(buf, 1, sectors * 32, st));
+    constexpr int BATCH = 8;
+    const int grid = h->num_sms * 4, block = 512;
+    uint32_t* sink = h->s_blk + SDT_SCAN_MAX_BLOCKS;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    auto run = [&](uint32_t n_it) {
+        if (via_l1) k_gather32<BATCH, true><<<grid, block, 0, st>>>(buf, (uint32_t)(sectors - 1), n_it, sink);
+        else k_gather32<BATCH, false><<<grid, block, 0, st>>>(buf, (uint32_t)(sectors - 1), n_it, sink);
+    };
+    run(iters / 4 + 1);                         // warm: pull the set into L2
+    cudaEventRecord(e0, st);
+    run(iters);
+    cudaEventRecord(e1, st);
+    h->launches += 2;
+    h->last_stream = st;
+    cudaError_t e = cudaEventSynchronize(e1);
+    float ms = 0.0f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    cudaFree(buf);
+    if (e != cudaSuccess) return sdt_fail(h, SDT_ERR_CUDA, std::string("sdt_measure_gather: ") + cudaGetErrorString(e));
+    *gbps = (float)((double)grid * block * (double)iters * BATCH * 32.0 / ((double)ms * 1e-3) / 1e9);
+    return SDT_OK;
+#else
+    (void)bytes; (void)iters; (void)via_l1; (void)stream;
+    *gbps = 0.0f;
+    return sdt_fail(h, SDT_ERR_STATE, "sdt_measure_gather: not available in the host emulation");
+#endif
+}
+
 extern "C" int sdt_measure_l2(sdt_handle h, uint64_t bytes, uint32_t passes, float* gbps, sdt_stream stream) {
     if (!h || !gbps) return SDT_ERR_INVALID;
+    SDT_ENTER(h);
 #ifndef SDT_HOSTEMU
     cudaStream_t st = (cudaStream_t)stream;
     uint4* buf = nullptr;

@@ -51,6 +51,7 @@ extern "C" int sdt_comm_unique_id(void* id128) {
 }
 extern "C" int sdt_comm_init(sdt_handle h, const void* id128, int32_t rank, int32_t nranks) {
     if (!h || !id128) return SDT_ERR_INVALID;
+    SDT_ENTER(h);
     SDT_CHECK(h, nranks >= 1 && rank >= 0 && rank < nranks, SDT_ERR_INVALID, "sdt_comm_init: bad rank / nranks");
     SDT_TRY(sdt_nccl_load(h));
     SDT_CUDA(h, cudaSetDevice(h->cfg.device));
@@ -66,14 +67,18 @@ extern "C" int sdt_comm_init(sdt_handle h, const void* id128, int32_t rank, int3
 // counts]; the interior sums are rebuilt afterwards from the reduced leaves, so every rank
 // ends with bit-identical buffers and the deterministic refine needs no broadcast.
 extern "C" int sdt_allreduce(sdt_handle h, sdt_stream stream) {
-    if (!h) return SDT_ERR_INVALID;
+    SDT_ENTER(h);
     SDT_CHECK(h, h->nccl_comm, SDT_ERR_STATE, "sdt_allreduce: call sdt_comm_init first");
     cudaStream_t st = (cudaStream_t)stream;
-    DevHeader H;
-    SDT_TRY(sdt_read_header(h, H));           // element counts (identical on every rank)
+    // element counts (identical on every rank): the sizes the last refine / upload reported -- its non-blocking header
+    // read-back has landed long before an iteration's passes are over; only if it has not, wait for it
+    (void)tree_view(h);
+    if (h->hdr_pending) { DevHeader H; SDT_TRY(sdt_read_header(h, H)); }
+    const uint32_t n_quad = h->n_quad_known, n_kd = h->kd_nodes_known;
+    sdt_order_after_last(h, st);
     int rc = g_nccl.group_start();
-    if (rc == 0) rc = g_nccl.allreduce(h->q_ecur, h->q_ecur, H.n_quad, /*ncclFloat32*/ 7, /*ncclSum*/ 0, h->nccl_comm, st);
-    if (rc == 0) rc = g_nccl.allreduce(h->kd_count, h->kd_count, H.n_kd, 7, 0, h->nccl_comm, st);
+    if (rc == 0) rc = g_nccl.allreduce(h->q_ecur, h->q_ecur, n_quad, /*ncclFloat32*/ 7, /*ncclSum*/ 0, h->nccl_comm, st);
+    if (rc == 0) rc = g_nccl.allreduce(h->kd_count, h->kd_count, n_kd, 7, 0, h->nccl_comm, st);
     const int rc2 = g_nccl.group_end();
     if (rc != 0 || rc2 != 0) return sdt_nccl_fail(h, "ncclAllReduce", rc ? rc : rc2);
     h->last_stream = st;

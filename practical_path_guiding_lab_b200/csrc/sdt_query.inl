@@ -142,18 +142,17 @@ static int launch_wavefront_c(sdt_handle h, cudaStream_t st, uint32_t n, const L
     }
     const size_t smem = (size_t)smem_nodes * 4u + (size_t)cnt_nodes * 4u + SDT_GRID_CELLS * 4u +
                         (COMPACT ? (size_t)block * SDT_TILE_MUL * 2u * (size_t)Lane::kModes : 0u);   // uint16 lists: 32*TM entries per warp and mode
-    static size_t attr_set = 0;
-    if (smem > 48u * 1024u && smem > attr_set) {
+    sdt_tree_s::LaunchCache& lc = h->launch_cache[(const void*)k_wavefront<Lane, COMPACT>];
+    if (smem > 48u * 1024u && smem > lc.attr_smem) {
         if (cudaFuncSetAttribute(k_wavefront<Lane, COMPACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess)
             return sdt_fail(h, SDT_ERR_CUDA, "cudaFuncSetAttribute(MaxDynamicSharedMemorySize) failed");
-        attr_set = 200 * 1024;
+        lc.attr_smem = 200 * 1024;
     }
-    static int occ_cache = 0, occ_block = 0;
-    static size_t occ_smem = ~(size_t)0;
-    if (occ_smem != smem || occ_block != block) {
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_cache, k_wavefront<Lane, COMPACT>, block, smem) != cudaSuccess || occ_cache < 1) occ_cache = 1;
-        occ_smem = smem; occ_block = block;
+    if (lc.occ_smem != smem || lc.occ_block != block) {
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&lc.occ, k_wavefront<Lane, COMPACT>, block, smem) != cudaSuccess || lc.occ < 1) lc.occ = 1;
+        lc.occ_smem = smem; lc.occ_block = block;
     }
+    const int occ_cache = lc.occ;
     int per_sm = ctas_per_sm < occ_cache ? ctas_per_sm : occ_cache;
     if (per_sm < 1) per_sm = 1;
     const uint32_t per_cta = (uint32_t)block * (COMPACT ? SDT_TILE_MUL : 1u);
@@ -348,7 +347,7 @@ struct MisMixtureItem {
 // ---------------------------------------------------------------------------- entry points
 extern "C" int sdt_locate(sdt_handle h, const sdt_vec3* pos, const uint8_t* active, uint32_t n,
                           uint32_t* leaf, uint32_t* root, uint32_t flags, sdt_stream stream) {
-    if (!h) return SDT_ERR_INVALID;
+    SDT_ENTER(h);
     if (n == 0) return SDT_OK;                          // empty wavefront: nothing to do (pointers may be NULL)
     SDT_CHECK(h, pos && pos->x, SDT_ERR_INVALID, "sdt_locate: pos is NULL");
     cudaStream_t st = (cudaStream_t)stream;
@@ -363,7 +362,7 @@ extern "C" int sdt_locate(sdt_handle h, const sdt_vec3* pos, const uint8_t* acti
 extern "C" int sdt_sample(sdt_handle h, const sdt_vec3* pos, const uint8_t* active, uint32_t n,
                           const float* u, uint32_t u_stride, uint32_t seed, uint32_t lane_offset,
                           const sdt_vec3_out* dir, float* pdf, uint32_t* dbg, uint32_t flags, sdt_stream stream) {
-    if (!h) return SDT_ERR_INVALID;
+    SDT_ENTER(h);
     if (n == 0) return SDT_OK;                          // empty wavefront: nothing to do (pointers may be NULL)
     SDT_CHECK(h, pos && pos->x && dir && dir->x && pdf, SDT_ERR_INVALID, "sdt_sample: pos / dir / pdf is NULL");
     SDT_CHECK(h, !u || u_stride >= 3, SDT_ERR_INVALID, "sdt_sample: u_stride must be >= 3");
@@ -386,7 +385,7 @@ extern "C" int sdt_sample(sdt_handle h, const sdt_vec3* pos, const uint8_t* acti
 
 extern "C" int sdt_pdf(sdt_handle h, const sdt_vec3* pos, const sdt_vec3* dir, const uint8_t* active,
                        uint32_t n, float* pdf, uint32_t* dbg, uint32_t flags, sdt_stream stream) {
-    if (!h) return SDT_ERR_INVALID;
+    SDT_ENTER(h);
     if (n == 0) return SDT_OK;                          // empty wavefront: nothing to do (pointers may be NULL)
     SDT_CHECK(h, pos && pos->x && dir && dir->x && pdf, SDT_ERR_INVALID, "sdt_pdf: pos / dir / pdf is NULL");
     cudaStream_t st = (cudaStream_t)stream;
@@ -401,7 +400,7 @@ extern "C" int sdt_pdf(sdt_handle h, const sdt_vec3* pos, const sdt_vec3* dir, c
 }
 
 extern "C" int sdt_guided(sdt_handle h, const sdt_guided_args* a, uint32_t n, uint32_t flags, sdt_stream stream) {
-    if (!h) return SDT_ERR_INVALID;
+    SDT_ENTER(h);
     if (n == 0) return SDT_OK;                          // empty wavefront: nothing to do (pointers may be NULL)
     SDT_CHECK(h, a && a->pos.x && a->mode && a->sdtree_pdf && a->dir.x, SDT_ERR_INVALID, "sdt_guided: pos / mode / dir / sdtree_pdf is NULL");
     SDT_CHECK(h, !a->u || a->u_stride >= 3, SDT_ERR_INVALID, "sdt_guided: u_stride must be >= 3");
@@ -448,7 +447,7 @@ extern "C" int sdt_mis_nee(sdt_handle h, uint32_t n, const float* bsdf_pdf_em, c
                            const float* pdf_with_delta, const float* pdf_without_delta, const float* ds_pdf,
                            const uint8_t* ds_delta, double bsdf_sampling_fraction, int32_t iteration,
                            float* surface_pdf_em, float* mis_em, uint32_t flags, sdt_stream stream) {
-    if (!h) return SDT_ERR_INVALID;
+    SDT_ENTER(h);
     if (n == 0) return SDT_OK;                          // empty wavefront: nothing to do (pointers may be NULL)
     SDT_CHECK(h, bsdf_pdf_em && (iteration <= 1 || (sdtree_pdf_em && pdf_with_delta && pdf_without_delta)) && (!mis_em || ds_pdf),
               SDT_ERR_INVALID, "sdt_mis_nee: missing input");
@@ -467,7 +466,7 @@ extern "C" int sdt_mis_nee(sdt_handle h, uint32_t n, const float* bsdf_pdf_em, c
 extern "C" int sdt_mis_mixture(sdt_handle h, uint32_t n, const float* bsdf_pdf, const float* sdtree_pdf,
                                const sdt_vec3* bsdf_value, const uint8_t* do_mis, double bsdf_sampling_fraction,
                                float* wo_pdf, const sdt_vec3_out* weight, uint32_t flags, sdt_stream stream) {
-    if (!h) return SDT_ERR_INVALID;
+    SDT_ENTER(h);
     if (n == 0) return SDT_OK;                          // empty wavefront: nothing to do (pointers may be NULL)
     SDT_CHECK(h, bsdf_pdf && sdtree_pdf, SDT_ERR_INVALID, "sdt_mis_mixture: missing input");
     cudaStream_t st = (cudaStream_t)stream;
@@ -503,7 +502,7 @@ struct CanonicalToDirItem {
 };
 
 extern "C" int sdt_dir_to_canonical(sdt_handle h, const sdt_vec3* dir, uint32_t n, float* out_xy, uint32_t flags, sdt_stream stream) {
-    if (!h) return SDT_ERR_INVALID;
+    SDT_ENTER(h);
     if (n == 0) return SDT_OK;                          // empty wavefront: nothing to do (pointers may be NULL)
     SDT_CHECK(h, dir && dir->x && out_xy, SDT_ERR_INVALID, "sdt_dir_to_canonical: NULL argument");
     cudaStream_t st = (cudaStream_t)stream;
@@ -517,7 +516,7 @@ extern "C" int sdt_dir_to_canonical(sdt_handle h, const sdt_vec3* dir, uint32_t 
 }
 
 extern "C" int sdt_canonical_to_dir(sdt_handle h, const sdt_vec2* pos, uint32_t n, const sdt_vec3_out* dir, uint32_t flags, sdt_stream stream) {
-    if (!h) return SDT_ERR_INVALID;
+    SDT_ENTER(h);
     if (n == 0) return SDT_OK;                          // empty wavefront: nothing to do (pointers may be NULL)
     SDT_CHECK(h, pos && pos->x && dir && dir->x, SDT_ERR_INVALID, "sdt_canonical_to_dir: NULL argument");
     cudaStream_t st = (cudaStream_t)stream;

@@ -330,8 +330,9 @@ struct KdRollItem {         // prev.vertCount <- current.vertCount; current <- 0
 struct ZeroItem { float* p; SDT_HD void operator()(uint32_t i) const { p[i] = 0.0f; } };
 
 extern "C" int sdt_refine(sdt_handle h, uint32_t flags, sdt_stream stream) {
-    if (!h) return SDT_ERR_INVALID;
+    SDT_ENTER(h);
     cudaStream_t st = (cudaStream_t)stream;
+    sdt_order_after_last(h, st);
     SDT_TRY(sdt_complete_stats(h, st));
     const ExecCtx x = exec_ctx(h, st);
     QuadSet& s0 = h->set[h->cur];
@@ -384,8 +385,9 @@ extern "C" int sdt_refine(sdt_handle h, uint32_t flags, sdt_stream stream) {
 }
 
 extern "C" int sdt_reset_stats(sdt_handle h, sdt_stream stream) {
-    if (!h) return SDT_ERR_INVALID;
+    SDT_ENTER(h);
     cudaStream_t st = (cudaStream_t)stream;
+    sdt_order_after_last(h, st);
     const ExecCtx x = exec_ctx(h, st);
     QuadSet& s = h->set[h->cur];
     launch_items(x, &s.hdr->n_kd, 0, ZeroItem{h->kd_count});

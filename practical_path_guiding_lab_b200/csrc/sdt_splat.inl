@@ -200,7 +200,7 @@ static int sdt_complete_stats(sdt_handle h, cudaStream_t st) {
 
 // ---------------------------------------------------------------------------- entry points
 extern "C" int sdt_splat_records(sdt_handle h, const sdt_records* rec, uint32_t n, uint32_t flags, sdt_stream stream) {
-    if (!h) return SDT_ERR_INVALID;
+    SDT_ENTER(h);
     if (n == 0) return SDT_OK;                          // empty wavefront: nothing to do (pointers may be NULL)
     SDT_CHECK(h, rec && rec->position.x && rec->direction.x && rec->radiance && rec->wo_pdf, SDT_ERR_INVALID, "sdt_splat_records: missing field");
     cudaStream_t st = (cudaStream_t)stream;
@@ -223,7 +223,7 @@ extern "C" int sdt_splat_records(sdt_handle h, const sdt_records* rec, uint32_t 
 }
 
 extern "C" int sdt_splat_path_data(sdt_handle h, const sdt_path_data* pd, uint32_t flags, sdt_stream stream) {
-    if (!h) return SDT_ERR_INVALID;
+    SDT_ENTER(h);
     if (pd && pd->slots == 0) return SDT_OK;            // empty wavefront: nothing to do (pointers may be NULL)
     SDT_CHECK(h, pd && pd->max_depth > 0 && pd->l_final.x && pd->throughput_radiance.x && pd->throughput_bsdf.x && pd->bsdf.x &&
                      pd->position.x && pd->direction.x && pd->wo_pdf, SDT_ERR_INVALID, "sdt_splat_path_data: missing field");

@@ -159,8 +159,9 @@ class PathGuidingCore:
                                   "refineAndPrepareSDTreeForNextIteration(); the device refine rebuilds prev and current together")
 
     def refineAndPrepareSDTreeForNextIteration(self):
-        """:566-586 -- one sdt_refine on the device"""
-        self.tree.refine(iteration=self.iteration)
+        """:566-586 -- one sdt_refine on the device.  Once per training iteration the sizes are read back: an
+        exhausted arena (device error flag) raises instead of silently training on a truncated tree."""
+        self.tree.refine(iteration=self.iteration, check=True)
 
     def saveSDTreeToFile(self, fileName):
         self.tree.save_npz(fileName, L.SDT_TREE_PREV)

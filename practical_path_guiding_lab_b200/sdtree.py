@@ -126,6 +126,7 @@ class SDTree:
     def __init__(self, bbox_min=(0, 0, 0), bbox_max=(1, 1, 1), kd_max_depth=20, quad_max_depth=20,
                  store_nee=True, device=0, kd_capacity=0, quad_capacity=0, lib_path=None):
         self._lib = L.load_library(lib_path)
+        self._lib_is_cuda = lib_path is None or not str(lib_path).endswith("libsdtree_hostemu.so")
         cfg = L.Config()
         cfg.bbox_min[:] = [float(np.float32(v)) for v in bbox_min]
         cfg.bbox_max[:] = [float(np.float32(v)) for v in bbox_max]
@@ -183,6 +184,23 @@ class SDTree:
         g = C.c_float()
         self._ck(self._lib.sdt_measure_l2(self._h, int(nbytes), int(passes), C.byref(g), None))
         return float(g.value)
+
+    def measure_gather(self, nbytes=16 << 20, iters=200, via_l1=True):
+        """random 32-byte-sector gather bandwidth over an L2-resident set (GB/s of sectors delivered)"""
+        g = C.c_float()
+        self._ck(self._lib.sdt_measure_gather(self._h, int(nbytes), int(iters), int(bool(via_l1)), C.byref(g), None))
+        return float(g.value)
+
+    def _stream(self, stream):
+        """stream of a call that takes no arrays: the caller's, else torch's current stream on this device (so that the
+        call is ordered after the splats / queries issued through torch tensors), else the NULL stream"""
+        if stream is not None:
+            return stream
+        import sys
+        torch = sys.modules.get("torch")
+        if torch is not None and self._lib_is_cuda and torch.cuda.is_available():
+            return torch.cuda.current_stream(self.device).cuda_stream
+        return None
 
     # ---- queries on prev --------------------------------------------------------------
     def locate(self, pos, active=None, sync=True):
@@ -381,15 +399,27 @@ class SDTree:
     def set_max_leaf_size(self, v):
         self._ck(self._lib.sdt_set_max_leaf_size(self._h, float(np.float32(v))))
 
-    def refine(self, iteration=None, kd=True, quad=True, sync=False, stream=None):
-        """refineAndPrepareSDTreeForNextIteration, on the device"""
+    def refine(self, iteration=None, kd=True, quad=True, sync=False, stream=None, check=False):
+        """refineAndPrepareSDTreeForNextIteration, on the device.  check=True waits for it and raises when an arena
+        overflowed (the device-side sticky error flag): the refined tree would be truncated, i.e. not the reference's"""
         if iteration is not None:
             self.set_iteration_threshold(iteration)
         flags = (0 if kd else L.SDT_REFINE_NO_KD) | (0 if quad else L.SDT_REFINE_NO_QUAD) | (L.SDT_SYNC if sync else 0)
-        self._ck(self._lib.sdt_refine(self._h, flags, stream))
+        self._ck(self._lib.sdt_refine(self._h, flags, self._stream(stream)))
+        if check:
+            self.check_error()
 
-    def reset_stats(self):
-        self._ck(self._lib.sdt_reset_stats(self._h, None))
+    def check_error(self):
+        """raises SDTreeError when the device-side error flag is set (1: spatial arena, 2: quadtree arena exhausted)"""
+        e = self.sizes()['error']
+        if e:
+            what = {1: "spatial node arena", 2: "quadtree node arena"}.get(e, "arena")
+            raise SDTreeError(-3,    # SDT_ERR_CAPACITY
+                              f"refine ran out of the {what} (device error flag {e}): the tree is truncated; "
+                              "create the SDTree with a larger kd_capacity / quad_capacity")
+
+    def reset_stats(self, stream=None):
+        self._ck(self._lib.sdt_reset_stats(self._h, self._stream(stream)))
 
     # ---- multi-GPU ------------------------------------------------------------------------
     def comm_unique_id(self):
@@ -404,7 +434,7 @@ class SDTree:
         self._ck(self._lib.sdt_comm_init(self._h, buf, int(rank), int(nranks)))
 
     def allreduce(self, stream=None):
-        self._ck(self._lib.sdt_allreduce(self._h, stream))
+        self._ck(self._lib.sdt_allreduce(self._h, self._stream(stream)))
 
     def stat_buffers(self):
         """(ptr_q_energy, n_quad, ptr_kd_count, n_kd) of current's statistics"""

@@ -63,9 +63,14 @@ def random_records(rng, n, lo, hi, nee, specials=True, negative=True):
         wo[pick(0.003)] = np.nan
     rec = so.SurfaceInteractionRecord(pos, d, radiance, wo)
     if nee:
-        # the Rec.709 luminance weights are not dyadic: NEE radiance stays 0 here (the NEE descent still runs
-        # and adds exact zeros); non-dyadic energies are covered by sdt_cases.case_splat_float_tolerance
+        # NEE radiance with an exactly dyadic luminance (sdt_cases.NEE_GREEN_UNIT): non-zero NEE energy, still
+        # order-independent sums; non-dyadic energies are covered by sdt_cases.case_splat_float_tolerance
+        rec.radiance_nee = cases.dyadic_nee(rng, n)
         rec.direction_nee = rng.random((n, 2)).astype(F)
+        if specials and n >= 64:
+            rec.direction_nee[rng.random(n) < 0.01] += F(1.5)
+            rec.direction_nee[rng.random(n) < 0.005, 1] = np.nan
+            rec.radiance_nee[rng.random(n) < 0.005, 0] = np.nan
     return rec, active
 
 

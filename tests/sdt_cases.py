@@ -35,6 +35,18 @@ class Ctx:
         return self.host(x).view(U) if self.host(x).dtype != U else self.host(x)
 
 
+# fl(NEE_GREEN_UNIT * 0.715160f) == 1.0f exactly, so mi.luminance((0, k * NEE_GREEN_UNIT, 0)) == k for every power of
+# two k: NEE energy that is NON-ZERO and still dyadic, i.e. topology after NEE deposits stays bit-reproducible
+NEE_GREEN_UNIT = np.array([1068694302], np.uint32).view(np.float32)[0]
+assert np.float32(NEE_GREEN_UNIT * np.float32(0.715160)) == np.float32(1.0)
+
+
+def dyadic_nee(rng, n):
+    nee = np.zeros((n, 3), F)
+    nee[:, 1] = rng.choice(np.array([0, 0, 0.25, 1, 2, 8], F), n) * NEE_GREEN_UNIT
+    return nee
+
+
 # ------------------------------------------------------------------------------ data
 def dyadic_records(n, seed, lobes=((0.3, 0.7, 0.02),), box=1.0, nee=False):
     """records whose radiance/woPdf are multiples of 1/16 (<= 8): fp32 sums of up to
@@ -50,8 +62,11 @@ def dyadic_records(n, seed, lobes=((0.3, 0.7, 0.02),), box=1.0, nee=False):
     wo = rng.choice(np.array([0.25, 0.5, 1.0, 2.0], F), n).astype(F)
     rec = so.SurfaceInteractionRecord(pos, d, radiance, wo)
     if nee:
-        rec.radiance_nee = (rng.integers(0, 3, (n, 3)) * np.array([0, 0, 0], F)).astype(F)
+        rec.radiance_nee = dyadic_nee(rng, n)
         rec.direction_nee = rng.random((n, 2)).astype(F)
+        m = rng.random(n) < 0.5                                  # an NEE lobe of its own: it shapes the quadtrees
+        rec.direction_nee[m] = np.clip(np.stack([0.15 + 0.01 * rng.standard_normal(m.sum()),
+                                                 0.85 + 0.01 * rng.standard_normal(m.sum())], 1), 0, 1).astype(F)
     return rec
 
 
@@ -536,6 +551,19 @@ def case_capacity_error(ctx):
     # the tree is still a valid tree: queries run
     leaf, root = t.locate(ctx.dev(rec.position[:100]))
     assert ctx.host(root).view(U).max() < s['n_roots']
+    # ... but it is NOT the reference's tree any more: the Python face raises on request (the integrator asks every iteration)
+    from practical_path_guiding_lab_b200.sdtree import SDTreeError
+    try:
+        t.check_error()
+        raise AssertionError("arena exhaustion not surfaced")
+    except SDTreeError as e:
+        assert e.code == -3 and "arena" in str(e)
+    splat(t, ctx, rec)
+    try:
+        t.refine(check=True)
+        raise AssertionError("arena exhaustion not surfaced by refine(check=True)")
+    except SDTreeError as e:
+        assert e.code == -3
 
 
 def case_zero_total_energy(ctx):
@@ -604,6 +632,16 @@ def case_edge_inputs_and_errors(ctx):
         raise AssertionError("invalid spatial layout accepted")
     except SDTreeError as e:
         assert e.code == -4 and "adjacent" in str(e)
+    # boxes that are not the midpoint split on axis depth % 3 (the descent recomputes planes, it does not read boxes)
+    bad = dict(prev.to_arrays())
+    bad['kdtree_bbox_max'] = bad['kdtree_bbox_max'].copy()
+    left = int(bad['kdtree_child_left_index'][0])
+    bad['kdtree_bbox_max'][left, 0] = np.nextafter(bad['kdtree_bbox_max'][left, 0], F(2))
+    try:
+        t2.upload(bad)
+        raise AssertionError("non-midpoint spatial boxes accepted")
+    except SDTreeError as e:
+        assert e.code == -4 and "midpoint" in str(e)
     small = ctx.make(kd_capacity=4, quad_capacity=16)
     try:
         small.upload(prev.to_arrays())

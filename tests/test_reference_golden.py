@@ -1,0 +1,91 @@
+"""Replays tests/golden/reference_on_shim.npz -- inputs and outputs of the reference's OWN source run on the
+numpy Dr.Jit / Mitsuba stand-ins (tests/golden/make_reference_golden.py) -- through the C ABI and demands the
+stored outputs: all 23 arrays of both trees after the splat / refine sequence (non-zero NEE energy included),
+leaf / root / quadtree node ids bit-exact, directions and pdfs bit-exact (the north_star asks 1e-5).
+No oracle in between.  CPU: host emulation of the kernels; `-m gpu`: libsdtree.so on the B200, device- and
+host-pointer modes."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+import sdt_cases as cases  # noqa: E402
+
+F, U = np.float32, np.uint32
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_on_shim.npz")
+NAMES = ("unit_nee", "box_shallow", "cube100")
+
+
+class _Rec:
+    pass
+
+
+def replay(ctx, name):
+    g = np.load(GOLD)
+    p = name + '/'
+    kd, qd, nee, leaf, iters, refine_last = (int(v) for v in g[p + 'cfg'])
+    t = ctx.make(bbox_min=tuple(g[p + 'lo']), bbox_max=tuple(g[p + 'hi']), kd_max_depth=kd, quad_max_depth=qd,
+                 store_nee=bool(nee), kd_capacity=1 << 12, quad_capacity=1 << 17)
+    for it in range(iters):
+        rec = _Rec()
+        for f in ('position', 'direction', 'radiance', 'woPdf', 'radiance_nee', 'direction_nee'):
+            setattr(rec, f, g[f'{p}it{it}/{f}'])
+        cases.splat(t, ctx, rec)
+        if it == iters - 1 and not refine_last:
+            break
+        t.set_max_leaf_size(leaf)
+        t.refine()
+    assert t.sizes()['error'] == 0
+    for which, tag in ((0, 'prev'), (1, 'cur')):
+        got = t.download(which)
+        for k in cases.so.KDTree.NPZ_KEYS:
+            w, v = g[f'{p}{tag}/{k}'], np.asarray(got[k])
+            if k == 'kdtree_maxLeafSize':
+                assert F(v) == F(w)
+                continue
+            assert v.shape == w.shape, (name, tag, k, v.shape, w.shape)
+            assert (cases.beq(v, w) if w.dtype == F else np.array_equal(v, w)), (name, tag, k)
+    if nee and not refine_last:
+        assert float(g[p + 'cur/quadtree_irradiance'].sum()) > 0
+    a = g[p + 'q/active']
+    am = ctx.dev(a.astype(np.uint8))
+    pos = ctx.dev(g[p + 'q/pos'])
+    lf, rt = t.locate(pos, am)
+    assert np.array_equal(ctx.host(lf).view(U), g[p + 'q/leaf']) and np.array_equal(ctx.host(rt).view(U), g[p + 'q/root'])
+    d, pdf, dbg = t.sample(pos, am, u=ctx.dev(g[p + 'q/u']), debug=True)
+    dbg = ctx.host(dbg).view(U)
+    assert np.array_equal(dbg[a, 2], g[p + 'q/sample_node'][a]), "sampled quadtree node"
+    assert cases.beq(ctx.host(d), g[p + 'q/sample_dir']) and cases.beq(ctx.host(pdf), g[p + 'q/sample_pdf'])
+    pp, pdbg = t.pdf(pos, ctx.dev(g[p + 'q/dirs']), am, debug=True)
+    assert np.array_equal(ctx.host(pdbg).view(U)[a, 2], g[p + 'q/pdf_node'][a])
+    assert cases.beq(ctx.host(pp), g[p + 'q/pdf'])
+
+
+@pytest.mark.parametrize("name", NAMES)
+def test_reference_golden_hostemu(name):
+    from hostemu.build_hostemu import build as build_hostemu
+    from practical_path_guiding_lab_b200 import SDTree
+    lib = build_hostemu()
+    replay(cases.Ctx(make=lambda **kw: SDTree(lib_path=lib, **kw)), name)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mode", ["device", "host"])
+@pytest.mark.parametrize("name", NAMES)
+def test_reference_golden_gpu(name, mode):
+    from test_gpu_parity import _ctx
+    replay(_ctx(mode), name)
+
+
+def test_fixture_is_current():
+    """the committed fixture is what the generator writes today (only where the reference tree exists)"""
+    from oracle import refshim
+    if not refshim.available():
+        pytest.skip("reference tree not present")
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("make_reference_golden", os.path.join(os.path.dirname(GOLD), "make_reference_golden.py"))
+    m = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(m)
+    assert tuple(c['name'] for c in m.CONFIGS) == NAMES
