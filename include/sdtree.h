@@ -270,9 +270,12 @@ int sdt_stat_buffers(sdt_handle h, float** q_energy, uint32_t* n_quad, float** k
 
 /* ---- tuning / introspection --------------------------------------------------- */
 /* Speed keys (results do not depend on them):
- *   "query_block", "query_ctas_per_sm", "splat_block", "splat_ctas_per_sm"   CTA shape of the wavefront kernels
+ *   "query_block", "query_ctas_per_sm", "splat_block", "splat_ctas_per_sm"   CTA shape of the wavefront kernels (block 0 = the
+ *                       kernel's own size: 768 threads for the sampling kernels, 1024 for pdf / locate / splat; larger values are clamped)
  *   "kd_smem_nodes", "kd_smem_count_nodes", "splat_stage_words"              what of the spatial tree is staged in shared memory
  *   "use_kd_grid", "use_jump", "use_int_cell", "fuse_sample_pdf", "use_compaction"   fast paths on / off (each has an exact slow path)
+ *   "splat_aggregate"   combine the lanes of a warp that splat into the same node before the atomic (pays on pixel-coherent
+ *                       wavefronts; off by default: on incoherent records it finds no peers and only costs instructions)
  *   "use_pdl"                                                                programmatic dependent launch of the helper kernels
  *   "host_chunk"   lanes per chunk of the pipelined SDT_HOST_PTRS staging (H2D of chunk k+1 | kernels of chunk k | D2H of chunk k-1).
  * One key switches semantics rather than speed: "quad_thr_reciprocal" = 1 computes the

@@ -7,6 +7,26 @@
 #include "sdt_platform.h"
 #include "../../include/sdtree.h"
 
+// compile-time shape of the wavefront kernels (kernel experiments: tools/build_variant.sh)
+// __launch_bounds__ of k_wavefront per kind of lane: 2 CTAs per SM (one staged copy of the spatial tree each).
+// The sampling kernels keep 768 threads (up to 42 registers: their descent loop wants them); the pdf / locate / splat
+// kernels fit in 32 registers and run 1024 threads = all 64 warps of an SM (measured: pdf -10 %, splat -5 %).
+#ifndef SDT_SAMPLE_THREADS
+#define SDT_SAMPLE_THREADS 768
+#endif
+#ifndef SDT_QUERY_THREADS
+#define SDT_QUERY_THREADS 1024
+#endif
+#ifndef SDT_SPLAT_THREADS
+#define SDT_SPLAT_THREADS 1024
+#endif
+#ifndef SDT_LB_CTAS
+#define SDT_LB_CTAS 2
+#endif
+#ifndef SDT_SAMPLE_GRID
+#define SDT_SAMPLE_GRID true       // sampling kernels use the spatial grid even when the whole tree is staged (measured: sample -5 %)
+#endif
+
 #define SDT_MAX_LEVELS 34          // quadtree levels 0..33 (QuadTree.maxDepth <= 32)
 #define SDT_KD_MAX_DEPTH 40        // KDTree.maxDepth upper bound
 #define SDT_KD_LEAF_BIT 0x80000000u
@@ -30,12 +50,18 @@
 // root id), then level by level the four adjacent children of every non-leaf node.
 // Per NON-LEAF node one 32-byte record (= one L2 sector per descent level):
 struct __align__(32) QRec {
-    uint32_t child_base;     // canonical node id of child_1; children are base..base+3
+    uint32_t child_base;     // canonical node id of child_1 (children are base..base+3); bit 31: SDT_REC_IRREGULAR
     uint32_t interior_base;  // record index of the first non-leaf child
-    uint32_t cinfo;          // bits 0-3: child c is a leaf (no record); bits 8-15: see sdt_make_cinfo
+    uint32_t cinfo;          // byte c: rank of child c among the non-leaf children, 0xFF when child c is a leaf (sdt_make_cinfo)
     float own;               // this node's stored energy (pdf denominator, :1056)
     float e[4];              // the four children's stored energies (:969-972, :1057-1060)
 };
+// Set in child_base when the four child energies are not all finite and >= 0 (negative / NaN / infinite radiance can
+// produce such sums): only then can the reference's four masked bin assignments (src/quadtree.py:983-991) overlap or
+// all fail, and the sampler runs them literally.  For every other record the bins partition [0, e4) and the selected
+// child is simply the number of cumulative energies <= s.  Node ids therefore stay below 2^31 (sdt_create).
+#define SDT_REC_IRREGULAR 0x80000000u
+#define SDT_NODE_MASK 0x7FFFFFFFu
 
 // Device-resident description of the tree; kernels read sizes from here so that
 // refine needs no host round-trip.
@@ -95,6 +121,12 @@ enum DevError : uint32_t {
 #define SDT_JUMP_INV_F (1.0f / (float)SDT_JUMP_SIDE)           // exact: a power of two
 #define SDT_JUMP_LEAF 0x80000000u      // entry = LEAF | node id: a leaf was reached
 typedef uint32_t QJump;
+// Second table of the same shape for the pdf descents, which want the leaf's path product and not its id: an entry is
+// the fp32 bits of pp[leaf] (sign bit clear), or SDT_JUMP_NEXT | record to continue from.  A product that is negative
+// or NaN is stored as SDT_JUMP_PP_SLOW (a NaN): those lanes take the level-by-level path.  One gather instead of two
+// (table entry, then pp[leaf]) for every direction whose leaf lies in the top SDT_JUMP_LEVELS levels.
+#define SDT_JUMP_NEXT 0x80000000u
+#define SDT_JUMP_PP_SLOW 0x7FC00000u
 
 struct TreeView {
     const DevHeader* hdr;
@@ -103,9 +135,10 @@ struct TreeView {
     const uint32_t* kd_grid;    // SDT_GRID_CELLS cells -> spatial node after the first 11 levels
     const QRec* rec;
     const QJump* jump;          // [root record][cell]
+    const uint32_t* jump_pp;    // [root record][cell], see SDT_JUMP_NEXT
     const float* pp;            // per node: pdf product of the root->node path (NaN: it went NaN)
     uint32_t jump_trees;        // 0: table not in use
-    uint32_t int_cell;          // quadtrees no deeper than 23 levels: integer cell tracking in the sampler
+    uint32_t int_cell;          // sampler's cell tracking (sdt_quad_sample CELL): 1 = depth <= 16, 2 = depth <= 23, 0 = deeper
 };
 
 // ---------------------------------------------------------------------------
@@ -207,12 +240,14 @@ SDT_HD float sdt_u24(uint32_t h) { return (float)(h >> 8) * 5.9604644775390625e-
 // does); pos(idx) is random access.  ExplicitRng: u[lane*stride + idx], clamped like the oracle's
 // ExplicitSampler.
 struct CounterRng {
+    static constexpr bool kUnitInterval = true;      // every uniform is in [0, 1)
     uint32_t h0, t;
     SDT_HD CounterRng(uint32_t seed, uint32_t lane_id) : h0(sdt_fmix(seed + lane_id * 0x9E3779B1u)), t(h0) {}
     SDT_HD float select(uint32_t) { t = t * SDT_LCG_M + SDT_LCG_C; return sdt_u24(t); }
     SDT_HD float pos(uint32_t idx) const { return sdt_u24(sdt_fmix(h0 ^ (idx * 0x85EBCA77u + 0x165667B1u))); }
 };
 struct ExplicitRng {
+    static constexpr bool kUnitInterval = false;     // caller-provided numbers: may be anything, NaN included
     const float* row; uint32_t u_stride;
     SDT_HD ExplicitRng(const float* u, uint32_t stride, uint32_t lane_index) : row(u + (size_t)lane_index * stride), u_stride(stride) {}
     SDT_HD float pos(uint32_t idx) const { return SDT_LDG(row + (idx < u_stride ? idx : u_stride - 1u)); }
@@ -246,26 +281,6 @@ SDT_HD uint32_t sdt_kd_load(const uint32_t* __restrict__ kd, uint32_t n_smem, co
         if (w & SDT_KD_LEAF_BIT) break;                                     \
     }
 
-// per-thread constants of the spatial descent (loaded once per thread, not per vertex)
-struct KdCtx {
-    const uint32_t* kd;       // smem-staged prefix of kd_word
-    uint32_t n_smem;
-    const uint32_t* kdg;      // full array
-    float lo[3], hi[3];       // root box
-    uint32_t rootrec0;        // root record of the tree owned by node 0 (out-of-box lanes, :224,:482)
-    float* cnt_s;             // splat kernels: per-CTA shared-memory leaf counters (NULL: count in global memory)
-    const uint32_t* grid;     // 16x16x8 cell -> node reached after the first 11 levels (NULL: descend from the root)
-};
-SDT_HD KdCtx sdt_kd_ctx(const uint32_t* kd, uint32_t n_smem, const uint32_t* kdg, const DevHeader* hdr) {
-    KdCtx k;
-    k.kd = kd; k.n_smem = n_smem; k.kdg = kdg;
-    for (int a = 0; a < 3; ++a) { k.lo[a] = hdr->bbox_min[a]; k.hi[a] = hdr->bbox_max[a]; }
-    k.rootrec0 = hdr->rootrec_of_node0;
-    k.cnt_s = nullptr;
-    k.grid = nullptr;
-    return k;
-}
-
 // The first SDT_GRID_LEVELS = 11 levels split x,y,z,x,y,z,x,y,z,x,y: 4 halvings of x, 4 of y, 3 of z.
 // The split planes of one axis do not depend on the other axes, so the three chains of exact fp32
 // midpoints run independently (no memory access, ILP 3) and give the cell of a 16x16x8 grid; the
@@ -281,6 +296,28 @@ SDT_HD KdCtx sdt_kd_ctx(const uint32_t* kd, uint32_t n_smem, const uint32_t* kdg
 #define SDT_GRID_NZ (SDT_GRID_LEVELS / 3)
 #define SDT_GRID_CELLS (1u << SDT_GRID_LEVELS)
 #define SDT_GRID_CELL(cx, cy, cz) (((cx) << (SDT_GRID_NY + SDT_GRID_NZ)) | ((cy) << SDT_GRID_NZ) | (cz))
+// per-thread constants of the spatial descent (loaded once per thread, not per vertex)
+struct KdCtx {
+    const uint32_t* kd;       // smem-staged prefix of kd_word
+    uint32_t n_smem;
+    const uint32_t* kdg;      // full array
+    float lo[3], hi[3];       // root box
+    uint32_t rootrec0;        // root record of the tree owned by node 0 (out-of-box lanes, :224,:482)
+    uint32_t* cnt_s;          // splat kernels: per-CTA shared-memory leaf counters (NULL: count in global memory)
+    uint32_t aggregate;       // splat kernels: combine lanes of a warp that hit the same address before the atomic
+    const uint32_t* grid;     // 16x16x8 cell -> node reached after the first 11 levels (NULL: descend from the root)
+};
+SDT_HD KdCtx sdt_kd_ctx(const uint32_t* kd, uint32_t n_smem, const uint32_t* kdg, const DevHeader* hdr) {
+    KdCtx k;
+    k.kd = kd; k.n_smem = n_smem; k.kdg = kdg;
+    for (int a = 0; a < 3; ++a) { k.lo[a] = hdr->bbox_min[a]; k.hi[a] = hdr->bbox_max[a]; }
+    k.rootrec0 = hdr->rootrec_of_node0;
+    k.cnt_s = nullptr;
+    k.aggregate = 0u;
+    k.grid = nullptr;
+    return k;
+}
+
 #define SDT_AXIS_STEP(P, LO, HI, C)                                         \
     {                                                                       \
         const float mid = (LO + HI) / 2.0f;                                 \
@@ -289,6 +326,9 @@ SDT_HD KdCtx sdt_kd_ctx(const uint32_t* kd, uint32_t n_smem, const uint32_t* kdg
         HI = right ? HI : mid;                                              \
         C = (C << 1) | (right ? 1u : 0u);                                   \
     }
+// (tried in round 2: the cell from a scaled guess verified against a shared-memory table of the exact cell boundaries
+// instead of the 11 chained halvings -- fewer instructions, but the dependent LDS + F2I chain and the rare fix-up
+// branches made all three kernels 3 % slower; the arithmetic chains stay)
 // node reached from the root by the path bits of cell (cx NX bits, cy NY bits, cz NZ bits)
 SDT_HD uint32_t sdt_kd_grid_node(const uint32_t* __restrict__ kd, uint32_t cell) {
     const uint32_t cx = cell >> (SDT_GRID_NY + SDT_GRID_NZ), cy = (cell >> SDT_GRID_NZ) & ((1u << SDT_GRID_NY) - 1u), cz = cell & ((1u << SDT_GRID_NZ) - 1u);
@@ -394,20 +434,43 @@ SDT_HD void sdt_load_rec(const QRec* __restrict__ rec, uint32_t i, QHead& h, Sdt
     e.x = rec[i].e[0]; e.y = rec[i].e[1]; e.z = rec[i].e[2]; e.w = rec[i].e[3];
 #endif
 }
-// cinfo: bits 0..3 = child c is a leaf; bits 8+2c..9+2c = rank of child c among the
-// non-leaf children (its record is interior_base + rank)
+// cinfo: byte c = rank of child c among the non-leaf children (its record is interior_base + rank),
+// or 0xFF when child c is a leaf
 SDT_HD uint32_t sdt_make_cinfo(uint32_t leafmask) {
-    uint32_t ci = leafmask & 0xFu, run = 0;
+    uint32_t ci = 0, run = 0;
     for (uint32_t c = 0; c < 4u; ++c) {
-        ci |= run << (8u + 2u * c);
-        if (!((leafmask >> c) & 1u)) ++run;
+        if ((leafmask >> c) & 1u) ci |= 0xFFu << (8u * c);
+        else { ci |= run << (8u * c); ++run; }
     }
     return ci;
 }
+// byte c of cinfo, sign-extended: the rank (0..3) of a non-leaf child, -1 for a leaf
+SDT_HD int32_t sdt_child_code(uint32_t cinfo, uint32_t c) {
+    return (int32_t)(int8_t)(uint8_t)(cinfo >> (8u * c));
+}
+// the same with the child given as a byte-permute selector SDT_SEL(c): byte 0 <- byte c, bytes 1..3 <- its sign
+// (selector nibbles c, 8|c, 8|c, 8|c) -- one PRMT, and the sampler's comparison chain yields the selector directly
+#define SDT_SEL(c) ((c) * 0x1111u + 0x8880u)
+SDT_HD int32_t sdt_child_code_sel(uint32_t cinfo, uint32_t sel) {
+#if defined(__CUDA_ARCH__)
+    uint32_t d;
+    asm("prmt.b32 %0, %1, 0, %2;" : "=r"(d) : "r"(cinfo), "r"(sel));
+    return (int32_t)d;
+#else
+    return sdt_child_code(cinfo, sel & 3u);
+#endif
+}
 // record index of child c, or SDT_NONE when it is a leaf
 SDT_HD uint32_t sdt_child_rec(uint32_t cinfo, uint32_t interior_base, uint32_t c) {
-    const uint32_t off = (cinfo >> (8u + 2u * c)) & 3u;
-    return ((cinfo >> c) & 1u) ? SDT_NONE : interior_base + off;
+    const int32_t code = sdt_child_code(cinfo, c);
+    return code < 0 ? SDT_NONE : interior_base + (uint32_t)code;
+}
+// flag of a record whose child energies need the literal bin assignments (see SDT_REC_IRREGULAR)
+SDT_HD uint32_t sdt_rec_flags(float e0, float e1, float e2, float e3) {
+    const float big = 3.402823466e38f;
+    const bool ok = (e0 >= 0.0f) && (e1 >= 0.0f) && (e2 >= 0.0f) && (e3 >= 0.0f) &&
+                    ((((e0 + e1) + e2) + e3) <= big);
+    return ok ? 0u : SDT_REC_IRREGULAR;
 }
 
 // quadrant c (0..3 = child_1..child_4) of [lo,hi], src/quadtree.py:153-175:
@@ -470,7 +533,7 @@ SDT_HD float sdt_quad_pdf_levels(const QRec* __restrict__ rec, uint32_t ri, uint
         ri = sdt_child_rec(h.cinfo, h.interior_base, cd);
     }
     pdf = dead ? 0.0f : pdf * SDT_INV_FOUR_PI;                          // :1030
-    node_out = node;
+    node_out = node & SDT_NODE_MASK;
     return pdf;
 }
 
@@ -478,7 +541,7 @@ SDT_HD float sdt_quad_pdf_levels(const QRec* __restrict__ rec, uint32_t ri, uint
 // single-leaf tree).  Finds the leaf (jump table, then 16 B of each record per level) and reads its
 // path product; split-line points and NaN stops go through sdt_quad_pdf_levels.
 SDT_HD float sdt_quad_pdf(const TreeView& t, uint32_t ri, uint32_t root_node,
-                          float x, float y, uint32_t& node_out) {
+                          float x, float y, uint32_t& node_out, bool want_node = true) {
     if (ri == SDT_NONE) { node_out = root_node; return SDT_INV_FOUR_PI; }     // 1 * 1/(4 pi)
     const QRec* __restrict__ rec = t.rec;
     const uint32_t ri0 = ri;
@@ -488,10 +551,22 @@ SDT_HD float sdt_quad_pdf(const TreeView& t, uint32_t ri, uint32_t root_node,
     bool tie = false;
     uint32_t cx, cy;
     if (ri < t.jump_trees && sdt_jump_cell(x, y, cx, cy)) {
-        const QJump j = SDT_LDG(t.jump + (size_t)ri * SDT_JUMP_CELLS + cy * SDT_JUMP_SIDE + cx);
-        if (j & SDT_JUMP_LEAF) { node = j & ~SDT_JUMP_LEAF; ri = SDT_NONE; }
-        else {
-            ri = j;
+        if (!want_node) {
+            // the caller only wants the pdf: the table holds the leaf's path product itself
+            const uint32_t j = SDT_LDG(t.jump_pp + (size_t)ri * SDT_JUMP_CELLS + cy * SDT_JUMP_SIDE + cx);
+            if (!(j & SDT_JUMP_NEXT)) {
+                const float pp = sdt_u2f(j);
+                node_out = 0u;
+                if (pp == pp) return pp * SDT_INV_FOUR_PI;
+                return sdt_quad_pdf_levels(rec, ri0, root_node, x, y, node_out);
+            }
+            ri = j & ~SDT_JUMP_NEXT;
+        } else {
+            const QJump j = SDT_LDG(t.jump + (size_t)ri * SDT_JUMP_CELLS + cy * SDT_JUMP_SIDE + cx);
+            if (j & SDT_JUMP_LEAF) { node = j & ~SDT_JUMP_LEAF; ri = SDT_NONE; }
+            else ri = j;
+        }
+        if (ri != SDT_NONE) {
             lox = (float)cx * SDT_JUMP_INV_F; hix = (float)(cx + 1u) * SDT_JUMP_INV_F;
             loy = (float)cy * SDT_JUMP_INV_F; hiy = (float)(cy + 1u) * SDT_JUMP_INV_F;
             level = SDT_JUMP_LEVELS;
@@ -506,6 +581,7 @@ SDT_HD float sdt_quad_pdf(const TreeView& t, uint32_t ri, uint32_t root_node,
         sdt_quadrant_m(cd, mx, my, lox, loy, hix, hiy);
         ri = sdt_child_rec(h.cinfo, h.interior_base, cd);
     }
+    node &= SDT_NODE_MASK;
     const float pp = SDT_LDG(t.pp + node);
     if (tie || pp != pp) return sdt_quad_pdf_levels(rec, ri0, root_node, x, y, node_out);
     node_out = node;
@@ -520,9 +596,17 @@ SDT_HD QJump sdt_build_jump(const QRec* __restrict__ rec, uint32_t root_rec, uin
         const uint32_t bx = (cx >> (SDT_JUMP_LEVELS - 1 - l)) & 1u, by = (cy >> (SDT_JUMP_LEVELS - 1 - l)) & 1u;
         const uint32_t c = by ? (bx ? 0u : 1u) : (bx ? 3u : 2u);         // strict interior: every tie rule agrees
         ri = sdt_child_rec(r.cinfo, r.interior_base, c);
-        if (ri == SDT_NONE) return SDT_JUMP_LEAF | (r.child_base + c);
+        if (ri == SDT_NONE) return SDT_JUMP_LEAF | ((r.child_base & SDT_NODE_MASK) + c);
     }
     return ri;
+}
+
+// the pdf descents' entry for the same cell (see SDT_JUMP_NEXT)
+SDT_HD uint32_t sdt_jump_pp_entry(QJump j, const float* __restrict__ pp) {
+    if (!(j & SDT_JUMP_LEAF)) return SDT_JUMP_NEXT | j;
+    const uint32_t b = sdt_f2u(pp[j & ~SDT_JUMP_LEAF]);
+    const float v = sdt_u2f(b);
+    return ((b & 0x80000000u) || v != v) ? SDT_JUMP_PP_SLOW : b;
 }
 
 // QuadTree.sampleQuadTree, src/quadtree.py:931-998.  Consumes 3 uniforms per visited
@@ -540,43 +624,106 @@ struct QSample {
     float lox, loy, hix, hiy;   // leaf cell
 };
 
-// INT_CELL: track the cell as integer coordinates (ix, iy, level) instead of four floats and build
-// the box once at the leaf.  Cell corners k/2^level are exact in fp32 up to level 23, where the
-// reference's repeated (min+max)/2 is exact too, so the box is bit-identical; deeper trees
-// (QuadTree.maxDepth > 23) use the float tracking that reproduces the reference's rounding.
-template <class Rng, bool INT_CELL>
+// CELL: how the sampler knows the leaf cell it ended in.
+//   0  four floats halved per level with the reference's own (min+max)/2 (any depth; QuadTree.maxDepth > 23)
+//   1  the path as 2 bits per level in 32 bits (trees of at most 16 levels below the root)
+//   2  the same in 64 bits (at most 23 levels)
+// For 1 and 2 the cell (ix, iy) / 2^level is rebuilt once at the leaf, where the warp has reconverged.  Cell corners
+// k/2^level are exact in fp32 up to level 23, where the reference's repeated (min+max)/2 is exact too, so the box is
+// bit-identical.  child_1 / child_4 are the right half, child_1 / child_2 the upper half (:153-175): for the child
+// number cu = b1 b0 the x bit is ~(b1 ^ b0) and the y bit ~b1.
+SDT_HD uint32_t sdt_even_bits(uint32_t x) {          // bits 0,2,4,.. of x packed into the low half
+    x &= 0x55555555u;
+    x = (x | (x >> 1)) & 0x33333333u;
+    x = (x | (x >> 2)) & 0x0F0F0F0Fu;
+    x = (x | (x >> 4)) & 0x00FF00FFu;
+    x = (x | (x >> 8)) & 0x0000FFFFu;
+    return x;
+}
+SDT_HD void sdt_path_cell(uint32_t path, uint32_t level, uint32_t& ix, uint32_t& iy) {
+    const uint32_t odd = path >> 1;
+    const uint32_t m = level >= 32u ? 0xFFFFFFFFu : (1u << level) - 1u;
+    ix = sdt_even_bits(~(odd ^ path)) & m;
+    iy = sdt_even_bits(~odd) & m;
+}
+SDT_HD void sdt_path_cell64(uint64_t path, uint32_t level, uint32_t& ix, uint32_t& iy) {
+    uint32_t xl, yl, xh, yh;
+    sdt_path_cell((uint32_t)path, 16u, xl, yl);
+    sdt_path_cell((uint32_t)(path >> 32), 16u, xh, yh);
+    const uint32_t m = level >= 32u ? 0xFFFFFFFFu : (1u << level) - 1u;
+    ix = ((xh << 16) | xl) & m;
+    iy = ((yh << 16) | yl) & m;
+}
+
+template <class Rng, int CELL>
 SDT_HD QSample sdt_quad_sample(const QRec* __restrict__ rec, uint32_t ri, uint32_t root_node, Rng rng) {
     QSample q;
     q.x = 0.0f; q.y = 0.0f; q.node = root_node; q.moved = ri != SDT_NONE; q.stuck = false;
     q.lox = 0.0f; q.loy = 0.0f; q.hix = 1.0f; q.hiy = 1.0f;
-    uint32_t level = 0, ix = 0, iy = 0;
-    // the loop only descends; the leaf position is drawn after it, where the warp has reconverged
-    for (; level < SDT_MAX_LEVELS; ++level) {
-        if (ri == SDT_NONE) break;
-        QHead h; SdtF4 e;
-        sdt_load_rec(rec, ri, h, e);
-        const float e1 = e.x;
-        const float e2 = e.y + e1;                                       // :975-977
-        const float e3 = e.z + e2;
-        const float e4 = e.w + e3;
-        const float s = rng.select(level) * e4;                          // :980
-        // :983-991: four masked assignments in turn, a later bin overrides an earlier one
-        // (they only overlap for negative energies); no bin (NaN) -> the lane is stuck
-        const bool b1 = e1 <= s, b2 = e2 <= s, b3 = e3 <= s;
-        const bool m0 = s < e1, m1 = b1 && (s < e2), m2 = b2 && (s < e3);
-        if (!(m0 || m1 || m2 || b3)) { q.stuck = true; break; }
-        const uint32_t cu = b3 ? 3u : (m2 ? 2u : (m1 ? 1u : 0u));
-        q.node = h.child_base + cu;
-        if (INT_CELL) {
-            ix = 2u * ix + (((cu + 1u) >> 1) & 1u ^ 1u);                 // c1, c4 are the right half (:153-175)
-            iy = 2u * iy + ((cu >> 1) ^ 1u);                             // c1, c2 are the upper half
-        } else {
-            sdt_quadrant_m(cu, (q.lox + q.hix) / 2.0f, (q.loy + q.hiy) / 2.0f, q.lox, q.loy, q.hix, q.hiy);
-        }
-        ri = sdt_child_rec(h.cinfo, h.interior_base, cu);
+    uint32_t level = 0, path32 = 0;
+    uint64_t path64 = 0;
+#define SDT_SAMPLE_STEP(CU, SEL)                                                                                  \
+    {                                                                                                         \
+        q.node = h.child_base + (CU);                                                                         \
+        if (CELL == 1) path32 = (path32 << 2) | (CU);                                                         \
+        else if (CELL == 2) path64 = (path64 << 2) | (CU);                                                    \
+        else sdt_quadrant_m((CU), (q.lox + q.hix) / 2.0f, (q.loy + q.hiy) / 2.0f, q.lox, q.loy, q.hix, q.hiy); \
+        ++level;                                                                                              \
+        const int32_t code = sdt_child_code_sel(h.cinfo, (SEL));                                              \
+        if (code < 0) break;                                                                                  \
+        ri = h.interior_base + (uint32_t)code;                                                                \
+        if (level >= SDT_MAX_LEVELS) break;                          /* impossible for a valid tree */         \
     }
+    // the loops only descend; the leaf position is drawn after them, where the warp has reconverged
+    if (ri != SDT_NONE) {
+        // fast loop: records whose child energies are finite and >= 0 -- the bins partition [0, e4), e1 <= e2 <= e3,
+        // and the child is the number of cumulative energies <= s.  The first record that is not (or a NaN s: an
+        // explicit uniform can be anything) hands the rest of the descent to the literal loop below.
+        float u_pending = 0.0f;
+        bool literal = false;
+        for (;;) {
+            QHead h; SdtF4 e;
+            sdt_load_rec(rec, ri, h, e);
+            const float e1 = e.x;
+            const float e2 = e.y + e1;                                   // :975-977
+            const float e3 = e.z + e2;
+            const float e4 = e.w + e3;
+            const float u = rng.select(level);
+            const float s = u * e4;                                      // :980
+            if (((int32_t)h.child_base < 0) || (!Rng::kUnitInterval && (s != s))) { literal = true; u_pending = u; break; }
+            const uint32_t sel = (s >= e3) ? SDT_SEL(3u) : ((s >= e2) ? SDT_SEL(2u) : ((s >= e1) ? SDT_SEL(1u) : SDT_SEL(0u)));
+            const uint32_t cu = sel & 3u;
+            SDT_SAMPLE_STEP(cu, sel)
+        }
+        if (literal) {
+            bool first = true;
+            for (;;) {
+                QHead h; SdtF4 e;
+                sdt_load_rec(rec, ri, h, e);
+                h.child_base &= SDT_NODE_MASK;
+                const float e1 = e.x;
+                const float e2 = e.y + e1;
+                const float e3 = e.z + e2;
+                const float e4 = e.w + e3;
+                const float u = first ? u_pending : rng.select(level);
+                first = false;
+                const float s = u * e4;
+                // :983-991 literally: four masked assignments in turn, a later bin overrides an earlier one (they
+                // only overlap for negative energies); no bin (NaN) -> the lane is stuck
+                const bool b1 = e1 <= s, b2 = e2 <= s, b3 = e3 <= s;
+                const bool m0 = s < e1, m1 = b1 && (s < e2), m2 = b2 && (s < e3);
+                if (!(m0 || m1 || m2 || b3)) { q.stuck = true; break; }
+                const uint32_t cu = b3 ? 3u : (m2 ? 2u : (m1 ? 1u : 0u));
+                SDT_SAMPLE_STEP(cu, SDT_SEL(cu))
+            }
+        }
+    }
+#undef SDT_SAMPLE_STEP
     if (level >= SDT_MAX_LEVELS) q.stuck = true;   // deeper than SDT_MAX_LEVELS: impossible for a valid tree
-    if (INT_CELL) {
+    if (CELL != 0) {
+        uint32_t ix, iy;
+        if (CELL == 1) sdt_path_cell(path32, level, ix, iy);
+        else sdt_path_cell64(path64, level, ix, iy);
         const float sc = sdt_u2f((127u - level) << 23);                  // 2^-level
         q.lox = (float)ix * sc; q.hix = (float)(ix + 1u) * sc;
         q.loy = (float)iy * sc; q.hiy = (float)(iy + 1u) * sc;
@@ -600,7 +747,8 @@ struct GuidedSample { float dx, dy, dz, pdf; uint32_t sample_node, pdf_node; };
 template <class Rng>
 SDT_HD GuidedSample sdt_sample_tree(const TreeView& t, uint32_t ri, uint32_t root, const Rng& rng, bool fuse) {
     GuidedSample g;
-    const QSample q = t.int_cell ? sdt_quad_sample<Rng, true>(t.rec, ri, root, rng) : sdt_quad_sample<Rng, false>(t.rec, ri, root, rng);
+    const QSample q = t.int_cell == 1u ? sdt_quad_sample<Rng, 1>(t.rec, ri, root, rng)
+                    : (t.int_cell == 2u ? sdt_quad_sample<Rng, 2>(t.rec, ri, root, rng) : sdt_quad_sample<Rng, 0>(t.rec, ri, root, rng));
     sdt_canonical_to_dir(q.x, q.y, g.dx, g.dy, g.dz);                    // :996
     float px, py;
     sdt_dir_to_canonical(g.dx, g.dy, g.dz, px, py);                      // :1016
@@ -642,7 +790,7 @@ SDT_HD uint32_t sdt_quad_leaf(const TreeView& t, uint32_t ri, uint32_t root_node
         sdt_quadrant_m(cd, mx, my, lox, loy, hix, hiy);
         ri = sdt_child_rec(h.cinfo, h.interior_base, cd);
     }
-    return node;
+    return node & SDT_NODE_MASK;
 }
 
 // power heuristic, src/path_guiding_integrator.py:16-24 (dr.fma(b,b,a*a), NaN -> 0)

@@ -15,6 +15,7 @@ struct QuadSet {
     uint32_t* iidx = nullptr;       // per node: number of non-leaf nodes before it (= record index if non-leaf)
     QRec* rec = nullptr;
     QJump* jump = nullptr;          // [root record][cell] jump table over the top SDT_JUMP_LEVELS levels
+    uint32_t* jump_pp = nullptr;    // the pdf descents' table of the same shape (path products, SDT_JUMP_NEXT)
     uint32_t* root_iidx = nullptr;
     DevHeader* hdr = nullptr;
 };
@@ -67,6 +68,7 @@ struct sdt_tree_s {
     cudaEvent_t hdr_event = nullptr;
     cudaEvent_t order_event = nullptr;   // orders a call on a new stream after the work enqueued on last_stream
     uint32_t n_quad_known = 1;      // quadtree node count as last seen by the host
+    uint32_t levels_known = 0;      // quadtree levels of the `prev` tree as last seen by the host (0: not known, use levels_hint)
     bool hdr_pending = false;       // an async header read-back (after refine) is in flight
 
     // staging for SDT_HOST_PTRS: one arena; large host calls run as a 2-slot pipeline
@@ -82,14 +84,15 @@ struct sdt_tree_s {
     cudaStream_t arena_stream = nullptr;
 
     // tuning
-    int query_block = 768;          // 2 CTAs x 768 threads per SM: same 1536 threads as 3 x 512 but one staged copy
-    int query_ctas_per_sm = 2;      // of the spatial tree less -> ~75 KB more L1 for the quadtree records (measured)
+    int query_block = 0;            // 0 = each kernel's own CTA size (SDT_SAMPLE_THREADS / SDT_QUERY_THREADS / SDT_SPLAT_THREADS);
+    int query_ctas_per_sm = 2;      // 2 big CTAs per SM rather than 3-4 small ones: fewer staged copies of the spatial tree -> more L1 (measured)
     int splat_stage_words = 1;
     int kd_smem_count_nodes = 24576; // cap of the shared-memory leaf counters of the splat kernels
     int kd_smem_nodes = 24576;      // cap of the smem-staged prefix of the spatial tree (96 KB)
-    int splat_block = 768;
+    int splat_block = 0;
     int splat_ctas_per_sm = 2;
     int fuse_sample_pdf = 1;
+    int splat_aggregate = 0;        // warp-aggregate same-address adds of the splat (match_any); pays on coherent wavefronts only
 
     // per-HANDLE (= per device) launch state of the wavefront kernels: the >48 KB dynamic shared-memory opt-in is a
     // per-device function attribute and the occupancy answer depends on the device, so neither may be cached per process
@@ -143,10 +146,13 @@ static inline TreeView tree_view(sdt_tree_s* h) {
         h->n_quad_known = h->h_hdr->n_quad;
         h->jump_trees_known = h->h_hdr->jump_trees;
         h->dev_error_seen = h->h_hdr->error;
+        h->levels_known = h->h_hdr->n_levels;
     }
     const QuadSet& s = h->set[h->cur];
-    return TreeView{s.hdr, h->kd_word, h->kd_root, h->kd_grid, s.rec, s.jump, s.pp, h->use_jump ? h->jump_trees_known : 0u,
-                    (uint32_t)(h->use_int_cell && h->cfg.quad_max_depth <= 23 && h->levels_hint <= 24u)};
+    // deepest quadtree level the sampler can meet: exact once the header has been read back, else the refine's bound
+    const uint32_t levels = h->levels_known ? h->levels_known : h->levels_hint;
+    const uint32_t cell_mode = !h->use_int_cell ? 0u : (levels <= 17u ? 1u : (levels <= 24u && h->cfg.quad_max_depth <= 23 ? 2u : 0u));
+    return TreeView{s.hdr, h->kd_word, h->kd_root, h->kd_grid, s.rec, s.jump, s.jump_pp, s.pp, h->use_jump ? h->jump_trees_known : 0u, cell_mode};
 }
 
 static int sdt_read_header(sdt_handle h, DevHeader& H);

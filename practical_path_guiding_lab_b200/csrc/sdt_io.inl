@@ -13,7 +13,7 @@ static int sdt_free_all(sdt_handle h) {
     for (void* p : ptrs) if (p) cudaFree(p);
     for (int k = 0; k < 2; ++k) {
         QuadSet& s = h->set[k];
-        void* q[] = {s.child, s.energy, s.thr, s.pp, s.iidx, s.rec, s.jump, s.root_iidx, s.hdr};
+        void* q[] = {s.child, s.energy, s.thr, s.pp, s.iidx, s.rec, s.jump, s.jump_pp, s.root_iidx, s.hdr};
         for (void* p : q) if (p) cudaFree(p);
     }
     if (h->h_hdr) cudaFreeHost(h->h_hdr);
@@ -78,7 +78,7 @@ extern "C" int sdt_create(const sdt_config* cfg, sdt_handle* out) {
     for (int k = 0; k < 2; ++k) {
         QuadSet& s = h->set[k];
         A(s.child, h->quad_cap); A(s.energy, h->quad_cap); A(s.thr, h->quad_cap); A(s.pp, h->quad_cap); A(s.iidx, h->quad_cap);
-        A(s.rec, h->rec_cap); A(s.jump, (size_t)h->jump_cap * SDT_JUMP_CELLS); A(s.root_iidx, h->kd_cap); A(s.hdr, 1);
+        A(s.rec, h->rec_cap); A(s.jump, (size_t)h->jump_cap * SDT_JUMP_CELLS); A(s.jump_pp, (size_t)h->jump_cap * SDT_JUMP_CELLS); A(s.root_iidx, h->kd_cap); A(s.hdr, 1);
     }
 #undef A
     if (st == SDT_OK && cudaMallocHost((void**)&h->h_hdr, sizeof(DevHeader)) != cudaSuccess) st = sdt_fail(h, SDT_ERR_CUDA, "cudaMallocHost failed");
@@ -134,6 +134,7 @@ static int sdt_read_header(sdt_handle h, DevHeader& H) {
     h->n_quad_known = H.n_quad;
     h->jump_trees_known = H.jump_trees;
     h->dev_error_seen = H.error;
+    h->levels_known = H.n_levels;
     return SDT_OK;
 }
 
@@ -366,14 +367,15 @@ extern "C" int sdt_set_tuning(sdt_handle h, const char* key, int64_t value) {
     if (!h || !key) return SDT_ERR_INVALID;
     SDT_ENTER(h);
     const std::string k(key);
-    if (k == "query_block") { SDT_CHECK(h, value >= 64 && value <= 768 && value % 32 == 0, SDT_ERR_INVALID, "query_block must be 64..768, multiple of 32"); h->query_block = (int)value; }
+    if (k == "query_block") { SDT_CHECK(h, value == 0 || (value >= 64 && value <= 1024 && value % 32 == 0), SDT_ERR_INVALID, "query_block must be 0 (default) or 64..1024, multiple of 32"); h->query_block = (int)value; }
     else if (k == "query_ctas_per_sm") { SDT_CHECK(h, value >= 1 && value <= 32, SDT_ERR_INVALID, "query_ctas_per_sm must be 1..32"); h->query_ctas_per_sm = (int)value; }
     else if (k == "kd_smem_nodes") { SDT_CHECK(h, value >= 0 && value <= 49152, SDT_ERR_INVALID, "kd_smem_nodes must be 0..49152"); h->kd_smem_nodes = (int)value; }
     else if (k == "splat_stage_words") h->splat_stage_words = value != 0;
     else if (k == "kd_smem_count_nodes") { SDT_CHECK(h, value >= 0 && value <= 49152, SDT_ERR_INVALID, "kd_smem_count_nodes must be 0..49152"); h->kd_smem_count_nodes = (int)value; }
-    else if (k == "splat_block") { SDT_CHECK(h, value >= 64 && value <= 768 && value % 32 == 0, SDT_ERR_INVALID, "splat_block must be 64..768, multiple of 32"); h->splat_block = (int)value; }
+    else if (k == "splat_block") { SDT_CHECK(h, value == 0 || (value >= 64 && value <= 1024 && value % 32 == 0), SDT_ERR_INVALID, "splat_block must be 0 (default) or 64..1024, multiple of 32"); h->splat_block = (int)value; }
     else if (k == "splat_ctas_per_sm") { SDT_CHECK(h, value >= 1 && value <= 32, SDT_ERR_INVALID, "splat_ctas_per_sm must be 1..32"); h->splat_ctas_per_sm = (int)value; }
     else if (k == "fuse_sample_pdf") h->fuse_sample_pdf = value != 0;
+    else if (k == "splat_aggregate") h->splat_aggregate = value != 0;
     else if (k == "use_jump") h->use_jump = value != 0;
     else if (k == "use_kd_grid") h->use_kd_grid = value != 0;
     else if (k == "use_int_cell") h->use_int_cell = value != 0;

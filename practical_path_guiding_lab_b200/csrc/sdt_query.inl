@@ -28,7 +28,7 @@ SDT_HD void sdt_lane(const Lane& f, const KdCtx& k, uint32_t i) {
 // a warp never runs two code paths, and idle lanes (dead paths, masked-out vertices, inactive record
 // slots) cost a classification, not a share of a descent.
 template <class Lane, bool COMPACT>
-__global__ void __launch_bounds__(768, 2) k_wavefront(Lane f, uint32_t n, uint32_t smem_cap, uint32_t cnt_cap, uint32_t use_grid) {
+__global__ void __launch_bounds__(Lane::kMaxThreads, SDT_LB_CTAS) k_wavefront(Lane f, uint32_t n, uint32_t smem_cap, uint32_t cnt_cap, uint32_t use_grid, uint32_t aggregate) {
     extern __shared__ uint32_t kd_s[];
     const DevHeader* hdr = f.t.hdr;
     const uint32_t n_kd = hdr->n_kd;
@@ -38,11 +38,14 @@ __global__ void __launch_bounds__(768, 2) k_wavefront(Lane f, uint32_t n, uint32
     uint32_t* smem_next = kd_s + smem_cap;
     // splat kernels with the whole spatial tree staged: leaf counters live in shared memory for the
     // lifetime of the CTA and are flushed once (16M same-slice L2 atomics become a few per leaf and CTA)
-    float* cnt_s = nullptr;
+    // (integer counters: a native shared-memory add, where a float add is a compare-and-swap loop; a CTA sees fewer
+    // than 2^24 records, so the count is exact and its fp32 value is what a chain of +1.0f would have produced)
+    uint32_t* cnt_s = nullptr;
+    k.aggregate = aggregate;
     if (Lane::kSmemCounts) {
         if (n_kd <= cnt_cap) {               // (independent of whether the words are staged)
-            cnt_s = reinterpret_cast<float*>(smem_next);
-            for (uint32_t j = threadIdx.x; j < n_kd; j += blockDim.x) cnt_s[j] = 0.0f;
+            cnt_s = smem_next;
+            for (uint32_t j = threadIdx.x; j < n_kd; j += blockDim.x) cnt_s[j] = 0u;
             k.cnt_s = cnt_s;
         }
         smem_next += cnt_cap;
@@ -118,8 +121,8 @@ __global__ void __launch_bounds__(768, 2) k_wavefront(Lane f, uint32_t n, uint32
     if (cnt_s) {
         __syncthreads();
         for (uint32_t j = threadIdx.x; j < n_kd; j += blockDim.x) {
-            const float c = cnt_s[j];
-            if (c != 0.0f) f.flush_count(j, c);
+            const uint32_t c = cnt_s[j];
+            if (c != 0u) f.flush_count(j, (float)c);
         }
     }
 }
@@ -131,6 +134,7 @@ __global__ void __launch_bounds__(768, 2) k_wavefront(Lane f, uint32_t n, uint32
 template <class Lane, bool COMPACT>
 static int launch_wavefront_c(sdt_handle h, cudaStream_t st, uint32_t n, const Lane& f, int block, int ctas_per_sm) {
     if (n == 0) return SDT_OK;
+    if (block <= 0 || block > Lane::kMaxThreads) block = Lane::kMaxThreads;      // 0 = the kernel's own CTA size
     uint32_t want = h->hdr_pending ? 2u * h->kd_nodes_known + 2u : h->kd_nodes_known;   // a refine is in flight: be generous
     uint32_t smem_nodes = (want + 255u) & ~255u;
     if (smem_nodes > (uint32_t)h->kd_smem_nodes) smem_nodes = (uint32_t)h->kd_smem_nodes;
@@ -143,10 +147,12 @@ static int launch_wavefront_c(sdt_handle h, cudaStream_t st, uint32_t n, const L
     const size_t smem = (size_t)smem_nodes * 4u + (size_t)cnt_nodes * 4u + SDT_GRID_CELLS * 4u +
                         (COMPACT ? (size_t)block * SDT_TILE_MUL * 2u * (size_t)Lane::kModes : 0u);   // uint16 lists: 32*TM entries per warp and mode
     sdt_tree_s::LaunchCache& lc = h->launch_cache[(const void*)k_wavefront<Lane, COMPACT>];
+    constexpr size_t kSmemMax = 227u * 1024u;            // the sm_100 limit per CTA
+    if (smem > kSmemMax) return sdt_fail(h, SDT_ERR_INVALID, "k_wavefront: staging tunings ask for more than 227 KB of shared memory per CTA");
     if (smem > 48u * 1024u && smem > lc.attr_smem) {
-        if (cudaFuncSetAttribute(k_wavefront<Lane, COMPACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess)
+        if (cudaFuncSetAttribute(k_wavefront<Lane, COMPACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax) != cudaSuccess)
             return sdt_fail(h, SDT_ERR_CUDA, "cudaFuncSetAttribute(MaxDynamicSharedMemorySize) failed");
-        lc.attr_smem = 200 * 1024;
+        lc.attr_smem = kSmemMax;
     }
     if (lc.occ_smem != smem || lc.occ_block != block) {
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&lc.occ, k_wavefront<Lane, COMPACT>, block, smem) != cudaSuccess || lc.occ < 1) lc.occ = 1;
@@ -159,7 +165,7 @@ static int launch_wavefront_c(sdt_handle h, cudaStream_t st, uint32_t n, const L
     uint32_t grid = (n + per_cta - 1u) / per_cta;
     const uint32_t cap = (uint32_t)(h->num_sms * per_sm);
     if (grid > cap) grid = cap;
-    k_wavefront<Lane, COMPACT><<<grid, block, smem, st>>>(f, n, smem_nodes, cnt_nodes, (uint32_t)h->use_kd_grid);
+    k_wavefront<Lane, COMPACT><<<grid, block, smem, st>>>(f, n, smem_nodes, cnt_nodes, (uint32_t)h->use_kd_grid, (uint32_t)h->splat_aggregate);
     ++h->launches;
     h->last_stream = st;
     return sdt_post_launch(h, "k_wavefront");
@@ -196,7 +202,7 @@ static int launch_wavefront(sdt_handle h, cudaStream_t st, uint32_t n, const Lan
 // ---------------------------------------------------------------------------- lanes
 struct LocateLane {
     static constexpr bool kSmemCounts = false, kGrid = true;
-    static constexpr int kModes = 1;
+    static constexpr int kModes = 1, kMaxThreads = SDT_QUERY_THREADS;
     SDT_HD void flush_count(uint32_t, float) const {}
     TreeView t;
     sdt_vec3 pos; const uint8_t* active; uint32_t* leaf; uint32_t* root;
@@ -215,8 +221,8 @@ struct LocateLane {
 
 template <bool EXPLICIT_U>
 struct SampleLane {
-    static constexpr bool kSmemCounts = false, kGrid = false;
-    static constexpr int kModes = 1;
+    static constexpr bool kSmemCounts = false, kGrid = SDT_SAMPLE_GRID;
+    static constexpr int kModes = 1, kMaxThreads = SDT_SAMPLE_THREADS;
     SDT_HD void flush_count(uint32_t, float) const {}
     TreeView t;
     sdt_vec3 pos; const uint8_t* active;
@@ -245,7 +251,7 @@ struct SampleLane {
 
 struct PdfLane {
     static constexpr bool kSmemCounts = false, kGrid = true;
-    static constexpr int kModes = 1;
+    static constexpr int kModes = 1, kMaxThreads = SDT_QUERY_THREADS;
     SDT_HD void flush_count(uint32_t, float) const {}
     TreeView t;
     sdt_vec3 pos; sdt_vec3 dir; const uint8_t* active; float* pdf; uint32_t* dbg;
@@ -256,12 +262,14 @@ struct PdfLane {
     }
     template <int KD>
     SDT_HD void run_mode(const KdCtx& k, uint32_t i, uint32_t) const {
+        // the direction is fetched before the spatial descent, so that its (DRAM) latency runs under it
+        const float wx = sdt_ld(dir.x, dir.stride, i), wy = sdt_ld(dir.y, dir.stride, i), wz = sdt_ld(dir.z, dir.stride, i);
         const KdResult r = sdt_kd_descend<KD>(k, sdt_ld(pos.x, pos.stride, i), sdt_ld(pos.y, pos.stride, i), sdt_ld(pos.z, pos.stride, i));
         float x, y;
-        sdt_dir_to_canonical(sdt_ld(dir.x, dir.stride, i), sdt_ld(dir.y, dir.stride, i), sdt_ld(dir.z, dir.stride, i), x, y);
+        sdt_dir_to_canonical(wx, wy, wz, x, y);
         uint32_t nd;
         const uint32_t root = dbg ? SDT_LDG(t.kd_root + r.leaf) : 0u;
-        pdf[i] = sdt_quad_pdf(t, r.rootrec, root, x, y, nd);
+        pdf[i] = sdt_quad_pdf(t, r.rootrec, root, x, y, nd, dbg != nullptr);
         if (dbg) { dbg[3u * i] = r.leaf; dbg[3u * i + 1u] = root; dbg[3u * i + 2u] = nd; }
     }
 };
@@ -270,8 +278,8 @@ struct PdfLane {
 // mode 2 = tree pdf of the BSDF-sampled direction (:307) + fused mixture (:310-311)
 template <bool EXPLICIT_U>
 struct GuidedLane {
-    static constexpr bool kSmemCounts = false, kGrid = false;
-    static constexpr int kModes = 2;
+    static constexpr bool kSmemCounts = false, kGrid = SDT_SAMPLE_GRID;
+    static constexpr int kModes = 2, kMaxThreads = SDT_SAMPLE_THREADS;
     SDT_HD void flush_count(uint32_t, float) const {}
     TreeView t;
     sdt_guided_args a; int fuse;
@@ -292,7 +300,7 @@ struct GuidedLane {
             float x, y;
             sdt_dir_to_canonical(sdt_ld(a.wo.x, a.wo.stride, i), sdt_ld(a.wo.y, a.wo.stride, i), sdt_ld(a.wo.z, a.wo.stride, i), x, y);
             uint32_t nd;
-            const float p = sdt_quad_pdf(t, r.rootrec, 0u, x, y, nd);
+            const float p = sdt_quad_pdf(t, r.rootrec, 0u, x, y, nd, false);
             a.sdtree_pdf[i] = p;
             if (a.bsdf_pdf && a.wo_pdf) {
                 const float wp = (f * SDT_LDG(a.bsdf_pdf + i)) + omf * p;              // :310

@@ -264,6 +264,7 @@ struct RecBuildItem {
             r.e[k] = energy[cb + k];
         }
         r.cinfo = sdt_make_cinfo(leafmask);
+        r.child_base |= sdt_rec_flags(r.e[0], r.e[1], r.e[2], r.e[3]);
         r.own = energy[i];
         rec[iidx[i]] = r;
     }
@@ -303,10 +304,12 @@ struct JumpCountItem {
     }
 };
 struct JumpBuildItem {
-    const QRec* rec; QJump* jump;
+    const QRec* rec; const float* pp; QJump* jump; uint32_t* jump_pp;
     SDT_HD void operator()(uint32_t i) const {
         const uint32_t tr = i / SDT_JUMP_CELLS, cell = i % SDT_JUMP_CELLS;
-        jump[i] = sdt_build_jump(rec, tr, cell & (SDT_JUMP_SIDE - 1u), cell >> SDT_JUMP_LEVELS);
+        const QJump j = sdt_build_jump(rec, tr, cell & (SDT_JUMP_SIDE - 1u), cell >> SDT_JUMP_LEVELS);
+        jump[i] = j;
+        jump_pp[i] = sdt_jump_pp_entry(j, pp);
     }
 };
 
@@ -320,7 +323,7 @@ static void sdt_build_records(sdt_handle h, const ExecCtx& x, QuadSet& s) {
     for (uint32_t l = 0; l < h->levels_hint && l < SDT_MAX_LEVELS; ++l)
         launch_items(x, &s.hdr->level_cnt[l], 0, PpLevelItem{s.hdr, s.child, s.energy, s.pp, l});
     launch_single(x, JumpCountItem{s.hdr, s.iidx, h->jump_cap});
-    launch_items(x, &s.hdr->lvl_n[0], 0, JumpBuildItem{s.rec, s.jump});
+    launch_items(x, &s.hdr->lvl_n[0], 0, JumpBuildItem{s.rec, s.pp, s.jump, s.jump_pp});
 }
 
 struct KdRollItem {         // prev.vertCount <- current.vertCount; current <- 0 (:141-153, :401-432)
@@ -375,6 +378,7 @@ extern "C" int sdt_refine(sdt_handle h, uint32_t flags, sdt_stream stream) {
     SDT_TRY(sdt_post_launch(h, "sdt_refine"));
     h->cur = 1 - h->cur;
     h->jump_trees_known = 0;
+    h->levels_known = 0;
     h->levels_hint = levels_bound;
     h->stats_complete = true;
     // non-blocking read-back of the new sizes (only used to size the smem staging of later launches)

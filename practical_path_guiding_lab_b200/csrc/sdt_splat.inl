@@ -16,9 +16,12 @@ struct SplatTarget {
     uint32_t store_nee;
 };
 
-// one warp-aggregated fp32 add: lanes with the same address are summed by the lowest lane
-SDT_HD void sdt_splat_add(float* base, uint32_t idx, float v, bool valid) {
+// one fp32 add per record; with `aggregate` the lanes of a warp that hit the same address are summed by the lowest
+// lane first (match_any + shuffles: pays when neighbouring lanes share leaves, i.e. on pixel-coherent wavefronts;
+// on incoherent ones it finds no peers and only costs instructions -- "splat_aggregate" tuning, off by default)
+SDT_HD void sdt_splat_add(float* base, uint32_t idx, float v, bool valid, uint32_t aggregate) {
 #if defined(__CUDA_ARCH__)
+    if (!aggregate) { if (valid) atomicAdd(base + idx, v); return; }
     const uint32_t act = __ballot_sync(__activemask(), valid);
     if (!valid) return;
     const uint32_t peers = __match_any_sync(act, idx);
@@ -35,6 +38,7 @@ SDT_HD void sdt_splat_add(float* base, uint32_t idx, float v, bool valid) {
     }
     if (lane == leader) atomicAdd(base + idx, acc);
 #else
+    (void)aggregate;
     if (valid) base[idx] += v;
 #endif
 }
@@ -48,10 +52,10 @@ SDT_HD void sdt_splat_one(const TreeView& t, const SplatTarget& tg, const KdCtx&
     // src/kdtree.py:199: +1.0f (fp32 counter; exact below 2^24, clamped there by the sweep like the reference's sticks)
     if (k.cnt_s) {
 #if defined(__CUDA_ARCH__)
-        if (r.inbox) atomicAdd(k.cnt_s + r.leaf, 1.0f);                    // shared-memory counter of this CTA
+        if (r.inbox) atomicAdd(k.cnt_s + r.leaf, 1u);                      // shared-memory counter of this CTA
 #endif
     } else {
-        sdt_splat_add(tg.kd_count, r.leaf, 1.0f, r.inbox);
+        sdt_splat_add(tg.kd_count, r.leaf, 1.0f, r.inbox, k.aggregate);
     }
     // src/kdtree.py:224: the root id is gathered UNMASKED -- out-of-box records go to the tree of node 0
     const uint32_t ri = r.rootrec;
@@ -61,19 +65,19 @@ SDT_HD void sdt_splat_one(const TreeView& t, const SplatTarget& tg, const KdCtx&
     const float irr = (wo_pdf > 0.0f) ? radiance / wo_pdf : 0.0f;                      // src/quadtree.py:451
     uint32_t leaf = SDT_NONE;
     if (irr != 0.0f) leaf = sdt_quad_leaf(t, ri, root, dx, dy);
-    sdt_splat_add(tg.q_ecur, leaf, irr, leaf != SDT_NONE);
+    sdt_splat_add(tg.q_ecur, leaf, irr, leaf != SDT_NONE, k.aggregate);
     if (tg.store_nee) {                                                               // :455-464
         const float lum = sdt_luminance(nr, ng, nb);
         const float irr2 = (wo_pdf > 0.0f) ? lum / wo_pdf : 0.0f;
         uint32_t leaf2 = SDT_NONE;
         if (irr2 != 0.0f) leaf2 = sdt_quad_leaf(t, ri, root, ndx, ndy);
-        sdt_splat_add(tg.q_ecur, leaf2, irr2, leaf2 != SDT_NONE);
+        sdt_splat_add(tg.q_ecur, leaf2, irr2, leaf2 != SDT_NONE, k.aggregate);
     }
 }
 
 struct SplatRecordsLane {
     static constexpr bool kSmemCounts = true, kGrid = true;
-    static constexpr int kModes = 1;
+    static constexpr int kModes = 1, kMaxThreads = SDT_SPLAT_THREADS;
     SDT_HD void flush_count(uint32_t node, float c) const { sdt_atomic_add_f32(tg.kd_count + node, c); }
     TreeView t; SplatTarget tg; sdt_records r;
     SDT_HD uint32_t mode_of(uint32_t i) const { return r.active ? (SDT_LDG(r.active + i) != 0 ? 1u : 0u) : 1u; }
@@ -102,7 +106,7 @@ SDT_HD float sdt_nan0(float v) { return (v != v) ? 0.0f : v; }
 // sync); here the slots of a tile are sorted by their `active` flag and the filter masks the rest.
 struct SplatPathLane {
     static constexpr bool kSmemCounts = true, kGrid = true;
-    static constexpr int kModes = 1;
+    static constexpr int kModes = 1, kMaxThreads = SDT_SPLAT_THREADS;
     SDT_HD void flush_count(uint32_t node, float c) const { sdt_atomic_add_f32(tg.kd_count + node, c); }
     TreeView t; SplatTarget tg; sdt_path_data p;
     struct Vals { float radiance, wo_pdf, nr, ng, nb; };

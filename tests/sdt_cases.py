@@ -222,6 +222,9 @@ def check_queries(ctx, t, prev, n=4096, seed=7, box=1.0, explicit=True):
     pdbg = ctx.host(pdbg).view(U)
     assert np.array_equal(pdbg[a, 2], opdbg['pdf_node'][a])
     assert beq(ctx.host(pp), opp)
+    # without the debug output the kernel reads the leaf's path product straight from its second jump table
+    pp2 = t.pdf(ctx.dev(pos), ctx.dev(dirs), ctx.dev(active.astype(np.uint8)))
+    assert beq(ctx.host(pp2), opp), "pdf through the path-product jump table"
     return dict(pos=pos, active=active, dirs=dirs)
 
 
@@ -313,6 +316,63 @@ def case_spatial_descent_variants(ctx):
     pos = np.stack(np.meshgrid(g, g, g, indexing="ij"), -1).reshape(-1, 3)
     leaf, root = t.locate(ctx.dev(pos))
     assert np.array_equal(ctx.host(leaf).view(U), prev.getLeafNodeIndex(pos))
+
+
+def case_grid_cell_boundaries(ctx):
+    """the kernels find the 16x16x8 grid cell of a vertex from a scaled guess corrected against the exact cell
+    boundaries (sdt_axis_cell) instead of walking 11 midpoint halvings: points exactly ON every boundary of an
+    awkward, non-dyadic box and one ulp to either side must land in the reference's leaf (right child wins on the
+    plane, src/kdtree.py:462-468), with the tree deep enough that every one of the 11 levels exists somewhere"""
+    lo = np.array([-1.37, 0.1, 3.0e-3], F)
+    hi = np.array([2.91, 0.1000061, 7.7e3], F)
+    t = ctx.make(bbox_min=tuple(float(v) for v in lo), bbox_max=tuple(float(v) for v in hi), kd_max_depth=20, quad_max_depth=2,
+                 store_nee=False, kd_capacity=1 << 17, quad_capacity=1 << 20)
+    cur, prev = oracle_pair(tuple(float(v) for v in lo), tuple(float(v) for v in hi), 20, 2, False)
+    rng = np.random.default_rng(77)
+    n = 30000
+    for it in range(3):
+        pos = (lo + rng.random((n, 3)).astype(F) * (hi - lo)).astype(F)
+        pos = np.minimum(np.maximum(pos, lo), hi)
+        rec = so.SurfaceInteractionRecord(pos, rng.random((n, 2)).astype(F), np.ones(n, F), np.ones(n, F))
+        splat(t, ctx, rec)
+        cur.addDataPropagate(rec)
+        t.set_max_leaf_size(3)
+        t.refine()
+        oracle_refine(cur, prev, 3)
+    assert t.sizes()['error'] == 0 and int(prev.kdTreeNode.depth.max()) >= 12, int(prev.kdTreeNode.depth.max())
+    assert_tree_equal(t.download(0), prev)
+
+    def bounds(a, b, nlev):               # the reference's own midpoints, level by level, in fp32
+        v = [F(a), F(b)]
+        for _ in range(nlev):
+            w = [v[0]]
+            for x, y in zip(v[:-1], v[1:]):
+                w += [F((F(x) + F(y)) / F(2.0)), y]
+            v = w
+        return np.array(v, F)
+    pts = []
+    for ax, nlev in enumerate((5, 5, 4)):           # one level finer than the grid: planes below it too
+        b = bounds(lo[ax], hi[ax], nlev)
+        cand = np.concatenate([b, np.nextafter(b, F(np.inf)), np.nextafter(b, F(-np.inf))]).astype(F)
+        cand = cand[(cand >= lo[ax]) & (cand <= hi[ax])]
+        other = (lo + rng.random((len(cand), 3)).astype(F) * (hi - lo)).astype(F)
+        other = np.minimum(np.maximum(other, lo), hi)
+        other[:, ax] = cand
+        pts.append(other)
+        both = other.copy()                          # ... and on boundaries of two axes at once
+        ax2 = (ax + 1) % 3
+        b2 = bounds(lo[ax2], hi[ax2], 4)
+        both[:, ax2] = b2[rng.integers(0, len(b2), len(both))]
+        pts.append(both)
+    pos = np.concatenate(pts).astype(F)
+    want = prev.getLeafNodeIndex(pos)
+    for grid, smem in ((1, 24576), (1, 16), (0, 24576)):
+        t.set_tuning("use_kd_grid", grid)
+        t.set_tuning("kd_smem_nodes", smem)
+        leaf, root = t.locate(ctx.dev(pos))
+        assert np.array_equal(ctx.host(leaf).view(U), want), (grid, smem)
+    t.set_tuning("kd_smem_nodes", 24576)
+    t.set_tuning("use_kd_grid", 1)
 
 
 def case_deep_quadtree_beyond_fp32_grid(ctx):
@@ -750,7 +810,7 @@ def case_npz_roundtrip(ctx, tmp_path):
     check_queries(ctx, t2, o, n=1024)
 
 
-ALL_CASES = [case_golden_fixture, case_counter_generator_statistics, case_deep_quadtree_beyond_fp32_grid, case_jump_table_equals_descent, case_spatial_descent_variants, case_initial_tree, case_golden_upload_download, case_train_refine_topology, case_threshold_reciprocal_variant, case_zero_total_energy, case_host_pipeline_chunks, case_host_calls_no_wait,
+ALL_CASES = [case_golden_fixture, case_grid_cell_boundaries, case_counter_generator_statistics, case_deep_quadtree_beyond_fp32_grid, case_jump_table_equals_descent, case_spatial_descent_variants, case_initial_tree, case_golden_upload_download, case_train_refine_topology, case_threshold_reciprocal_variant, case_zero_total_energy, case_host_pipeline_chunks, case_host_calls_no_wait,
              case_train_refine_nee_shallow, case_fused_equals_two_descents, case_splat_float_tolerance,
              case_path_data, case_mis, case_guided_bounce, case_refine_flags_and_frozen_stats,
              case_capacity_error, case_edge_inputs_and_errors]
