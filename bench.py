@@ -3,9 +3,11 @@
 workload of BASELINE.json configs[1].
 
 One STEP = one pass of the hot path over one wavefront of n = 2^24 path vertices:
-    sdt_sample (spatial descent + quadtree sample + pdf of the sample, A1+A3+A4)
-  + sdt_pdf    (spatial descent + quadtree pdf of a given direction,   A1+A4)
+    KDTree.sample  (spatial descent + quadtree sample + pdf of the sample, A1+A3+A4)
+  + KDTree.pdf     (quadtree pdf of a given direction at the same vertex,  A1+A4)      } sdt_sample_pdf: one call, one
+                                                                                         } spatial descent for both
   + sdt_splat_records (spatial descent + quadtree descent + accumulation, A6+A7)
+(the two query operations are also timed as the separate calls sdt_sample / sdt_pdf: roofline.per_kernel)
 on a frozen tree (~4k spatial leaves, quadtree depth <= 20) that the library itself
 trained on the synthetic records (splat + device-side refine, 6 iterations).
 `value` = vertices through the whole step per second with inputs resident in HBM;
@@ -247,15 +249,12 @@ def run_b200(args):
     def step(ev=None):
         if ev:
             ev[0].record()
-        tree.sample(d_pos, seed=3, lane_offset=lane0, out=(o_dir, o_pdf))
+        tree.sample_pdf(d_pos, d_dir, seed=3, lane_offset=lane0, out=(o_dir, o_pdf, o_pdf2))
         if ev:
             ev[1].record()
-        tree.pdf(d_pos, d_dir, out=o_pdf2)
-        if ev:
-            ev[2].record()
         tree.splat_records(d_rec['position'], d_rec['direction'], d_rec['radiance'], d_rec['wo_pdf'])
         if ev:
-            ev[3].record()
+            ev[2].record()
 
     def barrier():
         if world > 1:
@@ -264,7 +263,7 @@ def run_b200(args):
 
     for _ in range(args.warmup):
         step()
-    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(args.steps)]
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
     barrier()
     launches0 = tree.kernel_launches()
     with ClockSampler(local) as clk:
@@ -273,13 +272,29 @@ def run_b200(args):
             step(evs[k])
         barrier()
     launches = tree.kernel_launches() - launches0
-    total_ms = evs[0][0].elapsed_time(evs[-1][3])
-    k_ms = [float(np.mean([e[j].elapsed_time(e[j + 1]) for e in evs])) for j in range(3)]
+    total_ms = evs[0][0].elapsed_time(evs[-1][2])
+    f_ms = [float(np.mean([e[j].elapsed_time(e[j + 1]) for e in evs])) for j in range(2)]      # fused query call, splat
     t = torch.tensor([total_ms], device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_per_step = float(t.item()) / args.steps
     value = n * world / (ms_per_step * 1e-3)
+
+    def timeit(fn, reps=10):
+        for _ in range(3):
+            fn()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        a.record()
+        for _ in range(reps):
+            fn()
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / reps
+    # the two query operations as separate calls (what the step's fused call replaces)
+    k_ms = {"sample_pdf": f_ms[0], "splat": f_ms[1],
+            "sample": timeit(lambda: tree.sample(d_pos, seed=3, lane_offset=lane0, out=(o_dir, o_pdf))),
+            "pdf": timeit(lambda: tree.pdf(d_pos, d_dir, out=o_pdf2))}
 
     # ---- algorithmic bytes from the measured depths of a 2^20-lane subset
     m = min(n, 1 << 20)
@@ -291,12 +306,32 @@ def run_b200(args):
     dq_s = tr['quadtree_depth'][dbg[:, 2]].astype(np.float64).mean()
     redescend = float((dbg[:, 2] != dbg[:, 3]).mean())
     _, dbgp = tree.pdf(d_pos[:m], d_dir[:m], debug=True)
-    dq_p = tr['quadtree_depth'][dbgp.cpu().numpy().view(np.uint32)[:, 2]].astype(np.float64).mean()
+    dq_pl = tr['quadtree_depth'][dbgp.cpu().numpy().view(np.uint32)[:, 2]].astype(np.float64)
+    dq_p = dq_pl.mean()
+    # depth reached by the splat's directions (drawn from the lobes, deeper than the pdf's uniform ones): a pdf query with
+    # the record's own direction lands on the node the splat updates
+    cxy = rec['direction'][:m].astype(np.float64)
+    ct = 2.0 * cxy[:, 1] - 1.0
+    st_ = np.sqrt(np.maximum(0.0, 1.0 - ct * ct))
+    rdir = torch.from_numpy(np.stack([st_ * np.cos(2 * np.pi * cxy[:, 0]), st_ * np.sin(2 * np.pi * cxy[:, 0]), ct], 1).astype(np.float32)).to(dev)
+    _, dbgr = tree.pdf(d_rec['position'][:m], rdir, debug=True)
+    dq_rl = tr['quadtree_depth'][dbgr.cpu().numpy().view(np.uint32)[:, 2]].astype(np.float64)
+    dq_r = dq_rl.mean()
+    JL = 5                                                       # SDT_JUMP_LEVELS: depth <= 5 ends inside the jump table
+    below_p, below_r = np.maximum(dq_pl - JL, 0).mean(), np.maximum(dq_rl - JL, 0).mean()
+    deep_p = float((dq_pl > JL).mean())
     bytes_q = {"sample": 28 + 4 * ds + 4 + 20 * dq_s,            # ONE quadtree descent (fused pdf); re-descents not counted
                "pdf": 28 + 4 * ds + 4 + 20 * dq_p + 4,
-               "splat": 28 + 4 * ds + 4 + 4 * dq_p + 8}            # leaf-only update + sweep (Dq ~ pdf's for iid directions)
-    names = ["sample", "pdf", "splat"]
-    dom = int(np.argmax(k_ms))
+               "splat": 28 + 4 * ds + 4 + 4 * dq_r + 8}            # leaf-only update + sweep
+    bytes_q["sample_pdf"] = 44 + 4 * ds + 4 + 20 * dq_s + 20 * dq_p + 4          # pos 12 + dir 12 in, 16 + 4 out; one spatial descent
+    stream_b = {"sample": 28.0, "pdf": 28.0, "splat": 28.0, "sample_pdf": 44.0}  # query / record bytes streamed from and to HBM
+    # divergent sector requests per query actually issued (one lane, one unrelated 32 B sector, one slot of the SM's L1 -> L2
+    # request port): sampling = a record per level + the leaf's path product; pdf = a jump-table entry (+ records below the
+    # table and the leaf's product for the lanes that go below); splat = a jump-table entry + records below + the leaf RED
+    req_q = {"sample": dq_s + 1.0, "pdf": 1.0 + below_p + deep_p, "splat": 1.0 + below_r + 1.0}
+    req_q["sample_pdf"] = req_q["sample"] + req_q["pdf"]
+    names = ["sample_pdf", "splat", "sample", "pdf"]
+    dom = "sample_pdf"
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -306,57 +341,75 @@ def run_b200(args):
     l2_gbs = tree.measure_l2(32 << 20, 50)                    # sequential sweep of an L2-resident set (ld.global.cg)
     gather_gbs = tree.measure_gather(16 << 20, 200, True)     # random 32 B sectors of an L2-resident set, through L1 (the descents' pattern)
     gather_cg_gbs = tree.measure_gather(16 << 20, 200, False)
-    stream_b = {"sample": 28.0, "pdf": 28.0, "splat": 28.0}  # query / record bytes streamed from and to HBM
     tree_b = {k: bytes_q[k] - stream_b[k] for k in names}     # tree bytes: served by shared memory / L1 / L2
-    kname = ['SampleLane', 'PdfLane', 'SplatRecordsLane'][dom]
+    klane = {"sample_pdf": "SamplePdfLane", "splat": "SplatRecordsLane", "sample": "SampleLane", "pdf": "PdfLane"}
     traffic = None
     try:        # DRAM bytes per launch of this kernel from the committed ncu --set full capture (same 16 Mi-vertex launch)
         tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
         if n == N_DEFAULT:
-            key = [k for k in tj if k.startswith(kname)][0]
+            key = [k for k in tj if k.startswith(klane[dom])][0]
             traffic = tj[key]["dram_bytes_read"] + tj[key]["dram_bytes_write"]
     except Exception:
         pass
+    req_peak = gather_gbs / 32.0 if gather_gbs else None       # G requests/s: the probe delivers one sector per lane request
 
-    def per_kernel(j):
-        k = names[j]
-        sec = k_ms[j] * 1e-3
+    def per_kernel(k):
+        sec = k_ms[k] * 1e-3
         tree_gbs, stream_gbs = tree_b[k] * n / sec / 1e9, stream_b[k] * n / sec / 1e9
-        return {"ms": k_ms[j], "bytes_per_query": bytes_q[k], "tree_bytes_per_query": tree_b[k], "stream_bytes_per_query": stream_b[k],
+        greq = req_q[k] * n / sec / 1e9
+        return {"ms": k_ms[k], "bytes_per_query": bytes_q[k], "tree_bytes_per_query": tree_b[k], "stream_bytes_per_query": stream_b[k],
                 "tree_gbs": tree_gbs, "frac_of_l2": tree_gbs / l2_gbs if l2_gbs else None,
                 "frac_of_gather_roof": tree_gbs / gather_gbs if gather_gbs else None,
+                "sector_requests_per_query": req_q[k], "g_requests_per_s": greq, "frac_of_request_roof": greq / req_peak if req_peak else None,
                 "stream_gbs": stream_gbs, "frac_of_hbm": stream_gbs / hbm_peak, "queries_per_s": n / sec}
-    pk = {names[j]: per_kernel(j) for j in range(3)}
-    d = pk[names[dom]]
-    roof = {"bound": "l2", "kernel": f"k_wavefront<{kname}>", "achieved": d["tree_gbs"], "peak": l2_gbs, "unit": "GB/s",
+    pk = {k: per_kernel(k) for k in names}
+    d = pk[dom]
+    roof = {"bound": "l2", "kernel": f"k_wavefront<{klane[dom]}>", "achieved": d["tree_gbs"], "peak": l2_gbs, "unit": "GB/s",
             "frac": d["frac_of_l2"], "traffic": traffic,
             "peak_source": "measured in this run by sdt_measure_l2 (32 MiB resident set, 50 passes, ld.global.cg; an L2 figure is not in "
                            "MEASURED_PEAKS.json): the friendliest access pattern there is.  The descents read ONE unrelated 32 B sector per "
-                           "lane and level; that pattern's own roof is gather_roof below",
+                           "lane and level; that pattern's own roof is gather_roof / request_roof below",
             "what": "achieved = algorithmic TREE bytes of the dominant kernel (4 B per spatial level + 4 B root id + 20 B per quadtree "
-                    "level [+4 B path product / +8 B leaf update], SURVEY 8d) x queries / its launch time (CUDA events); the 28 B per "
-                    "query streamed from / to HBM are accounted separately (hbm)",
-            "algorithmic_bytes_per_query": bytes_q[names[dom]], "kernel_ms": k_ms[dom],
+                    "level [+4 B path product / +8 B leaf update], SURVEY 8d) x queries / its launch time (CUDA events); the bytes "
+                    "streamed from / to HBM per query are accounted separately (hbm)",
+            "algorithmic_bytes_per_query": bytes_q[dom], "kernel_ms": k_ms[dom],
             "gather_roof": {"gbs_via_l1": gather_gbs, "gbs_l2_only": gather_cg_gbs,
                             "how": "sdt_measure_gather: 16 MiB resident set, every lane loads one random 32 B sector per 256-bit load, 8 independent loads in flight per lane",
                             "frac": d["frac_of_gather_roof"]},
+            "request_roof": {"peak_g_requests_per_s": req_peak, "achieved_g_requests_per_s": d["g_requests_per_s"], "frac": d["frac_of_request_roof"],
+                             "what": "a lane that reads its own 32 B sector occupies one slot of the SM's L1 -> L2 request port whatever it needs of the "
+                                     "sector (ncu: l1tex__m_l1tex2xbar_req_cycles_active is the busiest unit of the sampling kernels); the gather probe "
+                                     "saturates that port (1.0 sector per clock and SM), so requests / s against it is the hardware roof of a per-lane "
+                                     "descent, and 20 algorithmic bytes of every 32 B sector cap frac_of_gather_roof at 0.625"},
             "hbm": {"achieved": d["stream_gbs"], "peak": hbm_peak, "frac": d["frac_of_hbm"],
                     "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if "hbm_gbs" in peaks else "fallback 6650"},
             "per_kernel": pk,
-            "mean_depths": {"spatial": ds, "quad_sample": dq_s, "quad_pdf": dq_p, "sample_redescend_frac": redescend}}
+            "step_unfused_ms": k_ms["sample"] + k_ms["pdf"] + k_ms["splat"],
+            "mean_depths": {"spatial": ds, "quad_sample": dq_s, "quad_pdf": dq_p, "quad_splat": dq_r, "sample_redescend_frac": redescend,
+                            "levels_below_jump_table": {"pdf": below_p, "splat": below_r}}}
 
-    # ---- refine + allreduce wall time (per training iteration, not part of a step)
-    e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
-    torch.cuda.synchronize()
-    e0.record()
-    if allreduce:
-        allreduce()
-    e1.record()
+    # ---- refine + allreduce wall time (per training iteration, not part of a step).  Steady state: the refine replays a
+    # CUDA graph captured on first use (one per buffer parity), so two untimed iterations come first; every timed refine
+    # follows a splat, i.e. it includes the bottom-up sweeps of the statistics like a training iteration's does.
     tree.set_max_leaf_size(1e9)            # statistics are K steps of the same records: keep the spatial tree frozen
-    tree.refine()
-    e2.record()
-    torch.cuda.synchronize()
-    per_iter = {"allreduce_ms": e0.elapsed_time(e1) if allreduce else 0.0, "refine_ms": e1.elapsed_time(e2)}
+    ms_ar, ms_rf, reps_rf = 0.0, 0.0, 4
+    for it in range(2 + reps_rf):
+        tree.splat_records(d_rec['position'], d_rec['direction'], d_rec['radiance'], d_rec['wo_pdf'])
+        e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+        torch.cuda.synchronize()
+        e0.record()
+        if allreduce:
+            allreduce()
+        e1.record()
+        tree.refine()
+        e2.record()
+        torch.cuda.synchronize()
+        if it >= 2:
+            ms_ar += e0.elapsed_time(e1) / reps_rf
+            ms_rf += e1.elapsed_time(e2) / reps_rf
+    per_iter = {"allreduce_ms": ms_ar if allreduce else 0.0, "refine_ms": ms_rf,
+                "what": f"mean of {reps_rf} training-iteration ends (sweeps + refine of the {sizes['n_quad']}-node forest) after 2 untimed ones"}
+    tree.upload(frozen_tree())             # back to the frozen benchmark tree for the extras / e2e legs
 
     # ---- extras (not part of the step): the integrator's own entry points on the same vertices
     extras = {}
@@ -374,17 +427,6 @@ def run_b200(args):
         bs_ = torch.rand(n, 3, device=dev, generator=gg)
         act_ = (torch.rand(n, device=dev, generator=gg) < 0.6).to(torch.uint8)
 
-        def timeit(fn, reps=10):
-            for _ in range(3):
-                fn()
-            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            torch.cuda.synchronize()
-            a.record()
-            for _ in range(reps):
-                fn()
-            b.record()
-            torch.cuda.synchronize()
-            return a.elapsed_time(b) / reps
         ms_g = timeit(lambda: tree.guided(d_pos, mode, wo=d_dir, seed=5, lane_offset=lane0, bsdf_pdf=bp, bsdf_value=bv,
                                           dir_out=g_dir, sdtree_pdf_out=g_sp, wo_pdf_out=g_wp, weight_out=g_w))
         ms_p = timeit(lambda: tree.splat_path_data(md, lfin, tr_, tb_, bs_, d_rec['position'], d_rec['direction'], d_rec['wo_pdf'], active=act_))
@@ -397,14 +439,38 @@ def run_b200(args):
                            "pdf_ms": timeit(lambda: tree.pdf(d_pos, d_dir, active=act15, out=o_pdf2)),
                            "sample_ms": timeit(lambda: tree.sample(d_pos, active=act15, seed=3, out=(o_dir, o_pdf)))}
         tree.set_tuning("use_compaction", 1)
-        extras = {"sparse_wavefront_15pct_active": dict(sparse, what="same calls with 15 % of the lanes active (late bounces / numRays*max_depth record slots): lanes of a tile sorted into dense warps vs plain masking"),
+        # ---- coherent wavefront: the SAME vertices / records ordered by spatial leaf, the way the lanes of a render
+        # wavefront are (neighbouring pixels see neighbouring surface points): the lanes of a warp then share a quadtree,
+        # its top records are fetched once per warp instead of once per lane, and records of one warp hit the same nodes
+        coherent = {}
+        try:
+            leaf_q, _ = tree.locate(d_pos)
+            oq = torch.argsort(leaf_q.view(torch.int32).to(torch.int64), stable=True)
+            c_pos, c_dir = d_pos[oq].contiguous(), d_dir[oq].contiguous()
+            leaf_r, _ = tree.locate(d_rec['position'])
+            orr = torch.argsort(leaf_r.view(torch.int32).to(torch.int64), stable=True)
+            c_rec = {k: v[orr].contiguous() for k, v in d_rec.items()}
+            del leaf_q, leaf_r, oq, orr
+            coherent["sample_ms"] = timeit(lambda: tree.sample(c_pos, seed=3, lane_offset=lane0, out=(o_dir, o_pdf)))
+            coherent["pdf_ms"] = timeit(lambda: tree.pdf(c_pos, c_dir, out=o_pdf2))
+            for agg in (0, 1):
+                tree.set_tuning("splat_aggregate", agg)
+                coherent[f"splat_ms_aggregate{agg}"] = timeit(lambda: tree.splat_records(c_rec['position'], c_rec['direction'], c_rec['radiance'], c_rec['wo_pdf']))
+                coherent[f"incoherent_splat_ms_aggregate{agg}"] = timeit(lambda: tree.splat_records(d_rec['position'], d_rec['direction'], d_rec['radiance'], d_rec['wo_pdf']))
+            tree.set_tuning("splat_aggregate", 0)
+            coherent["what"] = ("the step's vertices / records sorted by spatial leaf (stand-in for a pixel-coherent render wavefront); "
+                                "splat with and without the warp aggregation of same-node adds (splat_aggregate), on both orders")
+            del c_pos, c_dir, c_rec
+        except Exception as e:
+            coherent = {"error": repr(e)}
+        extras = {"coherent_wavefront": coherent, "sparse_wavefront_15pct_active": dict(sparse, what="same calls with 15 % of the lanes active (late bounces / numRays*max_depth record slots): lanes of a tile sorted into dense warps vs plain masking"),
                   "sdt_guided": {"ms": ms_g, "lanes_per_s": n / (ms_g * 1e-3), "what": "one bounce: ~45 % lanes sampled, ~45 % pdf + fused mixture, ~10 % idle"},
                   "sdt_splat_path_data": {"ms": ms_p, "slots_per_s": n / (ms_p * 1e-3), "what": f"processPathData + filter + splat fused, {n} slots (max_depth {md}), 60 % active"}}
         tree.reset_stats()
     except Exception as e:            # extras never break the contract line
         extras = {"error": repr(e)}
 
-    # ---- end to end: the same three C-ABI calls on HOST buffers (pinned)
+    # ---- end to end: the step's C-ABI calls on HOST buffers (pinned)
     e2e = None
     if not args.no_e2e:
         tree2 = tree
@@ -415,8 +481,7 @@ def run_b200(args):
         ho_pdf2 = torch.empty(n).pin_memory().numpy()
 
         def step_host():
-            tree2.sample(hp, seed=3, lane_offset=lane0, out=(ho_dir, ho_pdf))
-            tree2.pdf(hp, hd, out=ho_pdf2)
+            tree2.sample_pdf(hp, hd, seed=3, lane_offset=lane0, out=(ho_dir, ho_pdf, ho_pdf2))
             tree2.splat_records(hr['position'], hr['direction'], hr['radiance'], hr['wo_pdf'])
             tree2.synchronize()                         # every output of the step is in host memory here
             torch.cuda.synchronize()
@@ -436,7 +501,7 @@ def run_b200(args):
             return float(dt.item())
         tree2.host_wait = True                          # each call returns with its outputs on the host
         dt_wait = timed_host()
-        tree2.host_wait = False                         # SDT_NO_WAIT: the three calls overlap, one synchronize per step
+        tree2.host_wait = False                         # SDT_NO_WAIT: the calls overlap, one synchronize per step
         dt_e2e = timed_host()
         tree2.host_wait = True
         # what the link gives a plain pinned copy of the same size (context for the number above)
@@ -451,10 +516,10 @@ def run_b200(args):
         h2d_gbs = 4 * big.numel() / (time.perf_counter() - t0) / 1e9
         del big, dbig
         e2e = {"value": n * world / dt_e2e, "unit": UNIT, "ms_per_step": dt_e2e * 1e3,
-               "h2d_bytes_per_step": n * (12 + 24 + 28), "d2h_bytes_per_step": n * (16 + 4),
+               "h2d_bytes_per_step": n * (24 + 28), "d2h_bytes_per_step": n * (16 + 4),
                "ms_per_step_waiting_calls": dt_wait * 1e3, "pinned_h2d_copy_gbs": h2d_gbs,
-               "h2d_gbs_in_step": n * (12 + 24 + 28) / dt_e2e / 1e9,
-               "how": "sdt_sample + sdt_pdf + sdt_splat_records with SDT_HOST_PTRS | SDT_NO_WAIT on pinned host arrays and one "
+               "h2d_gbs_in_step": n * (24 + 28) / dt_e2e / 1e9,
+               "how": "sdt_sample_pdf (positions cross the bus once for both queries) + sdt_splat_records with SDT_HOST_PTRS | SDT_NO_WAIT on pinned host arrays and one "
                       "sdt_synchronize per step (all outputs on the host); staging copies inside the calls.  "
                       "ms_per_step_waiting_calls: the same without SDT_NO_WAIT, every call returning with its outputs on the "
                       "host; pinned_h2d_copy_gbs: a plain pinned H2D copy on this box -- the step is bound by the host link "

@@ -168,6 +168,15 @@ int sdt_sample(sdt_handle h, const sdt_vec3* pos, const uint8_t* active, uint32_
 int sdt_pdf(sdt_handle h, const sdt_vec3* pos, const sdt_vec3* dir, const uint8_t* active,
             uint32_t n, float* pdf, uint32_t* dbg, uint32_t flags, sdt_stream stream);
 
+/* KDTree.sample (src/kdtree.py:473-486) and KDTree.pdf (:489-496) of a second, GIVEN direction `qdir` on the same
+ * vertices with one spatial descent: what a path vertex asks of the tree when it draws the guided direction
+ * (src/path_guiding_integrator.py:301) and also needs the tree's pdf of the emitter direction for the NEE MIS weight
+ * (:244).  dir / pdf are exactly sdt_sample's outputs, qpdf exactly sdt_pdf's; the position crosses the bus once. */
+int sdt_sample_pdf(sdt_handle h, const sdt_vec3* pos, const uint8_t* active, uint32_t n,
+                   const float* u, uint32_t u_stride, uint32_t seed, uint32_t lane_offset,
+                   const sdt_vec3_out* dir, float* pdf, const sdt_vec3* qdir, float* qpdf,
+                   uint32_t flags, sdt_stream stream);
+
 /* One bounce of the integrator's guided/BSDF choice in ONE pass over the wavefront
  * (src/path_guiding_integrator.py:283-311): lanes with mode[i]==1 are sampled from
  * the tree (:301), lanes with mode[i]==2 get the tree pdf of the BSDF-sampled
@@ -277,6 +286,7 @@ int sdt_stat_buffers(sdt_handle h, float** q_energy, uint32_t* n_quad, float** k
  *   "splat_aggregate"   combine the lanes of a warp that splat into the same node before the atomic (pays on pixel-coherent
  *                       wavefronts; off by default: on incoherent records it finds no peers and only costs instructions)
  *   "use_pdl"                                                                programmatic dependent launch of the helper kernels
+ *   "use_graph"         replay the refine's ~200 launches as one captured CUDA graph per buffer parity
  *   "host_chunk"   lanes per chunk of the pipelined SDT_HOST_PTRS staging (H2D of chunk k+1 | kernels of chunk k | D2H of chunk k-1).
  * One key switches semantics rather than speed: "quad_thr_reciprocal" = 1 computes the
  * quadtree refinement threshold (src/quadtree.py:519, `E / 100`) as E * fp32(0.01), the

@@ -112,6 +112,8 @@ SYMBOLS = {
     "sdt_set_tuning": (C.c_int, [_H, C.c_char_p, C.c_int64]),
     "sdt_synchronize": (C.c_int, [_H, C.c_void_p]),
     "sdt_kernel_launches": (C.c_uint64, [_H]),
+    "sdt_sample_pdf": (C.c_int, [_H, C.POINTER(Vec3), C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32,
+                                 C.POINTER(Vec3), C.c_void_p, C.POINTER(Vec3), C.c_void_p, C.c_uint32, _S]),
     "sdt_measure_l2": (C.c_int, [_H, C.c_uint64, C.c_uint32, C.POINTER(C.c_float), _S]),
     "sdt_measure_gather": (C.c_int, [_H, C.c_uint64, C.c_uint32, C.c_int32, C.POINTER(C.c_float), _S]),
 }

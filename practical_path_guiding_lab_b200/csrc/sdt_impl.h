@@ -3,6 +3,7 @@
 
 #include <map>
 #include <string>
+#include <tuple>
 #include <vector>
 
 #include "sdt_exec.h"
@@ -99,6 +100,14 @@ struct sdt_tree_s {
     struct LaunchCache { size_t attr_smem = 0; int occ = 0, occ_block = 0; size_t occ_smem = ~(size_t)0; };
     std::map<const void*, LaunchCache> launch_cache;
     uint32_t dev_error_seen = 0;    // DevHeader.error as last read back (sticky device-side flag, see sdt_get_sizes)
+
+    // the refine's launch sequence, captured once per (buffer parity, flags, level bounds, settings) and replayed as one graph
+    typedef std::tuple<int, uint32_t, uint32_t, uint32_t, int, int, int, int> RefineKey;
+#ifndef SDT_HOSTEMU
+    struct RefineGraph { cudaGraphExec_t exec = nullptr; uint64_t launches = 0; };
+    std::map<RefineKey, RefineGraph> refine_graphs;
+#endif
+    int use_graph = 1;
 
     // NCCL
     void* nccl_comm = nullptr;

@@ -16,6 +16,10 @@ static int sdt_free_all(sdt_handle h) {
         void* q[] = {s.child, s.energy, s.thr, s.pp, s.iidx, s.rec, s.jump, s.jump_pp, s.root_iidx, s.hdr};
         for (void* p : q) if (p) cudaFree(p);
     }
+#ifndef SDT_HOSTEMU
+    for (auto& kv : h->refine_graphs) if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+    h->refine_graphs.clear();
+#endif
     if (h->h_hdr) cudaFreeHost(h->h_hdr);
     if (h->hdr_event) cudaEventDestroy(h->hdr_event);
 #ifndef SDT_HOSTEMU
@@ -262,7 +266,7 @@ extern "C" int sdt_upload(sdt_handle h, const sdt_arrays* a) {
     SDT_CUDA(h, cudaMemsetAsync(h->q_ecur, 0, 4ull * h->quad_cap, nullptr));
     const ExecCtx x = exec_ctx(h, nullptr);
     h->levels_hint = nlev > 0 ? nlev : 1;          // the per-level passes of sdt_build_records cover the uploaded tree
-    sdt_build_records(h, x, s);
+    sdt_build_records(h, x, s, true);
     SDT_TRY(sdt_post_launch(h, "sdt_upload"));
     SDT_CUDA(h, cudaStreamSynchronize(nullptr));
     h->levels_hint = nlev > 0 ? nlev : 1;
@@ -381,6 +385,7 @@ extern "C" int sdt_set_tuning(sdt_handle h, const char* key, int64_t value) {
     else if (k == "use_int_cell") h->use_int_cell = value != 0;
     else if (k == "quad_thr_reciprocal") h->quad_thr_reciprocal = value != 0;
     else if (k == "use_pdl") h->use_pdl = value != 0;
+    else if (k == "use_graph") h->use_graph = value != 0;
     else if (k == "use_compaction") h->use_compaction = value != 0;
     else if (k == "host_chunk") { SDT_CHECK(h, value >= 256, SDT_ERR_INVALID, "host_chunk must be >= 256 lanes"); h->host_chunk = (int)value; }
     else return sdt_fail(h, SDT_ERR_INVALID, "sdt_set_tuning: unknown key " + k);

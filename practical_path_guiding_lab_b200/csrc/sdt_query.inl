@@ -249,6 +249,42 @@ struct SampleLane {
     }
 };
 
+// KDTree.sample + KDTree.pdf of a second, given direction on the same vertices: ONE spatial descent, then the sampling
+// descent and the pdf descent in the same quadtree (a path vertex asks both: the guided sample, src/path_guiding_integrator.py:301,
+// and the tree's pdf of the emitter direction for the NEE MIS weight, :244)
+template <bool EXPLICIT_U>
+struct SamplePdfLane {
+    static constexpr bool kSmemCounts = false, kGrid = SDT_SAMPLE_GRID;
+    static constexpr int kModes = 1, kMaxThreads = SDT_SAMPLE_THREADS;
+    SDT_HD void flush_count(uint32_t, float) const {}
+    TreeView t;
+    sdt_vec3 pos; const uint8_t* active;
+    const float* u; uint32_t u_stride, seed, lane_offset;
+    sdt_vec3_out dir; float* pdf; sdt_vec3 qdir; float* qpdf; int fuse;
+    SDT_HD uint32_t mode_of(uint32_t i) const { return active ? (SDT_LDG(active + i) != 0 ? 1u : 0u) : 1u; }
+    SDT_HD void idle(uint32_t i) const {                 // as sdt_sample / sdt_pdf leave their inactive lanes
+        const int64_t o = (int64_t)i * dir.stride;
+        dir.x[o] = 0.0f; dir.y[o] = 0.0f; dir.z[o] = -1.0f;
+        pdf[i] = 1.0f;
+        qpdf[i] = 1.0f;
+    }
+    template <int KD>
+    SDT_HD void run_mode(const KdCtx& k, uint32_t i, uint32_t) const {
+        const KdResult r = sdt_kd_descend<KD>(k, sdt_ld(pos.x, pos.stride, i), sdt_ld(pos.y, pos.stride, i), sdt_ld(pos.z, pos.stride, i));
+        // the given direction: its pdf descent is issued first (short: jump table), the long sampling descent runs after it
+        float x, y;
+        sdt_dir_to_canonical(sdt_ld(qdir.x, qdir.stride, i), sdt_ld(qdir.y, qdir.stride, i), sdt_ld(qdir.z, qdir.stride, i), x, y);
+        uint32_t nd;
+        qpdf[i] = sdt_quad_pdf(t, r.rootrec, 0u, x, y, nd, false);
+        GuidedSample g;
+        if (EXPLICIT_U) g = sdt_sample_tree(t, r.rootrec, 0u, ExplicitRng(u, u_stride, i), fuse != 0);
+        else g = sdt_sample_tree(t, r.rootrec, 0u, CounterRng(seed, lane_offset + i), fuse != 0);
+        const int64_t o = (int64_t)i * dir.stride;
+        dir.x[o] = g.dx; dir.y[o] = g.dy; dir.z[o] = g.dz;
+        pdf[i] = g.pdf;
+    }
+};
+
 struct PdfLane {
     static constexpr bool kSmemCounts = false, kGrid = true;
     static constexpr int kModes = 1, kMaxThreads = SDT_QUERY_THREADS;
@@ -403,6 +439,31 @@ extern "C" int sdt_pdf(sdt_handle h, const sdt_vec3* pos, const sdt_vec3* dir, c
                   sg.out_t(sdt_offp(pdf, off), cnt), sg.out_t(sdt_offp(dbg, (size_t)off * 3), (size_t)cnt * 3)};
         if (sg.status != SDT_OK) return sg.status;
         sg.before_launch();
+        return launch_wavefront(h, st, cnt, f, h->query_block, h->query_ctas_per_sm, active != nullptr);
+    });
+}
+
+extern "C" int sdt_sample_pdf(sdt_handle h, const sdt_vec3* pos, const uint8_t* active, uint32_t n,
+                              const float* u, uint32_t u_stride, uint32_t seed, uint32_t lane_offset,
+                              const sdt_vec3_out* dir, float* pdf, const sdt_vec3* qdir, float* qpdf,
+                              uint32_t flags, sdt_stream stream) {
+    SDT_ENTER(h);
+    if (n == 0) return SDT_OK;                          // empty wavefront: nothing to do (pointers may be NULL)
+    SDT_CHECK(h, pos && pos->x && dir && dir->x && pdf && qdir && qdir->x && qpdf, SDT_ERR_INVALID, "sdt_sample_pdf: pos / dir / pdf / qdir / qpdf is NULL");
+    SDT_CHECK(h, !u || u_stride >= 3, SDT_ERR_INVALID, "sdt_sample_pdf: u_stride must be >= 3");
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t per_lane = 12 + 12 + 1 + 12 + 4 + 4 + (u ? 4ull * u_stride : 0) + 8;
+    return sdt_run_chunked(h, st, flags, n, per_lane, true, [&](Stager& sg, uint32_t off, uint32_t cnt) -> int {
+        SamplePdfLane<false> f{tree_view(h), sg.in3(sdt_off3(*pos, off), cnt), sg.in_t(sdt_offp(active, off), cnt),
+                               sg.in_t(sdt_offp(u, (size_t)off * u_stride), (size_t)cnt * u_stride), u_stride, seed, lane_offset + off,
+                               sg.out3(sdt_off3o(*dir, off), cnt), sg.out_t(sdt_offp(pdf, off), cnt),
+                               sg.in3(sdt_off3(*qdir, off), cnt), sg.out_t(sdt_offp(qpdf, off), cnt), h->fuse_sample_pdf};
+        if (sg.status != SDT_OK) return sg.status;
+        sg.before_launch();
+        if (u) {
+            SamplePdfLane<true> fe{f.t, f.pos, f.active, f.u, f.u_stride, f.seed, f.lane_offset, f.dir, f.pdf, f.qdir, f.qpdf, f.fuse};
+            return launch_wavefront(h, st, cnt, fe, h->query_block, h->query_ctas_per_sm, active != nullptr);
+        }
         return launch_wavefront(h, st, cnt, f, h->query_block, h->query_ctas_per_sm, active != nullptr);
     });
 }

@@ -28,6 +28,7 @@ struct RefineCtx {
     // quadtrees: old set + current statistics, new set + scratch
     const uint32_t* child0; const float* thr0; const float* e_cur;
     uint32_t* child1; float* energy1; float* thr1; uint32_t* iidx1; QRec* rec1; uint32_t* root_iidx1;
+    float* pp1;               // per-node pdf products of the tree being built (sdt_core.h), written top-down with the levels
     uint32_t* s_src; uint8_t* s_kind; uint8_t* s_srem;
     uint32_t no_quad;
     uint32_t thr_recip;   // threshold = E * fp32(1/100) instead of E / 100 (how Dr.Jit may lower the literal division)
@@ -144,6 +145,7 @@ struct QRootItem {          // level 0: tree r copies the tree of root_src[r]; t
         c.s_kind[r] = SDT_KIND_REACHED;
         const float e = c.e_cur[src];
         c.energy1[r] = e;
+        c.pp1[r] = 1.0f;
         c.thr1[r] = c.no_quad ? c.thr0[src] : (c.thr_recip ? e * 0.01f : e / 100.0f);
     }
 };
@@ -209,20 +211,25 @@ struct QLevelEmit {
         const uint32_t cb = H->level_off[level + 1u] + 4u * rank;
         c.child1[id] = cb;
         const float thr = c.thr1[id];
+        // the children's pdf products, parents before children like PpLevelItem: pp * ((4 * E_child) / E_node)  (:1084)
+        const float own = c.energy1[id], p = c.pp1[id];
         if (d.virt) {
-            const float e4 = c.energy1[id] / 4.0f;                // :133-134
+            const float e4 = own / 4.0f;                          // :133-134
             for (uint32_t k = 0; k < 4u; ++k) {
                 c.s_kind[cb + k] = SDT_KIND_VIRTUAL;
                 c.s_srem[cb + k] = (uint8_t)d.srem;
                 c.energy1[cb + k] = e4;
+                c.pp1[cb + k] = p * ((4.0f * e4) / own);
                 c.thr1[cb + k] = thr;                             // :139-143
             }
         } else {
             for (uint32_t k = 0; k < 4u; ++k) {
                 const uint32_t o = d.old_cb + k;
+                const float ec = c.e_cur[o];
                 c.s_src[cb + k] = o;
                 c.s_kind[cb + k] = d.reached ? SDT_KIND_REACHED : 0u;
-                c.energy1[cb + k] = c.e_cur[o];
+                c.energy1[cb + k] = ec;
+                c.pp1[cb + k] = p * ((4.0f * ec) / own);
                 c.thr1[cb + k] = c.no_quad ? c.thr0[o] : thr;
             }
         }
@@ -315,12 +322,13 @@ struct JumpBuildItem {
 
 struct KdGridItem { const uint32_t* kd_word; uint32_t* grid; SDT_HD void operator()(uint32_t c) const { grid[c] = sdt_kd_grid_node(kd_word, c); } };
 
-static void sdt_build_records(sdt_handle h, const ExecCtx& x, QuadSet& s) {
+// with_pp: also compute the per-node pdf products (an uploaded tree; the refine writes them while it builds the levels)
+static void sdt_build_records(sdt_handle h, const ExecCtx& x, QuadSet& s, bool with_pp) {
     launch_scan(x, &s.hdr->n_quad, 0, RecFlag{s.child}, RecEmit{s.iidx}, RecFin{s.hdr});
     launch_items(x, &s.hdr->n_quad, 0, RecBuildItem{s.hdr, s.child, s.energy, s.iidx, s.rec, s.root_iidx});
     launch_items(x, &s.hdr->n_kd, 0, KdLeafWordItem{s.hdr, h->kd_word, h->kd_root, s.root_iidx});
     launch_items(x, nullptr, SDT_GRID_CELLS, KdGridItem{h->kd_word, h->kd_grid});
-    for (uint32_t l = 0; l < h->levels_hint && l < SDT_MAX_LEVELS; ++l)
+    for (uint32_t l = 0; with_pp && l < h->levels_hint && l < SDT_MAX_LEVELS; ++l)
         launch_items(x, &s.hdr->level_cnt[l], 0, PpLevelItem{s.hdr, s.child, s.energy, s.pp, l});
     launch_single(x, JumpCountItem{s.hdr, s.iidx, h->jump_cap});
     launch_items(x, &s.hdr->lvl_n[0], 0, JumpBuildItem{s.rec, s.pp, s.jump, s.jump_pp});
@@ -332,10 +340,8 @@ struct KdRollItem {         // prev.vertCount <- current.vertCount; current <- 0
 };
 struct ZeroItem { float* p; SDT_HD void operator()(uint32_t i) const { p[i] = 0.0f; } };
 
-extern "C" int sdt_refine(sdt_handle h, uint32_t flags, sdt_stream stream) {
-    SDT_ENTER(h);
-    cudaStream_t st = (cudaStream_t)stream;
-    sdt_order_after_last(h, st);
+// the launch sequence of one refine on stream `st` (sweeps of the statistics included when they are due)
+static int sdt_refine_enqueue(sdt_handle h, cudaStream_t st, uint32_t flags, uint32_t levels_bound) {
     SDT_TRY(sdt_complete_stats(h, st));
     const ExecCtx x = exec_ctx(h, st);
     QuadSet& s0 = h->set[h->cur];
@@ -346,7 +352,7 @@ extern "C" int sdt_refine(sdt_handle h, uint32_t flags, sdt_stream stream) {
     c.kd_bmin = h->kd_bmin; c.kd_bmax = h->kd_bmax; c.kd_prev_count = h->kd_prev_count; c.kd_s = h->kd_s;
     c.kd_sel = h->kd_sel; c.kd_rank_cur = h->kd_rank[0]; c.kd_rank_prev = h->kd_rank[1]; c.root_src = h->root_src;
     c.child0 = s0.child; c.thr0 = s0.thr; c.e_cur = h->q_ecur;
-    c.child1 = s1.child; c.energy1 = s1.energy; c.thr1 = s1.thr; c.iidx1 = s1.iidx; c.rec1 = s1.rec; c.root_iidx1 = s1.root_iidx;
+    c.child1 = s1.child; c.energy1 = s1.energy; c.thr1 = s1.thr; c.iidx1 = s1.iidx; c.rec1 = s1.rec; c.root_iidx1 = s1.root_iidx; c.pp1 = s1.pp;
     c.s_src = h->s_src; c.s_kind = h->s_kind; c.s_srem = h->s_srem;
     c.no_quad = (flags & SDT_REFINE_NO_QUAD) ? 1u : 0u;
     c.thr_recip = h->quad_thr_reciprocal ? 1u : 0u;
@@ -362,20 +368,64 @@ extern "C" int sdt_refine(sdt_handle h, uint32_t flags, sdt_stream stream) {
             launch_items(x, &c.H1->kd_round_new, 0, KdMakeNodeItem{cr, r});
         }
     }
-    uint32_t levels_bound = (uint32_t)h->cfg.quad_max_depth + 1u;
-    if (levels_bound < h->levels_hint) levels_bound = h->levels_hint;
-    if (levels_bound > SDT_MAX_LEVELS) levels_bound = SDT_MAX_LEVELS;
     launch_single(x, QInit{c});
     launch_items(x, &c.H1->lvl_n[0], 0, QRootItem{c});
     for (uint32_t l = 0; l < levels_bound; ++l)
         launch_scan(x, &c.H1->lvl_n[l & 1u], 0, QLevelFlag{c, l, (uint32_t)(l + 1u == levels_bound)}, QLevelEmit{c, l}, QLevelFin{c, l});
     launch_single(x, QFinalize{c, levels_bound});
     h->levels_hint = levels_bound;
-    sdt_build_records(h, x, s1);
+    sdt_build_records(h, x, s1, false);
     // prev <- current, then reset current (:582-586)
     launch_items(x, &c.H1->n_kd, 0, KdRollItem{h->kd_count, h->kd_prev_count});
     launch_items(x, &c.H1->n_quad, 0, ZeroItem{h->q_ecur});
-    SDT_TRY(sdt_post_launch(h, "sdt_refine"));
+    return sdt_post_launch(h, "sdt_refine");
+}
+
+extern "C" int sdt_refine(sdt_handle h, uint32_t flags, sdt_stream stream) {
+    SDT_ENTER(h);
+    cudaStream_t st = (cudaStream_t)stream;
+    sdt_order_after_last(h, st);
+    uint32_t levels_bound = (uint32_t)h->cfg.quad_max_depth + 1u;
+    if (levels_bound < h->levels_hint) levels_bound = h->levels_hint;
+    if (levels_bound > SDT_MAX_LEVELS) levels_bound = SDT_MAX_LEVELS;
+    QuadSet& s1 = h->set[1 - h->cur];
+#ifndef SDT_HOSTEMU
+    // The sequence is ~200 tiny dependent kernels whose arguments only depend on the buffer parity and a few settings:
+    // it is captured once per such combination into a CUDA graph (programmatic-dependent-launch edges included) and
+    // replayed with ONE launch per training iteration -- the host no longer enqueues 200 launches (0.87 -> see DESIGN).
+    bool done = false;
+    if (h->use_graph) {
+        const sdt_tree_s::RefineKey key{h->cur, flags & (SDT_REFINE_NO_KD | SDT_REFINE_NO_QUAD), h->levels_hint, levels_bound,
+                                        h->cfg.kd_max_depth, h->quad_thr_reciprocal, h->use_pdl, h->stats_complete ? 1 : 0};
+        auto it = h->refine_graphs.find(key);
+        if (it == h->refine_graphs.end()) {
+            sdt_tree_s::RefineGraph g;
+            const uint64_t l0 = h->launches;
+            const bool sc0 = h->stats_complete; const uint32_t lh0 = h->levels_hint;
+            cudaGraph_t graph = nullptr;
+            if (cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+                const int rc = sdt_refine_enqueue(h, st, flags, levels_bound);
+                const cudaError_t ec = cudaStreamEndCapture(st, &graph);
+                if (rc == SDT_OK && ec == cudaSuccess && graph && cudaGraphInstantiate(&g.exec, graph, 0) == cudaSuccess) {
+                    g.launches = h->launches - l0;
+                    it = h->refine_graphs.emplace(key, g).first;
+                }
+                if (graph) cudaGraphDestroy(graph);
+            }
+            h->launches = l0; h->stats_complete = sc0; h->levels_hint = lh0;      // nothing has run yet
+            if (it == h->refine_graphs.end()) { cudaGetLastError(); h->use_graph = 0; }   // capture not possible here: plain launches from now on
+        }
+        if (it != h->refine_graphs.end()) {
+            SDT_CUDA(h, cudaGraphLaunch(it->second.exec, st));
+            h->launches += it->second.launches;
+            h->last_stream = st;
+            done = true;
+        }
+    }
+    if (!done) SDT_TRY(sdt_refine_enqueue(h, st, flags, levels_bound));
+#else
+    SDT_TRY(sdt_refine_enqueue(h, st, flags, levels_bound));
+#endif
     h->cur = 1 - h->cur;
     h->jump_trees_known = 0;
     h->levels_known = 0;

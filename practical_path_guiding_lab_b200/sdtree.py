@@ -237,6 +237,32 @@ class SDTree:
                                       C.byref(dv), pp, gp, self._flags(b), b.stream()))
         return (d, pdf, dbg) if debug else (d, pdf)
 
+    def sample_pdf(self, pos, qdir, active=None, u=None, seed=0, lane_offset=0, out=None):
+        """KDTree.sample and KDTree.pdf of the given directions `qdir` at the same vertices, one spatial descent
+        -> (dir (n,3), pdf (n,), qpdf (n,)); identical to sample(...) + pdf(pos, qdir)"""
+        b = _Buf()
+        n = _n_of(pos)
+        p = b.vec(pos, 3)
+        q = b.vec(qdir, 3)
+        a = b.arr(active, np.uint8)
+        up, us = None, 0
+        if u is not None:
+            us = int(u.shape[1])
+            up = b.arr(u, np.float32)
+        if out is not None:
+            d, pdf, qpdf = out
+            dv = b.vec(d, 3)
+            pp = b.arr(pdf, np.float32)
+            qp = b.arr(qpdf, np.float32)
+        else:
+            d, dp = b.new((n, 3), np.float32)
+            dv = L.Vec3(dp, dp + 4, dp + 8, 3)
+            pdf, pp = b.new((n,), np.float32)
+            qpdf, qp = b.new((n,), np.float32)
+        self._ck(self._lib.sdt_sample_pdf(self._h, C.byref(p), a, n, up, us, int(seed) & 0xFFFFFFFF, int(lane_offset),
+                                          C.byref(dv), pp, C.byref(q), qp, self._flags(b), b.stream()))
+        return d, pdf, qpdf
+
     def pdf(self, pos, direction, active=None, debug=False, out=None):
         """KDTree.pdf -> pdf (n,)[, dbg (n,3)]"""
         b = _Buf()

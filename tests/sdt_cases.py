@@ -225,6 +225,12 @@ def check_queries(ctx, t, prev, n=4096, seed=7, box=1.0, explicit=True):
     # without the debug output the kernel reads the leaf's path product straight from its second jump table
     pp2 = t.pdf(ctx.dev(pos), ctx.dev(dirs), ctx.dev(active.astype(np.uint8)))
     assert beq(ctx.host(pp2), opp), "pdf through the path-product jump table"
+    # sample + pdf of the given directions fused into one call (one spatial descent): the same bits as the two calls
+    if explicit:
+        fd, fp, fq = t.sample_pdf(ctx.dev(pos), ctx.dev(dirs), ctx.dev(active.astype(np.uint8)), u=ctx.dev(u))
+    else:
+        fd, fp, fq = t.sample_pdf(ctx.dev(pos), ctx.dev(dirs), ctx.dev(active.astype(np.uint8)), seed=1234, lane_offset=17)
+    assert beq(ctx.host(fd), od) and beq(ctx.host(fp), op) and beq(ctx.host(fq), opp), "fused sample + pdf"
     return dict(pos=pos, active=active, dirs=dirs)
 
 

@@ -28,8 +28,9 @@ for spec in sys.argv[1:]:
     d = json.loads(line[-1])
     pk = d["roofline"]["per_kernel"]
     ex = d.get("extras", {})
-    row = {"name": name, "sample": pk["sample"]["ms"], "pdf": pk["pdf"]["ms"], "splat": pk["splat"]["ms"], "step": d["ms_per_step"],
-           "guided": ex.get("sdt_guided", {}).get("ms"), "path": ex.get("sdt_splat_path_data", {}).get("ms"),
+    row = {"name": name, "fused": pk["sample_pdf"]["ms"], "sample": pk["sample"]["ms"], "pdf": pk["pdf"]["ms"], "splat": pk["splat"]["ms"], "step": d["ms_per_step"],
+           "req_frac": {k: round(v["frac_of_request_roof"], 3) for k, v in pk.items()},
+           "guided": ex.get("sdt_guided", {}).get("ms"), "coh": ex.get("coherent_wavefront"), "path": ex.get("sdt_splat_path_data", {}).get("ms"),
            "refine": d.get("refine_ms"), "mhz": d["clocks"]["sm_mhz"]}
     rows.append(row)
     print(json.dumps(row), flush=True)
