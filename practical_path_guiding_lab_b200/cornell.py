@@ -80,11 +80,21 @@ class CornellBox:
         self.sumL = None
         self.sumL2 = None
         self._gL = self._gL2 = None
+        self.p0, self.p1 = 0, self.W * self.H          # this rank's tile of the film: pixels [p0, p1) (driver.TorchDistRanks, tile sharding)
+        self._rank = 0
+        self._pin = None
+
+    def set_tile(self, rank, world):
+        """tile sharding (main.py:208-218 split by image tiles): this rank renders pixels [p0, p1) -- a band
+        of rows -- of EVERY pass; lanes keep globally unique RNG keys (generator seed and lane offset per rank)"""
+        P = self.W * self.H
+        self.p0, self.p1 = rank * P // world, (rank + 1) * P // world
+        self._rank = int(rank)
 
     # ---- what main.py does before the loop (main.py:45-64) -----------------------------------
     def setup(self, sdTreeMaxDepth=20, quadTreeMaxDepth=20, isStoreNEERadiance=True, bsdfSamplingFraction=0.5):
         eps = 1e-4
-        self.core.setup(self.W * self.H, self.bbox_min - eps, self.bbox_max + eps, sdTreeMaxDepth, quadTreeMaxDepth,
+        self.core.setup(self.p1 - self.p0, self.bbox_min - eps, self.bbox_max + eps, sdTreeMaxDepth, quadTreeMaxDepth,
                         isStoreNEERadiance, bsdfSamplingFraction)
         self.resetVarianceCounter()
 
@@ -123,8 +133,8 @@ class CornellBox:
         return tt, q, valid
 
     def camera_rays(self, spp, gen):
-        n = self.W * self.H * spp
-        pix = torch.arange(self.W * self.H, device=self.dev).repeat_interleave(spp)   # samples of a pixel adjacent
+        n = (self.p1 - self.p0) * spp
+        pix = torch.arange(self.p0, self.p1, device=self.dev).repeat_interleave(spp)   # samples of a pixel adjacent
         jit = torch.rand(n, 2, device=self.dev, generator=gen)
         sx = ((pix % self.W).float() + jit[:, 0]) / self.W
         sy = ((pix // self.W).float() + jit[:, 1]) / self.H
@@ -146,7 +156,7 @@ class CornellBox:
     def render(self, spp, seed):
         core = self.core
         dev = self.dev
-        gen = torch.Generator(device=dev).manual_seed(int(seed))
+        gen = torch.Generator(device=dev).manual_seed(int(seed) + self._rank * 0x9E3779B1)      # rank 0 / one GPU: the plain seed
         rnd = lambda *s: torch.rand(*s, device=dev, generator=gen)
         o, d, pix = self.camera_rays(spp, gen)
         n = o.shape[0]
@@ -166,7 +176,28 @@ class CornellBox:
         core._pass_seed += 1
         light_n = self.qn[self.light]
         bounce = 0
-        while bool(active.any()) and bounce < core.max_depth:
+        lane0 = self.p0 * spp
+        # "any lane still active?" is read back without stalling the queue: the flag of bounce b is copied to pinned memory
+        # asynchronously and looked at two bounces later (at most two fully masked bounces run past the end of the last path)
+        if self._pin is None and dev.type == "cuda":
+            self._pin = torch.zeros(core.max_depth + 2, dtype=torch.bool).pin_memory()
+        pending = []
+        while bounce < core.max_depth:
+            if dev.type == "cuda":
+                self._pin[bounce].copy_(active.any(), non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record()
+                pending.append((ev, bounce))
+                stop = False
+                while pending and (len(pending) > 2 or pending[0][0].query()):
+                    e, b = pending.pop(0)
+                    e.synchronize()
+                    if not bool(self._pin[b]):
+                        stop = True
+                if stop:
+                    break
+            elif not bool(active.any()):
+                break
             bounce += 1
             t, q, valid = self.intersect(o, d)
             valid = valid & active
@@ -219,7 +250,7 @@ class CornellBox:
             choose_u = rnd(n)
             if core.guiding:
                 mode, sd_dir, sd_pdf = core.choose_and_sample(self._x(p), self._x(wo), self._x(do_mis), self._x(choose_u),
-                                                              seed=(core._pass_seed * 1315423911 + bounce) & 0xFFFFFFFF)
+                                                              seed=(core._pass_seed * 1315423911 + bounce) & 0xFFFFFFFF, lane_offset=lane0)
                 mode, sd_dir, sd_pdf = self._t(mode), self._t(sd_dir), self._t(sd_pdf)
                 g = mode == 1
                 wo = torch.where(g[:, None], sd_dir, wo)
@@ -253,10 +284,14 @@ class CornellBox:
         if training:
             core.end_of_pass(self._x(L))
         # film + variance counters (:400-429)
-        Ls = L.view(self.W * self.H, spp, 3)
-        self.sumL += Ls.sum(1)
-        self.sumL2 += (Ls * Ls).sum(1)
-        return Ls.mean(1).view(self.H, self.W, 3)
+        Ls = L.view(self.p1 - self.p0, spp, 3)
+        self.sumL[self.p0:self.p1] += Ls.sum(1)
+        self.sumL2[self.p0:self.p1] += (Ls * Ls).sum(1)
+        if self.p1 - self.p0 == self.W * self.H:
+            return Ls.mean(1).view(self.H, self.W, 3)
+        img = torch.zeros(self.W * self.H, 3, device=dev)             # this rank's tile; the driver sums the ranks' images
+        img[self.p0:self.p1] = Ls.mean(1)
+        return img.view(self.H, self.W, 3)
 
     # ---- src/path_guiding_integrator.py:503-550 ------------------------------------------------
     def _lum(self, x):
@@ -287,7 +322,18 @@ class CornellBox:
 
     def allreduce_statistics(self, dist):
         """one exchange per iteration: SD-tree statistics (sdt_allreduce, NCCL) + variance counters"""
-        self.core.tree.allreduce(torch.cuda.current_stream().cuda_stream)
+        if self._host:
+            # host emulation (CPU tests, gloo): the same exchange through sdt_stat_buffers + torch.distributed
+            import ctypes
+            qp, nq, kp, nk = self.core.tree.stat_buffers()
+            q = np.ctypeslib.as_array(ctypes.cast(qp, ctypes.POINTER(ctypes.c_float)), shape=(nq,))
+            k = np.ctypeslib.as_array(ctypes.cast(kp, ctypes.POINTER(ctypes.c_float)), shape=(nk,))
+            buf = torch.from_numpy(np.concatenate([q, k]))
+            dist.all_reduce(buf)
+            q[:] = buf[:nq].numpy()
+            k[:] = buf[nq:].numpy()
+        else:
+            self.core.tree.allreduce(torch.cuda.current_stream().cuda_stream)
         self._gL, self._gL2 = self.sumL.clone(), self.sumL2.clone()      # local counters stay local
         dist.all_reduce(self._gL)
         dist.all_reduce(self._gL2)

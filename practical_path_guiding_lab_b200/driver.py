@@ -28,6 +28,7 @@ def possible_cumm_spps(budget_spp):
 
 class SingleRank:
     rank, world = 0, 1
+    tiles = False
 
     def sum_image(self, x):
         return x
@@ -37,16 +38,18 @@ class SingleRank:
 
 
 class TorchDistRanks:
-    """One process per GPU: the render passes of an iteration are dealt round-robin to
-    the ranks (pass p -> rank p % world, seed = seed0 + cumm_spp exactly as in the sequential loop);
-    at the end of the iteration the statistics of `current` are combined with ONE sdt_allreduce
-    (NCCL), the variance counters and the image with torch.distributed, and every rank runs the same
-    deterministic refine -> bit-identical trees without a broadcast."""
+    """One process per GPU.  tiles=True (default): every rank renders ITS TILE of the film in every pass
+    (the renderer was given the tile with set_tile; seed = seed0 + cumm_spp exactly as in the sequential loop, lanes keep
+    globally unique RNG keys) -- the early iterations, which have only 4 and 8 passes (main.py:170,208-218), keep all GPUs
+    busy.  tiles=False: whole passes are dealt round-robin (pass p -> rank p % world).  Either way, at the end of the
+    iteration the statistics of `current` are combined with ONE sdt_allreduce (NCCL), the variance counters and the image
+    with torch.distributed, and every rank runs the same deterministic refine -> bit-identical trees without a broadcast."""
 
-    def __init__(self):
+    def __init__(self, tiles=True):
         import torch.distributed as dist
         self.dist = dist
         self.rank, self.world = dist.get_rank(), dist.get_world_size()
+        self.tiles = bool(tiles)
 
     def sum_image(self, x):
         self.dist.all_reduce(x)
@@ -95,7 +98,7 @@ def train_and_render(renderer, budget_spp, seed=0, batch_spp=4, stable_variance_
         done = 0
         for p_i in range(passes):
             s = min(spp_per_pass, iter_spp - done)
-            if p_i % ranks.world == ranks.rank:
+            if ranks.tiles or p_i % ranks.world == ranks.rank:
                 one = renderer.render(s, seed + cumm_spp)              # main.py:218
                 w = one * float(s / iter_spp)
                 curr = w if curr is None else curr + w
@@ -234,6 +237,7 @@ def main(argv=None):
     ap.add_argument("--out", default=None)
     ap.add_argument("--ground-truth", default=None, help=".npy (H,W,3) linear RGB")
     ap.add_argument("--no-guiding", action="store_true", help="BSDF-only baseline: never refine (tree stays a single leaf)")
+    ap.add_argument("--shard", default="tiles", choices=["tiles", "passes"], help="multi-GPU work split: film tiles within every pass, or whole passes")
     ap.add_argument("--record-in-iteration", action="store_true", help="variance / MSE after every pass (main.py isRecordPerformanceInIteration; one GPU)")
     a = ap.parse_args(argv)
     from .cornell import CornellBox
@@ -244,14 +248,18 @@ def main(argv=None):
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-        ranks = TorchDistRanks()
+        ranks = TorchDistRanks(tiles=a.shard == "tiles")
     r = CornellBox(a.res, a.res, max_depth=a.max_depth, device=f"cuda:{local}")
+    if ranks is not None and ranks.tiles:
+        r.set_tile(ranks.rank, ranks.world)
     r.setup()
     if ranks is not None:
         r.comm_init(ranks.dist)
     gt = None
+    gt_native = None
     if a.ground_truth:
         g = np.load(a.ground_truth).astype(np.float32)
+        gt_native = torch.from_numpy(np.ascontiguousarray(g)).cuda()
         if g.shape[0] != a.res:                      # box-resample the fixture to the render resolution
             g = torch.nn.functional.interpolate(torch.from_numpy(g).permute(2, 0, 1)[None], size=(a.res, a.res), mode="area")[0].permute(1, 2, 0).numpy()
         gt = torch.from_numpy(np.ascontiguousarray(g)).cuda()
@@ -269,9 +277,19 @@ def main(argv=None):
         ranks.dist.all_reduce(lo, op=ranks.dist.ReduceOp.MIN)
         ranks.dist.all_reduce(hi, op=ranks.dist.ReduceOp.MAX)
         assert torch.equal(lo, hi), "trees differ between ranks"
+    extra = {}
+    if gt_native is not None and gt_native.shape[0] < a.res and a.res % gt_native.shape[0] == 0:
+        # a ground truth of lower resolution than the render was up-sampled above: every pixel of a block is compared with
+        # the block's mean, so mse_groundTruth has a floor (edges, texture inside a block) that no sample count removes.
+        # The same image box-filtered DOWN to the ground truth's own resolution has no such floor:
+        k = a.res // gt_native.shape[0]
+        img = res["image"].view(gt_native.shape[0], k, gt_native.shape[1], k, 3).mean(dim=(1, 3))
+        lum = torch.tensor([0.212671, 0.715160, 0.072169], device=img.device)
+        extra["mse_at_ground_truth_resolution"] = float((((img - gt_native) ** 2) * lum).sum(-1).clamp_max(10000).mean())
+        extra["ground_truth_resolution"] = int(gt_native.shape[0])
     if rank0:
-        print(json.dumps(dict(scene=a.scene, res=a.res, budget=a.budget, n_gpus=world, seconds=time.perf_counter() - t0,
-                              iterations=res["iterations"], final=res["records"][-1], tree=sizes)))
+        print(json.dumps(dict(scene=a.scene, res=a.res, budget=a.budget, n_gpus=world, shard=(a.shard if world > 1 else None),
+                              seconds=time.perf_counter() - t0, iterations=res["iterations"], final=res["records"][-1], tree=sizes, **extra)))
     if ranks is not None:
         ranks.dist.destroy_process_group()
 

@@ -67,7 +67,7 @@ class PathGuidingCore:
     # ---- record buffers (dr.zeros(SurfaceInteractionRecord, array_size), :111-118) -----
     def resetRayPathData(self, like):
         """zero-filled SoA record of `array_size` slots, same array kind as `like`"""
-        n = 1 if self.isFinalIter else self.array_size
+        n = 1 if self.isFinalIter else self.array_size + 1       # + one spare slot: the target of masked-out scatters
         if _is_torch(like):
             import torch
             z = lambda *s, dt=torch.float32: torch.zeros(*s, dtype=dt, device=like.device)
@@ -86,13 +86,6 @@ class PathGuidingCore:
         if self.isFinalIter:
             return
         m = store_flag != 0                             # uint8 / bool, numpy or torch -> boolean mask
-        if not bool(m.any()):
-            return
-        if _is_torch(ray_index):
-            ray_index, depth = ray_index.long(), depth.long()
-        else:
-            ray_index, depth = np.asarray(ray_index, np.int64), np.asarray(depth, np.int64)
-        gi = (ray_index * self.max_depth + depth)[m]
         n = m.shape[0]
 
         def wide(x):        # Dr.Jit literals (e.g. the initial throughput Spectrum(1)) have width 1: dr.scatter broadcasts them
@@ -102,6 +95,27 @@ class PathGuidingCore:
         position, wo_world, bsdf_weight, throughput_weight, L, radiance_nee, nee_dir_world, woPdf = (
             wide(x) for x in (position, wo_world, bsdf_weight, throughput_weight, L, radiance_nee, nee_dir_world, woPdf))
         r = self.record
+        if _is_torch(ray_index):
+            # masked scatter without a data-dependent shape (no host synchronisation): lanes that store nothing write
+            # into the spare slot behind the last real one
+            import torch
+            gi = torch.where(m, ray_index.long() * self.max_depth + depth.long(), torch.full_like(ray_index.long(), self.array_size))
+            one = torch.ones((), dtype=r['active'].dtype, device=gi.device).expand(n)
+            r['position'].index_copy_(0, gi, position.to(r['position'].dtype))
+            r['direction'].index_copy_(0, gi, self.tree.dir_to_canonical(wo_world.contiguous()))
+            r['active'].index_copy_(0, gi, one)
+            r['bsdf'].index_copy_(0, gi, bsdf_weight.to(r['bsdf'].dtype))
+            r['throughputBsdf'].index_copy_(0, gi, throughput_weight.to(r['bsdf'].dtype))
+            r['throughputRadiance'].index_copy_(0, gi, L.to(r['bsdf'].dtype))
+            if self.isStoreNEERadiance:
+                r['radiance_nee'].index_copy_(0, gi, radiance_nee.to(r['bsdf'].dtype))
+                r['direction_nee'].index_copy_(0, gi, self.tree.dir_to_canonical(nee_dir_world.contiguous()))
+            r['woPdf'].index_copy_(0, gi, woPdf.to(r['woPdf'].dtype))
+            return
+        if not bool(m.any()):
+            return
+        ray_index, depth = np.asarray(ray_index, np.int64), np.asarray(depth, np.int64)
+        gi = (ray_index * self.max_depth + depth)[m]
         r['position'][gi] = position[m]
         r['direction'][gi] = self.tree.dir_to_canonical(wo_world[m])
         r['active'][gi] = 1
@@ -150,7 +164,7 @@ class PathGuidingCore:
         """processPathData + scatterDataIntoSDTree + addDataPropagate (:388-395, :434-500)"""
         if self.isFinalIter or self.record is None:
             return
-        r = self.record
+        r = {k: v[:self.array_size] for k, v in self.record.items()}          # without the spare slot
         self.tree.splat_path_data(self.max_depth, Lfinal, r['throughputRadiance'], r['throughputBsdf'], r['bsdf'],
                                   r['position'], r['direction'], r['woPdf'], r['radiance_nee'], r['direction_nee'], r['active'])
 

@@ -121,4 +121,34 @@ def test_cornell_box_train_and_render_gpu():
     assert torch.isfinite(img).all()
     rel = float((img.mean((0, 1)) - gt.mean((0, 1))).abs().max() / gt.mean())
     assert rel < 0.05, rel                                   # unbiased up to noise: mean colour within 5 %
+    print("cornell 128x128 budget 64: final mse_groundTruth", res["records"][-1]["mse_groundTruth"], "mean colour error", rel)
     assert res["records"][-1]["mse_groundTruth"] < 0.05, res["records"][-1]
+
+
+def test_two_handles_on_two_devices():
+    """one handle per GPU in ONE process: the >48 KB shared-memory opt-in and the occupancy answer are per device, and every
+    entry point runs on its handle's device whatever device the caller has current (advisor finding, round 1)"""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    from practical_path_guiding_lab_b200 import SDTree
+    rec = cases.dyadic_records(20000, 5, ((0.3, 0.7, 0.02),))
+    trees = []
+    for dev in (0, 1):
+        t = SDTree(device=dev, kd_capacity=1 << 14, quad_capacity=1 << 18, store_nee=False)
+        torch.cuda.set_device(1 - dev)                 # the OTHER device is current while this handle works
+        d = lambda x: torch.from_numpy(np.ascontiguousarray(x)).to(f"cuda:{dev}")
+        for it in range(3):
+            t.splat_records(d(rec.position), d(rec.direction), d(rec.radiance), d(rec.woPdf))     # ~80 KB of dynamic shared memory
+            t.set_max_leaf_size(400)
+            t.refine()
+        trees.append(t)
+    a, b = trees[0].download(0), trees[1].download(0)
+    assert a['kdtree_depth'].shape[0] > 15
+    for k in a:
+        assert np.array_equal(np.asarray(a[k]), np.asarray(b[k])), k
+    pos = np.random.default_rng(1).random((4096, 3)).astype(np.float32)
+    torch.cuda.set_device(0)
+    d1, p1 = trees[1].sample(torch.from_numpy(pos).to("cuda:1"), seed=9)
+    d0, p0 = trees[0].sample(torch.from_numpy(pos).to("cuda:0"), seed=9)
+    assert cases.beq(d0.cpu().numpy(), d1.cpu().numpy()) and cases.beq(p0.cpu().numpy(), p1.cpu().numpy())

@@ -65,3 +65,40 @@ def test_two_rank_training_matches_single_rank(tmp_path):
         for k in one:
             a, b = np.asarray(one[k]), np.asarray(d[k])
             assert a.shape == b.shape and np.array_equal(a, b), (r, k)
+
+
+def _tile_worker(rank, world, port, lib, out_dir):
+    import torch
+    import torch.distributed as dist
+    sys.path.insert(0, ROOT)
+    from practical_path_guiding_lab_b200 import driver
+    from practical_path_guiding_lab_b200.cornell import CornellBox
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    ranks = driver.TorchDistRanks(tiles=True)
+    r = CornellBox(16, 16, max_depth=5, device="cpu", lib_path=lib, kd_capacity=1 << 12, quad_capacity=1 << 16)
+    r.set_tile(rank, world)
+    r.setup(sdTreeMaxDepth=8, quadTreeMaxDepth=6)
+    assert r.core.numRays == 128                      # half of the film per rank
+    res = driver.train_and_render(r, 28, seed=3, ranks=ranks)
+    np.savez(os.path.join(out_dir, f"tile_rank{rank}.npz"), image=res["image"].numpy(), **r.core.tree.download(0))
+    dist.destroy_process_group()
+
+
+def test_tile_sharded_driver_two_ranks(tmp_path):
+    """driver.TorchDistRanks(tiles=True): every rank renders its band of the film in every pass, one statistics exchange
+    per iteration -> the same tree on both ranks, and an image whose two halves both carry light"""
+    import torch.multiprocessing as mp
+    from hostemu.build_hostemu import build as build_hostemu
+    lib = build_hostemu()
+    port = 31500 + os.getpid() % 2000
+    mp.spawn(_tile_worker, args=(2, port, lib, str(tmp_path)), nprocs=2, join=True)
+    a = np.load(os.path.join(str(tmp_path), "tile_rank0.npz"))
+    b = np.load(os.path.join(str(tmp_path), "tile_rank1.npz"))
+    for k in a.files:
+        assert np.array_equal(a[k], b[k], equal_nan=True), k      # trees AND the all-reduced image
+    img = a["image"]
+    assert img.shape == (16, 16, 3) and np.isfinite(img).all()
+    assert img[:8].sum() > 0 and img[8:].sum() > 0
+    assert a["kdtree_depth"].shape[0] >= 1
