@@ -50,6 +50,7 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--tune", action="append", default=[], help="key=value passed to sdt_set_tuning (repeatable)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-numa-bind", action="store_true", help="do not pin the rank to its GPU's NUMA-local CPUs (e2e experiments)")
     ap.add_argument("--lib", default=None, help="path of an alternative build of libsdtree.so (kernel experiments)")
     return ap.parse_args()
 
@@ -192,6 +193,19 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+def bind_to_gpu_numa_node(index):
+    """pin this rank's threads to the CPUs NVML names as local to its GPU, BEFORE the pinned staging buffers are allocated
+    (first touch decides the NUMA node of pinned memory): a rank on the far socket pays the inter-socket link on every
+    H2D / D2H byte of the end-to-end leg.  -> (applied, cpus now allowed)"""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(index))
+        return True, len(os.sched_getaffinity(0))
+    except Exception:
+        return False, len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+
+
 # ------------------------------------------------------------------------------ B200 arm
 def run_b200(args):
     import torch
@@ -206,6 +220,7 @@ def run_b200(args):
         raise SystemExit("bench.py: no CUDA device (the product has no CPU fallback; use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa_bound, cpus_allowed = bind_to_gpu_numa_node(local) if not args.no_numa_bind else (False, len(os.sched_getaffinity(0)))
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     n = args.n
@@ -504,26 +519,39 @@ def run_b200(args):
         tree2.host_wait = False                         # SDT_NO_WAIT: the calls overlap, one synchronize per step
         dt_e2e = timed_host()
         tree2.host_wait = True
-        # what the link gives a plain pinned copy of the same size (context for the number above)
+        # what the link gives a plain pinned copy (context for the number above): this rank alone is not measurable under
+        # torchrun without serialising the ranks, so ALL ranks copy at the same time after a barrier -- the host fabric's
+        # ceiling at this GPU count (slowest rank and sum over ranks)
         big = torch.empty(256 << 20, dtype=torch.uint8).pin_memory()
         dbig = torch.empty_like(big, device=dev)
         dbig.copy_(big, non_blocking=True)
-        torch.cuda.synchronize()
+        barrier()
         t0 = time.perf_counter()
         for _ in range(4):
             dbig.copy_(big, non_blocking=True)
         torch.cuda.synchronize()
         h2d_gbs = 4 * big.numel() / (time.perf_counter() - t0) / 1e9
         del big, dbig
+        h2d_min, h2d_sum = h2d_gbs, h2d_gbs
+        if world > 1:
+            tt = torch.tensor([h2d_gbs], device=dev)
+            dist.all_reduce(tt, op=dist.ReduceOp.MIN)
+            h2d_min = float(tt.item())
+            tt = torch.tensor([h2d_gbs], device=dev)
+            dist.all_reduce(tt)
+            h2d_sum = float(tt.item())
         e2e = {"value": n * world / dt_e2e, "unit": UNIT, "ms_per_step": dt_e2e * 1e3,
                "h2d_bytes_per_step": n * (24 + 28), "d2h_bytes_per_step": n * (16 + 4),
-               "ms_per_step_waiting_calls": dt_wait * 1e3, "pinned_h2d_copy_gbs": h2d_gbs,
+               "ms_per_step_waiting_calls": dt_wait * 1e3, "pinned_h2d_copy_gbs": h2d_min, "pinned_h2d_copy_gbs_all_ranks": h2d_sum,
+               "h2d_gbs_in_step_all_ranks": n * world * (24 + 28) / dt_e2e / 1e9,
+               "numa_bound": numa_bound, "cpus_allowed_per_rank": cpus_allowed,
                "h2d_gbs_in_step": n * (24 + 28) / dt_e2e / 1e9,
                "how": "sdt_sample_pdf (positions cross the bus once for both queries) + sdt_splat_records with SDT_HOST_PTRS | SDT_NO_WAIT on pinned host arrays and one "
                       "sdt_synchronize per step (all outputs on the host); staging copies inside the calls.  "
                       "ms_per_step_waiting_calls: the same without SDT_NO_WAIT, every call returning with its outputs on the "
-                      "host; pinned_h2d_copy_gbs: a plain pinned H2D copy on this box -- the step is bound by the host link "
-                      "(h2d_gbs_in_step, with the D2H traffic beside it)"}
+                      "host; pinned_h2d_copy_gbs: a plain pinned H2D copy, all ranks copying at the same time (slowest rank; "
+                      "_all_ranks: their sum) -- the step is bound by the host link (h2d_gbs_in_step per rank / _all_ranks, with the "
+                      "D2H traffic beside it); numa_bound: the rank was pinned to its GPU's NUMA-local CPUs before the pinned buffers were allocated"}
 
     # ---- CPU port of the reference, timed beside it (rank 0, N=1)
     cpu = None
