@@ -531,9 +531,29 @@ def run_b200(args):
             dbig.copy_(big, non_blocking=True)
         torch.cuda.synchronize()
         h2d_gbs = 4 * big.numel() / (time.perf_counter() - t0) / 1e9
-        del big, dbig
+        # ... and the same H2D stream with the step's share of D2H traffic running against it on a second stream (the step
+        # moves 20 B back for every 52 B it sends): what the fabric gives the step's mix of directions
+        back = torch.empty(int(big.numel() * 20 / 52), dtype=torch.uint8).pin_memory()
+        dback = torch.empty_like(back, device=dev)
+        s2 = torch.cuda.Stream(device=dev)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(4):
+            dbig.copy_(big, non_blocking=True)
+            with torch.cuda.stream(s2):
+                back.copy_(dback, non_blocking=True)
+        torch.cuda.synchronize()
+        h2d_bidir_gbs = 4 * big.numel() / (time.perf_counter() - t0) / 1e9
+        del big, dbig, back, dback
         h2d_min, h2d_sum = h2d_gbs, h2d_gbs
+        bidir_min, bidir_sum = h2d_bidir_gbs, h2d_bidir_gbs
         if world > 1:
+            tt = torch.tensor([h2d_bidir_gbs], device=dev)
+            dist.all_reduce(tt, op=dist.ReduceOp.MIN)
+            bidir_min = float(tt.item())
+            tt = torch.tensor([h2d_bidir_gbs], device=dev)
+            dist.all_reduce(tt)
+            bidir_sum = float(tt.item())
             tt = torch.tensor([h2d_gbs], device=dev)
             dist.all_reduce(tt, op=dist.ReduceOp.MIN)
             h2d_min = float(tt.item())
@@ -543,6 +563,7 @@ def run_b200(args):
         e2e = {"value": n * world / dt_e2e, "unit": UNIT, "ms_per_step": dt_e2e * 1e3,
                "h2d_bytes_per_step": n * (24 + 28), "d2h_bytes_per_step": n * (16 + 4),
                "ms_per_step_waiting_calls": dt_wait * 1e3, "pinned_h2d_copy_gbs": h2d_min, "pinned_h2d_copy_gbs_all_ranks": h2d_sum,
+               "pinned_h2d_copy_gbs_with_d2h": bidir_min, "pinned_h2d_copy_gbs_with_d2h_all_ranks": bidir_sum,
                "h2d_gbs_in_step_all_ranks": n * world * (24 + 28) / dt_e2e / 1e9,
                "numa_bound": numa_bound, "cpus_allowed_per_rank": cpus_allowed,
                "h2d_gbs_in_step": n * (24 + 28) / dt_e2e / 1e9,
@@ -550,7 +571,7 @@ def run_b200(args):
                       "sdt_synchronize per step (all outputs on the host); staging copies inside the calls.  "
                       "ms_per_step_waiting_calls: the same without SDT_NO_WAIT, every call returning with its outputs on the "
                       "host; pinned_h2d_copy_gbs: a plain pinned H2D copy, all ranks copying at the same time (slowest rank; "
-                      "_all_ranks: their sum) -- the step is bound by the host link (h2d_gbs_in_step per rank / _all_ranks, with the "
+                      "_all_ranks: their sum; _with_d2h: the same with the step's 20:52 share of D2H bytes copied back on a second stream at the same time) -- the step is bound by the host link (h2d_gbs_in_step per rank / _all_ranks, with the "
                       "D2H traffic beside it); numa_bound: the rank was pinned to its GPU's NUMA-local CPUs before the pinned buffers were allocated"}
 
     # ---- CPU port of the reference, timed beside it (rank 0, N=1)

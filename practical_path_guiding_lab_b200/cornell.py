@@ -85,11 +85,14 @@ class CornellBox:
         self._pin = None
 
     def set_tile(self, rank, world):
-        """tile sharding (main.py:208-218 split by image tiles): this rank renders pixels [p0, p1) -- a band
-        of rows -- of EVERY pass; lanes keep globally unique RNG keys (generator seed and lane offset per rank)"""
+        """tile sharding (main.py:208-218 split by image tiles): from now on this rank renders pixels
+        [p0, p1) -- a band of rows -- of the passes it is given; lanes keep globally unique RNG keys (generator seed and
+        lane offset per tile).  The driver sets it per iteration (driver.shard_plan)."""
         P = self.W * self.H
         self.p0, self.p1 = rank * P // world, (rank + 1) * P // world
         self._rank = int(rank)
+        self.core.numRays = self.p1 - self.p0             # the per-pass record buffers follow the tile (resetRayPathData)
+        self.core.array_size = self.core.numRays * self.core.max_depth
 
     # ---- what main.py does before the loop (main.py:45-64) -----------------------------------
     def setup(self, sdTreeMaxDepth=20, quadTreeMaxDepth=20, isStoreNEERadiance=True, bsdfSamplingFraction=0.5):

@@ -26,9 +26,25 @@ def possible_cumm_spps(budget_spp):
     return out
 
 
+def shard_plan(passes, world, mode="auto"):
+    """-> (tiles_per_pass, groups): how `world` ranks share the `passes` render passes of one iteration.
+    Ranks form `groups` groups of `tiles_per_pass` ranks; pass p goes to group p % groups, and inside the group rank
+    r renders tile r % tiles_per_pass of the film.  auto: whole passes per rank while there are at least as many passes
+    as ranks (full-width wavefronts: the per-bounce host cost of a wavefront does not shrink with its width), film tiles
+    only in the early iterations that have fewer passes than ranks (4 and 8, main.py:170) so that no GPU idles."""
+    if mode == "passes" or world == 1:
+        return 1, world
+    if mode == "tiles":
+        return world, 1
+    t = 1
+    while passes * t < world and world % (2 * t) == 0:
+        t *= 2
+    return t, world // t
+
+
 class SingleRank:
     rank, world = 0, 1
-    tiles = False
+    mode = "passes"
 
     def sum_image(self, x):
         return x
@@ -38,18 +54,19 @@ class SingleRank:
 
 
 class TorchDistRanks:
-    """One process per GPU.  tiles=True (default): every rank renders ITS TILE of the film in every pass
-    (the renderer was given the tile with set_tile; seed = seed0 + cumm_spp exactly as in the sequential loop, lanes keep
-    globally unique RNG keys) -- the early iterations, which have only 4 and 8 passes (main.py:170,208-218), keep all GPUs
-    busy.  tiles=False: whole passes are dealt round-robin (pass p -> rank p % world).  Either way, at the end of the
-    iteration the statistics of `current` are combined with ONE sdt_allreduce (NCCL), the variance counters and the image
-    with torch.distributed, and every rank runs the same deterministic refine -> bit-identical trees without a broadcast."""
+    """One process per GPU.  The passes of an iteration (seed = seed0 + cumm_spp exactly as in the
+    sequential loop, main.py:208-218) are shared by image tiles and sample batches (shard_plan): mode "passes" deals whole
+    passes round-robin, "tiles" gives every rank its band of the film in every pass, "auto" (default) uses whole passes
+    and splits the film only while an iteration has fewer passes than there are ranks.  Lanes keep globally unique RNG
+    keys.  At the end of the iteration the statistics of `current` are combined with ONE sdt_allreduce (NCCL), the
+    variance counters and the image with torch.distributed, and every rank runs the same deterministic refine ->
+    bit-identical trees without a broadcast."""
 
-    def __init__(self, tiles=True):
+    def __init__(self, mode="auto", tiles=None):
         import torch.distributed as dist
         self.dist = dist
         self.rank, self.world = dist.get_rank(), dist.get_world_size()
-        self.tiles = bool(tiles)
+        self.mode = "tiles" if tiles else ("passes" if tiles is not None else mode)
 
     def sum_image(self, x):
         self.dist.all_reduce(x)
@@ -95,10 +112,15 @@ def train_and_render(renderer, budget_spp, seed=0, batch_spp=4, stable_variance_
         renderer.setIteration(it, is_final)
         spp_per_pass = batch_spp if is_final else 1                   # main.py:192-199
         passes = math.ceil(iter_spp / spp_per_pass)
+        tiles_per_pass, groups = shard_plan(passes, ranks.world, ranks.mode)
+        if ranks.world > 1 and hasattr(renderer, "set_tile"):
+            renderer.set_tile(ranks.rank % tiles_per_pass, tiles_per_pass)
+        elif tiles_per_pass > 1:
+            raise RuntimeError("this renderer cannot render film tiles: use shard mode 'passes'")
         done = 0
         for p_i in range(passes):
             s = min(spp_per_pass, iter_spp - done)
-            if ranks.tiles or p_i % ranks.world == ranks.rank:
+            if p_i % groups == ranks.rank // tiles_per_pass:
                 one = renderer.render(s, seed + cumm_spp)              # main.py:218
                 w = one * float(s / iter_spp)
                 curr = w if curr is None else curr + w
@@ -237,7 +259,8 @@ def main(argv=None):
     ap.add_argument("--out", default=None)
     ap.add_argument("--ground-truth", default=None, help=".npy (H,W,3) linear RGB")
     ap.add_argument("--no-guiding", action="store_true", help="BSDF-only baseline: never refine (tree stays a single leaf)")
-    ap.add_argument("--shard", default="tiles", choices=["tiles", "passes"], help="multi-GPU work split: film tiles within every pass, or whole passes")
+    ap.add_argument("--shard", default="auto", choices=["auto", "tiles", "passes"],
+                    help="multi-GPU work split: whole passes, film tiles within every pass, or (auto) tiles only while an iteration has fewer passes than ranks")
     ap.add_argument("--record-in-iteration", action="store_true", help="variance / MSE after every pass (main.py isRecordPerformanceInIteration; one GPU)")
     a = ap.parse_args(argv)
     from .cornell import CornellBox
@@ -248,10 +271,8 @@ def main(argv=None):
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-        ranks = TorchDistRanks(tiles=a.shard == "tiles")
+        ranks = TorchDistRanks(mode=a.shard)
     r = CornellBox(a.res, a.res, max_depth=a.max_depth, device=f"cuda:{local}")
-    if ranks is not None and ranks.tiles:
-        r.set_tile(ranks.rank, ranks.world)
     r.setup()
     if ranks is not None:
         r.comm_init(ranks.dist)

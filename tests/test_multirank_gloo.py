@@ -76,12 +76,11 @@ def _tile_worker(rank, world, port, lib, out_dir):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
-    ranks = driver.TorchDistRanks(tiles=True)
+    ranks = driver.TorchDistRanks(mode="tiles")
     r = CornellBox(16, 16, max_depth=5, device="cpu", lib_path=lib, kd_capacity=1 << 12, quad_capacity=1 << 16)
-    r.set_tile(rank, world)
     r.setup(sdTreeMaxDepth=8, quadTreeMaxDepth=6)
-    assert r.core.numRays == 128                      # half of the film per rank
     res = driver.train_and_render(r, 28, seed=3, ranks=ranks)
+    assert r.core.numRays == 128                      # half of the film per rank
     np.savez(os.path.join(out_dir, f"tile_rank{rank}.npz"), image=res["image"].numpy(), **r.core.tree.download(0))
     dist.destroy_process_group()
 
@@ -102,3 +101,25 @@ def test_tile_sharded_driver_two_ranks(tmp_path):
     assert img.shape == (16, 16, 3) and np.isfinite(img).all()
     assert img[:8].sum() > 0 and img[8:].sum() > 0
     assert a["kdtree_depth"].shape[0] >= 1
+
+
+def test_shard_plan_covers_every_pass_and_tile_once():
+    """driver.shard_plan: whole passes while an iteration has at least as many passes as ranks, film tiles below that"""
+    sys.path.insert(0, ROOT)
+    from practical_path_guiding_lab_b200 import driver
+    assert driver.shard_plan(4, 8) == (2, 4) and driver.shard_plan(8, 8) == (1, 8) and driver.shard_plan(256, 8) == (1, 8)
+    assert driver.shard_plan(4, 2) == (1, 2) and driver.shard_plan(1, 8) == (8, 1) and driver.shard_plan(4, 1) == (1, 1)
+    assert driver.shard_plan(4, 8, "tiles") == (8, 1) and driver.shard_plan(4, 8, "passes") == (1, 8)
+    for world in (1, 2, 4, 8):
+        for passes in (1, 2, 4, 8, 16, 128):
+            for mode in ("auto", "tiles", "passes"):
+                t, g = driver.shard_plan(passes, world, mode)
+                assert t * g == world
+                seen = {}
+                for rank in range(world):
+                    for p in range(passes):
+                        if p % g == rank // t:
+                            seen[(p, rank % t)] = seen.get((p, rank % t), 0) + 1
+                if mode != "passes" or passes >= 1:
+                    assert all(v == 1 for v in seen.values())
+                    assert len(seen) == passes * t, (world, passes, mode)
