@@ -8,11 +8,13 @@
 #include "sdt_core.h"
 
 #define SDT_SCAN_MAX_BLOCKS 1024
+// scratch of one scan: [0] ticket counter, [1] finished-blocks counter, then one 64-bit status word per block
+#define SDT_SCAN_STATE_WORDS (4 + 2 * SDT_SCAN_MAX_BLOCKS)
 
 struct ExecCtx {
     cudaStream_t st;
     int num_sms;
-    uint32_t* blk;        // SDT_SCAN_MAX_BLOCKS words of device scratch for the scans
+    uint32_t* blk;        // device scratch of the scans: SDT_SCAN_STATE_WORDS words, all zero between scans
     uint64_t* launches;   // kernel launch counter of the handle
     bool pdl;             // programmatic dependent launch for the helper kernels (see sdt_launch)
 };
@@ -100,39 +102,63 @@ __device__ __forceinline__ void sdt_chunk(uint32_t n, uint32_t& lo, uint32_t& hi
     hi = b < n ? (uint32_t)b : n;
 }
 
-template <class Flag>
-__global__ void __launch_bounds__(256) k_scan_reduce(Flag flag, const uint32_t* n_ptr, uint32_t n_imm, uint32_t* blk) {
+// Exclusive scan + emit + fin in ONE kernel (the refine is a chain of dependent launches, so a scan that costs one launch
+// instead of three shortens it by two launch latencies per level): single pass with decoupled look-back.  Blocks take
+// their chunk in the order they START (a ticket), so a block only ever waits for blocks that are already running -- no
+// co-residency assumption, safe under programmatic dependent launch.  Status word of a block: (kind << 32) | value with
+// kind 1 = its own total, 2 = inclusive prefix.  The last block to finish zeroes the scratch for the next scan.
+// Order of side effects: emit of every block may run BEFORE fin (fin runs on the block that holds the last chunk, after
+// its look-back); emit therefore must not depend on what fin writes.
+template <class Flag, class Emit, class Fin>
+__global__ void __launch_bounds__(256) k_scan_fused(Flag flag, Emit emit, Fin fin, const uint32_t* n_ptr, uint32_t n_imm, uint32_t* state) {
     __shared__ uint32_t ws[33];
+    __shared__ uint32_t s_b, s_prefix;
     sdt_grid_dep();
+    unsigned long long* status = reinterpret_cast<unsigned long long*>(state + 4);
+    if (threadIdx.x == 0) s_b = atomicAdd(state, 1u);
+    __syncthreads();
+    const uint32_t b = s_b;
     const uint32_t n = n_ptr ? *n_ptr : n_imm;
-    uint32_t lo, hi;
-    sdt_chunk(n, lo, hi);
+    uint32_t chunk = (n + gridDim.x - 1u) / gridDim.x;
+    chunk = (chunk + blockDim.x - 1u) / blockDim.x * blockDim.x;
+    const uint64_t a64 = (uint64_t)b * chunk, b64 = a64 + chunk;
+    const uint32_t lo = a64 < n ? (uint32_t)a64 : n, hi = b64 < n ? (uint32_t)b64 : n;
     uint32_t acc = 0;
     for (uint32_t i = lo + threadIdx.x; i < hi; i += blockDim.x) acc += flag(i);
-    uint32_t tot;
-    sdt_block_excl_scan(acc, ws, tot);
-    if (threadIdx.x == 0) blk[blockIdx.x] = tot;
-}
-
-template <class Fin>
-__global__ void __launch_bounds__(SDT_SCAN_MAX_BLOCKS) k_scan_blocks(uint32_t* blk, uint32_t nblk, Fin fin) {
-    __shared__ uint32_t ws[33];
-    sdt_grid_dep();
-    const uint32_t v = threadIdx.x < nblk ? blk[threadIdx.x] : 0u;
-    uint32_t tot;
-    const uint32_t ex = sdt_block_excl_scan(v, ws, tot);
-    if (threadIdx.x < nblk) blk[threadIdx.x] = ex;
-    if (threadIdx.x == 0) fin(tot);
-}
-
-template <class Flag, class Emit>
-__global__ void __launch_bounds__(256) k_scan_emit(Flag flag, Emit emit, const uint32_t* n_ptr, uint32_t n_imm, const uint32_t* blk) {
-    __shared__ uint32_t ws[33];
-    sdt_grid_dep();
-    const uint32_t n = n_ptr ? *n_ptr : n_imm;
-    uint32_t lo, hi;
-    sdt_chunk(n, lo, hi);
-    uint32_t carry = blk[blockIdx.x];
+    uint32_t total;
+    sdt_block_excl_scan(acc, ws, total);
+    if (threadIdx.x < 32u) {
+        const uint32_t lane = threadIdx.x;
+        if (lane == 0u) {
+            atomicExch(&status[b], ((unsigned long long)(b == 0u ? 2u : 1u) << 32) | total);
+        }
+        uint32_t prefix = 0;
+        if (b > 0u) {
+            int j = (int)b - 1;                       // look back, 32 predecessors at a time
+            for (;;) {
+                const int idx = j - (int)lane;
+                unsigned long long sv = 0;
+                if (idx >= 0) {
+                    do { sv = *reinterpret_cast<volatile unsigned long long*>(&status[idx]); } while ((sv >> 32) == 0ull);
+                } else sv = 2ull << 32;               // before the first block: an inclusive prefix of 0
+                const uint32_t kind = (uint32_t)(sv >> 32), val = (uint32_t)sv;
+                const uint32_t incl = __ballot_sync(0xFFFFFFFFu, kind == 2u);
+                // lanes up to and including the nearest inclusive prefix contribute
+                const uint32_t first = incl ? (uint32_t)__ffs(incl) - 1u : 32u;
+                uint32_t v = lane <= first ? val : 0u;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
+                prefix += v;
+                if (incl) break;
+                j -= 32;
+            }
+            if (lane == 0u) atomicExch(&status[b], (2ull << 32) | (unsigned long long)(prefix + total));
+        }
+        if (lane == 0u) s_prefix = prefix;
+    }
+    __syncthreads();
+    uint32_t carry = s_prefix;
+    if (threadIdx.x == 0 && b == gridDim.x - 1u) fin(carry + total);
     for (uint32_t base = lo; base < hi; base += blockDim.x) {
         const uint32_t i = base + threadIdx.x;
         const uint32_t v = i < hi ? flag(i) : 0u;
@@ -141,10 +167,21 @@ __global__ void __launch_bounds__(256) k_scan_emit(Flag flag, Emit emit, const u
         if (i < hi) emit(i, carry + ex, v);
         carry += tot;
     }
+    // the last block out resets the scratch (every block is past its look-back by then)
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        s_b = atomicAdd(state + 1, 1u);
+    }
+    __syncthreads();
+    if (s_b == gridDim.x - 1u) {
+        for (uint32_t k = threadIdx.x; k < 2u * gridDim.x; k += blockDim.x) state[4u + k] = 0u;
+        if (threadIdx.x == 0) { state[0] = 0u; state[1] = 0u; }
+    }
 }
 
-// for i < n: emit(i, sum_{j<i} flag(j), flag(i)); then fin(sum over all) on one thread.
-// flag must be pure and must not read anything emit writes.
+// for i < n: emit(i, sum_{j<i} flag(j), flag(i)); fin(sum over all) on one thread, possibly AFTER some emits.
+// flag must be pure and must not read anything emit or fin writes.
 template <class Flag, class Emit, class Fin>
 static inline void launch_scan(const ExecCtx& x, const uint32_t* n_ptr, uint32_t n_imm, Flag flag, Emit emit, Fin fin) {
     uint32_t grid = (uint32_t)x.num_sms * 4u;
@@ -153,10 +190,8 @@ static inline void launch_scan(const ExecCtx& x, const uint32_t* n_ptr, uint32_t
         const uint32_t g = (n_imm + 255u) / 256u;
         if (g < grid) grid = g ? g : 1u;
     }
-    sdt_launch(x, k_scan_reduce<Flag>, grid, 256u, flag, n_ptr, n_imm, x.blk);
-    sdt_launch(x, k_scan_blocks<Fin>, 1u, (uint32_t)SDT_SCAN_MAX_BLOCKS, x.blk, grid, fin);
-    sdt_launch(x, k_scan_emit<Flag, Emit>, grid, 256u, flag, emit, n_ptr, n_imm, (const uint32_t*)x.blk);
-    *x.launches += 3;
+    sdt_launch(x, k_scan_fused<Flag, Emit, Fin>, grid, 256u, flag, emit, fin, n_ptr, n_imm, x.blk);
+    *x.launches += 1;
 }
 
 template <class F>
@@ -178,16 +213,15 @@ static inline void launch_items(const ExecCtx& x, const uint32_t* n_ptr, uint32_
 template <class Flag, class Emit, class Fin>
 static inline void launch_scan(const ExecCtx& x, const uint32_t* n_ptr, uint32_t n_imm, Flag flag, Emit emit, Fin fin) {
     const uint32_t n = n_ptr ? *n_ptr : n_imm;
-    // like the device version: ranks from a first evaluation of flag, fin, then emit with
-    // flag evaluated AGAIN (fin may have changed what it reads, e.g. a capacity cut-off)
+    // like the device version: ranks from a first evaluation of flag, emit with flag evaluated AGAIN, and fin LAST (on
+    // the device fin runs on one block while others may already have emitted: emit must not depend on it)
     uint32_t run = 0;
     uint32_t* ranks = (uint32_t*)malloc(sizeof(uint32_t) * (n ? n : 1));
-    uint32_t* vals = (uint32_t*)malloc(sizeof(uint32_t) * (n ? n : 1));
-    for (uint32_t i = 0; i < n; ++i) { vals[i] = flag(i); ranks[i] = run; run += vals[i]; }
-    fin(run);
+    for (uint32_t i = 0; i < n; ++i) { ranks[i] = run; run += flag(i); }
     for (uint32_t i = 0; i < n; ++i) emit(i, ranks[i], flag(i));
-    free(ranks); free(vals);
-    *x.launches += 3;
+    fin(run);
+    free(ranks);
+    *x.launches += 1;
 }
 template <class F>
 static inline void launch_single(const ExecCtx& x, F f) { f(); ++*x.launches; }

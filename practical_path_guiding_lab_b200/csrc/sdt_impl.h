@@ -52,7 +52,9 @@ struct sdt_tree_s {
     uint8_t* s_srem = nullptr;
     uint32_t* s_blk = nullptr;
 
-    bool stats_complete = true;     // interior statistics of `current` are valid
+    bool stats_complete = true;     // interior quadtree energies of `current` are valid
+    bool kd_complete = true;        // interior spatial counts of `current` are valid
+    bool prev_kd_dirty = false;     // prev.vertCount holds leaf counts only (the refine rolled un-swept counts): sweep before showing them
     DevHeader* h_hdr = nullptr;     // pinned mirror
     cudaStream_t last_stream = nullptr;
     uint64_t launches = 0;

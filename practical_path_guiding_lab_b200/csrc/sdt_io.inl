@@ -78,7 +78,7 @@ extern "C" int sdt_create(const sdt_config* cfg, sdt_handle* out) {
     A(h->kd_bmin, 3ull * h->kd_cap); A(h->kd_bmax, 3ull * h->kd_cap); A(h->kd_prev_count, h->kd_cap); A(h->kd_s, h->kd_cap);
     A(h->kd_sel, h->kd_cap); A(h->kd_rank[0], h->kd_cap); A(h->kd_rank[1], h->kd_cap); A(h->root_src, h->kd_cap); A(h->kd_grid, SDT_GRID_CELLS);
     A(h->q_ecur, h->quad_cap); A(h->s_src, h->quad_cap); A(h->s_kind, h->quad_cap); A(h->s_srem, h->quad_cap);
-    A(h->s_blk, SDT_SCAN_MAX_BLOCKS + 64);
+    A(h->s_blk, SDT_SCAN_STATE_WORDS + 64);
     for (int k = 0; k < 2; ++k) {
         QuadSet& s = h->set[k];
         A(s.child, h->quad_cap); A(s.energy, h->quad_cap); A(s.thr, h->quad_cap); A(s.pp, h->quad_cap); A(s.iidx, h->quad_cap);
@@ -113,7 +113,7 @@ extern "C" int sdt_create(const sdt_config* cfg, sdt_handle* out) {
         cudaMemcpy(h->set[0].thr, &inf, 4, cudaMemcpyHostToDevice);
         cudaMemcpy(h->set[0].root_iidx, &none, 4, cudaMemcpyHostToDevice);
         if (cudaDeviceSynchronize() != cudaSuccess) st = sdt_fail(h, SDT_ERR_CUDA, "sdt_create: initialisation failed");
-        h->cur = 0; h->levels_hint = 1; h->stats_complete = true;
+        h->cur = 0; h->levels_hint = 1; h->stats_complete = true; h->kd_complete = true;
     }
     if (st != SDT_OK) { g_create_err = h->err; sdt_free_all(h); delete h; return st; }
     *out = h;
@@ -270,9 +270,10 @@ extern "C" int sdt_upload(sdt_handle h, const sdt_arrays* a) {
     SDT_TRY(sdt_post_launch(h, "sdt_upload"));
     SDT_CUDA(h, cudaStreamSynchronize(nullptr));
     h->levels_hint = nlev > 0 ? nlev : 1;
+    h->prev_kd_dirty = false;                      // the uploaded vertCount array is complete
     h->kd_nodes_known = nk;
     h->hdr_pending = false;
-    h->stats_complete = true;
+    h->stats_complete = true; h->kd_complete = true;
     { DevHeader H2; SDT_TRY(sdt_read_header(h, H2)); }      // jump_trees of the uploaded tree
     return SDT_OK;
 }
@@ -284,7 +285,7 @@ extern "C" int sdt_upload_stats(sdt_handle h, const float* q_irradiance, const f
     SDT_TRY(sdt_read_header(h, H));
     if (q_irradiance) SDT_CUDA(h, cudaMemcpy(h->q_ecur, q_irradiance, 4ull * H.n_quad, cudaMemcpyHostToDevice));
     if (kd_vert_count) SDT_CUDA(h, cudaMemcpy(h->kd_count, kd_vert_count, 4ull * H.n_kd, cudaMemcpyHostToDevice));
-    h->stats_complete = true;       // the caller's interior values are taken as they are
+    h->stats_complete = true; h->kd_complete = true;       // the caller's interior values are taken as they are
     return SDT_OK;
 }
 
@@ -294,6 +295,7 @@ extern "C" int sdt_download(sdt_handle h, int which, sdt_arrays* out) {
     SDT_ENTER(h);
     SDT_CHECK(h, which == SDT_TREE_PREV || which == SDT_TREE_CURRENT, SDT_ERR_INVALID, "sdt_download: which must be 0 or 1");
     if (which == SDT_TREE_CURRENT) SDT_TRY(sdt_complete_stats(h, h->last_stream));
+    else SDT_TRY(sdt_sweep_prev_counts(h, h->last_stream));
     DevHeader H;
     SDT_TRY(sdt_read_header(h, H));
     SDT_CHECK(h, out->n_kd >= H.n_kd && out->n_quad >= H.n_quad && out->n_roots >= H.n_roots, SDT_ERR_CAPACITY,
@@ -363,7 +365,7 @@ extern "C" int sdt_stat_buffers(sdt_handle h, float** q_energy, uint32_t* n_quad
     if (n_quad) *n_quad = H.n_quad;
     if (kd_count) *kd_count = h->kd_count;
     if (n_kd) *n_kd = H.n_kd;
-    h->stats_complete = false;      // the caller may reduce into the buffers: interiors are re-swept from the leaves
+    h->stats_complete = false; h->kd_complete = false;      // the caller may reduce into the buffers: interiors are re-swept from the leaves
     return SDT_OK;
 }
 
@@ -454,7 +456,7 @@ extern "C" int sdt_measure_gather(sdt_handle h, uint64_t bytes, uint32_t iters, 
     SDT_CUDA(h, cudaMemsetAsync(buf, 1, sectors * 32, st));
     constexpr int BATCH = 8;
     const int grid = h->num_sms * 4, block = 512;
-    uint32_t* sink = h->s_blk + SDT_SCAN_MAX_BLOCKS;
+    uint32_t* sink = h->s_blk + SDT_SCAN_STATE_WORDS;
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0); cudaEventCreate(&e1);
     auto run = [&](uint32_t n_it) {
@@ -495,9 +497,9 @@ extern "C" int sdt_measure_l2(sdt_handle h, uint64_t bytes, uint32_t passes, flo
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0); cudaEventCreate(&e1);
     const int grid = h->num_sms * 8;
-    k_l2_read<<<grid, 256, 0, st>>>(buf, n16, 2, h->s_blk + SDT_SCAN_MAX_BLOCKS);      // warm: pull the set into L2
+    k_l2_read<<<grid, 256, 0, st>>>(buf, n16, 2, h->s_blk + SDT_SCAN_STATE_WORDS);      // warm: pull the set into L2
     cudaEventRecord(e0, st);
-    k_l2_read<<<grid, 256, 0, st>>>(buf, n16, passes, h->s_blk + SDT_SCAN_MAX_BLOCKS);
+    k_l2_read<<<grid, 256, 0, st>>>(buf, n16, passes, h->s_blk + SDT_SCAN_STATE_WORDS);
     cudaEventRecord(e1, st);
     h->launches += 2;
     cudaError_t e = cudaEventSynchronize(e1);

@@ -82,7 +82,7 @@ extern "C" int sdt_allreduce(sdt_handle h, sdt_stream stream) {
     const int rc2 = g_nccl.group_end();
     if (rc != 0 || rc2 != 0) return sdt_nccl_fail(h, "ncclAllReduce", rc ? rc : rc2);
     h->last_stream = st;
-    h->stats_complete = false;                // interiors are recomputed from the reduced leaves
+    h->stats_complete = false; h->kd_complete = false;                // interiors are recomputed from the reduced leaves
     return SDT_OK;
 }
 #else

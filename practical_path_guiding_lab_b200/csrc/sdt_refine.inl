@@ -54,7 +54,9 @@ struct KdLevelsItem {       // s per original leaf (KDTree.refine's condition, :
         if (c.kd_word[i] & SDT_KD_LEAF_BIT) {
             const float T = c.H1->max_leaf_size;
             const uint32_t d = c.kd_depth[i], maxd = c.H1->kd_max_depth;
+            // a leaf counter fed by per-CTA partial sums can pass 2^24, where the reference's chain of "+1.0f" sticks
             float v = c.kd_count[i];
+            if (v > 16777216.0f) { v = 16777216.0f; c.kd_count[i] = v; }
             while (v > T && d + s < maxd) { if (v > 0.0f) v = v / 2.0f; ++s; }    // :261-264
         }
         c.kd_s[i] = (uint8_t)s;
@@ -64,7 +66,9 @@ struct RootIdentityItem { uint32_t* root_src; SDT_HD void operator()(uint32_t r)
 
 struct KdRoundFlag {
     RefineCtx c; uint32_t r;
-    SDT_HD uint32_t operator()(uint32_t i) const { return (!c.H1->kd_stop && c.kd_s[i] >= r) ? 1u : 0u; }
+    // kd_stop = the round whose nodes no longer fitted the arena (set by that round's own fin, which may run while
+    // blocks of the same scan still emit: only LATER rounds look at it)
+    SDT_HD uint32_t operator()(uint32_t i) const { return (!(c.H1->kd_stop && r > c.H1->kd_stop) && c.kd_s[i] >= r) ? 1u : 0u; }
 };
 struct KdRoundEmit {
     RefineCtx c;
@@ -78,7 +82,7 @@ struct KdRoundFin {
         DevHeader* H = c.H1;
         uint64_t splits = (uint64_t)total << (r - 1u);
         if ((uint64_t)H->n_kd + 2u * splits > H->kd_cap) {     // arena exhausted: stop splitting, flag it
-            if (total) { H->error |= DEV_ERR_KD_CAPACITY; H->kd_stop = 1; }
+            if (total) { H->error |= DEV_ERR_KD_CAPACITY; if (!H->kd_stop) H->kd_stop = r; }
             splits = 0; total = 0;
         }
         H->kd_sel = total;
@@ -183,18 +187,28 @@ SDT_HD QDecision sdt_q_decide(const RefineCtx& c, uint32_t id, uint32_t level) {
 struct QLevelFlag {
     RefineCtx c; uint32_t level; uint32_t last;   // last: deepest level the arena layout allows
     SDT_HD uint32_t operator()(uint32_t i) const {
-        if (c.H1->lvl_trunc || last) return 0u;
+        // lvl_trunc = 1 + the level whose children no longer fitted the arena: every deeper level is all leaves.  (It is
+        // written by that level's own fin, possibly while blocks of the same scan still emit: this level must not see it.)
+        if ((c.H1->lvl_trunc && level >= c.H1->lvl_trunc) || last) return 0u;
         return sdt_q_decide(c, c.H1->level_off[level] + i, level).nonleaf;
     }
 };
+// children of this level's non-leaf nodes that still fit the arena (the scan may run emit before fin, so both derive
+// the cut from the same numbers: a node whose four children would not fit becomes a leaf)
+SDT_HD uint32_t sdt_q_fit(const DevHeader* H, uint32_t level) {
+    const uint32_t next_off = H->level_off[level + 1u];
+    return next_off >= H->quad_cap ? 0u : (H->quad_cap - next_off) / 4u;
+}
 struct QLevelFin {
     RefineCtx c; uint32_t level;
     SDT_HD void operator()(uint32_t total) const {
         DevHeader* H = c.H1;
         const uint32_t next_off = H->level_off[level + 1u];
-        if ((uint64_t)next_off + 4ull * total > H->quad_cap) {   // arena exhausted: cut the forest here
-            if (total) { H->error |= DEV_ERR_QUAD_CAPACITY; H->lvl_trunc = 1; }
-            total = 0;
+        const uint32_t fit = sdt_q_fit(H, level);
+        if (total > fit) {                                        // arena exhausted: cut the forest here
+            H->error |= DEV_ERR_QUAD_CAPACITY;
+            if (!H->lvl_trunc) H->lvl_trunc = level + 1u;
+            total = fit;
         }
         H->level_cnt[level] = H->level_off[level + 1u] - H->level_off[level];
         H->level_off[level + 2u] = next_off + 4u * total;
@@ -206,7 +220,7 @@ struct QLevelEmit {
     SDT_HD void operator()(uint32_t i, uint32_t rank, uint32_t v) const {
         const DevHeader* H = c.H1;
         const uint32_t id = H->level_off[level] + i;
-        if (!v) { c.child1[id] = 0u; return; }
+        if (!v || rank >= sdt_q_fit(H, level)) { c.child1[id] = 0u; return; }
         const QDecision d = sdt_q_decide(c, id, level);
         const uint32_t cb = H->level_off[level + 1u] + 4u * rank;
         c.child1[id] = cb;
@@ -342,7 +356,7 @@ struct ZeroItem { float* p; SDT_HD void operator()(uint32_t i) const { p[i] = 0.
 
 // the launch sequence of one refine on stream `st` (sweeps of the statistics included when they are due)
 static int sdt_refine_enqueue(sdt_handle h, cudaStream_t st, uint32_t flags, uint32_t levels_bound) {
-    SDT_TRY(sdt_complete_stats(h, st));
+    SDT_TRY(sdt_complete_stats(h, st, false));
     const ExecCtx x = exec_ctx(h, st);
     QuadSet& s0 = h->set[h->cur];
     QuadSet& s1 = h->set[1 - h->cur];
@@ -426,11 +440,12 @@ extern "C" int sdt_refine(sdt_handle h, uint32_t flags, sdt_stream stream) {
 #else
     SDT_TRY(sdt_refine_enqueue(h, st, flags, levels_bound));
 #endif
+    h->prev_kd_dirty = !h->kd_complete;          // un-swept interior counts were rolled into prev
     h->cur = 1 - h->cur;
     h->jump_trees_known = 0;
     h->levels_known = 0;
     h->levels_hint = levels_bound;
-    h->stats_complete = true;
+    h->stats_complete = true; h->kd_complete = true;
     // non-blocking read-back of the new sizes (only used to size the smem staging of later launches)
     if (cudaMemcpyAsync(h->h_hdr, s1.hdr, sizeof(DevHeader), cudaMemcpyDeviceToHost, st) == cudaSuccess &&
         cudaEventRecord(h->hdr_event, st) == cudaSuccess) h->hdr_pending = true;
@@ -446,6 +461,6 @@ extern "C" int sdt_reset_stats(sdt_handle h, sdt_stream stream) {
     QuadSet& s = h->set[h->cur];
     launch_items(x, &s.hdr->n_kd, 0, ZeroItem{h->kd_count});
     launch_items(x, &s.hdr->n_quad, 0, ZeroItem{h->q_ecur});
-    h->stats_complete = true;
+    h->stats_complete = true; h->kd_complete = true;
     return sdt_post_launch(h, "sdt_reset_stats");
 }

@@ -188,17 +188,35 @@ struct KdSweepItem {
     }
 };
 
-static int sdt_complete_stats(sdt_handle h, cudaStream_t st) {
-    if (h->stats_complete) return SDT_OK;
+// interior statistics of `current` from its leaf statistics.  with_kd = false (the refine): only the quadtree energies --
+// the refine reads spatial counts of LEAVES only, so the 21 per-depth passes over the spatial tree are left to whoever
+// wants to SEE interior counts (a download of either tree; sdt_sweep_prev_counts for the counts the refine rolled into prev)
+static int sdt_complete_stats(sdt_handle h, cudaStream_t st, bool with_kd = true) {
+    if (h->stats_complete && (h->kd_complete || !with_kd)) return SDT_OK;
     const ExecCtx x = exec_ctx(h, st);
     const QuadSet& s = h->set[h->cur];
     // level sizes live on the device
-    for (int l = (int)h->levels_hint - 1; l >= 0; --l)
-        launch_items(x, &s.hdr->level_cnt[l], 0, QuadSweepItem{s.hdr, s.child, h->q_ecur, (uint32_t)l});
-    for (int d = h->cfg.kd_max_depth; d >= 0; --d)
-        launch_items(x, &s.hdr->n_kd, 0, KdSweepItem{h->kd_word, h->kd_depth, h->kd_count, (uint32_t)d});
+    if (!h->stats_complete)
+        for (int l = (int)h->levels_hint - 1; l >= 0; --l)
+            launch_items(x, &s.hdr->level_cnt[l], 0, QuadSweepItem{s.hdr, s.child, h->q_ecur, (uint32_t)l});
+    if (with_kd && !h->kd_complete) {
+        for (int d = h->cfg.kd_max_depth; d >= 0; --d)
+            launch_items(x, &s.hdr->n_kd, 0, KdSweepItem{h->kd_word, h->kd_depth, h->kd_count, (uint32_t)d});
+        h->kd_complete = true;
+    }
     SDT_TRY(sdt_post_launch(h, "sdt_complete_stats"));
     h->stats_complete = true;
+    return SDT_OK;
+}
+// prev.vertCount as the refine left it holds leaf counts only (see above): interiors on demand
+static int sdt_sweep_prev_counts(sdt_handle h, cudaStream_t st) {
+    if (!h->prev_kd_dirty) return SDT_OK;
+    const ExecCtx x = exec_ctx(h, st);
+    const QuadSet& s = h->set[h->cur];
+    for (int d = h->cfg.kd_max_depth; d >= 0; --d)
+        launch_items(x, &s.hdr->n_kd, 0, KdSweepItem{h->kd_word, h->kd_depth, h->kd_prev_count, (uint32_t)d});
+    SDT_TRY(sdt_post_launch(h, "sdt_sweep_prev_counts"));
+    h->prev_kd_dirty = false;
     return SDT_OK;
 }
 
@@ -209,7 +227,7 @@ extern "C" int sdt_splat_records(sdt_handle h, const sdt_records* rec, uint32_t 
     SDT_CHECK(h, rec && rec->position.x && rec->direction.x && rec->radiance && rec->wo_pdf, SDT_ERR_INVALID, "sdt_splat_records: missing field");
     cudaStream_t st = (cudaStream_t)stream;
     const bool nee = h->cfg.store_nee != 0;
-    h->stats_complete = false;
+    h->stats_complete = false; h->kd_complete = false;
     const size_t per_lane = 12 + 8 + 4 + 4 + (nee ? 20 : 0) + 1 + 8;
     return sdt_run_chunked(h, st, flags, n, per_lane, false, [&](Stager& sg, uint32_t off, uint32_t cnt) -> int {
         sdt_records d = *rec;
@@ -250,7 +268,7 @@ extern "C" int sdt_splat_path_data(sdt_handle h, const sdt_path_data* pd, uint32
     d.radiance_out = sg.out_t(pd->radiance_out, n);
     if (sg.status != SDT_OK) return sg.status;
     SplatPathLane f{tree_view(h), SplatTarget{h->kd_count, h->q_ecur, (uint32_t)(h->cfg.store_nee != 0)}, d};
-    h->stats_complete = false;
+    h->stats_complete = false; h->kd_complete = false;
     SDT_TRY(launch_wavefront(h, st, n, f, h->splat_block, h->splat_ctas_per_sm, pd->active != nullptr));
     return sg.finish(flags);
 }

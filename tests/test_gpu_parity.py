@@ -102,8 +102,10 @@ def test_large_wavefront_properties():
 def test_cornell_box_train_and_render_gpu():
     """config-1 shape on the GPU: the reference driver loop (iteration doubling, refine per
     iteration, guiding from iteration 2) on the analytic Cornell box, MSE against the reference's
-    own ground truth (TungstenRender.exr, box-downsampled fixture).  Stated bound: the 60-spp
-    image has per-pixel luminance MSE (clamped like computeMSE) below 0.05 at 128x128."""
+    own ground truth (TungstenRender.exr, box-downsampled fixture).  Stated bound: the final image of the
+    64-spp budget has per-pixel luminance MSE (clamped like computeMSE) below 2e-3 at 128x128 -- 2.6x the
+    7.7e-4 measured on the B200 (seed 3; the noise of 36 blended samples per pixel) -- and a mean colour within
+    2 % of the ground truth's (measured 0.35 %): a biased estimator (a wrong mixture pdf or MIS weight) fails both."""
     import torch
     from practical_path_guiding_lab_b200 import driver
     from practical_path_guiding_lab_b200.build import build
@@ -120,9 +122,9 @@ def test_cornell_box_train_and_render_gpu():
     img = res["image"]
     assert torch.isfinite(img).all()
     rel = float((img.mean((0, 1)) - gt.mean((0, 1))).abs().max() / gt.mean())
-    assert rel < 0.05, rel                                   # unbiased up to noise: mean colour within 5 %
+    assert rel < 0.02, rel                                   # unbiased up to noise
     print("cornell 128x128 budget 64: final mse_groundTruth", res["records"][-1]["mse_groundTruth"], "mean colour error", rel)
-    assert res["records"][-1]["mse_groundTruth"] < 0.05, res["records"][-1]
+    assert res["records"][-1]["mse_groundTruth"] < 2e-3, res["records"][-1]
 
 
 def test_two_handles_on_two_devices():
