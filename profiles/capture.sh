@@ -16,4 +16,4 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --csv --log-fi
 # 6 tree-build splats + 3 warm-up steps x 2 kernels precede the timed steps: skip 12, capture the step's two launches
 # (fused sample + pdf, splat); the separate sample / pdf kernels are captured by name from their own timing loop
 ncu --set full --clock-control none --import-source on -k regex:k_wavefront -s 12 -c 2 -o $OUT/prof_${TAG} $B > $OUT/${TAG}_ncu2.log 2>&1; echo "ncu full (step) rc=$?"
-ncu --set full --clock-control none --import-source on -k "regex:k_wavefront<(SampleLane|PdfLane)" -c 2 -o $OUT/prof_${TAG}_sep $B > $OUT/${TAG}_ncu3.log 2>&1; echo "ncu full (separate) rc=$?"
+ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k "regex:k_wavefront<(SampleLane<|PdfLane,)" -c 2 -o $OUT/prof_${TAG}_sep $B > $OUT/${TAG}_ncu3.log 2>&1; echo "ncu full (separate) rc=$?"

@@ -7,9 +7,16 @@ import csv
 import json
 import sys
 
+import os
+
 tag = sys.argv[1]
 rows = list(csv.reader(open(f'profiles/{tag}_ncu_full_wavefront_raw.csv')))
 hdr, units = rows[0], rows[1]
+sep = f'profiles/{tag}_ncu_full_separate_raw.csv'          # the separate sample / pdf kernels (same columns)
+if os.path.exists(sep):
+    extra = list(csv.reader(open(sep)))
+    assert extra[0] == hdr
+    rows += extra[2:]
 
 
 def val(r, k):
@@ -34,7 +41,9 @@ for r in rows[2:]:
                  num(r, 'smsp__thread_inst_executed_per_inst_executed.ratio'), num(r, 'lts__t_sector_hit_rate.pct'),
                  num(r, 'l1tex__t_sector_hit_rate.pct'), num(r, 'lts__throughput.avg.pct_of_peak_sustained_elapsed'),
                  num(r, 'gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed'), num(r, 'sm__warps_active.avg.pct_of_peak_sustained_active'),
-                 num(r, 'launch__registers_per_thread'), val(r, 'dram__bytes_read.sum') + val(r, 'dram__bytes_write.sum')))
+                 num(r, 'launch__registers_per_thread'), val(r, 'dram__bytes_read.sum') + val(r, 'dram__bytes_write.sum'),
+                 num(r, 'l1tex__m_l1tex2xbar_req_cycles_active.avg.pct_of_peak_sustained_elapsed') if 'l1tex__m_l1tex2xbar_req_cycles_active.avg.pct_of_peak_sustained_elapsed' in hdr else float('nan'),
+                 num(r, 'l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed') if 'l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed' in hdr else float('nan')))
 json.dump(out, open('profiles/traffic.json', 'w'), indent=1)
 
 lines = [l for l in open(f'profiles/{tag}_launches_bench_steps2.csv') if not l.startswith('==')]
@@ -50,16 +59,18 @@ for row in csv.DictReader(lines):
     agg[row['Kernel Name']][1] += v
     seq.append((row['Kernel Name'], v))
 wf = [(n, v) for n, v in seq if 'k_wavefront' in n and 'Locate' not in n]
-steps = [wf[i:i + 3] for i in range(len(wf) - 2) if 'SampleLane' in wf[i][0] and 'PdfLane' in wf[i + 1][0] and 'Splat' in wf[i + 2][0]]
+steps = [wf[i:i + 2] for i in range(len(wf) - 1) if 'SamplePdfLane' in wf[i][0] and 'SplatRecords' in wf[i + 1][0]]
 st = steps[4] if len(steps) > 4 else steps[-1]
 tot = sum(v for _, v in st)
 with open(f'profiles/{tag}_summary.md', 'w') as f:
     f.write(f"# Profile summary {tag} (B200, bench.py config: 16 Mi vertices per launch, tree 8193 spatial nodes / 1.62 M quadtree nodes)\n\n")
     f.write(f"Source files: `{tag}_ncu_full_wavefront_raw.csv` (ncu --set full --clock-control none, one launch of each wavefront kernel), "
             f"`{tag}_launches_bench_steps2.csv` (gpu__time_duration.sum of every launch of `bench.py --steps 2 --warmup 3`), `{tag}_bench_n1.json` (the plain bench line).\n\n")
-    f.write("| kernel | ncu time ms | warp instr | issue active % | threads/instr | L2 hit % | L1 hit % | L2 throughput % | DRAM throughput % | warps active % | regs | DRAM bytes |\n|---|---|---|---|---|---|---|---|---|---|---|---|\n")
+    f.write("| kernel | ncu time ms | warp instr | issue active % | threads/instr | L2 hit % | L1 hit % | L2 throughput % | DRAM throughput % | warps active % | regs | DRAM bytes | L1->L2 request port busy % | LSU data pipe % |\n|---|---|---|---|---|---|---|---|---|---|---|---|---|---|\n")
     for s_ in summ:
-        f.write(f"| k_wavefront<{s_[0]}> | {s_[1]:.3f} | {s_[2]:.3e} | {s_[3]:.1f} | {s_[4]:.1f} | {s_[5]:.1f} | {s_[6]:.1f} | {s_[7]:.1f} | {s_[8]:.1f} | {s_[9]:.1f} | {int(s_[10])} | {s_[11] / 1e6:.0f} MB |\n")
+        f.write(f"| k_wavefront<{s_[0]}> | {s_[1]:.3f} | {s_[2]:.3e} | {s_[3]:.1f} | {s_[4]:.1f} | {s_[5]:.1f} | {s_[6]:.1f} | {s_[7]:.1f} | {s_[8]:.1f} | {s_[9]:.1f} | {int(s_[10])} | {s_[11] / 1e6:.0f} MB | {s_[12]:.1f} | {s_[13]:.1f} |\n")
+    f.write("\n(L1->L2 request port = `l1tex__m_l1tex2xbar_req_cycles_active`: one slot per 32 B sector a lane asks for -- the unit the per-lane descents saturate first; "
+            "`bench.py`'s `roofline.request_roof` measures the same against the random-sector gather probe.)\n")
     f.write("\nTensor pipes: idle by design (nothing on this path is a dense contraction).\n\n")
     f.write("Share of one step in the serialised launch list (cold-cache, per ncu): " +
             ", ".join(f"{n.split('<')[1].split('>')[0].split('<')[0].split(',')[0]} {v:.0f} us ({v / tot * 100:.0f} %)" for n, v in st) +
@@ -67,6 +78,6 @@ with open(f'profiles/{tag}_summary.md', 'w') as f:
     ref = sum(v for n, (c, v) in agg.items() if 'k_wavefront' not in n and 'k_l2_read' not in n)
     cnt = sum(c for n, (c, v) in agg.items() if 'k_wavefront' not in n and 'k_l2_read' not in n)
     f.write(f"Refine + sweeps (all `k_scan_*`, `k_items<...>`, `k_single<...>` launches): {cnt} launches, {ref / 1e3:.2f} ms of kernel time over the 7 refines "
-            f"of the bench run (6 tree-build iterations + 1 timed), ~{ref / 7 / 1e3:.2f} ms each when serialised by ncu; the wall time of one refine is `per_iteration.refine_ms` of the bench line "
-            f"({json.load(open(f'profiles/{tag}_bench_n1.json'))['per_iteration']['refine_ms']:.2f} ms: launch-latency bound, the helper kernels overlap their launches by programmatic dependent launch).\n")
+            f"of the bench run (tree-build iterations + timed ones), serialised by ncu; the wall time of one refine is `per_iteration.refine_ms` of the bench line "
+            f"({json.load(open(f'profiles/{tag}_bench_n1.json'))['per_iteration']['refine_ms']:.2f} ms: a chain of dependent launches whose latencies overlap by programmatic dependent launch).\n")
 print(open(f'profiles/{tag}_summary.md').read())
