@@ -12,7 +12,6 @@ $TR bench.py --gpus $N > $OUT/${TAG}_bench_n$N.log 2>&1; echo "bench n=$N rc=$?"
 $TR bench.py --gpus $N --impl reference --steps 3 --warmup 1 > $OUT/${TAG}_bench_ref_n$N.log 2>&1; echo "reference arm n=$N rc=$?"
 G=tests/golden/cornell_box_tungsten_256.npy
 D="-m practical_path_guiding_lab_b200.driver --res 1024 --budget 1020 --max-depth 13 --ground-truth $G"
-$TR $D --shard tiles > $OUT/${TAG}_cornell1024_tiles_n$N.log 2>&1; echo "cornell tiles n=$N rc=$?"; tail -1 $OUT/${TAG}_cornell1024_tiles_n$N.log | cut -c1-300
-if [ "$N" = "8" ]; then
-  $TR $D --shard passes > $OUT/${TAG}_cornell1024_passes_n$N.log 2>&1; echo "cornell passes n=$N rc=$?"; tail -1 $OUT/${TAG}_cornell1024_passes_n$N.log | cut -c1-300
-fi
+for SH in ${SHARDS:-auto}; do
+  $TR $D --shard $SH > $OUT/${TAG}_cornell1024_${SH}_n$N.log 2>&1; echo "cornell $SH n=$N rc=$?"; tail -1 $OUT/${TAG}_cornell1024_${SH}_n$N.log | cut -c1-200
+done
