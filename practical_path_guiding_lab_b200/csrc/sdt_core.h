@@ -27,6 +27,10 @@
 #define SDT_SAMPLE_GRID true       // sampling kernels use the spatial grid even when the whole tree is staged (measured: sample -5 %)
 #endif
 
+#ifndef SDT_L1_HINTS
+#define SDT_L1_HINTS 1             // L1 cache hints on the sampler's record loads (sdt_load_rec)
+#endif
+
 #define SDT_MAX_LEVELS 34          // quadtree levels 0..33 (QuadTree.maxDepth <= 32)
 #define SDT_KD_MAX_DEPTH 40        // KDTree.maxDepth upper bound
 #define SDT_KD_LEAF_BIT 0x80000000u
@@ -422,12 +426,27 @@ SDT_HD QHead sdt_load_head(const QRec* __restrict__ rec, uint32_t i) {
 }
 // the whole 32-byte record with ONE load instruction (sm_100 256-bit global load): for a
 // divergent gather the L1 tag stage is charged per instruction and lane, so one LDG.256
-// costs half of two LDG.128 on the same sector
+// costs half of two LDG.128 on the same sector.
+// HINT: 0 = plain, 1 = keep in L1 (evict last), 2 = do not allocate in L1.  The sampler loads the ROOT record of a
+// quadtree with 1 and every deeper record with 2: the root records of the forest (32 B x trees = 131 KB on the config-2
+// tree) are the only level small enough to live in an SM's L1 next to the staged spatial tree, the deeper ones are
+// never re-used before they are evicted and only push the roots out.  Every L1 hit is one slot less on the L1 -> L2
+// request port the sampling kernels are bound by (measured: sample 0.651 -> 0.623 ms, fused query 0.745 -> 0.724 ms;
+// also tried: two levels kept, the leaf's path product / the jump tables / the pdf and splat record loads not
+// allocated -- each slower, the last by 7 % on the splat, which does re-use them).
+template <int HINT = 0>
 SDT_HD void sdt_load_rec(const QRec* __restrict__ rec, uint32_t i, QHead& h, SdtF4& e) {
 #if defined(__CUDA_ARCH__)
     uint32_t a, b, c, d;
-    asm("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-        : "=r"(a), "=r"(b), "=r"(c), "=r"(d), "=f"(e.x), "=f"(e.y), "=f"(e.z), "=f"(e.w) : "l"(rec + i));
+    if (HINT == 1 && SDT_L1_HINTS)
+        asm("ld.global.nc.L1::evict_last.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+            : "=r"(a), "=r"(b), "=r"(c), "=r"(d), "=f"(e.x), "=f"(e.y), "=f"(e.z), "=f"(e.w) : "l"(rec + i));
+    else if (HINT == 2 && SDT_L1_HINTS)
+        asm("ld.global.nc.L1::no_allocate.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+            : "=r"(a), "=r"(b), "=r"(c), "=r"(d), "=f"(e.x), "=f"(e.y), "=f"(e.z), "=f"(e.w) : "l"(rec + i));
+    else
+        asm("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+            : "=r"(a), "=r"(b), "=r"(c), "=r"(d), "=f"(e.x), "=f"(e.y), "=f"(e.z), "=f"(e.w) : "l"(rec + i));
     h.child_base = a; h.interior_base = b; h.cinfo = c; h.own = __uint_as_float(d);
 #else
     h.child_base = rec[i].child_base; h.interior_base = rec[i].interior_base; h.cinfo = rec[i].cinfo; h.own = rec[i].own;
@@ -683,7 +702,8 @@ SDT_HD QSample sdt_quad_sample(const QRec* __restrict__ rec, uint32_t ri, uint32
         bool literal = false;
         for (;;) {
             QHead h; SdtF4 e;
-            sdt_load_rec(rec, ri, h, e);
+            if (level == 0u) sdt_load_rec<1>(rec, ri, h, e);             // the root record: keep it in L1
+            else sdt_load_rec<2>(rec, ri, h, e);                         // deeper records: do not displace the roots
             const float e1 = e.x;
             const float e2 = e.y + e1;                                   // :975-977
             const float e3 = e.z + e2;
