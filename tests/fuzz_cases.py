@@ -153,6 +153,10 @@ def _queries(ctx, t, prev, rng, lo, hi, n=1500):
     opp, opdbg = prev.pdf(pos, dirs, active, return_debug=True)
     assert np.array_equal(ctx.host(pdbg).view(U)[active, 2], opdbg['pdf_node'][active])
     assert cases.beq(ctx.host(pp), opp)
+    # the same pdf through the path-product jump table (no debug output), and sample + pdf fused into one call
+    assert cases.beq(ctx.host(t.pdf(ctx.dev(pos), ctx.dev(dirs), ctx.dev(a8))), opp)
+    fd, fp, fq = t.sample_pdf(ctx.dev(pos), ctx.dev(dirs), ctx.dev(a8), seed=99, lane_offset=3)
+    assert cases.beq(ctx.host(fd), od2) and cases.beq(ctx.host(fp), op2) and cases.beq(ctx.host(fq), opp)
 
 
 def _salt(rng, a, frac=0.02):
