@@ -54,6 +54,13 @@ struct sdt_tree_s {
 
     bool stats_complete = true;     // interior quadtree energies of `current` are valid
     bool kd_complete = true;        // interior spatial counts of `current` are valid
+    // upper bound of the records splatted into `current` since its statistics were last zero, and the host's copy of
+    // KDTree.maxLeafSize: together they bound the number of split rounds the next refine can need (no leaf count exceeds
+    // the number of records), so the rounds nobody can reach are not launched.  Invalid (all rounds run) once statistics
+    // come from elsewhere: an all-reduce, sdt_upload_stats, a caller writing through sdt_stat_buffers.
+    uint64_t splat_bound = 0;
+    bool splat_bound_valid = true;
+    float max_leaf_host = 1.0f;
     bool prev_kd_dirty = false;     // prev.vertCount holds leaf counts only (the refine rolled un-swept counts): sweep before showing them
     DevHeader* h_hdr = nullptr;     // pinned mirror
     cudaStream_t last_stream = nullptr;
@@ -104,7 +111,7 @@ struct sdt_tree_s {
     uint32_t dev_error_seen = 0;    // DevHeader.error as last read back (sticky device-side flag, see sdt_get_sizes)
 
     // the refine's launch sequence, captured once per (buffer parity, flags, level bounds, settings) and replayed as one graph
-    typedef std::tuple<int, uint32_t, uint32_t, uint32_t, int, int, int, int> RefineKey;
+    typedef std::tuple<int, uint32_t, uint32_t, uint32_t, int, int, int, int, uint32_t> RefineKey;
 #ifndef SDT_HOSTEMU
     struct RefineGraph { cudaGraphExec_t exec = nullptr; uint64_t launches = 0; };
     std::map<RefineKey, RefineGraph> refine_graphs;

@@ -271,6 +271,7 @@ extern "C" int sdt_upload(sdt_handle h, const sdt_arrays* a) {
     SDT_CUDA(h, cudaStreamSynchronize(nullptr));
     h->levels_hint = nlev > 0 ? nlev : 1;
     h->prev_kd_dirty = false;                      // the uploaded vertCount array is complete
+    h->splat_bound = 0; h->splat_bound_valid = true; h->max_leaf_host = a->kd_max_leaf_size;
     h->kd_nodes_known = nk;
     h->hdr_pending = false;
     h->stats_complete = true; h->kd_complete = true;
@@ -286,6 +287,7 @@ extern "C" int sdt_upload_stats(sdt_handle h, const float* q_irradiance, const f
     if (q_irradiance) SDT_CUDA(h, cudaMemcpy(h->q_ecur, q_irradiance, 4ull * H.n_quad, cudaMemcpyHostToDevice));
     if (kd_vert_count) SDT_CUDA(h, cudaMemcpy(h->kd_count, kd_vert_count, 4ull * H.n_kd, cudaMemcpyHostToDevice));
     h->stats_complete = true; h->kd_complete = true;       // the caller's interior values are taken as they are
+    h->splat_bound_valid = false;
     return SDT_OK;
 }
 
@@ -347,6 +349,7 @@ extern "C" int sdt_download(sdt_handle h, int which, sdt_arrays* out) {
 // ---------------------------------------------------------------------------- thresholds
 extern "C" int sdt_set_max_leaf_size(sdt_handle h, float max_leaf_size) {
     SDT_ENTER(h);
+    h->max_leaf_host = max_leaf_size;
     launch_single(exec_ctx(h, h->last_stream), SetLeafSize{h->set[h->cur].hdr, max_leaf_size});
     return sdt_post_launch(h, "sdt_set_max_leaf_size");
 }
@@ -366,6 +369,7 @@ extern "C" int sdt_stat_buffers(sdt_handle h, float** q_energy, uint32_t* n_quad
     if (kd_count) *kd_count = h->kd_count;
     if (n_kd) *n_kd = H.n_kd;
     h->stats_complete = false; h->kd_complete = false;      // the caller may reduce into the buffers: interiors are re-swept from the leaves
+    h->splat_bound_valid = false;
     return SDT_OK;
 }
 

@@ -83,6 +83,7 @@ extern "C" int sdt_allreduce(sdt_handle h, sdt_stream stream) {
     if (rc != 0 || rc2 != 0) return sdt_nccl_fail(h, "ncclAllReduce", rc ? rc : rc2);
     h->last_stream = st;
     h->stats_complete = false; h->kd_complete = false;                // interiors are recomputed from the reduced leaves
+    h->splat_bound_valid = false;                                     // counts of other ranks' records arrived
     return SDT_OK;
 }
 #else

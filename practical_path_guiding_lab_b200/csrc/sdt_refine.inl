@@ -355,7 +355,19 @@ struct KdRollItem {         // prev.vertCount <- current.vertCount; current <- 0
 struct ZeroItem { float* p; SDT_HD void operator()(uint32_t i) const { p[i] = 0.0f; } };
 
 // the launch sequence of one refine on stream `st` (sweeps of the statistics included when they are due)
-static int sdt_refine_enqueue(sdt_handle h, cudaStream_t st, uint32_t flags, uint32_t levels_bound) {
+// split rounds the next refine can need at most (see sdt_tree_s::splat_bound): KDTree.refine's own loop (:346-347, :261-264)
+// run on the largest count any leaf can hold
+static uint32_t sdt_kd_rounds_bound(sdt_handle h) {
+    const uint32_t maxd = (uint32_t)h->cfg.kd_max_depth;
+    if (!h->splat_bound_valid) return maxd;
+    float v = h->splat_bound > 16777216ull ? 16777216.0f : (float)h->splat_bound;
+    const float T = h->max_leaf_host;
+    uint32_t s = 0;
+    while (v > T && s < maxd) { if (v > 0.0f) v = v / 2.0f; ++s; }
+    return s;
+}
+
+static int sdt_refine_enqueue(sdt_handle h, cudaStream_t st, uint32_t flags, uint32_t levels_bound, uint32_t kd_rounds) {
     SDT_TRY(sdt_complete_stats(h, st, false));
     const ExecCtx x = exec_ctx(h, st);
     QuadSet& s0 = h->set[h->cur];
@@ -375,7 +387,7 @@ static int sdt_refine_enqueue(sdt_handle h, cudaStream_t st, uint32_t flags, uin
     launch_items(x, &c.H1->n_roots_old, 0, RootIdentityItem{h->root_src});
     if (!(flags & SDT_REFINE_NO_KD)) {
         launch_items(x, &c.H1->kd_n_old, 0, KdLevelsItem{c});
-        for (uint32_t r = 1; r <= (uint32_t)h->cfg.kd_max_depth; ++r) {
+        for (uint32_t r = 1; r <= kd_rounds; ++r) {
             RefineCtx cr = c;
             cr.kd_rank_cur = h->kd_rank[r & 1u]; cr.kd_rank_prev = h->kd_rank[(r & 1u) ^ 1u];
             launch_scan(x, &c.H1->kd_n_old, 0, KdRoundFlag{cr, r}, KdRoundEmit{cr}, KdRoundFin{cr, r});
@@ -403,6 +415,7 @@ extern "C" int sdt_refine(sdt_handle h, uint32_t flags, sdt_stream stream) {
     if (levels_bound < h->levels_hint) levels_bound = h->levels_hint;
     if (levels_bound > SDT_MAX_LEVELS) levels_bound = SDT_MAX_LEVELS;
     QuadSet& s1 = h->set[1 - h->cur];
+    const uint32_t kd_rounds = sdt_kd_rounds_bound(h);
 #ifndef SDT_HOSTEMU
     // The sequence is ~200 tiny dependent kernels whose arguments only depend on the buffer parity and a few settings:
     // it is captured once per such combination into a CUDA graph (programmatic-dependent-launch edges included) and
@@ -410,7 +423,7 @@ extern "C" int sdt_refine(sdt_handle h, uint32_t flags, sdt_stream stream) {
     bool done = false;
     if (h->use_graph) {
         const sdt_tree_s::RefineKey key{h->cur, flags & (SDT_REFINE_NO_KD | SDT_REFINE_NO_QUAD), h->levels_hint, levels_bound,
-                                        h->cfg.kd_max_depth, h->quad_thr_reciprocal, h->use_pdl, h->stats_complete ? 1 : 0};
+                                        (int)kd_rounds, h->quad_thr_reciprocal, h->use_pdl, h->stats_complete ? 1 : 0, sdt_sweep_levels(h)};
         auto it = h->refine_graphs.find(key);
         if (it == h->refine_graphs.end()) {
             sdt_tree_s::RefineGraph g;
@@ -418,7 +431,7 @@ extern "C" int sdt_refine(sdt_handle h, uint32_t flags, sdt_stream stream) {
             const bool sc0 = h->stats_complete; const uint32_t lh0 = h->levels_hint;
             cudaGraph_t graph = nullptr;
             if (cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
-                const int rc = sdt_refine_enqueue(h, st, flags, levels_bound);
+                const int rc = sdt_refine_enqueue(h, st, flags, levels_bound, kd_rounds);
                 const cudaError_t ec = cudaStreamEndCapture(st, &graph);
                 if (rc == SDT_OK && ec == cudaSuccess && graph && cudaGraphInstantiate(&g.exec, graph, 0) == cudaSuccess) {
                     g.launches = h->launches - l0;
@@ -436,9 +449,9 @@ extern "C" int sdt_refine(sdt_handle h, uint32_t flags, sdt_stream stream) {
             done = true;
         }
     }
-    if (!done) SDT_TRY(sdt_refine_enqueue(h, st, flags, levels_bound));
+    if (!done) SDT_TRY(sdt_refine_enqueue(h, st, flags, levels_bound, kd_rounds));
 #else
-    SDT_TRY(sdt_refine_enqueue(h, st, flags, levels_bound));
+    SDT_TRY(sdt_refine_enqueue(h, st, flags, levels_bound, kd_rounds));
 #endif
     h->prev_kd_dirty = !h->kd_complete;          // un-swept interior counts were rolled into prev
     h->cur = 1 - h->cur;
@@ -446,6 +459,7 @@ extern "C" int sdt_refine(sdt_handle h, uint32_t flags, sdt_stream stream) {
     h->levels_known = 0;
     h->levels_hint = levels_bound;
     h->stats_complete = true; h->kd_complete = true;
+    h->splat_bound = 0; h->splat_bound_valid = true;          // current's statistics are zero again
     // non-blocking read-back of the new sizes (only used to size the smem staging of later launches)
     if (cudaMemcpyAsync(h->h_hdr, s1.hdr, sizeof(DevHeader), cudaMemcpyDeviceToHost, st) == cudaSuccess &&
         cudaEventRecord(h->hdr_event, st) == cudaSuccess) h->hdr_pending = true;
@@ -462,5 +476,6 @@ extern "C" int sdt_reset_stats(sdt_handle h, sdt_stream stream) {
     launch_items(x, &s.hdr->n_kd, 0, ZeroItem{h->kd_count});
     launch_items(x, &s.hdr->n_quad, 0, ZeroItem{h->q_ecur});
     h->stats_complete = true; h->kd_complete = true;
+    h->splat_bound = 0; h->splat_bound_valid = true;
     return sdt_post_launch(h, "sdt_reset_stats");
 }

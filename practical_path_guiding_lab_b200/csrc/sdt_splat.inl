@@ -188,6 +188,13 @@ struct KdSweepItem {
     }
 };
 
+// quadtree levels the energy sweep has to visit: `current` has the topology of `prev`, whose level count the host knows
+// exactly after the last refine's (non-blocking) header read-back, and bounds by levels_hint before that
+static inline uint32_t sdt_sweep_levels(sdt_handle h) {
+    (void)tree_view(h);                                  // picks up a header read-back that has landed
+    return (h->levels_known && h->levels_known < h->levels_hint) ? h->levels_known : h->levels_hint;
+}
+
 // interior statistics of `current` from its leaf statistics.  with_kd = false (the refine): only the quadtree energies --
 // the refine reads spatial counts of LEAVES only, so the 21 per-depth passes over the spatial tree are left to whoever
 // wants to SEE interior counts (a download of either tree; sdt_sweep_prev_counts for the counts the refine rolled into prev)
@@ -195,9 +202,9 @@ static int sdt_complete_stats(sdt_handle h, cudaStream_t st, bool with_kd = true
     if (h->stats_complete && (h->kd_complete || !with_kd)) return SDT_OK;
     const ExecCtx x = exec_ctx(h, st);
     const QuadSet& s = h->set[h->cur];
-    // level sizes live on the device
+    // level sizes live on the device; the number of levels in use is exact once the last refine's header has been read back
     if (!h->stats_complete)
-        for (int l = (int)h->levels_hint - 1; l >= 0; --l)
+        for (int l = (int)sdt_sweep_levels(h) - 1; l >= 0; --l)
             launch_items(x, &s.hdr->level_cnt[l], 0, QuadSweepItem{s.hdr, s.child, h->q_ecur, (uint32_t)l});
     if (with_kd && !h->kd_complete) {
         for (int d = h->cfg.kd_max_depth; d >= 0; --d)
@@ -228,6 +235,7 @@ extern "C" int sdt_splat_records(sdt_handle h, const sdt_records* rec, uint32_t 
     cudaStream_t st = (cudaStream_t)stream;
     const bool nee = h->cfg.store_nee != 0;
     h->stats_complete = false; h->kd_complete = false;
+    h->splat_bound += n;
     const size_t per_lane = 12 + 8 + 4 + 4 + (nee ? 20 : 0) + 1 + 8;
     return sdt_run_chunked(h, st, flags, n, per_lane, false, [&](Stager& sg, uint32_t off, uint32_t cnt) -> int {
         sdt_records d = *rec;
@@ -269,6 +277,7 @@ extern "C" int sdt_splat_path_data(sdt_handle h, const sdt_path_data* pd, uint32
     if (sg.status != SDT_OK) return sg.status;
     SplatPathLane f{tree_view(h), SplatTarget{h->kd_count, h->q_ecur, (uint32_t)(h->cfg.store_nee != 0)}, d};
     h->stats_complete = false; h->kd_complete = false;
+    h->splat_bound += n;
     SDT_TRY(launch_wavefront(h, st, n, f, h->splat_block, h->splat_ctas_per_sm, pd->active != nullptr));
     return sg.finish(flags);
 }
