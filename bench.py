@@ -444,6 +444,12 @@ def run_b200(args):
 
         ms_g = timeit(lambda: tree.guided(d_pos, mode, wo=d_dir, seed=5, lane_offset=lane0, bsdf_pdf=bp, bsdf_value=bv,
                                           dir_out=g_dir, sdtree_pdf_out=g_sp, wo_pdf_out=g_wp, weight_out=g_w))
+        em_act = (torch.rand(n, device=dev, generator=gg) < 0.8).to(torch.uint8)
+        g_ep = torch.ones(n, device=dev)
+        ms_ge = timeit(lambda: tree.guided(d_pos, mode, wo=d_dir, seed=5, lane_offset=lane0, bsdf_pdf=bp, bsdf_value=bv,
+                                           dir_out=g_dir, sdtree_pdf_out=g_sp, wo_pdf_out=g_wp, weight_out=g_w,
+                                           em_dir=o_dir, em_active=em_act, sdtree_pdf_em_out=g_ep))
+        ms_pe = timeit(lambda: tree.pdf(d_pos, o_dir, active=em_act, out=o_pdf2))
         ms_p = timeit(lambda: tree.splat_path_data(md, lfin, tr_, tb_, bs_, d_rec['position'], d_rec['direction'], d_rec['wo_pdf'], active=act_))
         act15 = (torch.rand(n, device=dev, generator=gg) < 0.15).to(torch.uint8)
         sparse = {}
@@ -479,7 +485,9 @@ def run_b200(args):
         except Exception as e:
             coherent = {"error": repr(e)}
         extras = {"coherent_wavefront": coherent, "sparse_wavefront_15pct_active": dict(sparse, what="same calls with 15 % of the lanes active (late bounces / numRays*max_depth record slots): lanes of a tile sorted into dense warps vs plain masking"),
-                  "sdt_guided": {"ms": ms_g, "lanes_per_s": n / (ms_g * 1e-3), "what": "one bounce: ~45 % lanes sampled, ~45 % pdf + fused mixture, ~10 % idle"},
+                  "sdt_guided": {"ms": ms_g, "lanes_per_s": n / (ms_g * 1e-3), "what": "one bounce: ~45 % lanes sampled, ~45 % pdf + fused mixture, ~10 % idle",
+                                 "ms_with_emitter_pdf": ms_ge, "ms_emitter_pdf_as_a_separate_call": ms_pe,
+                                 "what_with_emitter_pdf": "the same call also returning the tree's pdf of the emitter direction (NEE MIS) on 80 % of the lanes: every tree query of a path vertex in one launch.  The emitter directions of this measurement are directions SAMPLED from the tree (deep leaves: the expensive case for a pdf); ms_emitter_pdf_as_a_separate_call = sdt_pdf of the same directions and mask"},
                   "sdt_splat_path_data": {"ms": ms_p, "slots_per_s": n / (ms_p * 1e-3), "what": f"processPathData + filter + splat fused, {n} slots (max_depth {md}), 60 % active"}}
         tree.reset_stats()
     except Exception as e:            # extras never break the contract line

@@ -183,7 +183,10 @@ int sdt_sample_pdf(sdt_handle h, const sdt_vec3* pos, const uint8_t* active, uin
  * direction `wo` (:307) and, when bsdf_pdf/bsdf_value are given, the fused one-sample
  * mixture woPdf = f*bsdf_pdf + (1-f)*sdtree_pdf, weight = bsdf_value/woPdf (:310-311);
  * mode 0 lanes are untouched.  Outputs: dir (mode 1), sdtree_pdf (mode 1,2), wo_pdf and
- * weight (mode 2 when fused).  The reference runs two full descents for this. */
+ * weight (mode 2 when fused).  The reference runs two full descents for this.
+ * Optional third query of the same vertex: with em_dir given, every lane whose em_active is set (all lanes when it is
+ * NULL) -- whatever its mode -- also gets the tree's pdf of the emitter direction, sdtree_pdf_em = sdTree_prev.pdf(si.p,
+ * ds.d) of the NEE MIS weight (:244), from the same spatial descent; other lanes' sdtree_pdf_em stays untouched. */
 typedef struct sdt_guided_args {
     sdt_vec3 pos;
     sdt_vec3 wo;               /* BSDF-sampled world direction (mode 2) */
@@ -197,6 +200,9 @@ typedef struct sdt_guided_args {
     float* sdtree_pdf;
     float* wo_pdf;             /* optional */
     sdt_vec3_out weight;       /* optional */
+    sdt_vec3 em_dir;           /* optional (x == NULL -> none): world direction towards the emitter sample */
+    const uint8_t* em_active;  /* optional mask of em_dir */
+    float* sdtree_pdf_em;      /* out, required with em_dir */
 } sdt_guided_args;
 int sdt_guided(sdt_handle h, const sdt_guided_args* a, uint32_t n, uint32_t flags, sdt_stream stream);
 

@@ -59,7 +59,8 @@ class GuidedArgs(C.Structure):
     _fields_ = [("pos", Vec3), ("wo", Vec3), ("mode", C.c_void_p),
                 ("u", C.c_void_p), ("u_stride", C.c_uint32), ("seed", C.c_uint32), ("lane_offset", C.c_uint32),
                 ("bsdf_pdf", C.c_void_p), ("bsdf_value", Vec3), ("bsdf_sampling_fraction", C.c_double),
-                ("dir", Vec3), ("sdtree_pdf", C.c_void_p), ("wo_pdf", C.c_void_p), ("weight", Vec3)]
+                ("dir", Vec3), ("sdtree_pdf", C.c_void_p), ("wo_pdf", C.c_void_p), ("weight", Vec3),
+                ("em_dir", Vec3), ("em_active", C.c_void_p), ("sdtree_pdf_em", C.c_void_p)]
 
 
 class Records(C.Structure):

@@ -234,11 +234,7 @@ class CornellBox:
             bsdf_pdf_em = torch.where(active_em & (cos_s > 0), cos_s / math.pi, torch.zeros_like(cos_s))
             bsdf_val_em = alb * bsdf_pdf_em[:, None]
             act_sd_em = active_em & core.guiding
-            mis_em = self._t(core.nee_mis(self._x(p), self._x(wl), self._x(act_sd_em), self._x(bsdf_pdf_em), self._x(bsdf_pdf_em),
-                                          self._x(bsdf_pdf_em), self._x(ds_pdf), self._x(torch.zeros(n, dtype=torch.uint8, device=dev))))
-            Lr_dir = thr * mis_em[:, None] * bsdf_val_em * em_weight
-            L = L + Le + Lr_dir
-            # -- continuation: BSDF sample, guided/BSDF choice, one-sample mixture (:272-311)
+            # -- continuation: BSDF sample (:272-281); the tree is asked once per vertex, below
             u1, u2 = rnd(n), rnd(n)
             r = u1.sqrt()
             ph = 2 * math.pi * u2
@@ -251,9 +247,19 @@ class CornellBox:
             bsdf_weight = torch.where((bsdf_pdf > 0)[:, None], alb, torch.zeros_like(alb))
             do_mis = active_next & core.guiding
             choose_u = rnd(n)
+            no_delta = self._x(torch.zeros(n, dtype=torch.uint8, device=dev))
             if core.guiding:
-                mode, sd_dir, sd_pdf = core.choose_and_sample(self._x(p), self._x(wo), self._x(do_mis), self._x(choose_u),
-                                                              seed=(core._pass_seed * 1315423911 + bounce) & 0xFFFFFFFF, lane_offset=lane0)
+                # ONE library call / spatial descent per vertex: tree pdf of the emitter direction (:244) + guided / BSDF choice (:283-307)
+                sd_em, mode, sd_dir, sd_pdf = core.bounce(self._x(p), self._x(wl), self._x(act_sd_em), self._x(wo), self._x(do_mis), self._x(choose_u),
+                                                          seed=(core._pass_seed * 1315423911 + bounce) & 0xFFFFFFFF, lane_offset=lane0)
+                mis_em = self._t(core.nee_mis_from_pdf(sd_em, self._x(bsdf_pdf_em), self._x(bsdf_pdf_em), self._x(bsdf_pdf_em), self._x(ds_pdf), no_delta))
+            else:
+                mis_em = self._t(core.nee_mis(self._x(p), self._x(wl), self._x(act_sd_em), self._x(bsdf_pdf_em), self._x(bsdf_pdf_em),
+                                              self._x(bsdf_pdf_em), self._x(ds_pdf), no_delta))
+            Lr_dir = thr * mis_em[:, None] * bsdf_val_em * em_weight
+            L = L + Le + Lr_dir
+            # -- one-sample mixture of the guided / BSDF choice (:301-311)
+            if core.guiding:
                 mode, sd_dir, sd_pdf = self._t(mode), self._t(sd_dir), self._t(sd_pdf)
                 g = mode == 1
                 wo = torch.where(g[:, None], sd_dir, wo)

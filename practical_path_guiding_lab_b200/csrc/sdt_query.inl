@@ -79,7 +79,7 @@ __global__ void __launch_bounds__(Lane::kMaxThreads, SDT_LB_CTAS) k_wavefront(La
         const uint32_t warp_id = blockIdx.x * (blockDim.x >> 5) + wib;
         for (uint64_t tile64 = (uint64_t)warp_id * tile_w; tile64 < n; tile64 += (uint64_t)warps_total * tile_w) {
             const uint32_t tile = (uint32_t)tile64;
-            uint32_t cnt[2] = {0u, 0u};
+            uint32_t cnt[3] = {0u, 0u, 0u};
             uint32_t mq = 0;                 // modes of this thread's lanes, 2 bits each
 #pragma unroll
             for (uint32_t q = 0; q < TM; ++q) {
@@ -311,20 +311,34 @@ struct PdfLane {
 };
 
 // one bounce: mode 1 = sample the tree (src/path_guiding_integrator.py:301),
-// mode 2 = tree pdf of the BSDF-sampled direction (:307) + fused mixture (:310-311)
-template <bool EXPLICIT_U>
+// mode 2 = tree pdf of the BSDF-sampled direction (:307) + fused mixture (:310-311);
+// with em_dir given, every lane whose em_active is set also gets the tree's pdf of the emitter direction (:244) from the
+// SAME spatial descent (lanes that do nothing else run as mode 3)
+template <bool EXPLICIT_U, bool WITH_EM>
 struct GuidedLane {
     static constexpr bool kSmemCounts = false, kGrid = SDT_SAMPLE_GRID;
-    static constexpr int kModes = 2, kMaxThreads = SDT_SAMPLE_THREADS;
+    static constexpr int kModes = WITH_EM ? 3 : 2, kMaxThreads = SDT_SAMPLE_THREADS;
     SDT_HD void flush_count(uint32_t, float) const {}
     TreeView t;
     sdt_guided_args a; int fuse;
     float f, omf;           // fp32(bsdfSamplingFraction), fp32(1 - bsdfSamplingFraction) with the difference formed in double
-    SDT_HD uint32_t mode_of(uint32_t i) const { const uint32_t m = SDT_LDG(a.mode + i); return m <= 2u ? m : 0u; }
+    SDT_HD bool em_of(uint32_t i) const { return WITH_EM && (a.em_active ? SDT_LDG(a.em_active + i) != 0 : true); }
+    SDT_HD uint32_t mode_of(uint32_t i) const {
+        uint32_t m = SDT_LDG(a.mode + i);
+        if (m > 2u) m = 0u;
+        return (m == 0u && em_of(i)) ? 3u : m;
+    }
     SDT_HD void idle(uint32_t) const {}
     template <int KD>
     SDT_HD void run_mode(const KdCtx& k, uint32_t i, uint32_t m) const {
         const KdResult r = sdt_kd_descend<KD>(k, sdt_ld(a.pos.x, a.pos.stride, i), sdt_ld(a.pos.y, a.pos.stride, i), sdt_ld(a.pos.z, a.pos.stride, i));
+        if (WITH_EM && (m == 3u || em_of(i))) {
+            float x, y;
+            sdt_dir_to_canonical(sdt_ld(a.em_dir.x, a.em_dir.stride, i), sdt_ld(a.em_dir.y, a.em_dir.stride, i), sdt_ld(a.em_dir.z, a.em_dir.stride, i), x, y);
+            uint32_t nd;
+            a.sdtree_pdf_em[i] = sdt_quad_pdf(t, r.rootrec, 0u, x, y, nd, false);
+            if (m == 3u) return;
+        }
         if (m == 1u) {
             GuidedSample g;
             if (EXPLICIT_U) g = sdt_sample_tree(t, r.rootrec, 0u, ExplicitRng(a.u, a.u_stride, i), fuse != 0);
@@ -473,9 +487,10 @@ extern "C" int sdt_guided(sdt_handle h, const sdt_guided_args* a, uint32_t n, ui
     if (n == 0) return SDT_OK;                          // empty wavefront: nothing to do (pointers may be NULL)
     SDT_CHECK(h, a && a->pos.x && a->mode && a->sdtree_pdf && a->dir.x, SDT_ERR_INVALID, "sdt_guided: pos / mode / dir / sdtree_pdf is NULL");
     SDT_CHECK(h, !a->u || a->u_stride >= 3, SDT_ERR_INVALID, "sdt_guided: u_stride must be >= 3");
+    SDT_CHECK(h, !a->em_dir.x || a->sdtree_pdf_em, SDT_ERR_INVALID, "sdt_guided: em_dir needs sdtree_pdf_em");
     cudaStream_t st = (cudaStream_t)stream;
     Stager sg(h, st, flags);
-    SDT_TRY(sg.reserve((size_t)n * (12 + 12 + 1 + 4 + 12 + 12 + 4 + 4 + 12 + (a->u ? 4ull * a->u_stride : 0)) + 16384));
+    SDT_TRY(sg.reserve((size_t)n * (12 + 12 + 1 + 4 + 12 + 12 + 4 + 4 + 12 + 12 + 1 + 4 + (a->u ? 4ull * a->u_stride : 0)) + 32768));
     sdt_guided_args d = *a;
     d.pos = sg.in3(a->pos, n);
     d.wo = sg.in3(a->wo, n);
@@ -483,6 +498,8 @@ extern "C" int sdt_guided(sdt_handle h, const sdt_guided_args* a, uint32_t n, ui
     d.u = sg.in_t(a->u, (size_t)n * a->u_stride);
     d.bsdf_pdf = sg.in_t(a->bsdf_pdf, n);
     d.bsdf_value = sg.in3(a->bsdf_value, n);
+    d.em_dir = sg.in3(a->em_dir, n);
+    d.em_active = sg.in_t(a->em_active, n);
     if (sg.host) {
         // outputs are partial (mode-dependent): stage the caller's current contents first
         SDT_CHECK(h, a->dir.stride == 3 || a->dir.stride == 1, SDT_ERR_INVALID, "sdt_guided: host dir must have stride 3 or 1");
@@ -494,6 +511,7 @@ extern "C" int sdt_guided(sdt_handle h, const sdt_guided_args* a, uint32_t n, ui
         const float* sp = sg.in_t((const float*)a->sdtree_pdf, n);
         d.sdtree_pdf = (float*)sp; sg.outs.push_back(Stager::Out{a->sdtree_pdf, (void*)sp, (size_t)n * 4});
         if (a->wo_pdf) { const float* wp = sg.in_t((const float*)a->wo_pdf, n); d.wo_pdf = (float*)wp; sg.outs.push_back(Stager::Out{a->wo_pdf, (void*)wp, (size_t)n * 4}); }
+        if (a->em_dir.x) { const float* ep = sg.in_t((const float*)a->sdtree_pdf_em, n); d.sdtree_pdf_em = (float*)ep; sg.outs.push_back(Stager::Out{a->sdtree_pdf_em, (void*)ep, (size_t)n * 4}); }
         if (a->weight.x) {
             SDT_CHECK(h, a->weight.stride == 3, SDT_ERR_INVALID, "sdt_guided: host weight must be interleaved (stride 3)");
             const float* ww = sg.in_t((const float*)a->weight.x, (size_t)n * 3);
@@ -502,13 +520,15 @@ extern "C" int sdt_guided(sdt_handle h, const sdt_guided_args* a, uint32_t n, ui
         }
     }
     if (sg.status != SDT_OK) return sg.status;
-    if (d.u) {
-        GuidedLane<true> f{tree_view(h), d, h->fuse_sample_pdf, (float)a->bsdf_sampling_fraction, (float)(1.0 - a->bsdf_sampling_fraction)};
-        SDT_TRY(launch_wavefront(h, st, n, f, h->query_block, h->query_ctas_per_sm, true));
-    } else {
-        GuidedLane<false> f{tree_view(h), d, h->fuse_sample_pdf, (float)a->bsdf_sampling_fraction, (float)(1.0 - a->bsdf_sampling_fraction)};
-        SDT_TRY(launch_wavefront(h, st, n, f, h->query_block, h->query_ctas_per_sm, true));
+    const float fr = (float)a->bsdf_sampling_fraction, omf = (float)(1.0 - a->bsdf_sampling_fraction);
+#define SDT_GUIDED_LAUNCH(EXPL, EM)                                                                              \
+    {                                                                                                            \
+        GuidedLane<EXPL, EM> f{tree_view(h), d, h->fuse_sample_pdf, fr, omf};                                    \
+        SDT_TRY(launch_wavefront(h, st, n, f, h->query_block, h->query_ctas_per_sm, true));                      \
     }
+    if (d.u) { if (d.em_dir.x) SDT_GUIDED_LAUNCH(true, true) else SDT_GUIDED_LAUNCH(true, false) }
+    else { if (d.em_dir.x) SDT_GUIDED_LAUNCH(false, true) else SDT_GUIDED_LAUNCH(false, false) }
+#undef SDT_GUIDED_LAUNCH
     return sg.finish(flags);
 }
 

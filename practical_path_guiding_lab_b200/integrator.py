@@ -142,6 +142,27 @@ class PathGuidingCore:
                                    self.bsdfSamplingFraction, self.iteration)
         return mis
 
+    def nee_mis_from_pdf(self, sdtree_pdf_em, bsdf_pdf_em, pdf_with_delta, pdf_without_delta, ds_pdf, ds_delta):
+        """:241-253 with the tree's pdf of the emitter direction already known (from `bounce`) -> mis_em"""
+        _, mis = self.tree.mis_nee(bsdf_pdf_em, sdtree_pdf_em, pdf_with_delta, pdf_without_delta, ds_pdf, ds_delta,
+                                   self.bsdfSamplingFraction, self.iteration)
+        return mis
+
+    def bounce(self, position, ds_d, active_em, wo_world_bsdf, do_mis, choose_u, seed, lane_offset=0, u=None):
+        """Every tree query of one path vertex in ONE library call and one spatial descent (guiding iterations): the tree's
+        pdf of the emitter direction for the NEE MIS weight (:244) on the `active_em` lanes, and `choose_and_sample`
+        (:283-307) -> (sdtree_pdf_em, mode, sdtree_dir, sdtree_pdf)"""
+        do_mis = do_mis != 0
+        guided = (choose_u > self.bsdfSamplingFraction) & do_mis
+        mode = guided.astype(np.uint8) if not _is_torch(guided) else guided.to(dtype=__import__("torch").uint8)
+        bs = do_mis & ~guided
+        mode = mode + 2 * (bs.astype(np.uint8) if not _is_torch(bs) else bs.to(dtype=mode.dtype))
+        em = active_em != 0
+        em = em.astype(np.uint8) if not _is_torch(em) else em.to(dtype=mode.dtype)
+        d, sp, _, _, ep = self.tree.guided(position, mode, wo=wo_world_bsdf, u=u, seed=seed, lane_offset=lane_offset,
+                                           bsdf_sampling_fraction=self.bsdfSamplingFraction, em_dir=ds_d, em_active=em)
+        return ep, mode, d, sp
+
     def choose_and_sample(self, position, wo_world_bsdf, do_mis, choose_u, seed, lane_offset=0, u=None):
         """:283-307: lanes with choose_u > bsdfSamplingFraction (and do_mis) are sampled from the
         tree, the other do_mis lanes get the tree pdf of the BSDF-sampled direction.
@@ -333,15 +354,7 @@ if _HAVE_MITSUBA:                                      # pragma: no cover
                 pdf_without_delta = bsdf.pdf(bsdf_ctx, si, bs_nd.wo, act_sd_em)
                 bsdf_ctx.component = prev_component
                 pdf_with_delta = bsdf.pdf(bsdf_ctx, si, bs_nd.wo, act_sd_em)
-                # A4 + A5 on the device library
-                p_t = _t(si.p)
-                mis_em_t = core.nee_mis(p_t, _t(ds.d), _t(act_sd_em), _t(bsdf_pdf_em), _t(pdf_with_delta),
-                                        _t(pdf_without_delta), _t(ds.pdf), _t(ds.delta))
-                _sync()
-                mis_em = mi.Float(mis_em_t)
-                Lr_dir = throughput * mis_em * bsdf_value_em * em_weight
-                L = dr.select(active, L + Le + Lr_dir, L)
-                # continuation
+                # continuation: BSDF sample (the sampler is advanced in the reference's order; the tree is asked once, below)
                 bsdf_sample, bsdf_weight = bsdf.sample(bsdf_ctx, si, sampler.next_1d(active_next), sampler.next_2d(active_next), active_next)
                 bsdf_pdf = mi.Float(bsdf_sample.pdf)
                 bsdf_value = bsdf_weight * bsdf_pdf
@@ -351,10 +364,20 @@ if _HAVE_MITSUBA:                                      # pragma: no cover
                 delta = mi.has_flag(bsdf_sample.sampled_type, mi.BSDFFlags.Delta)
                 do_mis = active_next & ~delta & (core.iteration > 1)
                 choose_u = sampler.next_1d(active_next)
+                # A4 + A5 on the device library: every tree query of the vertex in ONE call and one spatial descent
+                p_t = _t(si.p)
                 if core.iteration > 1:
-                    mode_t, sd_dir_t, sd_pdf_t = core.choose_and_sample(p_t, _t(wo_world), _t(do_mis), _t(choose_u),
-                                                                        seed=core._pass_seed * 1315423911 + it)
-                    _sync()
+                    sd_em_t, mode_t, sd_dir_t, sd_pdf_t = core.bounce(p_t, _t(ds.d), _t(act_sd_em), _t(wo_world), _t(do_mis), _t(choose_u),
+                                                                      seed=core._pass_seed * 1315423911 + it)
+                    mis_em_t = core.nee_mis_from_pdf(sd_em_t, _t(bsdf_pdf_em), _t(pdf_with_delta), _t(pdf_without_delta), _t(ds.pdf), _t(ds.delta))
+                else:
+                    mis_em_t = core.nee_mis(p_t, _t(ds.d), _t(act_sd_em), _t(bsdf_pdf_em), _t(pdf_with_delta),
+                                            _t(pdf_without_delta), _t(ds.pdf), _t(ds.delta))
+                _sync()
+                mis_em = mi.Float(mis_em_t)
+                Lr_dir = throughput * mis_em * bsdf_value_em * em_weight
+                L = dr.select(active, L + Le + Lr_dir, L)
+                if core.iteration > 1:
                     guided = mi.Bool(mode_t == 1)
                     sd_dir = dr.unravel(mi.Vector3f, mi.Float(sd_dir_t.reshape(-1)))
                     wo_world[guided] = sd_dir

@@ -280,9 +280,13 @@ class SDTree:
         return (pdf, dbg) if debug else pdf
 
     def guided(self, pos, mode, wo=None, u=None, seed=0, lane_offset=0, bsdf_pdf=None, bsdf_value=None,
-               bsdf_sampling_fraction=0.5, dir_out=None, sdtree_pdf_out=None, wo_pdf_out=None, weight_out=None):
+               bsdf_sampling_fraction=0.5, dir_out=None, sdtree_pdf_out=None, wo_pdf_out=None, weight_out=None,
+               em_dir=None, em_active=None, sdtree_pdf_em_out=None):
         """one bounce: mode 1 lanes are sampled, mode 2 lanes get the pdf of `wo` (+ fused mixture).
-        Output arrays are updated in place on the lanes concerned; fresh ones are zero-filled."""
+        Output arrays are updated in place on the lanes concerned; fresh ones are zero-filled.
+        With em_dir the lanes of em_active (all when None) also get the tree's pdf of that direction from the same
+        spatial descent; the return value then has a fifth element, sdtree_pdf_em (fresh: 1 on the other lanes, like
+        KDTree.pdf leaves inactive lanes)."""
         b = _Buf()
         n = _n_of(pos)
         g = L.GuidedArgs()
@@ -312,8 +316,19 @@ class SDTree:
         fused = bsdf_pdf is not None
         wp = out_or_new(wo_pdf_out, (n,)) if fused else None
         wt = out_or_new(weight_out, (n, 3)) if fused and bsdf_value is not None else None
+        ep = None
+        if em_dir is not None:
+            g.em_dir = b.vec(em_dir, 3)
+            g.em_active = b.arr(em_active, np.uint8)
+            ep = sdtree_pdf_em_out
+            if ep is None:
+                ep, _ = b.new((n,), np.float32)
+                if b.host:
+                    ep[...] = 1
+                else:
+                    ep.fill_(1)
         if b.host:
-            for t in (d, sp, wp, wt):
+            for t in (d, sp, wp, wt, ep):
                 if t is not None and not (t.flags.c_contiguous and t.dtype == np.float32):
                     raise TypeError("guided(): host output arrays must be C-contiguous float32")
             g.dir = L.Vec3(d.ctypes.data, d.ctypes.data + 4, d.ctypes.data + 8, 3)
@@ -322,6 +337,8 @@ class SDTree:
                 g.wo_pdf = wp.ctypes.data
             if wt is not None:
                 g.weight = L.Vec3(wt.ctypes.data, wt.ctypes.data + 4, wt.ctypes.data + 8, 3)
+            if ep is not None:
+                g.sdtree_pdf_em = ep.ctypes.data
         else:
             g.dir = L.Vec3(d.data_ptr(), d.data_ptr() + 4, d.data_ptr() + 8, 3)
             g.sdtree_pdf = sp.data_ptr()
@@ -329,8 +346,10 @@ class SDTree:
                 g.wo_pdf = wp.data_ptr()
             if wt is not None:
                 g.weight = L.Vec3(wt.data_ptr(), wt.data_ptr() + 4, wt.data_ptr() + 8, 3)
+            if ep is not None:
+                g.sdtree_pdf_em = ep.data_ptr()
         self._ck(self._lib.sdt_guided(self._h, C.byref(g), n, self._flags(b), b.stream()))
-        return d, sp, wp, wt
+        return (d, sp, wp, wt) if em_dir is None else (d, sp, wp, wt, ep)
 
     def mis_nee(self, bsdf_pdf_em, sdtree_pdf_em, pdf_with_delta, pdf_without_delta, ds_pdf, ds_delta,
                 bsdf_sampling_fraction, iteration):

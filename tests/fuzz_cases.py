@@ -179,9 +179,17 @@ def _bounce_and_path_data(ctx, t, cur, prev, rng, lo, hi, store_nee, n=1200):
     bp = _salt(rng, (rng.random(n) * 2).astype(F))
     bv = _salt(rng, rng.random((n, 3)).astype(F))
     frac = float(rng.choice([0.5, 0.25, 0.9]))
-    d, sp, wp, wt = t.guided(ctx.dev(pos), ctx.dev(mode), wo=ctx.dev(wo), seed=5, lane_offset=11, bsdf_pdf=ctx.dev(bp),
-                             bsdf_value=ctx.dev(bv), bsdf_sampling_fraction=frac)
-    d, sp, wp, wt = ctx.host(d), ctx.host(sp), ctx.host(wp), ctx.host(wt)
+    # the emitter direction's pdf rides along on a random subset of the lanes, whatever their mode (idle lanes included)
+    em = rng.standard_normal((n, 3)).astype(F)
+    em /= np.linalg.norm(em, axis=1, keepdims=True)
+    em[:3] = np.array([[0, 0, -1], [0, np.nan, 0], [1, 0, 0]], F)
+    em_act = rng.random(n) < 0.7
+    d, sp, wp, wt, ep = t.guided(ctx.dev(pos), ctx.dev(mode), wo=ctx.dev(wo), seed=5, lane_offset=11, bsdf_pdf=ctx.dev(bp),
+                                 bsdf_value=ctx.dev(bv), bsdf_sampling_fraction=frac, em_dir=ctx.dev(em),
+                                 em_active=ctx.dev(em_act.astype(np.uint8)))
+    d, sp, wp, wt, ep = ctx.host(d), ctx.host(sp), ctx.host(wp), ctx.host(wt), ctx.host(ep)
+    oep = prev.pdf(pos, em, em_act)
+    assert cases.beq(ep[em_act], oep[em_act]) and np.all(ep[~em_act] == 1.0), "emitter-direction pdf fused into the bounce"
     m1, m2 = mode == 1, mode == 2
     od, op = prev.sample(pos, so.ExplicitSampler(seed=5, n=n, lane_offset=11), m1)
     assert cases.beq(d[m1], od[m1]) and cases.beq(sp[m1], op[m1])

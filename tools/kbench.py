@@ -30,7 +30,7 @@ for spec in sys.argv[1:]:
     ex = d.get("extras", {})
     row = {"name": name, "fused": pk["sample_pdf"]["ms"], "sample": pk["sample"]["ms"], "pdf": pk["pdf"]["ms"], "splat": pk["splat"]["ms"], "step": d["ms_per_step"],
            "req_frac": {k: round(v["frac_of_request_roof"], 3) for k, v in pk.items()},
-           "guided": ex.get("sdt_guided", {}).get("ms"), "coh": ex.get("coherent_wavefront"), "path": ex.get("sdt_splat_path_data", {}).get("ms"),
+           "guided": ex.get("sdt_guided", {}).get("ms"), "guided_em": ex.get("sdt_guided", {}).get("ms_with_emitter_pdf"), "pdf_em_sep": ex.get("sdt_guided", {}).get("ms_emitter_pdf_as_a_separate_call"), "coh": ex.get("coherent_wavefront"), "path": ex.get("sdt_splat_path_data", {}).get("ms"),
            "refine": d.get("refine_ms"), "mhz": d["clocks"]["sm_mhz"]}
     rows.append(row)
     print(json.dumps(row), flush=True)
