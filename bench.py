@@ -332,18 +332,19 @@ def run_b200(args):
     _, dbgr = tree.pdf(d_rec['position'][:m], rdir, debug=True)
     dq_rl = tr['quadtree_depth'][dbgr.cpu().numpy().view(np.uint32)[:, 2]].astype(np.float64)
     dq_r = dq_rl.mean()
-    JL = 5                                                       # SDT_JUMP_LEVELS: depth <= 5 ends inside the jump table
-    below_p, below_r = np.maximum(dq_pl - JL, 0).mean(), np.maximum(dq_rl - JL, 0).mean()
-    deep_p = float((dq_pl > JL).mean())
+    JL, J2 = 5, 8                                                # depth <= 5 ends inside the root jump table, <= 8 inside a second-stage table
+    below_p, below_r = np.maximum(dq_pl - J2, 0).mean(), np.maximum(dq_rl - J2, 0).mean()      # records walked below the tables
+    mid_p, mid_r = float((dq_pl > JL).mean()), float((dq_rl > JL).mean())                      # one more gather: second-stage entry (or the level-5 record)
+    deep_p = float((dq_pl > J2).mean())                                                        # pdf below the tables: the leaf's path product is a gather of its own
     bytes_q = {"sample": 28 + 4 * ds + 4 + 20 * dq_s,            # ONE quadtree descent (fused pdf); re-descents not counted
                "pdf": 28 + 4 * ds + 4 + 20 * dq_p + 4,
                "splat": 28 + 4 * ds + 4 + 4 * dq_r + 8}            # leaf-only update + sweep
     bytes_q["sample_pdf"] = 44 + 4 * ds + 4 + 20 * dq_s + 20 * dq_p + 4          # pos 12 + dir 12 in, 16 + 4 out; one spatial descent
     stream_b = {"sample": 28.0, "pdf": 28.0, "splat": 28.0, "sample_pdf": 44.0}  # query / record bytes streamed from and to HBM
     # divergent sector requests per query actually issued (one lane, one unrelated 32 B sector, one slot of the SM's L1 -> L2
-    # request port): sampling = a record per level + the leaf's path product; pdf = a jump-table entry (+ records below the
-    # table and the leaf's product for the lanes that go below); splat = a jump-table entry + records below + the leaf RED
-    req_q = {"sample": dq_s + 1.0, "pdf": 1.0 + below_p + deep_p, "splat": 1.0 + below_r + 1.0}
+    # request port): sampling = a record per level + the leaf's path product; pdf = a jump-table entry (+ a second-stage
+    # entry beyond level 5, + records and the leaf's product beyond level 8); splat = the same entries + records + the leaf RED
+    req_q = {"sample": dq_s + 1.0, "pdf": 1.0 + mid_p + below_p + deep_p, "splat": 1.0 + mid_r + below_r + 1.0}
     req_q["sample_pdf"] = req_q["sample"] + req_q["pdf"]
     names = ["sample_pdf", "splat", "sample", "pdf"]
     dom = "sample_pdf"
@@ -401,7 +402,8 @@ def run_b200(args):
             "per_kernel": pk,
             "step_unfused_ms": k_ms["sample"] + k_ms["pdf"] + k_ms["splat"],
             "mean_depths": {"spatial": ds, "quad_sample": dq_s, "quad_pdf": dq_p, "quad_splat": dq_r, "sample_redescend_frac": redescend,
-                            "levels_below_jump_table": {"pdf": below_p, "splat": below_r}}}
+                            "records_below_the_jump_tables": {"pdf": below_p, "splat": below_r},
+                            "lanes_beyond_the_root_table": {"pdf": mid_p, "splat": mid_r}}}
 
     # ---- refine + allreduce wall time (per training iteration, not part of a step).  Steady state: the refine replays a
     # CUDA graph captured on first use (one per buffer parity), so two untimed iterations come first; every timed refine

@@ -85,6 +85,7 @@ typedef struct sdt_sizes {
     uint32_t error;      /* sticky device-side error flag (0 = none) */
     uint32_t refine_count;
     uint32_t jump_trees; /* quadtrees covered by the 32x32 jump table over their top 5 levels */
+    uint32_t jump2_tables; /* level-5 nodes that own a second-stage 8x8 table over their next 3 levels */
 } sdt_sizes;
 
 /* The reference's on-disk contract: the 23 arrays of KDTree.saveToFile
@@ -288,7 +289,7 @@ int sdt_stat_buffers(sdt_handle h, float** q_energy, uint32_t* n_quad, float** k
  *   "query_block", "query_ctas_per_sm", "splat_block", "splat_ctas_per_sm"   CTA shape of the wavefront kernels (block 0 = the
  *                       kernel's own size: 768 threads for the sampling kernels, 1024 for pdf / locate / splat; larger values are clamped)
  *   "kd_smem_nodes", "kd_smem_count_nodes", "splat_stage_words"              what of the spatial tree is staged in shared memory
- *   "use_kd_grid", "use_jump", "use_int_cell", "fuse_sample_pdf", "use_compaction"   fast paths on / off (each has an exact slow path)
+ *   "use_kd_grid", "use_jump", "use_jump2", "use_int_cell", "fuse_sample_pdf", "use_compaction"   fast paths on / off (each has an exact slow path)
  *   "splat_aggregate"   combine the lanes of a warp that splat into the same node before the atomic (pays on pixel-coherent
  *                       wavefronts; off by default: on incoherent records it finds no peers and only costs instructions)
  *   "use_pdl"                                                                programmatic dependent launch of the helper kernels

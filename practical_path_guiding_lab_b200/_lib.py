@@ -40,7 +40,7 @@ class Config(C.Structure):
 
 class Sizes(C.Structure):
     _fields_ = [(k, C.c_uint32) for k in ("n_kd", "n_quad", "n_roots", "n_interior", "n_levels",
-                                         "kd_leaves", "error", "refine_count", "jump_trees")]
+                                         "kd_leaves", "error", "refine_count", "jump_trees", "jump2_tables")]
 
 
 class Arrays(C.Structure):

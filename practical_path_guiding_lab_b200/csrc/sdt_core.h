@@ -75,10 +75,11 @@ struct DevHeader {
     uint32_t kd_max_depth, quad_max_depth, store_nee;
     uint32_t rootrec_of_node0;              // record index of that tree's root (SDT_NONE: single-leaf tree)
     uint32_t jump_trees;                    // trees covered by the jump table (0: none)
-    uint32_t pad0[2];
+    uint32_t s2_tables;                     // second-stage tables in use (0: none), see SDT_JUMP_TABLE
+    uint32_t s2_rec_lo;                     // records [s2_rec_lo, s2_rec_hi) = the non-leaf nodes of level SDT_JUMP_LEVELS
     float bbox_min[3], bbox_max[3];         // spatial root box
     float max_leaf_size;                    // KDTree.maxLeafSize as fp32
-    uint32_t pad1;
+    uint32_t s2_rec_hi;
     uint32_t level_off[SDT_MAX_LEVELS + 2];  // quadtree level l = nodes [level_off[l], level_off[l+1])
     uint32_t level_cnt[SDT_MAX_LEVELS + 2];  // level_off[l+1] - level_off[l]
     // ---- refine scratch ----
@@ -131,6 +132,18 @@ typedef uint32_t QJump;
 // (table entry, then pp[leaf]) for every direction whose leaf lies in the top SDT_JUMP_LEVELS levels.
 #define SDT_JUMP_NEXT 0x80000000u
 #define SDT_JUMP_PP_SLOW 0x7FC00000u
+// Second stage: a node of level SDT_JUMP_LEVELS that still has a non-leaf child owns an 8x8 table over its next
+// SDT_S2_LEVELS = 3 levels (256 B; on the config-2 forest 23 k of the 60 k level-5 nodes, 5.9 MB per table kind).  The root
+// table's continuation entry for such a node is SDT_JUMP_TABLE | table id instead of its record, so a descent that goes
+// deep pays one more 4-byte gather for three levels instead of three 16 / 32-byte ones.  Entries: as in the first stage
+// (leaf id / path product, or the level-8 record to continue from).  Points on a 1/256 grid line, and every point when the
+// stage is switched off ("use_jump2"), continue level by level from the node's record, s2_rec[table id].
+#define SDT_S2_LEVELS 3
+#define SDT_S2_SIDE (1u << SDT_S2_LEVELS)
+#define SDT_S2_CELLS (SDT_S2_SIDE * SDT_S2_SIDE)
+#define SDT_JUMP_TABLE 0x40000000u     // in a continuation entry: the rest is a second-stage table id, not a record
+#define SDT_S2_FINE_F ((float)(SDT_JUMP_SIDE * SDT_S2_SIDE))               // 256
+#define SDT_S2_FINE_INV_F (1.0f / (float)(SDT_JUMP_SIDE * SDT_S2_SIDE))
 
 struct TreeView {
     const DevHeader* hdr;
@@ -140,6 +153,10 @@ struct TreeView {
     const QRec* rec;
     const QJump* jump;          // [root record][cell]
     const uint32_t* jump_pp;    // [root record][cell], see SDT_JUMP_NEXT
+    const uint32_t* s2;         // [table][8x8] second stage of `jump` (SDT_JUMP_TABLE)
+    const uint32_t* s2_pp;      // ... of `jump_pp`
+    const uint32_t* s2_rec;     // [table] record of the node the table belongs to
+    uint32_t use_s2;            // 0: walk level by level from s2_rec instead
     const float* pp;            // per node: pdf product of the root->node path (NaN: it went NaN)
     uint32_t jump_trees;        // 0: table not in use
     uint32_t int_cell;          // sampler's cell tracking (sdt_quad_sample CELL): 1 = depth <= 16, 2 = depth <= 23, 0 = deeper
@@ -556,6 +573,20 @@ SDT_HD float sdt_quad_pdf_levels(const QRec* __restrict__ rec, uint32_t ri, uint
     return pdf;
 }
 
+// Follows a SDT_JUMP_TABLE continuation of the first stage.  In: table id.  Out: `entry` = the second-stage entry when
+// the point lies strictly inside a 1/256 cell (then cx8 / cy8 name it), else false with ri = the node's own record.
+SDT_HD bool sdt_s2_lookup(const TreeView& t, const uint32_t* __restrict__ tab, uint32_t tid, float x, float y,
+                          uint32_t& entry, uint32_t& cx8, uint32_t& cy8, uint32_t& ri) {
+    const float fx = x * SDT_S2_FINE_F, fy = y * SDT_S2_FINE_F;             // exact scalings; the point is inside [0,1)^2 here
+    cx8 = (uint32_t)fx; cy8 = (uint32_t)fy;
+    if (t.use_s2 && fx != (float)cx8 && fy != (float)cy8) {
+        entry = SDT_LDG(tab + (size_t)tid * SDT_S2_CELLS + (cy8 & (SDT_S2_SIDE - 1u)) * SDT_S2_SIDE + (cx8 & (SDT_S2_SIDE - 1u)));
+        return true;
+    }
+    ri = SDT_LDG(t.s2_rec + tid);
+    return false;
+}
+
 // pdfQuadTree from canonical position (x,y) in [0,1]^2.  ri = record index of the root (SDT_NONE:
 // single-leaf tree).  Finds the leaf (jump table, then 16 B of each record per level) and reads its
 // path product; split-line points and NaN stops go through sdt_quad_pdf_levels.
@@ -570,6 +601,7 @@ SDT_HD float sdt_quad_pdf(const TreeView& t, uint32_t ri, uint32_t root_node,
     bool tie = false;
     uint32_t cx, cy;
     if (ri < t.jump_trees && sdt_jump_cell(x, y, cx, cy)) {
+        uint32_t cont;                           // continuation: a record, or SDT_JUMP_TABLE | table id
         if (!want_node) {
             // the caller only wants the pdf: the table holds the leaf's path product itself
             const uint32_t j = SDT_LDG(t.jump_pp + (size_t)ri * SDT_JUMP_CELLS + cy * SDT_JUMP_SIDE + cx);
@@ -579,17 +611,36 @@ SDT_HD float sdt_quad_pdf(const TreeView& t, uint32_t ri, uint32_t root_node,
                 if (pp == pp) return pp * SDT_INV_FOUR_PI;
                 return sdt_quad_pdf_levels(rec, ri0, root_node, x, y, node_out);
             }
-            ri = j & ~SDT_JUMP_NEXT;
+            cont = j & ~SDT_JUMP_NEXT;
         } else {
             const QJump j = SDT_LDG(t.jump + (size_t)ri * SDT_JUMP_CELLS + cy * SDT_JUMP_SIDE + cx);
-            if (j & SDT_JUMP_LEAF) { node = j & ~SDT_JUMP_LEAF; ri = SDT_NONE; }
-            else ri = j;
+            if (j & SDT_JUMP_LEAF) { node = j & ~SDT_JUMP_LEAF; cont = SDT_NONE; }
+            else cont = j;
+        }
+        ri = cont;
+        float inv = SDT_JUMP_INV_F;
+        level = SDT_JUMP_LEVELS;
+        if (cont != SDT_NONE && (cont & SDT_JUMP_TABLE)) {
+            uint32_t e, cx8, cy8;
+            if (sdt_s2_lookup(t, want_node ? t.s2 : t.s2_pp, cont & ~SDT_JUMP_TABLE, x, y, e, cx8, cy8, ri)) {
+                if (!want_node) {
+                    if (!(e & SDT_JUMP_NEXT)) {
+                        const float pp = sdt_u2f(e);
+                        node_out = 0u;
+                        if (pp == pp) return pp * SDT_INV_FOUR_PI;
+                        return sdt_quad_pdf_levels(rec, ri0, root_node, x, y, node_out);
+                    }
+                    ri = e & ~SDT_JUMP_NEXT;
+                } else if (e & SDT_JUMP_LEAF) { node = e & ~SDT_JUMP_LEAF; ri = SDT_NONE; }
+                else ri = e;
+                cx = cx8; cy = cy8; inv = SDT_S2_FINE_INV_F;
+                level = SDT_JUMP_LEVELS + SDT_S2_LEVELS;
+            }
         }
         if (ri != SDT_NONE) {
-            lox = (float)cx * SDT_JUMP_INV_F; hix = (float)(cx + 1u) * SDT_JUMP_INV_F;
-            loy = (float)cy * SDT_JUMP_INV_F; hiy = (float)(cy + 1u) * SDT_JUMP_INV_F;
-            level = SDT_JUMP_LEVELS;
-        }
+            lox = (float)cx * inv; hix = (float)(cx + 1u) * inv;
+            loy = (float)cy * inv; hiy = (float)(cy + 1u) * inv;
+        } else level = 0;
     }
     for (; level < SDT_MAX_LEVELS && ri != SDT_NONE; ++level) {
         const QHead h = sdt_load_head(rec, ri);
@@ -608,11 +659,11 @@ SDT_HD float sdt_quad_pdf(const TreeView& t, uint32_t ri, uint32_t root_node,
 }
 
 // one jump-table entry: where the descent arrives for any interior point of cell (cx,cy)
-SDT_HD QJump sdt_build_jump(const QRec* __restrict__ rec, uint32_t root_rec, uint32_t cx, uint32_t cy) {
+SDT_HD QJump sdt_build_jump(const QRec* __restrict__ rec, uint32_t root_rec, uint32_t cx, uint32_t cy, int levels = SDT_JUMP_LEVELS) {
     uint32_t ri = root_rec;
-    for (int l = 0; l < SDT_JUMP_LEVELS; ++l) {
+    for (int l = 0; l < levels; ++l) {
         const QRec r = rec[ri];
-        const uint32_t bx = (cx >> (SDT_JUMP_LEVELS - 1 - l)) & 1u, by = (cy >> (SDT_JUMP_LEVELS - 1 - l)) & 1u;
+        const uint32_t bx = (cx >> (levels - 1 - l)) & 1u, by = (cy >> (levels - 1 - l)) & 1u;
         const uint32_t c = by ? (bx ? 0u : 1u) : (bx ? 3u : 2u);         // strict interior: every tie rule agrees
         ri = sdt_child_rec(r.cinfo, r.interior_base, c);
         if (ri == SDT_NONE) return SDT_JUMP_LEAF | ((r.child_base & SDT_NODE_MASK) + c);
@@ -798,9 +849,19 @@ SDT_HD uint32_t sdt_quad_leaf(const TreeView& t, uint32_t ri, uint32_t root_node
         const QJump j = SDT_LDG(t.jump + (size_t)ri * SDT_JUMP_CELLS + cy * SDT_JUMP_SIDE + cx);
         if (j & SDT_JUMP_LEAF) return j & ~SDT_JUMP_LEAF;
         ri = j;
-        lox = (float)cx * SDT_JUMP_INV_F; hix = (float)(cx + 1u) * SDT_JUMP_INV_F;
-        loy = (float)cy * SDT_JUMP_INV_F; hiy = (float)(cy + 1u) * SDT_JUMP_INV_F;
+        float inv = SDT_JUMP_INV_F;
         level = SDT_JUMP_LEVELS;
+        if (j & SDT_JUMP_TABLE) {
+            uint32_t e, cx8, cy8;
+            if (sdt_s2_lookup(t, t.s2, j & ~SDT_JUMP_TABLE, x, y, e, cx8, cy8, ri)) {
+                if (e & SDT_JUMP_LEAF) return e & ~SDT_JUMP_LEAF;
+                ri = e;
+                cx = cx8; cy = cy8; inv = SDT_S2_FINE_INV_F;
+                level = SDT_JUMP_LEVELS + SDT_S2_LEVELS;
+            }
+        }
+        lox = (float)cx * inv; hix = (float)(cx + 1u) * inv;
+        loy = (float)cy * inv; hiy = (float)(cy + 1u) * inv;
     }
     for (; level < SDT_MAX_LEVELS && ri != SDT_NONE; ++level) {
         const QHead h = sdt_load_head(rec, ri);      // 16 of the record's 32 bytes

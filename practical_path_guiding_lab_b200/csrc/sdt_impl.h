@@ -17,6 +17,10 @@ struct QuadSet {
     QRec* rec = nullptr;
     QJump* jump = nullptr;          // [root record][cell] jump table over the top SDT_JUMP_LEVELS levels
     uint32_t* jump_pp = nullptr;    // the pdf descents' table of the same shape (path products, SDT_JUMP_NEXT)
+    uint32_t* s2 = nullptr;         // second-stage tables [table][8x8] of `jump` (SDT_JUMP_TABLE), ...
+    uint32_t* s2_pp = nullptr;      // ... of `jump_pp`
+    uint32_t* s2_rec = nullptr;     // [table] -> record of its node
+    uint32_t* s2_of = nullptr;      // [level-5 record - s2_rec_lo] -> table id or SDT_NONE
     uint32_t* root_iidx = nullptr;
     DevHeader* hdr = nullptr;
 };
@@ -67,6 +71,8 @@ struct sdt_tree_s {
     uint64_t launches = 0;
     uint32_t levels_hint = 1;       // upper bound of quadtree levels in use
     uint32_t jump_cap = 0;          // trees the jump table can hold
+    uint32_t s2_cap = 0;            // second-stage tables the arena can hold
+    int use_jump2 = 1;
     uint32_t jump_trees_known = 0;  // trees covered, as last seen by the host (0 until known: slow path)
     int use_jump = 1;
     int use_int_cell = 1;
@@ -170,7 +176,8 @@ static inline TreeView tree_view(sdt_tree_s* h) {
     // deepest quadtree level the sampler can meet: exact once the header has been read back, else the refine's bound
     const uint32_t levels = h->levels_known ? h->levels_known : h->levels_hint;
     const uint32_t cell_mode = !h->use_int_cell ? 0u : (levels <= 17u ? 1u : (levels <= 24u && h->cfg.quad_max_depth <= 23 ? 2u : 0u));
-    return TreeView{s.hdr, h->kd_word, h->kd_root, h->kd_grid, s.rec, s.jump, s.jump_pp, s.pp, h->use_jump ? h->jump_trees_known : 0u, cell_mode};
+    return TreeView{s.hdr, h->kd_word, h->kd_root, h->kd_grid, s.rec, s.jump, s.jump_pp, s.s2, s.s2_pp, s.s2_rec,
+                    (uint32_t)(h->use_jump2 != 0), s.pp, h->use_jump ? h->jump_trees_known : 0u, cell_mode};
 }
 
 static int sdt_read_header(sdt_handle h, DevHeader& H);

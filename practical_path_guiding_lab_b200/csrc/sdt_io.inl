@@ -13,7 +13,7 @@ static int sdt_free_all(sdt_handle h) {
     for (void* p : ptrs) if (p) cudaFree(p);
     for (int k = 0; k < 2; ++k) {
         QuadSet& s = h->set[k];
-        void* q[] = {s.child, s.energy, s.thr, s.pp, s.iidx, s.rec, s.jump, s.jump_pp, s.root_iidx, s.hdr};
+        void* q[] = {s.child, s.energy, s.thr, s.pp, s.iidx, s.rec, s.jump, s.jump_pp, s.s2, s.s2_pp, s.s2_rec, s.s2_of, s.root_iidx, s.hdr};
         for (void* p : q) if (p) cudaFree(p);
     }
 #ifndef SDT_HOSTEMU
@@ -64,6 +64,7 @@ extern "C" int sdt_create(const sdt_config* cfg, sdt_handle* out) {
     h->rec_cap = h->quad_cap / 4u + 1u;
     h->jump_cap = h->kd_cap / 2u + 1u < 262144u ? h->kd_cap / 2u + 1u : 262144u;   // one table per tree = per spatial leaf
     if ((uint64_t)h->jump_cap * SDT_JUMP_CELLS > 4ull * h->quad_cap) h->jump_cap = (uint32_t)(4ull * h->quad_cap / SDT_JUMP_CELLS);
+    h->s2_cap = h->rec_cap < (1u << 19) ? h->rec_cap : (1u << 19);       // second-stage tables: 256 B each, two kinds
 #ifndef SDT_HOSTEMU
     {
         cudaError_t e = cudaSetDevice(cfg->device);
@@ -82,7 +83,8 @@ extern "C" int sdt_create(const sdt_config* cfg, sdt_handle* out) {
     for (int k = 0; k < 2; ++k) {
         QuadSet& s = h->set[k];
         A(s.child, h->quad_cap); A(s.energy, h->quad_cap); A(s.thr, h->quad_cap); A(s.pp, h->quad_cap); A(s.iidx, h->quad_cap);
-        A(s.rec, h->rec_cap); A(s.jump, (size_t)h->jump_cap * SDT_JUMP_CELLS); A(s.jump_pp, (size_t)h->jump_cap * SDT_JUMP_CELLS); A(s.root_iidx, h->kd_cap); A(s.hdr, 1);
+        A(s.rec, h->rec_cap); A(s.jump, (size_t)h->jump_cap * SDT_JUMP_CELLS); A(s.jump_pp, (size_t)h->jump_cap * SDT_JUMP_CELLS);
+        A(s.s2, (size_t)h->s2_cap * SDT_S2_CELLS); A(s.s2_pp, (size_t)h->s2_cap * SDT_S2_CELLS); A(s.s2_rec, h->s2_cap); A(s.s2_of, h->rec_cap); A(s.root_iidx, h->kd_cap); A(s.hdr, 1);
     }
 #undef A
     if (st == SDT_OK && cudaMallocHost((void**)&h->h_hdr, sizeof(DevHeader)) != cudaSuccess) st = sdt_fail(h, SDT_ERR_CUDA, "cudaMallocHost failed");
@@ -148,7 +150,7 @@ extern "C" int sdt_get_sizes(sdt_handle h, sdt_sizes* out) {
     DevHeader H;
     SDT_TRY(sdt_read_header(h, H));
     out->n_kd = H.n_kd; out->n_quad = H.n_quad; out->n_roots = H.n_roots; out->n_interior = H.n_interior;
-    out->n_levels = H.n_levels; out->kd_leaves = H.kd_leaves; out->error = H.error; out->refine_count = H.refine_count; out->jump_trees = H.jump_trees;
+    out->n_levels = H.n_levels; out->kd_leaves = H.kd_leaves; out->error = H.error; out->refine_count = H.refine_count; out->jump_trees = H.jump_trees; out->jump2_tables = H.s2_tables;
     h->levels_hint = H.n_levels > 0 ? H.n_levels : 1;
     return SDT_OK;
 }
@@ -387,6 +389,7 @@ extern "C" int sdt_set_tuning(sdt_handle h, const char* key, int64_t value) {
     else if (k == "fuse_sample_pdf") h->fuse_sample_pdf = value != 0;
     else if (k == "splat_aggregate") h->splat_aggregate = value != 0;
     else if (k == "use_jump") h->use_jump = value != 0;
+    else if (k == "use_jump2") h->use_jump2 = value != 0;
     else if (k == "use_kd_grid") h->use_kd_grid = value != 0;
     else if (k == "use_int_cell") h->use_int_cell = value != 0;
     else if (k == "quad_thr_reciprocal") h->quad_thr_reciprocal = value != 0;

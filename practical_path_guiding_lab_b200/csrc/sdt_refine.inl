@@ -318,19 +318,60 @@ struct PpLevelItem {
 // jump table: trees with a root record are records 0 .. iidx[n_roots]-1 (records follow node order)
 struct JumpCountItem {
     DevHeader* H; const uint32_t* iidx; uint32_t cap;
+    SDT_HD uint32_t rec_at(uint32_t node) const { return node < H->n_quad ? iidx[node] : H->n_interior; }
     SDT_HD void operator()() const {
         const uint32_t trees = H->n_roots < H->n_quad ? iidx[H->n_roots] : H->n_interior;
         H->jump_trees = trees <= cap ? trees : 0u;            // does not fit: table off, kernels take the level-by-level path
         H->lvl_n[0] = H->jump_trees * SDT_JUMP_CELLS;
+        // the non-leaf nodes of level SDT_JUMP_LEVELS (records follow node order, levels are contiguous): candidates for a
+        // second-stage table
+        H->s2_rec_lo = rec_at(H->level_off[SDT_JUMP_LEVELS]);
+        H->s2_rec_hi = rec_at(H->level_off[SDT_JUMP_LEVELS + 1]);
+        H->lvl_n[1] = H->jump_trees ? H->s2_rec_hi - H->s2_rec_lo : 0u;
+        H->s2_tables = 0;
+        H->kd_round_new = 0;                                  // scratch: second-stage entries to build
+    }
+};
+// second-stage tables go to the level-SDT_JUMP_LEVELS nodes that still have a non-leaf child (one more level below them
+// is answered by their own record just as fast)
+struct S2Flag {
+    const DevHeader* H; const QRec* rec;
+    SDT_HD uint32_t operator()(uint32_t i) const { return rec[H->s2_rec_lo + i].cinfo != 0xFFFFFFFFu ? 1u : 0u; }
+};
+struct S2Emit {
+    const DevHeader* H; uint32_t* s2_of; uint32_t* s2_rec; uint32_t cap;
+    SDT_HD void operator()(uint32_t i, uint32_t rank, uint32_t v) const {
+        s2_of[i] = (v && rank < cap) ? rank : SDT_NONE;
+        if (v && rank < cap) s2_rec[rank] = H->s2_rec_lo + i;
+    }
+};
+struct S2Fin {
+    DevHeader* H; uint32_t cap;
+    SDT_HD void operator()(uint32_t total) const {
+        H->s2_tables = total <= cap ? total : cap;            // (beyond the cap: those nodes simply keep their record)
+        H->kd_round_new = H->s2_tables * SDT_S2_CELLS;
     }
 };
 struct JumpBuildItem {
-    const QRec* rec; const float* pp; QJump* jump; uint32_t* jump_pp;
+    const DevHeader* H; const QRec* rec; const float* pp; const uint32_t* s2_of; QJump* jump; uint32_t* jump_pp;
     SDT_HD void operator()(uint32_t i) const {
         const uint32_t tr = i / SDT_JUMP_CELLS, cell = i % SDT_JUMP_CELLS;
-        const QJump j = sdt_build_jump(rec, tr, cell & (SDT_JUMP_SIDE - 1u), cell >> SDT_JUMP_LEVELS);
+        QJump j = sdt_build_jump(rec, tr, cell & (SDT_JUMP_SIDE - 1u), cell >> SDT_JUMP_LEVELS);
+        if (!(j & SDT_JUMP_LEAF) && H->s2_tables && j >= H->s2_rec_lo && j < H->s2_rec_hi) {
+            const uint32_t tid = s2_of[j - H->s2_rec_lo];
+            if (tid != SDT_NONE) j = SDT_JUMP_TABLE | tid;
+        }
         jump[i] = j;
         jump_pp[i] = sdt_jump_pp_entry(j, pp);
+    }
+};
+struct S2BuildItem {
+    const QRec* rec; const float* pp; const uint32_t* s2_rec; uint32_t* s2; uint32_t* s2_pp;
+    SDT_HD void operator()(uint32_t i) const {
+        const uint32_t tid = i / SDT_S2_CELLS, cell = i % SDT_S2_CELLS;
+        const QJump j = sdt_build_jump(rec, s2_rec[tid], cell & (SDT_S2_SIDE - 1u), cell >> SDT_S2_LEVELS, SDT_S2_LEVELS);
+        s2[i] = j;
+        s2_pp[i] = sdt_jump_pp_entry(j, pp);
     }
 };
 
@@ -345,7 +386,9 @@ static void sdt_build_records(sdt_handle h, const ExecCtx& x, QuadSet& s, bool w
     for (uint32_t l = 0; with_pp && l < h->levels_hint && l < SDT_MAX_LEVELS; ++l)
         launch_items(x, &s.hdr->level_cnt[l], 0, PpLevelItem{s.hdr, s.child, s.energy, s.pp, l});
     launch_single(x, JumpCountItem{s.hdr, s.iidx, h->jump_cap});
-    launch_items(x, &s.hdr->lvl_n[0], 0, JumpBuildItem{s.rec, s.pp, s.jump, s.jump_pp});
+    launch_scan(x, &s.hdr->lvl_n[1], 0, S2Flag{s.hdr, s.rec}, S2Emit{s.hdr, s.s2_of, s.s2_rec, h->s2_cap}, S2Fin{s.hdr, h->s2_cap});
+    launch_items(x, &s.hdr->lvl_n[0], 0, JumpBuildItem{s.hdr, s.rec, s.pp, s.s2_of, s.jump, s.jump_pp});
+    launch_items(x, &s.hdr->kd_round_new, 0, S2BuildItem{s.rec, s.pp, s.s2_rec, s.s2, s.s2_pp});
 }
 
 struct KdRollItem {         // prev.vertCount <- current.vertCount; current <- 0 (:141-153, :401-432)

@@ -272,10 +272,12 @@ def case_train_refine_nee_shallow(ctx):
 
 
 def case_jump_table_equals_descent(ctx):
-    """the 32x32 jump table over the top 5 quadtree levels answers pdf / splat descents with the
-    same bits as the level-by-level descent (grid-line points included: they take the slow path)"""
-    t, cur, prev = train(ctx, iters=4)
-    assert t.sizes()['jump_trees'] > 0
+    """the 32x32 jump table over the top 5 quadtree levels and the 8x8 second-stage tables over the next 3 answer pdf /
+    splat descents with the same bits as the level-by-level descent (points on the 1/32 and 1/256 grid lines included:
+    they take the slow paths)"""
+    t, cur, prev = train(ctx, iters=6, n=30000, caps=dict(kd_capacity=1 << 14, quad_capacity=1 << 20))
+    assert t.sizes()['jump_trees'] > 0 and t.sizes()['jump2_tables'] > 0
+    assert int(prev.quadTree.quadTreeNode.depth.max()) > 9
     rng = np.random.default_rng(17)
     n = 20000
     pos = rng.random((n, 3)).astype(F)
@@ -284,19 +286,30 @@ def case_jump_table_equals_descent(ctx):
     d2 = rng.random((n, 2)).astype(F)
     d2[:64] = (rng.integers(0, 33, (64, 2)) / 32.0).astype(F)            # exactly on the 1/32 grid lines
     d2[64:128, 0] = (rng.integers(0, 33, 64) / 32.0).astype(F)
-    dirs[:128] = dm.canonical_to_dir(d2[:128])
+    d2[128:192] = (rng.integers(0, 257, (64, 2)) / 256.0).astype(F)      # ... on the 1/256 lines of the second stage
+    d2[192:256, 1] = (rng.integers(0, 257, 64) / 256.0).astype(F)
+    m = slice(256, 6000)                                                  # many points in the lobes: the deep subtrees
+    d2[m] = np.clip(np.stack([0.3 + 0.004 * rng.standard_normal(5744), 0.7 + 0.004 * rng.standard_normal(5744)], 1), 0, 1).astype(F)
+    dirs[:6000] = dm.canonical_to_dir(d2[:6000])
     out = {}
-    for use in (1, 0):
+    for use, use2 in ((1, 1), (1, 0), (0, 1)):
         t.set_tuning("use_jump", use)
+        t.set_tuning("use_jump2", use2)
         p, dbg = t.pdf(ctx.dev(pos), ctx.dev(dirs), debug=True)
+        p2 = t.pdf(ctx.dev(pos), ctx.dev(dirs))                           # through the path-product tables
         t.reset_stats()
         t.splat_records(ctx.dev(pos), ctx.dev(d2), ctx.dev(np.ones(n, F)), ctx.dev(np.ones(n, F)))
-        out[use] = (ctx.host(p).copy(), ctx.host(dbg).copy(), t.download(1)['quadtree_irradiance'].copy())
+        out[(use, use2)] = (ctx.host(p).copy(), ctx.host(dbg).copy(), t.download(1)['quadtree_irradiance'].copy(), ctx.host(p2).copy())
     t.set_tuning("use_jump", 1)
+    t.set_tuning("use_jump2", 1)
     t.reset_stats()
-    assert beq(out[1][0], out[0][0]) and np.array_equal(out[1][1], out[0][1]) and np.array_equal(out[1][2], out[0][2])
+    ref = out[(0, 1)]
+    for k in ((1, 1), (1, 0)):
+        assert beq(out[k][0], ref[0]) and np.array_equal(out[k][1], ref[1]) and np.array_equal(out[k][2], ref[2]) and beq(out[k][3], ref[0]), k
     op, odbg = prev.pdf(pos, dirs, True, return_debug=True)
-    assert beq(out[1][0], op) and np.array_equal(out[1][1].view(U)[:, 2], odbg['pdf_node'])
+    assert beq(ref[0], op) and np.array_equal(ref[1].view(U)[:, 2], odbg['pdf_node'])
+    depth = prev.quadTree.quadTreeNode.depth[odbg['pdf_node']]
+    assert (depth > 8).sum() > 500 and ((depth > 5) & (depth <= 8)).sum() > 500      # both stages and the records below them were used
 
 
 def case_spatial_descent_variants(ctx):
