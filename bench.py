@@ -50,18 +50,22 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--tune", action="append", default=[], help="key=value passed to sdt_set_tuning (repeatable)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--layout", default="aos", choices=["soa", "aos"],
+                    help="device-resident vectors interleaved (n,3) or as separate component planes (Dr.Jit's Vector3f layout); measured within 1 %% of each other")
     ap.add_argument("--no-numa-bind", action="store_true", help="do not pin the rank to its GPU's NUMA-local CPUs (e2e experiments)")
     ap.add_argument("--lib", default=None, help="path of an alternative build of libsdtree.so (kernel experiments)")
     return ap.parse_args()
 
 
-def workload_config(n, world):
+def workload_config(n, world, layout="aos"):
     from practical_path_guiding_lab_b200 import synthetic as syn
     return {"workload": "synthetic frozen SD-tree microbench (BASELINE configs[1])",
             "queries_per_step_per_gpu": n, "ops_per_query": ["sample", "pdf", "splat"],
             "tree_build": {"iterations": syn.BUILD_ITERS, "records_iter0": syn.BUILD_N0, "c": syn.BUILD_C,
                            "seed": syn.BUILD_SEED},
             "l2_policy": "inputs (>= 200 MB per array set) larger than the 126 MB L2; the tree (~13 MB of records) is meant to stay L2-resident",
+            "vector_layout": {"soa": "component planes (Dr.Jit Vector3f: x, y, z separate arrays) for the device-resident step; the host-buffer e2e leg sends interleaved (n,3) arrays",
+                              "aos": "interleaved (n,3)"}[layout],
             "parallelism": f"replicated tree, vertices sharded x{world}"}
 
 
@@ -257,6 +261,13 @@ def run_b200(args):
     d_pos, d_dir = h_pos.to(dev), h_dir.to(dev)
     d_rec = {k: v.to(dev) for k, v in h_rec.items()}
     o_dir = torch.empty(n, 3, device=dev)
+    if args.layout == "soa":
+        # component planes: mi.Vector3f / Point3f are three separate arrays in Dr.Jit, so this is the layout the integrator's
+        # buffers have; a lane's x, y, z are then three coalesced accesses instead of three 12-byte-strided ones
+        planes = lambda t: tuple(t[:, k].contiguous() for k in range(t.shape[1]))
+        d_pos, d_dir, o_dir = planes(d_pos), planes(d_dir), planes(o_dir)
+        d_rec = dict(d_rec, position=planes(d_rec['position']), direction=planes(d_rec['direction']))
+    sub = lambda v, ix: tuple(c[ix].contiguous() for c in v) if isinstance(v, tuple) else v[ix].contiguous()      # rows of a vector array in either layout
     o_pdf = torch.empty(n, device=dev)
     o_pdf2 = torch.empty(n, device=dev)
     lane0 = rank * n
@@ -314,13 +325,13 @@ def run_b200(args):
     # ---- algorithmic bytes from the measured depths of a 2^20-lane subset
     m = min(n, 1 << 20)
     tr = tree.download(0)
-    leaf, _ = tree.locate(d_pos[:m])
+    leaf, _ = tree.locate(sub(d_pos, slice(0, m)))
     ds = tr['kdtree_depth'][leaf.cpu().numpy().view(np.uint32)].astype(np.float64).mean()
-    _, _, dbg = tree.sample(d_pos[:m], seed=3, lane_offset=lane0, debug=True)
+    _, _, dbg = tree.sample(sub(d_pos, slice(0, m)), seed=3, lane_offset=lane0, debug=True)
     dbg = dbg.cpu().numpy().view(np.uint32)
     dq_s = tr['quadtree_depth'][dbg[:, 2]].astype(np.float64).mean()
     redescend = float((dbg[:, 2] != dbg[:, 3]).mean())
-    _, dbgp = tree.pdf(d_pos[:m], d_dir[:m], debug=True)
+    _, dbgp = tree.pdf(sub(d_pos, slice(0, m)), sub(d_dir, slice(0, m)), debug=True)
     dq_pl = tr['quadtree_depth'][dbgp.cpu().numpy().view(np.uint32)[:, 2]].astype(np.float64)
     dq_p = dq_pl.mean()
     # depth reached by the splat's directions (drawn from the lobes, deeper than the pdf's uniform ones): a pdf query with
@@ -329,7 +340,7 @@ def run_b200(args):
     ct = 2.0 * cxy[:, 1] - 1.0
     st_ = np.sqrt(np.maximum(0.0, 1.0 - ct * ct))
     rdir = torch.from_numpy(np.stack([st_ * np.cos(2 * np.pi * cxy[:, 0]), st_ * np.sin(2 * np.pi * cxy[:, 0]), ct], 1).astype(np.float32)).to(dev)
-    _, dbgr = tree.pdf(d_rec['position'][:m], rdir, debug=True)
+    _, dbgr = tree.pdf(sub(d_rec['position'], slice(0, m)), rdir, debug=True)
     dq_rl = tr['quadtree_depth'][dbgr.cpu().numpy().view(np.uint32)[:, 2]].astype(np.float64)
     dq_r = dq_rl.mean()
     JL, J2 = 5, 8                                                # depth <= 5 ends inside the root jump table, <= 8 inside a second-stage table
@@ -469,10 +480,10 @@ def run_b200(args):
         try:
             leaf_q, _ = tree.locate(d_pos)
             oq = torch.argsort(leaf_q.view(torch.int32).to(torch.int64), stable=True)
-            c_pos, c_dir = d_pos[oq].contiguous(), d_dir[oq].contiguous()
+            c_pos, c_dir = sub(d_pos, oq), sub(d_dir, oq)
             leaf_r, _ = tree.locate(d_rec['position'])
             orr = torch.argsort(leaf_r.view(torch.int32).to(torch.int64), stable=True)
-            c_rec = {k: v[orr].contiguous() for k, v in d_rec.items()}
+            c_rec = {k: sub(v, orr) for k, v in d_rec.items()}
             del leaf_q, leaf_r, oq, orr
             coherent["sample_ms"] = timeit(lambda: tree.sample(c_pos, seed=3, lane_offset=lane0, out=(o_dir, o_pdf)))
             coherent["pdf_ms"] = timeit(lambda: tree.pdf(c_pos, c_dir, out=o_pdf2))
@@ -596,7 +607,7 @@ def run_b200(args):
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-                "data": "synthetic", "config": workload_config(n, world), "clocks": clk.summary(), "e2e": e2e,
+                "data": "synthetic", "config": workload_config(n, world, args.layout), "clocks": clk.summary(), "e2e": e2e,
                 "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu,
                 "tree": {k: sizes[k] for k in ("n_kd", "kd_leaves", "n_quad", "n_interior", "n_levels")},
                 "tree_device_trained": dict({k: sizes_trained[k] for k in ("n_kd", "kd_leaves", "n_quad", "n_interior", "n_levels")},

@@ -15,7 +15,7 @@ for spec in sys.argv[1:]:
     name = parts[0]
     lib = parts[1] if len(parts) > 1 and parts[1] else None
     tunes = parts[2].split(",") if len(parts) > 2 and parts[2] else []
-    cmd = [sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "20", "--warmup", "5", "--no-e2e", "--no-cpu-baseline"]
+    cmd = [sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "20", "--warmup", "5", "--no-e2e", "--no-cpu-baseline"] + (["--layout", "soa"] if name.startswith("soa") else [])
     if lib:
         cmd += ["--lib", os.path.join(ROOT, lib)]
     for t in tunes:
