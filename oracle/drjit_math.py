@@ -15,8 +15,8 @@ algorithm is restated here with every operation a separately rounded IEEE fp32
 multiply/add (numpy has no fused multiply-add), so the CUDA library -- built with
 -fmad=false, IEEE div/sqrt -- reproduces these functions BIT FOR BIT.  They are
 NOT claimed bit-identical to Dr.Jit itself (Dr.Jit contracts to FMA and, on its
-CUDA backend, may use approximate div/sqrt): PARITY UNPINNED against the real
-Dr.Jit; the north_star tolerance (1e-5 relative on directions/pdfs) is what a real
+CUDA backend, may use approximate div/sqrt): this file is the one part of the
+oracle the reference-on-stand-ins leg cannot pin (the stand-ins call it); the north_star tolerance (1e-5 relative on directions/pdfs) is what a real
 Dr.Jit run would be held to.  tests/test_oracle_math.py checks these against
 float64 libm to a few ulp.
 """

@@ -8,13 +8,17 @@ Every method cites the reference lines it follows.  The code is deliberately
 scatter_reduce / compress / masked assignment), host `while` loops where the
 reference has host loops, lane-masked loops where it has recorded `mi.Loop`s.
 
-PARITY UNPINNED: the reference ships no tests, golden vectors or saved trees for
-this path and Mitsuba 3 + Dr.Jit (un-vendored, un-pinned
-dependencies) are not installable here, so this oracle cannot be checked against
-outputs of the reference itself.  It is anchored instead on (i) the topology
-vectors hand-derived from the reference source (tests/test_oracle_golden.py),
-(ii) the reference's own validators and conservation checks
-(src/kdtree.py:361-398,769-772; src/quadtree.py:468-509,1205-1218).
+PINNED AGAINST THE REFERENCE'S OWN SOURCE (round 2): the reference ships no tests, golden vectors or saved
+trees for this path and Mitsuba 3 + Dr.Jit are not installable here, but its
+source files run UNMODIFIED on the numpy stand-ins for Dr.Jit / Mitsuba in oracle/refshim/
+(load_reference()).  tests/test_reference_on_shim.py holds this oracle against that leg bit for bit:
+every parity case of tests/sdt_cases.py, 40 randomised differential seeds, train / query sequences,
+the reference's own __main__ self-tests and validators (src/kdtree.py:361-398,769-772;
+src/quadtree.py:468-509,1205-1218).  What that does NOT pin is the semantics of the Dr.Jit
+primitives themselves (listed below, and the CEPHES sincos / atan2 of oracle/drjit_math.py): they
+are assumptions of the stand-ins.  tools/record_reference_fixtures.py records the same vectors from
+a real Mitsuba installation when one is at hand.  Further anchors: (i) topology vectors hand-derived
+from the reference source (tests/test_oracle_golden.py), (ii) conservation checks.
 
 Third-party semantics assumed (Dr.Jit 0.4.x / Mitsuba 3.0-3.5):
   * BoundingBox.contains is inclusive on both ends; NaN is outside.

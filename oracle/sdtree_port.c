@@ -6,8 +6,9 @@
  * and tests the stored child bounding boxes exactly as the Dr.Jit code does.  It exists so that
  * bench.py can time "the reference's algorithm on all host cores" (Mitsuba 3 / Dr.Jit are not
  * installable in this image); tests/test_oracle_port.py holds it against the numpy
- * oracle (bit-exact directions / pdfs / node ids).  PARITY UNPINNED against real Dr.Jit, like the
- * numpy oracle.  Build: oracle/Makefile -> oracle/_build/libsdtree_port.so
+ * oracle (bit-exact directions / pdfs / node ids), which itself is pinned to the reference's own
+ * source run on numpy stand-ins for Dr.Jit (oracle/refshim, tests/test_reference_on_shim.py); the
+ * semantics of the Dr.Jit primitives stay assumed.  Build: oracle/Makefile -> oracle/_build/libsdtree_port.so
  *   gcc -O2 -fopenmp -ffp-contract=off -fno-fast-math (fp32 ops separately rounded, like numpy)
  */
 #include <math.h>

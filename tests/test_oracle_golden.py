@@ -2,8 +2,9 @@
 reference offers for this path: topology vectors hand-derived from the
 reference source, the reference's own validators (child bbox inside parent) and its
 conservation checks (root energy = sum of leaves = sum radiance/woPdf; sum of leaf
-counts = number of records).  The reference has no stored expected outputs, so parity
-with the real Dr.Jit implementation stays UNPINNED (stated in the oracle header)."""
+counts = number of records).  The reference has no stored expected outputs; the oracle is
+pinned to the reference's own source run on numpy stand-ins for Dr.Jit / Mitsuba in
+tests/test_reference_on_shim.py (the primitives' semantics stay assumed, see the oracle header)."""
 import numpy as np
 
 from oracle import sdtree_oracle as so
