@@ -82,7 +82,8 @@ typedef struct sdt_sizes {
     uint32_t n_interior; /* non-leaf quadtree nodes                */
     uint32_t n_levels;   /* quadtree levels in use                 */
     uint32_t kd_leaves;
-    uint32_t error;      /* sticky device-side error flag (0 = none) */
+    uint32_t error;      /* sticky device-side error flags (0 = none; 1 spatial arena, 2 quadtree arena exhausted: tree truncated;
+                            4 a refine scan stalled: internal error, tree invalid) */
     uint32_t refine_count;
     uint32_t jump_trees; /* quadtrees covered by the 32x32 jump table over their top 5 levels */
     uint32_t jump2_tables; /* level-5 nodes that own a second-stage 8x8 table over their next 3 levels */

@@ -95,10 +95,12 @@ struct DevHeader {
     uint32_t lvl_trunc;                     // capacity exhausted: the level being built becomes all leaves
     uint32_t n_roots_old, n_quad_old;
     uint32_t pad2[2];
+    uint32_t int_off[SDT_MAX_LEVELS + 2];    // non-leaf nodes in the levels above level l of the forest being built
 };
 
 enum DevError : uint32_t {
-    DEV_OK = 0, DEV_ERR_KD_CAPACITY = 1, DEV_ERR_QUAD_CAPACITY = 2
+    DEV_OK = 0, DEV_ERR_KD_CAPACITY = 1, DEV_ERR_QUAD_CAPACITY = 2,
+    DEV_ERR_SCAN_STALL = 4       // a scan block gave up waiting for a lower-numbered block (see k_scan_fused): results are invalid
 };
 
 // What the query kernels need (by value).
@@ -658,17 +660,28 @@ SDT_HD float sdt_quad_pdf(const TreeView& t, uint32_t ri, uint32_t root_node,
     return pp * SDT_INV_FOUR_PI;
 }
 
-// one jump-table entry: where the descent arrives for any interior point of cell (cx,cy)
-SDT_HD QJump sdt_build_jump(const QRec* __restrict__ rec, uint32_t root_rec, uint32_t cx, uint32_t cy, int levels = SDT_JUMP_LEVELS) {
+// Jump-table entries: where the descent arrives for any interior point of a cell (strict interior: every tie rule agrees).
+// the four entries of the 2 x 2 block of cells (2qx + bx, 2qy + by), out[by * 2 + bx]: the block shares every level of the
+// descent but the last, so a table costs a quarter of the dependent loads of one descent per cell
+SDT_HD void sdt_build_jump4(const QRec* __restrict__ rec, uint32_t root_rec, uint32_t qx, uint32_t qy, int levels, QJump out[4]) {
     uint32_t ri = root_rec;
-    for (int l = 0; l < levels; ++l) {
+    for (int l = 0; l + 1 < levels; ++l) {
         const QRec r = rec[ri];
-        const uint32_t bx = (cx >> (levels - 1 - l)) & 1u, by = (cy >> (levels - 1 - l)) & 1u;
-        const uint32_t c = by ? (bx ? 0u : 1u) : (bx ? 3u : 2u);         // strict interior: every tie rule agrees
+        const uint32_t bx = (qx >> (levels - 2 - l)) & 1u, by = (qy >> (levels - 2 - l)) & 1u;
+        const uint32_t c = by ? (bx ? 0u : 1u) : (bx ? 3u : 2u);
         ri = sdt_child_rec(r.cinfo, r.interior_base, c);
-        if (ri == SDT_NONE) return SDT_JUMP_LEAF | ((r.child_base & SDT_NODE_MASK) + c);
+        if (ri == SDT_NONE) {
+            out[0] = out[1] = out[2] = out[3] = SDT_JUMP_LEAF | ((r.child_base & SDT_NODE_MASK) + c);
+            return;
+        }
     }
-    return ri;
+    const QRec r = rec[ri];
+    for (uint32_t k = 0; k < 4u; ++k) {
+        const uint32_t bx = k & 1u, by = k >> 1;
+        const uint32_t c = by ? (bx ? 0u : 1u) : (bx ? 3u : 2u);
+        const uint32_t nri = sdt_child_rec(r.cinfo, r.interior_base, c);
+        out[k] = nri == SDT_NONE ? (SDT_JUMP_LEAF | ((r.child_base & SDT_NODE_MASK) + c)) : nri;
+    }
 }
 
 // the pdf descents' entry for the same cell (see SDT_JUMP_NEXT)

@@ -8,16 +8,20 @@
 #include "sdt_core.h"
 
 #define SDT_SCAN_MAX_BLOCKS 1024
-// scratch of one scan: [0] ticket counter, [1] finished-blocks counter, then one 64-bit status word per block
+// scratch of the scans: [0] scan counter (the epoch that tags the status words), [1] stall flag, then one 64-bit status word per block
 #define SDT_SCAN_STATE_WORDS (4 + 2 * SDT_SCAN_MAX_BLOCKS)
 
 struct ExecCtx {
     cudaStream_t st;
     int num_sms;
-    uint32_t* blk;        // device scratch of the scans: SDT_SCAN_STATE_WORDS words, all zero between scans
+    uint32_t* blk;        // device scratch of the scans: SDT_SCAN_STATE_WORDS words (zero at creation, never reset)
     uint64_t* launches;   // kernel launch counter of the handle
     bool pdl;             // programmatic dependent launch for the helper kernels (see sdt_launch)
 };
+
+// what a scan adds up: the flag functor returns the 0/1 count itself, or a struct that carries it together with whatever
+// the emit wants back (overload sdt_scan_count next to the struct)
+SDT_HD uint32_t sdt_scan_count(uint32_t v) { return v; }
 
 #ifndef SDT_HOSTEMU
 // ---------------------------------------------------------------------------- CUDA
@@ -103,45 +107,80 @@ __device__ __forceinline__ void sdt_chunk(uint32_t n, uint32_t& lo, uint32_t& hi
 }
 
 // Exclusive scan + emit + fin in ONE kernel (the refine is a chain of dependent launches, so a scan that costs one launch
-// instead of three shortens it by two launch latencies per level): single pass with decoupled look-back.  Blocks take
-// their chunk in the order they START (a ticket), so a block only ever waits for blocks that are already running -- no
-// co-residency assumption, safe under programmatic dependent launch.  Status word of a block: (kind << 32) | value with
-// kind 1 = its own total, 2 = inclusive prefix.  The last block to finish zeroes the scratch for the next scan.
+// instead of three shortens it by two launch latencies per level): single pass with decoupled look-back.
+//
+// What the chain pays per scan is LATENCY, and the first version of this kernel spent most of it on two same-address
+// atomics per block (a start-order ticket and a finished-blocks counter for the scratch reset: ~4 ns each, 8-11 us for an
+// EMPTY level at 592 blocks).  Now there is none:
+//  * the grid is fixed (n lives on the device) at 4 blocks of 256 threads per SM, which __launch_bounds__(256, 4) makes
+//    co-resident by construction -- so a block may wait for any lower-numbered block whatever order they start in (blocks
+//    of the previous kernel, still around under programmatic dependent launch, leave on their own);
+//  * only ceil(n / chunk) blocks take part, the others return at once: on a level of a few thousand nodes the look-back
+//    chain is as short as the data;
+//  * status words are tagged with the scan's number: (epoch << 34) | (kind << 32) | value, kind 1 = the block's own total,
+//    2 = inclusive prefix.  Words left by earlier scans never match, so nothing is reset; the epoch lives in state[0] and is
+//    advanced by the block that holds the last chunk once its look-back is through -- every other participant has
+//    published by then, hence read the epoch.
+//  * a thread takes as few items as the grid allows (one up to 151 k items on 148 SMs); while a chunk fits SDT_SCAN_ITEMS
+//    items per thread each thread evaluates flag ONCE, keeps the results in registers -- flag may return a struct
+//    (sdt_scan_count names its 0/1 count), emit gets it back -- and ONE block scan yields the block total and the ranks;
+//    larger inputs loop over the chunk twice and evaluate flag again for the emit.
 // Order of side effects: emit of every block may run BEFORE fin (fin runs on the block that holds the last chunk, after
 // its look-back); emit therefore must not depend on what fin writes.
+#define SDT_SCAN_ITEMS 4
+#define SDT_SCAN_BLOCKS_PER_SM 4
 template <class Flag, class Emit, class Fin>
-__global__ void __launch_bounds__(256) k_scan_fused(Flag flag, Emit emit, Fin fin, const uint32_t* n_ptr, uint32_t n_imm, uint32_t* state) {
+__global__ void __launch_bounds__(256, SDT_SCAN_BLOCKS_PER_SM) k_scan_fused(Flag flag, Emit emit, Fin fin, const uint32_t* n_ptr, uint32_t n_imm, uint32_t* state) {
+    typedef decltype(flag(0u)) V;
     __shared__ uint32_t ws[33];
-    __shared__ uint32_t s_b, s_prefix;
+    __shared__ uint32_t s_prefix;
     sdt_grid_dep();
     unsigned long long* status = reinterpret_cast<unsigned long long*>(state + 4);
-    if (threadIdx.x == 0) s_b = atomicAdd(state, 1u);
-    __syncthreads();
-    const uint32_t b = s_b;
     const uint32_t n = n_ptr ? *n_ptr : n_imm;
     uint32_t chunk = (n + gridDim.x - 1u) / gridDim.x;
     chunk = (chunk + blockDim.x - 1u) / blockDim.x * blockDim.x;
+    if (chunk < blockDim.x) chunk = blockDim.x;
+    uint32_t eff = (uint32_t)(((uint64_t)n + chunk - 1u) / chunk);   // blocks that take part (block 0 always does: fin)
+    if (eff == 0u) eff = 1u;
+    const uint32_t b = blockIdx.x;
+    if (b >= eff) return;
     const uint64_t a64 = (uint64_t)b * chunk, b64 = a64 + chunk;
     const uint32_t lo = a64 < n ? (uint32_t)a64 : n, hi = b64 < n ? (uint32_t)b64 : n;
+    const bool cached = chunk <= SDT_SCAN_ITEMS * blockDim.x;
+    const uint32_t per = chunk / blockDim.x;                          // items per thread (thread-contiguous)
+    const uint32_t t0 = lo + threadIdx.x * per;
+    uint32_t e_raw = 0;
+    if (threadIdx.x == 0) e_raw = *reinterpret_cast<volatile uint32_t*>(state);
+    V vals[SDT_SCAN_ITEMS];
     uint32_t acc = 0;
-    for (uint32_t i = lo + threadIdx.x; i < hi; i += blockDim.x) acc += flag(i);
+    if (cached) {
+#pragma unroll
+        for (uint32_t k = 0; k < SDT_SCAN_ITEMS; ++k)
+            if (k < per && t0 + k < hi) { vals[k] = flag(t0 + k); acc += sdt_scan_count(vals[k]); }
+    } else {
+        for (uint32_t i = lo + threadIdx.x; i < hi; i += blockDim.x) acc += sdt_scan_count(flag(i));
+    }
     uint32_t total;
-    sdt_block_excl_scan(acc, ws, total);
+    const uint32_t ex0 = sdt_block_excl_scan(acc, ws, total);
     if (threadIdx.x < 32u) {
         const uint32_t lane = threadIdx.x;
-        if (lane == 0u) {
-            atomicExch(&status[b], ((unsigned long long)(b == 0u ? 2u : 1u) << 32) | total);
-        }
+        e_raw = __shfl_sync(0xFFFFFFFFu, e_raw, 0);
+        const unsigned long long epoch = (unsigned long long)(e_raw % 0x3FFFFFFFu) + 1ull;     // 1 .. 2^30 - 1: zeroed scratch never matches
+        if (lane == 0u) atomicExch(&status[b], (epoch << 34) | ((unsigned long long)(b == 0u ? 2u : 1u) << 32) | total);
         uint32_t prefix = 0;
         if (b > 0u) {
-            int j = (int)b - 1;                       // look back, 32 predecessors at a time
+            int j = (int)b - 1;                           // look back, 32 predecessors at a time
             for (;;) {
                 const int idx = j - (int)lane;
                 unsigned long long sv = 0;
                 if (idx >= 0) {
-                    do { sv = *reinterpret_cast<volatile unsigned long long*>(&status[idx]); } while ((sv >> 32) == 0ull);
-                } else sv = 2ull << 32;               // before the first block: an inclusive prefix of 0
-                const uint32_t kind = (uint32_t)(sv >> 32), val = (uint32_t)sv;
+                    // (the bound only keeps a broken co-residency assumption from hanging the GPU: state[1] is raised and
+                    // surfaces as DEV_ERR_SCAN_STALL with the next header read-back)
+                    uint32_t spins = 0;
+                    do { sv = *reinterpret_cast<volatile unsigned long long*>(&status[idx]); } while ((sv >> 34) != epoch && ++spins < (1u << 24));
+                    if ((sv >> 34) != epoch) { state[1] = 1u; sv = 2ull << 32; }
+                } else sv = 2ull << 32;                   // before the first block: an inclusive prefix of 0
+                const uint32_t kind = (uint32_t)(sv >> 32) & 3u, val = (uint32_t)sv;
                 const uint32_t incl = __ballot_sync(0xFFFFFFFFu, kind == 2u);
                 // lanes up to and including the nearest inclusive prefix contribute
                 const uint32_t first = incl ? (uint32_t)__ffs(incl) - 1u : 32u;
@@ -152,31 +191,33 @@ __global__ void __launch_bounds__(256) k_scan_fused(Flag flag, Emit emit, Fin fi
                 if (incl) break;
                 j -= 32;
             }
-            if (lane == 0u) atomicExch(&status[b], (2ull << 32) | (unsigned long long)(prefix + total));
+            if (lane == 0u) atomicExch(&status[b], (epoch << 34) | (2ull << 32) | (unsigned long long)(prefix + total));
         }
-        if (lane == 0u) s_prefix = prefix;
+        if (lane == 0u) {
+            s_prefix = prefix;
+            if (b == eff - 1u) {
+                fin(prefix + total);
+                *reinterpret_cast<volatile uint32_t*>(state) = e_raw + 1u;    // the next scan's epoch
+            }
+        }
     }
     __syncthreads();
     uint32_t carry = s_prefix;
-    if (threadIdx.x == 0 && b == gridDim.x - 1u) fin(carry + total);
-    for (uint32_t base = lo; base < hi; base += blockDim.x) {
-        const uint32_t i = base + threadIdx.x;
-        const uint32_t v = i < hi ? flag(i) : 0u;
-        uint32_t tot;
-        const uint32_t ex = sdt_block_excl_scan(v, ws, tot);
-        if (i < hi) emit(i, carry + ex, v);
-        carry += tot;
-    }
-    // the last block out resets the scratch (every block is past its look-back by then)
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        __threadfence();
-        s_b = atomicAdd(state + 1, 1u);
-    }
-    __syncthreads();
-    if (s_b == gridDim.x - 1u) {
-        for (uint32_t k = threadIdx.x; k < 2u * gridDim.x; k += blockDim.x) state[4u + k] = 0u;
-        if (threadIdx.x == 0) { state[0] = 0u; state[1] = 0u; }
+    if (cached) {
+        uint32_t r = carry + ex0;
+#pragma unroll
+        for (uint32_t k = 0; k < SDT_SCAN_ITEMS; ++k)
+            if (k < per && t0 + k < hi) { emit(t0 + k, r, vals[k]); r += sdt_scan_count(vals[k]); }
+    } else {
+        for (uint32_t base = lo; base < hi; base += blockDim.x) {
+            const uint32_t i = base + threadIdx.x;
+            V v = V();
+            if (i < hi) v = flag(i);
+            uint32_t tot;
+            const uint32_t ex = sdt_block_excl_scan(i < hi ? sdt_scan_count(v) : 0u, ws, tot);
+            if (i < hi) emit(i, carry + ex, v);
+            carry += tot;
+        }
     }
 }
 
@@ -184,7 +225,7 @@ __global__ void __launch_bounds__(256) k_scan_fused(Flag flag, Emit emit, Fin fi
 // flag must be pure and must not read anything emit or fin writes.
 template <class Flag, class Emit, class Fin>
 static inline void launch_scan(const ExecCtx& x, const uint32_t* n_ptr, uint32_t n_imm, Flag flag, Emit emit, Fin fin) {
-    uint32_t grid = (uint32_t)x.num_sms * 4u;
+    uint32_t grid = (uint32_t)x.num_sms * SDT_SCAN_BLOCKS_PER_SM;      // co-resident by the kernel's launch bounds
     if (grid > SDT_SCAN_MAX_BLOCKS) grid = SDT_SCAN_MAX_BLOCKS;
     if (!n_ptr) {
         const uint32_t g = (n_imm + 255u) / 256u;
@@ -213,14 +254,17 @@ static inline void launch_items(const ExecCtx& x, const uint32_t* n_ptr, uint32_
 template <class Flag, class Emit, class Fin>
 static inline void launch_scan(const ExecCtx& x, const uint32_t* n_ptr, uint32_t n_imm, Flag flag, Emit emit, Fin fin) {
     const uint32_t n = n_ptr ? *n_ptr : n_imm;
-    // like the device version: ranks from a first evaluation of flag, emit with flag evaluated AGAIN, and fin LAST (on
-    // the device fin runs on one block while others may already have emitted: emit must not depend on it)
+    // like the device version: flag evaluated for every item first (ranks), emit with those values afterwards, and fin
+    // LAST (on the device fin runs on one block while others may already have emitted: emit must not depend on it)
+    typedef decltype(flag(0u)) V;
     uint32_t run = 0;
     uint32_t* ranks = (uint32_t*)malloc(sizeof(uint32_t) * (n ? n : 1));
-    for (uint32_t i = 0; i < n; ++i) { ranks[i] = run; run += flag(i); }
-    for (uint32_t i = 0; i < n; ++i) emit(i, ranks[i], flag(i));
+    V* vals = (V*)malloc(sizeof(V) * (n ? n : 1));
+    for (uint32_t i = 0; i < n; ++i) { vals[i] = flag(i); ranks[i] = run; run += sdt_scan_count(vals[i]); }
+    for (uint32_t i = 0; i < n; ++i) emit(i, ranks[i], vals[i]);
     fin(run);
     free(ranks);
+    free(vals);
     *x.launches += 1;
 }
 template <class F>

@@ -135,6 +135,11 @@ static int sdt_read_header(sdt_handle h, DevHeader& H) {
     SDT_CUDA(h, cudaStreamSynchronize(h->last_stream));
     SDT_CUDA(h, cudaMemcpy(h->h_hdr, h->set[h->cur].hdr, sizeof(DevHeader), cudaMemcpyDeviceToHost));
     H = *h->h_hdr;
+#ifndef SDT_HOSTEMU
+    uint32_t stall = 0;
+    SDT_CUDA(h, cudaMemcpy(&stall, h->s_blk + 1, sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    if (stall) H.error |= DEV_ERR_SCAN_STALL;
+#endif
     h->hdr_pending = false;
     h->kd_nodes_known = H.n_kd;
     h->n_quad_known = H.n_quad;

@@ -9,6 +9,7 @@
 // _lib.py loads libsdtree.so and nothing else) and nothing is measured through it.
 #pragma once
 
+#include <stddef.h>
 #include <stdint.h>
 #include <stdlib.h>
 #include <string.h>

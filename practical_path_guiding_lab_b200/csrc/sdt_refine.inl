@@ -34,15 +34,21 @@ struct RefineCtx {
     uint32_t thr_recip;   // threshold = E * fp32(1/100) instead of E / 100 (how Dr.Jit may lower the literal division)
 };
 
+// header of the tree being built <- header of the tree being refined, with the refine's counters reset: one thread per
+// 32-bit word (a single thread copying the ~700-byte struct was an 8-11 us link of the launch chain)
 struct RefineInit {
     RefineCtx c;
-    SDT_HD void operator()() const {
-        *c.H1 = *c.H0;
-        DevHeader* H = c.H1;
-        H->kd_n_old = H->n_kd; H->n_roots_old = H->n_roots; H->n_quad_old = H->n_quad;
-        H->kd_sel = 0; H->kd_round_new = 0; H->kd_round_base = H->n_kd; H->kd_prev_round_base = H->n_kd;
-        H->kd_round_root_base = H->n_roots; H->kd_stop = 0; H->lvl_trunc = 0;
-        H->refine_count = H->refine_count + 1u;
+    SDT_HD void operator()(uint32_t w) const {
+        const DevHeader* H0 = c.H0;
+        uint32_t v = reinterpret_cast<const uint32_t*>(H0)[w];
+#define SDT_HDR_WORD(field) (offsetof(DevHeader, field) / 4u)
+        if (w == SDT_HDR_WORD(kd_n_old) || w == SDT_HDR_WORD(kd_round_base) || w == SDT_HDR_WORD(kd_prev_round_base)) v = H0->n_kd;
+        else if (w == SDT_HDR_WORD(n_roots_old) || w == SDT_HDR_WORD(kd_round_root_base)) v = H0->n_roots;
+        else if (w == SDT_HDR_WORD(n_quad_old)) v = H0->n_quad;
+        else if (w == SDT_HDR_WORD(kd_sel) || w == SDT_HDR_WORD(kd_round_new) || w == SDT_HDR_WORD(kd_stop) || w == SDT_HDR_WORD(lvl_trunc)) v = 0u;
+        else if (w == SDT_HDR_WORD(refine_count)) v = H0->refine_count + 1u;
+#undef SDT_HDR_WORD
+        reinterpret_cast<uint32_t*>(c.H1)[w] = v;
     }
 };
 
@@ -50,6 +56,8 @@ struct RefineInit {
 struct KdLevelsItem {       // s per original leaf (KDTree.refine's condition, :346-347)
     RefineCtx c;
     SDT_HD void operator()(uint32_t i) const {
+        if (i < c.H1->n_roots_old) c.root_src[i] = i;           // every tree starts as a copy of itself (roots <= nodes ...
+        if (i == 0u) for (uint32_t r = c.H1->kd_n_old; r < c.H1->n_roots_old; ++r) c.root_src[r] = r;   // ... in any well-formed tree)
         uint32_t s = 0;
         if (c.kd_word[i] & SDT_KD_LEAF_BIT) {
             const float T = c.H1->max_leaf_size;
@@ -130,20 +138,20 @@ struct KdMakeNodeItem {
 };
 
 // ---- quadtrees --------------------------------------------------------------------
-struct QInit {
-    RefineCtx c;
-    SDT_HD void operator()() const {
-        DevHeader* H = c.H1;
-        uint32_t R = H->n_roots;
-        if (R > H->quad_cap) { H->error |= DEV_ERR_QUAD_CAPACITY; R = H->quad_cap; }
-        for (int l = 0; l < SDT_MAX_LEVELS + 2; ++l) { H->level_off[l] = R; H->level_cnt[l] = 0; }
-        H->level_off[0] = 0;
-        H->lvl_n[0] = R; H->lvl_n[1] = 0; H->lvl_trunc = 0;
-    }
-};
 struct QRootItem {          // level 0: tree r copies the tree of root_src[r]; thr = E_root/100 (:519)
     RefineCtx c;
     SDT_HD void operator()(uint32_t r) const {
+        DevHeader* H = c.H1;
+        const uint32_t cap = H->quad_cap;
+        if (r == 0u) {                                        // level bookkeeping of the forest being built
+            uint32_t R = H->n_roots;
+            if (R > cap) { H->error |= DEV_ERR_QUAD_CAPACITY; R = cap; }
+            for (int l = 0; l < SDT_MAX_LEVELS + 2; ++l) { H->level_off[l] = R; H->level_cnt[l] = 0; }
+            H->level_off[0] = 0;
+            H->lvl_n[0] = R; H->lvl_n[1] = 0; H->lvl_trunc = 0;
+            H->int_off[0] = 0;
+        }
+        if (r >= cap) return;
         const uint32_t src = c.root_src[r];
         c.s_src[r] = src;
         c.s_kind[r] = SDT_KIND_REACHED;
@@ -154,19 +162,24 @@ struct QRootItem {          // level 0: tree r copies the tree of root_src[r]; t
     }
 };
 
-struct QDecision { uint32_t nonleaf; uint32_t virt; uint32_t srem; uint32_t reached; uint32_t old_cb; };
+// what a node of the level being built becomes; the level's scan keeps it in registers between the ranking and the emit
+struct QDecision { uint32_t old_cb; uint8_t nonleaf, virt, srem, reached; };
+SDT_HD uint32_t sdt_scan_count(const QDecision& d) { return d.nonleaf; }
 
 SDT_HD QDecision sdt_q_decide(const RefineCtx& c, uint32_t id, uint32_t level) {
     QDecision d;
     d.nonleaf = 0; d.virt = 0; d.srem = 0; d.reached = 0; d.old_cb = 0;
+    // everything indexed by the node itself is requested up front (the rebuild is a chain of launches that pays latency:
+    // one round of loads, then the one dependent gather)
     const uint32_t kind = c.s_kind[id];
+    const uint32_t srem = c.s_srem[id], src = c.s_src[id];            // one of the two is stale scratch, and unused
+    const float e = c.energy1[id], thr = c.thr1[id];
     if (kind & SDT_KIND_VIRTUAL) {
-        const uint32_t s = c.s_srem[id];
-        d.nonleaf = s > 0u; d.virt = 1; d.srem = s ? s - 1u : 0u;
+        const uint32_t s = srem;
+        d.nonleaf = s > 0u; d.virt = 1; d.srem = (uint8_t)(s ? s - 1u : 0u);
         return d;
     }
-    const uint32_t cb = c.child0[c.s_src[id]];
-    const float e = c.energy1[id], thr = c.thr1[id];
+    const uint32_t cb = c.child0[src];
     const bool reached = (kind & SDT_KIND_REACHED) != 0u;
     if (c.no_quad) { d.nonleaf = cb != 0u; d.old_cb = cb; d.reached = reached; return d; }
     // merge pass (:574-611): a reached non-leaf below the threshold becomes a leaf
@@ -180,17 +193,17 @@ SDT_HD QDecision sdt_q_decide(const RefineCtx& c, uint32_t id, uint32_t level) {
     float v = e;
     const uint32_t maxd = c.H1->quad_max_depth;
     while (v > thr && level + s < maxd) { v = v / 4.0f; ++s; }
-    d.nonleaf = s > 0u; d.virt = 1; d.srem = s ? s - 1u : 0u;
+    d.nonleaf = s > 0u; d.virt = 1; d.srem = (uint8_t)(s ? s - 1u : 0u);
     return d;
 }
 
 struct QLevelFlag {
     RefineCtx c; uint32_t level; uint32_t last;   // last: deepest level the arena layout allows
-    SDT_HD uint32_t operator()(uint32_t i) const {
+    SDT_HD QDecision operator()(uint32_t i) const {
         // lvl_trunc = 1 + the level whose children no longer fitted the arena: every deeper level is all leaves.  (It is
         // written by that level's own fin, possibly while blocks of the same scan still emit: this level must not see it.)
-        if ((c.H1->lvl_trunc && level >= c.H1->lvl_trunc) || last) return 0u;
-        return sdt_q_decide(c, c.H1->level_off[level] + i, level).nonleaf;
+        if ((c.H1->lvl_trunc && level >= c.H1->lvl_trunc) || last) { QDecision d; d.old_cb = 0; d.nonleaf = d.virt = d.srem = d.reached = 0; return d; }
+        return sdt_q_decide(c, c.H1->level_off[level] + i, level);
     }
 };
 // children of this level's non-leaf nodes that still fit the arena (the scan may run emit before fin, so both derive
@@ -213,15 +226,19 @@ struct QLevelFin {
         H->level_cnt[level] = H->level_off[level + 1u] - H->level_off[level];
         H->level_off[level + 2u] = next_off + 4u * total;
         H->lvl_n[(level + 1u) & 1u] = 4u * total;
+        H->int_off[level + 1u] = H->int_off[level] + total;      // non-leaf nodes of the levels above the next one
     }
 };
 struct QLevelEmit {
     RefineCtx c; uint32_t level;
-    SDT_HD void operator()(uint32_t i, uint32_t rank, uint32_t v) const {
+    SDT_HD void operator()(uint32_t i, uint32_t rank, const QDecision& d) const {
         const DevHeader* H = c.H1;
         const uint32_t id = H->level_off[level] + i;
-        if (!v || rank >= sdt_q_fit(H, level)) { c.child1[id] = 0u; return; }
-        const QDecision d = sdt_q_decide(c, id, level);
+        const uint32_t fit = sdt_q_fit(H, level);
+        // record index = number of non-leaf nodes in front of this one (records follow node order, levels are contiguous;
+        // int_off[level] was written by the previous level's fin)
+        c.iidx1[id] = H->int_off[level] + (rank < fit ? rank : fit);
+        if (!d.nonleaf || rank >= fit) { c.child1[id] = 0u; return; }
         const uint32_t cb = H->level_off[level + 1u] + 4u * rank;
         c.child1[id] = cb;
         const float thr = c.thr1[id];
@@ -254,6 +271,7 @@ struct QFinalize {
     SDT_HD void operator()() const {
         DevHeader* H = c.H1;
         H->n_quad = H->level_off[levels_bound];
+        H->n_interior = H->int_off[levels_bound];
         uint32_t nl = 0;
         for (uint32_t l = 0; l < SDT_MAX_LEVELS + 1u; ++l) {
             if (l >= levels_bound) { H->level_off[l + 1u] = H->n_quad; }
@@ -267,12 +285,15 @@ struct QFinalize {
 };
 
 // ---- records for the query kernels ----------------------------------------------
+// (uploaded trees only; the refine numbers the records in its level scans)
 struct RecFlag { const uint32_t* child; SDT_HD uint32_t operator()(uint32_t i) const { return child[i] ? 1u : 0u; } };
 struct RecEmit { uint32_t* iidx; SDT_HD void operator()(uint32_t i, uint32_t rank, uint32_t) const { iidx[i] = rank; } };
 struct RecFin { DevHeader* H; SDT_HD void operator()(uint32_t total) const { H->n_interior = total; } };
 struct RecBuildItem {
     const DevHeader* H; const uint32_t* child; const float* energy; const uint32_t* iidx; QRec* rec; uint32_t* root_iidx;
+    float* zero;             // refine: the statistics of `current`, consumed by the level build, start again from 0 (:586)
     SDT_HD void operator()(uint32_t i) const {
+        if (zero) zero[i] = 0.0f;
         const uint32_t cb = child[i];
         if (i < H->n_roots) root_iidx[i] = cb ? iidx[i] : SDT_NONE;
         if (!cb) return;
@@ -294,7 +315,9 @@ struct RecBuildItem {
 // spatial leaf word <- record of the root of the leaf's quadtree (see the layout note in sdt_core.h)
 struct KdLeafWordItem {
     DevHeader* H; uint32_t* kd_word; const uint32_t* kd_root; const uint32_t* root_iidx;
+    float* cnt; float* prev;  // refine: prev.vertCount <- current.vertCount; current <- 0 (:141-153, :401-432, :585)
     SDT_HD void operator()(uint32_t i) const {
+        if (cnt) { prev[i] = cnt[i]; cnt[i] = 0.0f; }
         const uint32_t ri = root_iidx[kd_root[i]];
         if (i == 0u) H->rootrec_of_node0 = ri;
         if (kd_word[i] & SDT_KD_LEAF_BIT) kd_word[i] = SDT_KD_LEAF_BIT | (ri == SDT_NONE ? 0x7FFFFFFFu : ri);
@@ -322,7 +345,7 @@ struct JumpCountItem {
     SDT_HD void operator()() const {
         const uint32_t trees = H->n_roots < H->n_quad ? iidx[H->n_roots] : H->n_interior;
         H->jump_trees = trees <= cap ? trees : 0u;            // does not fit: table off, kernels take the level-by-level path
-        H->lvl_n[0] = H->jump_trees * SDT_JUMP_CELLS;
+        H->lvl_n[0] = H->jump_trees * (SDT_JUMP_CELLS / 4u);   // one thread per 2 x 2 block of cells
         // the non-leaf nodes of level SDT_JUMP_LEVELS (records follow node order, levels are contiguous): candidates for a
         // second-stage table
         H->s2_rec_lo = rec_at(H->level_off[SDT_JUMP_LEVELS]);
@@ -349,52 +372,71 @@ struct S2Fin {
     DevHeader* H; uint32_t cap;
     SDT_HD void operator()(uint32_t total) const {
         H->s2_tables = total <= cap ? total : cap;            // (beyond the cap: those nodes simply keep their record)
-        H->kd_round_new = H->s2_tables * SDT_S2_CELLS;
+        H->kd_round_new = H->s2_tables * (SDT_S2_CELLS / 4u);
     }
 };
 struct JumpBuildItem {
     const DevHeader* H; const QRec* rec; const float* pp; const uint32_t* s2_of; QJump* jump; uint32_t* jump_pp;
     SDT_HD void operator()(uint32_t i) const {
-        const uint32_t tr = i / SDT_JUMP_CELLS, cell = i % SDT_JUMP_CELLS;
-        QJump j = sdt_build_jump(rec, tr, cell & (SDT_JUMP_SIDE - 1u), cell >> SDT_JUMP_LEVELS);
-        if (!(j & SDT_JUMP_LEAF) && H->s2_tables && j >= H->s2_rec_lo && j < H->s2_rec_hi) {
-            const uint32_t tid = s2_of[j - H->s2_rec_lo];
-            if (tid != SDT_NONE) j = SDT_JUMP_TABLE | tid;
+        // One thread per 2 x 2 block of cells (sdt_build_jump4); the threads of a warp take 32 blocks in Z order (16 x 8
+        // cells): their descents share the upper records and mostly end in the same few leaves, and the warp writes whole
+        // sectors of the row-major table.
+        constexpr uint32_t Q = SDT_JUMP_CELLS / 4u;
+        const uint32_t tr = i / Q, z = i % Q;
+        const uint32_t qx = sdt_even_bits(z), qy = sdt_even_bits(z >> 1);
+        QJump j[4];
+        sdt_build_jump4(rec, tr, qx, qy, SDT_JUMP_LEVELS, j);
+        for (uint32_t k = 0; k < 4u; ++k) {
+            if (!(j[k] & SDT_JUMP_LEAF) && H->s2_tables && j[k] >= H->s2_rec_lo && j[k] < H->s2_rec_hi) {
+                const uint32_t tid = s2_of[j[k] - H->s2_rec_lo];
+                if (tid != SDT_NONE) j[k] = SDT_JUMP_TABLE | tid;
+            }
+            const size_t o = (size_t)tr * SDT_JUMP_CELLS + (2u * qy + (k >> 1)) * SDT_JUMP_SIDE + 2u * qx + (k & 1u);
+            jump[o] = j[k];
+            jump_pp[o] = sdt_jump_pp_entry(j[k], pp);
         }
-        jump[i] = j;
-        jump_pp[i] = sdt_jump_pp_entry(j, pp);
     }
 };
 struct S2BuildItem {
     const QRec* rec; const float* pp; const uint32_t* s2_rec; uint32_t* s2; uint32_t* s2_pp;
     SDT_HD void operator()(uint32_t i) const {
-        const uint32_t tid = i / SDT_S2_CELLS, cell = i % SDT_S2_CELLS;
-        const QJump j = sdt_build_jump(rec, s2_rec[tid], cell & (SDT_S2_SIDE - 1u), cell >> SDT_S2_LEVELS, SDT_S2_LEVELS);
-        s2[i] = j;
-        s2_pp[i] = sdt_jump_pp_entry(j, pp);
+        constexpr uint32_t Q = SDT_S2_CELLS / 4u;                                    // 2 x 2 blocks in Z order, as above
+        const uint32_t tid = i / Q, z = i % Q;
+        const uint32_t qx = sdt_even_bits(z), qy = sdt_even_bits(z >> 1);
+        QJump j[4];
+        sdt_build_jump4(rec, s2_rec[tid], qx, qy, SDT_S2_LEVELS, j);
+        for (uint32_t k = 0; k < 4u; ++k) {
+            const size_t o = (size_t)tid * SDT_S2_CELLS + (2u * qy + (k >> 1)) * SDT_S2_SIDE + 2u * qx + (k & 1u);
+            s2[o] = j[k];
+            s2_pp[o] = sdt_jump_pp_entry(j[k], pp);
+        }
     }
+};
+
+struct QFinalizeAndCount {   // last step of the forest rebuild + the sizes of the tables that follow: one launch
+    QFinalize fin; JumpCountItem cnt;
+    SDT_HD void operator()() const { fin(); cnt(); }
 };
 
 struct KdGridItem { const uint32_t* kd_word; uint32_t* grid; SDT_HD void operator()(uint32_t c) const { grid[c] = sdt_kd_grid_node(kd_word, c); } };
 
-// with_pp: also compute the per-node pdf products (an uploaded tree; the refine writes them while it builds the levels)
-static void sdt_build_records(sdt_handle h, const ExecCtx& x, QuadSet& s, bool with_pp) {
-    launch_scan(x, &s.hdr->n_quad, 0, RecFlag{s.child}, RecEmit{s.iidx}, RecFin{s.hdr});
-    launch_items(x, &s.hdr->n_quad, 0, RecBuildItem{s.hdr, s.child, s.energy, s.iidx, s.rec, s.root_iidx});
-    launch_items(x, &s.hdr->n_kd, 0, KdLeafWordItem{s.hdr, h->kd_word, h->kd_root, s.root_iidx});
+// uploaded: the tree came through sdt_upload -- record indices (one scan over all nodes), per-node pdf products (one pass
+// per level) and the table sizes are computed here; the refine has them already: it numbers the records and writes the
+// products while it builds the levels, and sizes the tables in its finalize step
+static void sdt_build_records(sdt_handle h, const ExecCtx& x, QuadSet& s, bool uploaded) {
+    if (uploaded) launch_scan(x, &s.hdr->n_quad, 0, RecFlag{s.child}, RecEmit{s.iidx}, RecFin{s.hdr});
+    launch_items(x, &s.hdr->n_quad, 0, RecBuildItem{s.hdr, s.child, s.energy, s.iidx, s.rec, s.root_iidx, uploaded ? nullptr : h->q_ecur});
+    launch_items(x, &s.hdr->n_kd, 0, KdLeafWordItem{s.hdr, h->kd_word, h->kd_root, s.root_iidx,
+                                                    uploaded ? nullptr : h->kd_count, uploaded ? nullptr : h->kd_prev_count});
     launch_items(x, nullptr, SDT_GRID_CELLS, KdGridItem{h->kd_word, h->kd_grid});
-    for (uint32_t l = 0; with_pp && l < h->levels_hint && l < SDT_MAX_LEVELS; ++l)
+    for (uint32_t l = 0; uploaded && l < h->levels_hint && l < SDT_MAX_LEVELS; ++l)
         launch_items(x, &s.hdr->level_cnt[l], 0, PpLevelItem{s.hdr, s.child, s.energy, s.pp, l});
-    launch_single(x, JumpCountItem{s.hdr, s.iidx, h->jump_cap});
+    if (uploaded) launch_single(x, JumpCountItem{s.hdr, s.iidx, h->jump_cap});
     launch_scan(x, &s.hdr->lvl_n[1], 0, S2Flag{s.hdr, s.rec}, S2Emit{s.hdr, s.s2_of, s.s2_rec, h->s2_cap}, S2Fin{s.hdr, h->s2_cap});
     launch_items(x, &s.hdr->lvl_n[0], 0, JumpBuildItem{s.hdr, s.rec, s.pp, s.s2_of, s.jump, s.jump_pp});
     launch_items(x, &s.hdr->kd_round_new, 0, S2BuildItem{s.rec, s.pp, s.s2_rec, s.s2, s.s2_pp});
 }
 
-struct KdRollItem {         // prev.vertCount <- current.vertCount; current <- 0 (:141-153, :401-432)
-    float* cnt; float* prev;
-    SDT_HD void operator()(uint32_t i) const { prev[i] = cnt[i]; cnt[i] = 0.0f; }
-};
 struct ZeroItem { float* p; SDT_HD void operator()(uint32_t i) const { p[i] = 0.0f; } };
 
 // the launch sequence of one refine on stream `st` (sweeps of the statistics included when they are due)
@@ -426,9 +468,9 @@ static int sdt_refine_enqueue(sdt_handle h, cudaStream_t st, uint32_t flags, uin
     c.no_quad = (flags & SDT_REFINE_NO_QUAD) ? 1u : 0u;
     c.thr_recip = h->quad_thr_reciprocal ? 1u : 0u;
 
-    launch_single(x, RefineInit{c});
-    launch_items(x, &c.H1->n_roots_old, 0, RootIdentityItem{h->root_src});
-    if (!(flags & SDT_REFINE_NO_KD)) {
+    launch_items(x, nullptr, (uint32_t)(sizeof(DevHeader) / 4u), RefineInit{c});
+    if (flags & SDT_REFINE_NO_KD) launch_items(x, &c.H1->n_roots_old, 0, RootIdentityItem{h->root_src});
+    else {
         launch_items(x, &c.H1->kd_n_old, 0, KdLevelsItem{c});
         for (uint32_t r = 1; r <= kd_rounds; ++r) {
             RefineCtx cr = c;
@@ -437,16 +479,13 @@ static int sdt_refine_enqueue(sdt_handle h, cudaStream_t st, uint32_t flags, uin
             launch_items(x, &c.H1->kd_round_new, 0, KdMakeNodeItem{cr, r});
         }
     }
-    launch_single(x, QInit{c});
-    launch_items(x, &c.H1->lvl_n[0], 0, QRootItem{c});
+    launch_items(x, &c.H1->n_roots, 0, QRootItem{c});
     for (uint32_t l = 0; l < levels_bound; ++l)
         launch_scan(x, &c.H1->lvl_n[l & 1u], 0, QLevelFlag{c, l, (uint32_t)(l + 1u == levels_bound)}, QLevelEmit{c, l}, QLevelFin{c, l});
-    launch_single(x, QFinalize{c, levels_bound});
+    launch_single(x, QFinalizeAndCount{QFinalize{c, levels_bound}, JumpCountItem{s1.hdr, s1.iidx, h->jump_cap}});
     h->levels_hint = levels_bound;
     sdt_build_records(h, x, s1, false);
-    // prev <- current, then reset current (:582-586)
-    launch_items(x, &c.H1->n_kd, 0, KdRollItem{h->kd_count, h->kd_prev_count});
-    launch_items(x, &c.H1->n_quad, 0, ZeroItem{h->q_ecur});
+    // (prev <- current and the reset of current, :582-586, ride on the record / leaf-word passes above)
     return sdt_post_launch(h, "sdt_refine");
 }
 

@@ -455,8 +455,12 @@ class SDTree:
             self.check_error()
 
     def check_error(self):
-        """raises SDTreeError when the device-side error flag is set (1: spatial arena, 2: quadtree arena exhausted)"""
+        """raises SDTreeError when the device-side error flag is set (bit 0: spatial arena, bit 1: quadtree arena
+        exhausted; bit 2: a refine scan stalled -- an internal error, the tree is invalid)"""
         e = self.sizes()['error']
+        if e & 4:
+            raise SDTreeError(-2,    # SDT_ERR_CUDA
+                              f"a refine scan gave up waiting for another block (device error flag {e}): the tree is invalid")
         if e:
             what = {1: "spatial node arena", 2: "quadtree node arena"}.get(e, "arena")
             raise SDTreeError(-3,    # SDT_ERR_CAPACITY
