@@ -50,6 +50,7 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--tune", action="append", default=[], help="key=value passed to sdt_set_tuning (repeatable)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-config-shapes", action="store_true", help="skip extras.config_shaped_passes (the scene configs' wavefront shapes)")
     ap.add_argument("--layout", default="aos", choices=["soa", "aos"],
                     help="device-resident vectors interleaved (n,3) or as separate component planes (Dr.Jit's Vector3f layout); measured within 1 %% of each other")
     ap.add_argument("--no-numa-bind", action="store_true", help="do not pin the rank to its GPU's NUMA-local CPUs (e2e experiments)")
@@ -503,6 +504,12 @@ def run_b200(args):
                                  "what_with_emitter_pdf": "the same call also returning the tree's pdf of the emitter direction (NEE MIS) on 80 % of the lanes: every tree query of a path vertex in one launch.  The emitter directions of this measurement are directions SAMPLED from the tree (deep leaves: the expensive case for a pdf); ms_emitter_pdf_as_a_separate_call = sdt_pdf of the same directions and mask"},
                   "sdt_splat_path_data": {"ms": ms_p, "slots_per_s": n / (ms_p * 1e-3), "what": f"processPathData + filter + splat fused, {n} slots (max_depth {md}), 60 % active"}}
         tree.reset_stats()
+        if not args.no_config_shapes:
+            try:
+                extras["config_shaped_passes"] = config_shaped_passes(tree, dev, rank)
+            except Exception as e:
+                extras["config_shaped_passes"] = {"error": repr(e)}
+            tree.reset_stats()
     except Exception as e:            # extras never break the contract line
         extras = {"error": repr(e)}
 
@@ -618,6 +625,80 @@ def run_b200(args):
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+# BASELINE.json configs 1 / 3 / 4 / 5 need a renderer (Mitsuba's cuda variant; absent from this image).  What the LIBRARY
+# does in one training pass of each of them depends on the scene only through the SHAPE of the wavefront -- lanes per pass
+# = W x H, record slots = lanes x max_depth -- so the tree work of such a pass is measured here on synthetic
+# vertices of that shape against the frozen benchmark tree: per bounce ONE sdt_guided call with the emitter-direction pdf
+# (every tree query of a path vertex, what PathGuidingCore.bounce issues) on the lanes still alive, then ONE
+# sdt_splat_path_data over all record slots.  Path lengths are geometric (75 % of the lanes survive a bounce, the deep
+# bounces run a few percent of the lanes through the tile compaction), vertices uniform in the box.
+CONFIG_SHAPES = [("cornell-box 256x256 (config 1)", 256, 256, 30), ("torus 512x512 (config 3)", 512, 512, 30),
+                 ("veach-ajar 1024x1024 (config 4)", 1024, 1024, 13), ("veach-bidir 3840x2160 (config 5)", 3840, 2160, 7)]
+
+
+def config_shaped_passes(tree, dev, rank, survive=0.75, reps=3):
+    import torch
+    out = []
+    for name, w, h, md in CONFIG_SHAPES:
+        lanes, slots = w * h, w * h * md
+        g = torch.Generator(device=dev).manual_seed(1234 + rank)
+        length = torch.clamp((torch.log(torch.rand(lanes, device=dev, generator=g)) / np.log(survive)).floor() + 1, max=md).to(torch.int32)
+        pos = torch.rand(slots, 3, device=dev, generator=g)
+        cdir = torch.rand(slots, 2, device=dev, generator=g)
+        wo = torch.nn.functional.normalize(torch.randn(lanes, 3, device=dev, generator=g), dim=1)
+        em = torch.nn.functional.normalize(torch.randn(lanes, 3, device=dev, generator=g), dim=1)
+        lfin = torch.rand(lanes, 3, device=dev, generator=g) * 4
+        tr_, tb_, bs_ = (torch.rand(slots, 3, device=dev, generator=g) for _ in range(3))
+        wop = torch.rand(slots, device=dev, generator=g) + 0.05
+        depth_of_slot = torch.arange(md, device=dev, dtype=torch.int32).repeat(lanes)
+        act = (depth_of_slot < length.repeat_interleave(md)).to(torch.uint8)
+        del depth_of_slot
+        bp, bv = torch.rand(lanes, device=dev, generator=g), torch.rand(lanes, 3, device=dev, generator=g)
+        choose = (torch.rand(lanes, device=dev, generator=g) < 0.5)
+        modes = [torch.where(length > b, torch.where(choose, 1, 2), 0).to(torch.uint8) for b in range(md)]     # mode 1 sampled, 2 pdf + mixture, 0 dead
+        alive = [int((m != 0).sum().item()) for m in modes]
+        em_act = [(m != 0).to(torch.uint8) for m in modes]
+        o_dir, o_sp, o_wp, o_w, o_em = (torch.zeros(lanes, 3, device=dev), torch.zeros(lanes, device=dev), torch.zeros(lanes, device=dev),
+                                        torch.zeros(lanes, 3, device=dev), torch.ones(lanes, device=dev))
+        pos_b = torch.rand(md, lanes, 3, device=dev, generator=g)          # per-bounce vertex positions, contiguous per bounce
+
+        def one_pass():
+            for b in range(md):
+                if alive[b] == 0:
+                    break
+                tree.guided(pos_b[b], modes[b], wo=wo, seed=7 + b, bsdf_pdf=bp, bsdf_value=bv, dir_out=o_dir, sdtree_pdf_out=o_sp,
+                            wo_pdf_out=o_wp, weight_out=o_w, em_dir=em, em_active=em_act[b], sdtree_pdf_em_out=o_em)
+            tree.splat_path_data(md, lfin, tr_, tb_, bs_, pos, cdir, wop, active=act)
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+        one_pass()
+        torch.cuda.synchronize()
+        l0 = tree.kernel_launches()
+        ev[0].record()
+        for _ in range(reps):
+            for b in range(md):
+                if alive[b] == 0:
+                    break
+                tree.guided(pos_b[b], modes[b], wo=wo, seed=7 + b, bsdf_pdf=bp, bsdf_value=bv, dir_out=o_dir, sdtree_pdf_out=o_sp,
+                            wo_pdf_out=o_wp, weight_out=o_w, em_dir=em, em_active=em_act[b], sdtree_pdf_em_out=o_em)
+        ev[1].record()
+        for _ in range(reps):
+            tree.splat_path_data(md, lfin, tr_, tb_, bs_, pos, cdir, wop, active=act)
+        ev[2].record()
+        torch.cuda.synchronize()
+        ms_b, ms_s = ev[0].elapsed_time(ev[1]) / reps, ev[1].elapsed_time(ev[2]) / reps
+        verts = int(sum(alive))
+        out.append({"config": name, "lanes_per_pass": lanes, "max_depth": md, "record_slots": slots, "path_vertices_per_pass": verts,
+                    "bounce_calls_ms": ms_b, "splat_path_data_ms": ms_s, "tree_ms_per_pass": ms_b + ms_s,
+                    "guided_samples_per_s": verts / ((ms_b + ms_s) * 1e-3), "launches_per_pass": (tree.kernel_launches() - l0) / reps})
+        del pos, cdir, tr_, tb_, bs_, wop, act, modes, em_act, pos_b
+        torch.cuda.empty_cache()
+    return {"passes": out,
+            "what": "tree work of ONE training pass (1 spp) at the wavefront shape of each scene config: max_depth sdt_guided calls with the "
+                    "emitter-direction pdf on the surviving lanes + one sdt_splat_path_data over lanes x max_depth record slots; synthetic "
+                    "vertices, frozen benchmark tree, device-resident buffers, host enqueue included (no synchronisation inside a pass); "
+                    "the renderer's own work (Mitsuba ray tracing / BSDFs) is not part of it"}
 
 
 def main():

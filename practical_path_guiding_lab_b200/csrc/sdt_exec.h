@@ -177,7 +177,7 @@ __global__ void __launch_bounds__(256, SDT_SCAN_BLOCKS_PER_SM) k_scan_fused(Flag
                     // (the bound only keeps a broken co-residency assumption from hanging the GPU: state[1] is raised and
                     // surfaces as DEV_ERR_SCAN_STALL with the next header read-back)
                     uint32_t spins = 0;
-                    do { sv = *reinterpret_cast<volatile unsigned long long*>(&status[idx]); } while ((sv >> 34) != epoch && ++spins < (1u << 24));
+                    do { sv = *reinterpret_cast<volatile unsigned long long*>(&status[idx]); } while ((sv >> 34) != epoch && ++spins < (1u << 20));
                     if ((sv >> 34) != epoch) { state[1] = 1u; sv = 2ull << 32; }
                 } else sv = 2ull << 32;                   // before the first block: an inclusive prefix of 0
                 const uint32_t kind = (uint32_t)(sv >> 32) & 3u, val = (uint32_t)sv;

@@ -174,6 +174,26 @@ struct QuadSweepItem {
         if (cb) e[id] = ((e[cb] + e[cb + 1u]) + e[cb + 2u]) + e[cb + 3u];
     }
 };
+// Two levels per launch (the sweep is a chain of dependent launches that pays latency, not bandwidth): a thread owns a node
+// of level `level`, first completes those of its children that are interior from THEIR children (level + 2, final by
+// then), then sums its own.  Same additions in the same order as two single-level passes.
+struct QuadSweep2Item {
+    const DevHeader* hdr; const uint32_t* child; float* e; uint32_t level;
+    SDT_HD void operator()(uint32_t i) const {
+        const uint32_t id = hdr->level_off[level] + i;
+        const uint32_t cb = child[id];
+        if (!cb) return;
+        uint32_t gcb[4];
+        for (uint32_t k = 0; k < 4u; ++k) gcb[k] = child[cb + k];
+        float s[4];
+        for (uint32_t k = 0; k < 4u; ++k) {
+            const uint32_t g = gcb[k];
+            if (g) { s[k] = ((e[g] + e[g + 1u]) + e[g + 2u]) + e[g + 3u]; e[cb + k] = s[k]; }
+            else s[k] = e[cb + k];
+        }
+        e[id] = ((s[0] + s[1]) + s[2]) + s[3];
+    }
+};
 // spatial nodes of depth d: interior count = left + right, sticking at 2^24 like a
 // chain of fp32 "+1.0f" atomics does
 struct KdSweepItem {
@@ -203,9 +223,13 @@ static int sdt_complete_stats(sdt_handle h, cudaStream_t st, bool with_kd = true
     const ExecCtx x = exec_ctx(h, st);
     const QuadSet& s = h->set[h->cur];
     // level sizes live on the device; the number of levels in use is exact once the last refine's header has been read back
-    if (!h->stats_complete)
-        for (int l = (int)sdt_sweep_levels(h) - 1; l >= 0; --l)
-            launch_items(x, &s.hdr->level_cnt[l], 0, QuadSweepItem{s.hdr, s.child, h->q_ecur, (uint32_t)l});
+    if (!h->stats_complete) {
+        // the deepest level in use holds leaves only; from there upwards in pairs of levels, a single one if one is left
+        int l = (int)sdt_sweep_levels(h) - 2;
+        for (; l >= 1; l -= 2)
+            launch_items(x, &s.hdr->level_cnt[l - 1], 0, QuadSweep2Item{s.hdr, s.child, h->q_ecur, (uint32_t)(l - 1)});
+        if (l == 0) launch_items(x, &s.hdr->level_cnt[0], 0, QuadSweepItem{s.hdr, s.child, h->q_ecur, 0u});
+    }
     if (with_kd && !h->kd_complete) {
         for (int d = h->cfg.kd_max_depth; d >= 0; --d)
             launch_items(x, &s.hdr->n_kd, 0, KdSweepItem{h->kd_word, h->kd_depth, h->kd_count, (uint32_t)d});
