@@ -294,7 +294,9 @@ int sdt_stat_buffers(sdt_handle h, float** q_energy, uint32_t* n_quad, float** k
  *   "splat_aggregate"   combine the lanes of a warp that splat into the same node before the atomic (pays on pixel-coherent
  *                       wavefronts; off by default: on incoherent records it finds no peers and only costs instructions)
  *   "use_pdl"                                                                programmatic dependent launch of the helper kernels
- *   "use_graph"         replay the refine's ~200 launches as one captured CUDA graph per buffer parity
+ *   "use_graph"         replay the refine's launch chain as one captured CUDA graph per buffer parity
+ *   "helper_ctas_per_sm"   grid of the refine / sweep helper launches whose item count lives on the device: that many CTAs of
+ *                       256 threads per SM (1..8, default 8 = every thread slot of an SM; the scans use at most 4)
  *   "host_chunk"   lanes per chunk of the pipelined SDT_HOST_PTRS staging (H2D of chunk k+1 | kernels of chunk k | D2H of chunk k-1).
  * One key switches semantics rather than speed: "quad_thr_reciprocal" = 1 computes the
  * quadtree refinement threshold (src/quadtree.py:519, `E / 100`) as E * fp32(0.01), the

@@ -17,6 +17,7 @@ struct ExecCtx {
     uint32_t* blk;        // device scratch of the scans: SDT_SCAN_STATE_WORDS words (zero at creation, never reset)
     uint64_t* launches;   // kernel launch counter of the handle
     bool pdl;             // programmatic dependent launch for the helper kernels (see sdt_launch)
+    int ctas_per_sm;      // grid of the device-sized helper launches ("helper_ctas_per_sm")
 };
 
 // what a scan adds up: the flag functor returns the 0/1 count itself, or a struct that carries it together with whatever
@@ -58,7 +59,7 @@ __global__ void __launch_bounds__(256) k_items(F f, const uint32_t* n_ptr, uint3
 template <class F>
 static inline void launch_items(const ExecCtx& x, const uint32_t* n_ptr, uint32_t n_imm, F f) {
     uint32_t grid;
-    if (n_ptr) grid = (uint32_t)x.num_sms * 4u;
+    if (n_ptr) grid = (uint32_t)x.num_sms * (uint32_t)x.ctas_per_sm;
     else {
         if (n_imm == 0) return;
         grid = (n_imm + 255u) / 256u;
@@ -225,7 +226,8 @@ __global__ void __launch_bounds__(256, SDT_SCAN_BLOCKS_PER_SM) k_scan_fused(Flag
 // flag must be pure and must not read anything emit or fin writes.
 template <class Flag, class Emit, class Fin>
 static inline void launch_scan(const ExecCtx& x, const uint32_t* n_ptr, uint32_t n_imm, Flag flag, Emit emit, Fin fin) {
-    uint32_t grid = (uint32_t)x.num_sms * SDT_SCAN_BLOCKS_PER_SM;      // co-resident by the kernel's launch bounds
+    // co-resident by the kernel's launch bounds
+    uint32_t grid = (uint32_t)x.num_sms * (uint32_t)(x.ctas_per_sm < SDT_SCAN_BLOCKS_PER_SM ? x.ctas_per_sm : SDT_SCAN_BLOCKS_PER_SM);
     if (grid > SDT_SCAN_MAX_BLOCKS) grid = SDT_SCAN_MAX_BLOCKS;
     if (!n_ptr) {
         const uint32_t g = (n_imm + 255u) / 256u;

@@ -77,6 +77,7 @@ struct sdt_tree_s {
     int use_jump = 1;
     int use_int_cell = 1;
     int use_pdl = 1;                // programmatic dependent launch for the refine / sweep helper kernels
+    int helper_ctas_per_sm = 8;     // CTAs (256 threads) per SM of the helper launches whose item count lives on the device (measured 1 / 2 / 3 / 4 / 8: refine 0.74 / 0.51 / 0.47 / 0.42 / 0.39 ms on a 3.2 M-node forest)
     int quad_thr_reciprocal = 0;    // semantics switch, see sdt_set_tuning in sdtree.h
     int use_compaction = 1;         // sort the lanes of a tile by mode when a wavefront has idle / mixed lanes
     int use_kd_grid = 1;            // per-CTA 16x16x8 grid over the first 11 spatial levels
@@ -159,7 +160,7 @@ static inline int sdt_enter(sdt_handle h) {
 
 static inline ExecCtx exec_ctx(sdt_handle h, cudaStream_t st) {
     h->last_stream = st;
-    return ExecCtx{st, h->num_sms, h->s_blk, &h->launches, h->use_pdl != 0};
+    return ExecCtx{st, h->num_sms, h->s_blk, &h->launches, h->use_pdl != 0, h->helper_ctas_per_sm};
 }
 
 static inline TreeView tree_view(sdt_tree_s* h) {

@@ -400,6 +400,14 @@ extern "C" int sdt_set_tuning(sdt_handle h, const char* key, int64_t value) {
     else if (k == "quad_thr_reciprocal") h->quad_thr_reciprocal = value != 0;
     else if (k == "use_pdl") h->use_pdl = value != 0;
     else if (k == "use_graph") h->use_graph = value != 0;
+    else if (k == "helper_ctas_per_sm") {
+        SDT_CHECK(h, value >= 1 && value <= 8, SDT_ERR_INVALID, "helper_ctas_per_sm must be 1..8");
+        h->helper_ctas_per_sm = (int)value;
+#ifndef SDT_HOSTEMU
+        for (auto& kv : h->refine_graphs) if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);     // captured with the old grids
+        h->refine_graphs.clear();
+#endif
+    }
     else if (k == "use_compaction") h->use_compaction = value != 0;
     else if (k == "host_chunk") { SDT_CHECK(h, value >= 256, SDT_ERR_INVALID, "host_chunk must be >= 256 lanes"); h->host_chunk = (int)value; }
     else return sdt_fail(h, SDT_ERR_INVALID, "sdt_set_tuning: unknown key " + k);
