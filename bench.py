@@ -239,7 +239,7 @@ def run_b200(args):
         ids = [tree.comm_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(ids, src=0)
         tree.comm_init(ids[0], rank, world)
-        allreduce = lambda: tree.allreduce(torch.cuda.current_stream().cuda_stream)
+        allreduce = lambda records=None: tree.allreduce(torch.cuda.current_stream().cuda_stream, records_all_ranks=records)
     t_build0 = time.perf_counter()
     syn.build_tree(tree, to_dev=to_dev, rank=rank, world=world, allreduce=allreduce)
     torch.cuda.synchronize()
@@ -428,7 +428,7 @@ def run_b200(args):
         torch.cuda.synchronize()
         e0.record()
         if allreduce:
-            allreduce()
+            allreduce(n * world)             # every rank splatted n records: no leaf can have counted more (sdt_hint_records)
         e1.record()
         tree.refine()
         e2.record()

@@ -83,7 +83,8 @@ typedef struct sdt_sizes {
     uint32_t n_levels;   /* quadtree levels in use                 */
     uint32_t kd_leaves;
     uint32_t error;      /* sticky device-side error flags (0 = none; 1 spatial arena, 2 quadtree arena exhausted: tree truncated;
-                            4 a refine scan stalled: internal error, tree invalid) */
+                            4 a refine scan stalled: internal error, tree invalid;
+                            8 sdt_hint_records was given less than the records splatted: spatial splits are missing) */
     uint32_t refine_count;
     uint32_t jump_trees; /* quadtrees covered by the 32x32 jump table over their top 5 levels */
     uint32_t jump2_tables; /* level-5 nodes that own a second-stage 8x8 table over their next 3 levels */
@@ -281,6 +282,15 @@ int sdt_comm_unique_id(void* id128);
 int sdt_comm_init(sdt_handle h, const void* id128, int32_t rank, int32_t nranks);
 /* ncclAllReduce(sum) over current's [quadtree energies | spatial leaf counts] */
 int sdt_allreduce(sdt_handle h, sdt_stream stream);
+/* Optional, after sdt_allreduce (or after writing through sdt_stat_buffers / sdt_upload_stats): an UPPER BOUND of the number
+ * of records that were splatted into `current`, over all ranks, since its statistics were last zero -- e.g. passes x rays x
+ * max_depth of the iteration, which every rank can compute without communication.  KDTree.refine's loop
+ * (src/kdtree.py:346-347: split while vertCount > maxLeafSize, children get half) cannot run more rounds than that many
+ * records allow, so the refine does not launch the split rounds nobody can reach (a single rank keeps this bound by itself;
+ * the counts of other ranks' records arrive unannounced, and without the hint all kd_max_depth rounds are launched).  No
+ * reference counterpart: its refine is a host loop.  A bound that is too small does not go unnoticed: a leaf that wants
+ * more rounds than were launched raises device error flag 8 (sdt_sizes.error). */
+int sdt_hint_records(sdt_handle h, uint64_t records_all_ranks);
 /* device pointers + element counts of those two buffers (for callers that bring
  * their own collective, e.g. torch.distributed) */
 int sdt_stat_buffers(sdt_handle h, float** q_energy, uint32_t* n_quad, float** kd_count, uint32_t* n_kd);

@@ -108,6 +108,7 @@ SYMBOLS = {
     "sdt_comm_unique_id": (C.c_int, [C.c_void_p]),
     "sdt_comm_init": (C.c_int, [_H, C.c_void_p, C.c_int32, C.c_int32]),
     "sdt_allreduce": (C.c_int, [_H, _S]),
+    "sdt_hint_records": (C.c_int, [_H, C.c_uint64]),
     "sdt_stat_buffers": (C.c_int, [_H, C.POINTER(C.c_void_p), C.POINTER(C.c_uint32), C.POINTER(C.c_void_p),
                                    C.POINTER(C.c_uint32)]),
     "sdt_set_tuning": (C.c_int, [_H, C.c_char_p, C.c_int64]),

@@ -329,8 +329,11 @@ class CornellBox:
         dist.broadcast_object_list(ids, src=0)
         self.core.tree.comm_init(ids[0], dist.get_rank(), dist.get_world_size())
 
-    def allreduce_statistics(self, dist):
-        """one exchange per iteration: SD-tree statistics (sdt_allreduce, NCCL) + variance counters"""
+    def allreduce_statistics(self, dist, passes=None):
+        """one exchange per iteration: SD-tree statistics (sdt_allreduce, NCCL) + variance counters.  passes = passes of
+        the iteration over all ranks: passes x pixels x max_depth record slots bound what any spatial leaf can have
+        counted, which every rank knows without asking the others (sdt_hint_records)"""
+        bound = None if passes is None else int(passes) * self.W * self.H * int(self.core.max_depth)
         if self._host:
             # host emulation (CPU tests, gloo): the same exchange through sdt_stat_buffers + torch.distributed
             import ctypes
@@ -341,8 +344,10 @@ class CornellBox:
             dist.all_reduce(buf)
             q[:] = buf[:nq].numpy()
             k[:] = buf[nq:].numpy()
+            if bound is not None:
+                self.core.tree.hint_records(bound)
         else:
-            self.core.tree.allreduce(torch.cuda.current_stream().cuda_stream)
+            self.core.tree.allreduce(torch.cuda.current_stream().cuda_stream, records_all_ranks=bound)
         self._gL, self._gL2 = self.sumL.clone(), self.sumL2.clone()      # local counters stay local
         dist.all_reduce(self._gL)
         dist.all_reduce(self._gL2)

@@ -100,7 +100,8 @@ struct DevHeader {
 
 enum DevError : uint32_t {
     DEV_OK = 0, DEV_ERR_KD_CAPACITY = 1, DEV_ERR_QUAD_CAPACITY = 2,
-    DEV_ERR_SCAN_STALL = 4       // a scan block gave up waiting for a lower-numbered block (see k_scan_fused): results are invalid
+    DEV_ERR_SCAN_STALL = 4,      // a scan block gave up waiting for a lower-numbered block (see k_scan_fused): results are invalid
+    DEV_ERR_KD_ROUNDS = 8        // a leaf wanted more split rounds than the host launched (sdt_hint_records bound too small)
 };
 
 // What the query kernels need (by value).

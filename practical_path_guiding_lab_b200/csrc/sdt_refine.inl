@@ -31,6 +31,7 @@ struct RefineCtx {
     float* pp1;               // per-node pdf products of the tree being built (sdt_core.h), written top-down with the levels
     uint32_t* s_src; uint8_t* s_kind; uint8_t* s_srem;
     uint32_t no_quad;
+    uint32_t kd_rounds;   // split rounds the host launches (sdt_kd_rounds_bound)
     uint32_t thr_recip;   // threshold = E * fp32(1/100) instead of E / 100 (how Dr.Jit may lower the literal division)
 };
 
@@ -66,6 +67,13 @@ struct KdLevelsItem {       // s per original leaf (KDTree.refine's condition, :
             float v = c.kd_count[i];
             if (v > 16777216.0f) { v = 16777216.0f; c.kd_count[i] = v; }
             while (v > T && d + s < maxd) { if (v > 0.0f) v = v / 2.0f; ++s; }    // :261-264
+            if (s > c.kd_rounds) {            // the host's bound of the rounds was wrong (sdt_hint_records): say so
+#if defined(__CUDA_ARCH__)
+                atomicOr(&c.H1->error, (uint32_t)DEV_ERR_KD_ROUNDS);
+#else
+                c.H1->error |= DEV_ERR_KD_ROUNDS;
+#endif
+            }
         }
         c.kd_s[i] = (uint8_t)s;
     }
@@ -466,6 +474,7 @@ static int sdt_refine_enqueue(sdt_handle h, cudaStream_t st, uint32_t flags, uin
     c.child1 = s1.child; c.energy1 = s1.energy; c.thr1 = s1.thr; c.iidx1 = s1.iidx; c.rec1 = s1.rec; c.root_iidx1 = s1.root_iidx; c.pp1 = s1.pp;
     c.s_src = h->s_src; c.s_kind = h->s_kind; c.s_srem = h->s_srem;
     c.no_quad = (flags & SDT_REFINE_NO_QUAD) ? 1u : 0u;
+    c.kd_rounds = kd_rounds;
     c.thr_recip = h->quad_thr_reciprocal ? 1u : 0u;
 
     launch_items(x, nullptr, (uint32_t)(sizeof(DevHeader) / 4u), RefineInit{c});
@@ -546,6 +555,13 @@ extern "C" int sdt_refine(sdt_handle h, uint32_t flags, sdt_stream stream) {
     if (cudaMemcpyAsync(h->h_hdr, s1.hdr, sizeof(DevHeader), cudaMemcpyDeviceToHost, st) == cudaSuccess &&
         cudaEventRecord(h->hdr_event, st) == cudaSuccess) h->hdr_pending = true;
     if (flags & SDT_SYNC) SDT_CUDA(h, cudaStreamSynchronize(st));
+    return SDT_OK;
+}
+
+extern "C" int sdt_hint_records(sdt_handle h, uint64_t records_all_ranks) {
+    SDT_ENTER(h);
+    h->splat_bound = records_all_ranks;
+    h->splat_bound_valid = true;
     return SDT_OK;
 }
 

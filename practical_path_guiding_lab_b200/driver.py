@@ -49,7 +49,7 @@ class SingleRank:
     def sum_image(self, x):
         return x
 
-    def sync_iteration(self, renderer):
+    def sync_iteration(self, renderer, passes=None):
         pass
 
 
@@ -72,8 +72,8 @@ class TorchDistRanks:
         self.dist.all_reduce(x)
         return x
 
-    def sync_iteration(self, renderer):
-        renderer.allreduce_statistics(self.dist)
+    def sync_iteration(self, renderer, passes=None):
+        renderer.allreduce_statistics(self.dist, passes)
 
 
 def train_and_render(renderer, budget_spp, seed=0, batch_spp=4, stable_variance_spp_threshold=256,
@@ -136,7 +136,7 @@ def train_and_render(renderer, budget_spp, seed=0, batch_spp=4, stable_variance_
             if curr is None:
                 curr = renderer.zero_image()
             curr = ranks.sum_image(curr)
-            ranks.sync_iteration(renderer)                             # one exchange per iteration
+            ranks.sync_iteration(renderer, passes)                     # one exchange per iteration
         if is_final and not is_train and prev_iter_image is not None:   # main.py:287-291
             image = (curr * iter_spp + prev_iter_image * (image_spp - iter_spp)) / image_spp
         else:

@@ -461,6 +461,10 @@ class SDTree:
         if e & 4:
             raise SDTreeError(-2,    # SDT_ERR_CUDA
                               f"a refine scan gave up waiting for another block (device error flag {e}): the tree is invalid")
+        if e & 8:
+            raise SDTreeError(-1,    # SDT_ERR_INVALID
+                              f"hint_records() was given fewer records than were splatted (device error flag {e}): "
+                              "spatial splits are missing from the tree")
         if e:
             what = {1: "spatial node arena", 2: "quadtree node arena"}.get(e, "arena")
             raise SDTreeError(-3,    # SDT_ERR_CAPACITY
@@ -482,8 +486,16 @@ class SDTree:
         buf = (C.c_char * 128).from_buffer_copy(unique_id)
         self._ck(self._lib.sdt_comm_init(self._h, buf, int(rank), int(nranks)))
 
-    def allreduce(self, stream=None):
+    def allreduce(self, stream=None, records_all_ranks=None):
+        """one NCCL all-reduce over current's leaf statistics; records_all_ranks: see hint_records"""
         self._ck(self._lib.sdt_allreduce(self._h, self._stream(stream)))
+        if records_all_ranks is not None:
+            self.hint_records(records_all_ranks)
+
+    def hint_records(self, records_all_ranks):
+        """upper bound of the records splatted into `current` over all ranks since its statistics were zero (e.g. passes x
+        rays x max_depth): lets the refine skip the split rounds no leaf can reach (sdt_hint_records)"""
+        self._ck(self._lib.sdt_hint_records(self._h, int(records_all_ranks)))
 
     def stat_buffers(self):
         """(ptr_q_energy, n_quad, ptr_kd_count, n_kd) of current's statistics"""

@@ -95,7 +95,8 @@ def build_schedule(iters=BUILD_ITERS, n0=BUILD_N0, c=BUILD_C):
 def build_tree(tree, scene=None, schedule=None, to_dev=None, rank=0, world=1, allreduce=None):
     """trains `tree` (an SDTree) on the synthetic records: splat + device-side refine per
     iteration.  With world > 1 every rank splats its slice of the iteration's records and
-    `allreduce()` combines the statistics before the (deterministic) refine."""
+    `allreduce(records)` combines the statistics before the (deterministic) refine; records = the iteration's records
+    over all ranks (SDTree.allreduce's records_all_ranks: bounds the spatial split rounds)."""
     scene = scene or Scene()
     to_dev = to_dev or (lambda x: x)
     for it in (schedule or build_schedule()):
@@ -103,7 +104,7 @@ def build_tree(tree, scene=None, schedule=None, to_dev=None, rank=0, world=1, al
         sl = slice(rank * it['n'] // world, (rank + 1) * it['n'] // world)
         tree.splat_records(to_dev(rec['position'][sl]), to_dev(rec['direction'][sl]), to_dev(rec['radiance'][sl]), to_dev(rec['wo_pdf'][sl]))
         if allreduce is not None:
-            allreduce()
+            allreduce(it['n'])
         tree.set_max_leaf_size(it['max_leaf_size'])
         tree.refine()
     return tree

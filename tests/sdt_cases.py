@@ -619,6 +619,41 @@ def case_refine_flags_and_frozen_stats(ctx):
     assert_tree_equal(t.download(0), prev)
 
 
+def case_record_bound_hint(ctx):
+    """sdt_hint_records: after statistics arrive from elsewhere (an all-reduce, sdt_upload_stats) the refine launches every
+    split round unless the caller bounds the records behind them; the right bound gives the same tree with fewer launches,
+    a bound that is too small raises device error flag 8"""
+    from practical_path_guiding_lab_b200.sdtree import SDTreeError
+    rec = dyadic_records(20000, 7, ((0.3, 0.7, 0.02),))
+    trees, launches = [], []
+    for bound in (None, 20000, 2 * 20000 + 5):
+        t = ctx.make(bbox_min=(0, 0, 0), bbox_max=(1, 1, 1), kd_max_depth=20, quad_max_depth=20, store_nee=False,
+                     kd_capacity=1 << 14, quad_capacity=1 << 18)
+        splat(t, ctx, rec)
+        tr = t.download(1)
+        t.reset_stats()
+        # "another rank's" identical statistics arrive: twice the counts / energies of one splat
+        t.upload_stats(2 * tr['quadtree_irradiance'], 2 * tr['kdtree_vertCount'])
+        if bound is not None:
+            t.hint_records(bound)
+        t.set_max_leaf_size(300)
+        l0 = t.kernel_launches()
+        t.refine()
+        launches.append(t.kernel_launches() - l0)
+        trees.append((t, t.download(0), t.sizes()['error']))
+    (t0, full, e0), (t1, short, e1), (t2, good, e2) = trees
+    assert e0 == 0 and e2 == 0 and e1 == 8, (e0, e1, e2)
+    for k in full:
+        np.testing.assert_array_equal(full[k], good[k], err_msg=k)
+    assert launches[2] < launches[0], launches                       # the split rounds nobody can reach were not launched
+    assert short['kdtree_depth'].shape[0] < full['kdtree_depth'].shape[0]      # the wrong bound cut the splits short ...
+    try:
+        t1.check_error()                                               # ... and that does not go unnoticed
+        raise AssertionError("a record bound that is too small was not surfaced")
+    except SDTreeError as e:
+        assert e.code == -1 and "hint_records" in str(e)
+
+
 def case_capacity_error(ctx):
     t = ctx.make(kd_capacity=8, quad_capacity=64, kd_max_depth=20, quad_max_depth=20, store_nee=False)
     rec = dyadic_records(20000, 1)
@@ -832,4 +867,4 @@ def case_npz_roundtrip(ctx, tmp_path):
 ALL_CASES = [case_golden_fixture, case_grid_cell_boundaries, case_counter_generator_statistics, case_deep_quadtree_beyond_fp32_grid, case_jump_table_equals_descent, case_spatial_descent_variants, case_initial_tree, case_golden_upload_download, case_train_refine_topology, case_threshold_reciprocal_variant, case_zero_total_energy, case_host_pipeline_chunks, case_host_calls_no_wait,
              case_train_refine_nee_shallow, case_fused_equals_two_descents, case_splat_float_tolerance,
              case_path_data, case_mis, case_guided_bounce, case_refine_flags_and_frozen_stats,
-             case_capacity_error, case_edge_inputs_and_errors]
+             case_capacity_error, case_record_bound_hint, case_edge_inputs_and_errors]
