@@ -688,16 +688,34 @@ def config_shaped_passes(tree, dev, rank, survive=0.75, reps=3):
         ev[2].record()
         torch.cuda.synchronize()
         ms_b, ms_s = ev[0].elapsed_time(ev[1]) / reps, ev[1].elapsed_time(ev[2]) / reps
+        launches_per_pass = (tree.kernel_launches() - l0) / reps
+        # the same bounce calls with their argument structs built once (SDTree.prepare_guided: a wavefront loop that keeps
+        # its buffers): what is left of the host side is the ctypes call and the launch
+        calls = [tree.prepare_guided(pos_b[b], modes[b], wo=wo, seed=7 + b, bsdf_pdf=bp, bsdf_value=bv, dir_out=o_dir, sdtree_pdf_out=o_sp,
+                                     wo_pdf_out=o_wp, weight_out=o_w, em_dir=em, em_active=em_act[b], sdtree_pdf_em_out=o_em)
+                 for b in range(md) if alive[b] > 0]
+        for c in calls:
+            c()
+        torch.cuda.synchronize()
+        ev[0].record()
+        for _ in range(reps):
+            for c in calls:
+                c()
+        ev[1].record()
+        torch.cuda.synchronize()
+        ms_bp = ev[0].elapsed_time(ev[1]) / reps
         verts = int(sum(alive))
         out.append({"config": name, "lanes_per_pass": lanes, "max_depth": md, "record_slots": slots, "path_vertices_per_pass": verts,
-                    "bounce_calls_ms": ms_b, "splat_path_data_ms": ms_s, "tree_ms_per_pass": ms_b + ms_s,
-                    "guided_samples_per_s": verts / ((ms_b + ms_s) * 1e-3), "launches_per_pass": (tree.kernel_launches() - l0) / reps})
-        del pos, cdir, tr_, tb_, bs_, wop, act, modes, em_act, pos_b
+                    "bounce_calls_ms": ms_b, "bounce_calls_prepared_ms": ms_bp, "splat_path_data_ms": ms_s, "tree_ms_per_pass": ms_b + ms_s,
+                    "tree_ms_per_pass_prepared": ms_bp + ms_s, "guided_samples_per_s": verts / ((ms_b + ms_s) * 1e-3),
+                    "guided_samples_per_s_prepared": verts / ((ms_bp + ms_s) * 1e-3), "launches_per_pass": launches_per_pass})
+        del pos, cdir, tr_, tb_, bs_, wop, act, modes, em_act, pos_b, calls
         torch.cuda.empty_cache()
     return {"passes": out,
             "what": "tree work of ONE training pass (1 spp) at the wavefront shape of each scene config: max_depth sdt_guided calls with the "
                     "emitter-direction pdf on the surviving lanes + one sdt_splat_path_data over lanes x max_depth record slots; synthetic "
-                    "vertices, frozen benchmark tree, device-resident buffers, host enqueue included (no synchronisation inside a pass); "
+                    "vertices, frozen benchmark tree, device-resident buffers, host enqueue included (no synchronisation inside a pass; "
+                    "_prepared: the bounce calls through SDTree.prepare_guided, argument structs built once); "
                     "the renderer's own work (Mitsuba ray tracing / BSDFs) is not part of it"}
 
 

@@ -122,6 +122,24 @@ def _n_of(x):
     return int(x.shape[0])
 
 
+class _PreparedGuided:
+    """an sdt_guided call with its argument struct already built (SDTree.prepare_guided)"""
+    __slots__ = ("_tree", "_g", "_ref", "_n", "_flags", "_buf", "_outs", "_fn", "_h")
+
+    def __init__(self, tree, g, n, flags, buf, outs):
+        self._tree, self._g, self._n, self._flags, self._buf, self._outs = tree, g, n, flags, buf, outs
+        self._ref = C.byref(g)
+        self._fn, self._h = tree._lib.sdt_guided, tree._h
+
+    def __call__(self, seed=None):
+        if seed is not None:
+            self._g.seed = int(seed) & 0xFFFFFFFF
+        rc = self._fn(self._h, self._ref, self._n, self._flags, self._buf.stream())       # on the caller's current stream
+        if rc != 0:
+            self._tree._ck(rc)
+        return self._outs
+
+
 class SDTree:
     def __init__(self, bbox_min=(0, 0, 0), bbox_max=(1, 1, 1), kd_max_depth=20, quad_max_depth=20,
                  store_nee=True, device=0, kd_capacity=0, quad_capacity=0, lib_path=None):
@@ -287,6 +305,18 @@ class SDTree:
         With em_dir the lanes of em_active (all when None) also get the tree's pdf of that direction from the same
         spatial descent; the return value then has a fifth element, sdtree_pdf_em (fresh: 1 on the other lanes, like
         KDTree.pdf leaves inactive lanes)."""
+        call = self.prepare_guided(pos, mode, wo, u, seed, lane_offset, bsdf_pdf, bsdf_value, bsdf_sampling_fraction, dir_out,
+                                   sdtree_pdf_out, wo_pdf_out, weight_out, em_dir, em_active, sdtree_pdf_em_out)
+        return call()
+
+    def prepare_guided(self, pos, mode, wo=None, u=None, seed=0, lane_offset=0, bsdf_pdf=None, bsdf_value=None,
+                       bsdf_sampling_fraction=0.5, dir_out=None, sdtree_pdf_out=None, wo_pdf_out=None, weight_out=None,
+                       em_dir=None, em_active=None, sdtree_pdf_em_out=None):
+        """guided() with the marshalling done ONCE: returns a callable that issues the same sdt_guided call on the same
+        buffers every time it is invoked (`call(seed=...)` changes the generator seed) and returns the same output arrays.
+        For wavefront loops that keep their buffers between bounces: no argument marshalling per call (measured on the
+        65 k-lane wavefronts of a 256 x 256 pass: 30 bounce calls 0.74 -> 0.68 ms; the rest is the launches' own latency,
+        DESIGN.md section 7).  The arrays must stay alive and in place (the callable holds references to them)."""
         b = _Buf()
         n = _n_of(pos)
         g = L.GuidedArgs()
@@ -348,8 +378,8 @@ class SDTree:
                 g.weight = L.Vec3(wt.data_ptr(), wt.data_ptr() + 4, wt.data_ptr() + 8, 3)
             if ep is not None:
                 g.sdtree_pdf_em = ep.data_ptr()
-        self._ck(self._lib.sdt_guided(self._h, C.byref(g), n, self._flags(b), b.stream()))
-        return (d, sp, wp, wt) if em_dir is None else (d, sp, wp, wt, ep)
+        outs = (d, sp, wp, wt) if em_dir is None else (d, sp, wp, wt, ep)
+        return _PreparedGuided(self, g, n, self._flags(b), b, outs)
 
     def mis_nee(self, bsdf_pdf_em, sdtree_pdf_em, pdf_with_delta, pdf_without_delta, ds_pdf, ds_delta,
                 bsdf_sampling_fraction, iteration):

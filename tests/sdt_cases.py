@@ -594,6 +594,15 @@ def case_guided_bounce(ctx):
     owo, ow = so.mixture(bp, op2, bv, m2, 0.5)
     assert beq(wp[m2], owo[m2]) and beq(wt[m2], ow[m2])
     assert not d[mode == 0].any() and not sp[mode == 0].any()
+    # the prepared form of the same call (argument struct built once, re-issued on the same buffers): same results every
+    # time, and a new seed draws new directions
+    call = t.prepare_guided(ctx.dev(pos), ctx.dev(mode), wo=ctx.dev(wo), seed=77, bsdf_pdf=ctx.dev(bp), bsdf_value=ctx.dev(bv))
+    for _ in range(2):
+        d2, sp2, wp2, wt2 = (ctx.host(x).copy() for x in call())
+        assert beq(d2, d) and beq(sp2, sp) and beq(wp2, wp) and beq(wt2, wt)
+    d3 = ctx.host(call(seed=78)[0])
+    od3, _ = prev.sample(pos, so.ExplicitSampler(seed=78, n=n), m1)
+    assert beq(d3[m1], od3[m1])
 
 
 def case_refine_flags_and_frozen_stats(ctx):
