@@ -26,7 +26,7 @@ SDT_HD uint32_t sdt_scan_count(uint32_t v) { return v; }
 
 #ifndef SDT_HOSTEMU
 // ---------------------------------------------------------------------------- CUDA
-// The refine is a chain of ~200 tiny dependent kernels: launch latency is all it costs.  Every helper
+// The refine is a chain of some 45 small dependent kernels: latency is what it costs.  Every helper
 // kernel therefore starts with sdt_grid_dep(): it lets the NEXT kernel of the stream be scheduled right
 // away (griddepcontrol.launch_dependents) and then waits until the PREVIOUS one has completed and
 // flushed (griddepcontrol.wait) -- the dependency is kept, the launch latencies overlap.  Both are no-ops

@@ -508,9 +508,9 @@ extern "C" int sdt_refine(sdt_handle h, uint32_t flags, sdt_stream stream) {
     QuadSet& s1 = h->set[1 - h->cur];
     const uint32_t kd_rounds = sdt_kd_rounds_bound(h);
 #ifndef SDT_HOSTEMU
-    // The sequence is ~200 tiny dependent kernels whose arguments only depend on the buffer parity and a few settings:
+    // The sequence is some 45 small dependent kernels whose arguments only depend on the buffer parity and a few settings:
     // it is captured once per such combination into a CUDA graph (programmatic-dependent-launch edges included) and
-    // replayed with ONE launch per training iteration -- the host no longer enqueues 200 launches (0.87 -> see DESIGN).
+    // replayed with ONE launch per training iteration (the device-side chain is the bound: graph and plain launches time the same).
     bool done = false;
     if (h->use_graph) {
         const sdt_tree_s::RefineKey key{h->cur, flags & (SDT_REFINE_NO_KD | SDT_REFINE_NO_QUAD), h->levels_hint, levels_bound,
