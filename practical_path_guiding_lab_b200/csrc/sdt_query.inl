@@ -15,6 +15,9 @@
 #ifndef SDT_TILE_MUL
 #define SDT_TILE_MUL 8u       // lanes per thread and warp tile in the compacting kernel (tile = 256 lanes per warp)
 #endif
+#ifndef SDT_TILE_MUL_SMALL
+#define SDT_TILE_MUL_SMALL 2u // ... on wavefronts too small to give every resident thread that many lanes (launch_wavefront)
+#endif
 template <class Lane, int KD>
 SDT_HD void sdt_lane(const Lane& f, const KdCtx& k, uint32_t i) {
     const uint32_t m = f.mode_of(i);
@@ -27,7 +30,7 @@ SDT_HD void sdt_lane(const Lane& f, const KdCtx& k, uint32_t i) {
 // 256-lane tile by mode into shared-memory lists and then works through every list with all 32 threads:
 // a warp never runs two code paths, and idle lanes (dead paths, masked-out vertices, inactive record
 // slots) cost a classification, not a share of a descent.
-template <class Lane, bool COMPACT>
+template <class Lane, bool COMPACT, uint32_t TILE_MUL = SDT_TILE_MUL>
 __global__ void __launch_bounds__(Lane::kMaxThreads, SDT_LB_CTAS) k_wavefront(Lane f, uint32_t n, uint32_t smem_cap, uint32_t cnt_cap, uint32_t use_grid, uint32_t aggregate) {
     extern __shared__ uint32_t kd_s[];
     const DevHeader* hdr = f.t.hdr;
@@ -71,7 +74,7 @@ __global__ void __launch_bounds__(Lane::kMaxThreads, SDT_LB_CTAS) k_wavefront(La
     if (COMPACT) {
         // warp-local: every warp sorts its own tile of 32*SDT_TILE_MUL lanes into its slice of the
         // shared-memory lists (no CTA barrier: a warp never waits for the deepest descent of another warp)
-        constexpr uint32_t TM = SDT_TILE_MUL;
+        constexpr uint32_t TM = TILE_MUL;
         constexpr uint32_t tile_w = 32u * TM;
         const uint32_t lane = threadIdx.x & 31u, wib = threadIdx.x >> 5;
         uint16_t* list = reinterpret_cast<uint16_t*>(smem_next) + wib * tile_w * (uint32_t)Lane::kModes;
@@ -131,7 +134,7 @@ __global__ void __launch_bounds__(Lane::kMaxThreads, SDT_LB_CTAS) k_wavefront(La
 // host last saw (exact after upload / get_sizes; after a refine a non-blocking header read-back
 // refreshes it), capped by the "kd_smem_nodes" tuning; a larger tree falls back to global loads
 // for the nodes beyond the staged prefix.
-template <class Lane, bool COMPACT>
+template <class Lane, bool COMPACT, uint32_t TILE_MUL = SDT_TILE_MUL>
 static int launch_wavefront_c(sdt_handle h, cudaStream_t st, uint32_t n, const Lane& f, int block, int ctas_per_sm) {
     if (n == 0) return SDT_OK;
     if (block <= 0 || block > Lane::kMaxThreads) block = Lane::kMaxThreads;      // 0 = the kernel's own CTA size
@@ -145,27 +148,27 @@ static int launch_wavefront_c(sdt_handle h, cudaStream_t st, uint32_t n, const L
         if (cnt_nodes > (uint32_t)h->kd_smem_count_nodes) cnt_nodes = (uint32_t)h->kd_smem_count_nodes;
     }
     const size_t smem = (size_t)smem_nodes * 4u + (size_t)cnt_nodes * 4u + SDT_GRID_CELLS * 4u +
-                        (COMPACT ? (size_t)block * SDT_TILE_MUL * 2u * (size_t)Lane::kModes : 0u);   // uint16 lists: 32*TM entries per warp and mode
-    sdt_tree_s::LaunchCache& lc = h->launch_cache[(const void*)k_wavefront<Lane, COMPACT>];
+                        (COMPACT ? (size_t)block * TILE_MUL * 2u * (size_t)Lane::kModes : 0u);   // uint16 lists: 32*TM entries per warp and mode
+    sdt_tree_s::LaunchCache& lc = h->launch_cache[(const void*)k_wavefront<Lane, COMPACT, TILE_MUL>];
     constexpr size_t kSmemMax = 227u * 1024u;            // the sm_100 limit per CTA
     if (smem > kSmemMax) return sdt_fail(h, SDT_ERR_INVALID, "k_wavefront: staging tunings ask for more than 227 KB of shared memory per CTA");
     if (smem > 48u * 1024u && smem > lc.attr_smem) {
-        if (cudaFuncSetAttribute(k_wavefront<Lane, COMPACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax) != cudaSuccess)
+        if (cudaFuncSetAttribute(k_wavefront<Lane, COMPACT, TILE_MUL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax) != cudaSuccess)
             return sdt_fail(h, SDT_ERR_CUDA, "cudaFuncSetAttribute(MaxDynamicSharedMemorySize) failed");
         lc.attr_smem = kSmemMax;
     }
     if (lc.occ_smem != smem || lc.occ_block != block) {
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&lc.occ, k_wavefront<Lane, COMPACT>, block, smem) != cudaSuccess || lc.occ < 1) lc.occ = 1;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&lc.occ, k_wavefront<Lane, COMPACT, TILE_MUL>, block, smem) != cudaSuccess || lc.occ < 1) lc.occ = 1;
         lc.occ_smem = smem; lc.occ_block = block;
     }
     const int occ_cache = lc.occ;
     int per_sm = ctas_per_sm < occ_cache ? ctas_per_sm : occ_cache;
     if (per_sm < 1) per_sm = 1;
-    const uint32_t per_cta = (uint32_t)block * (COMPACT ? SDT_TILE_MUL : 1u);
+    const uint32_t per_cta = (uint32_t)block * (COMPACT ? TILE_MUL : 1u);
     uint32_t grid = (n + per_cta - 1u) / per_cta;
     const uint32_t cap = (uint32_t)(h->num_sms * per_sm);
     if (grid > cap) grid = cap;
-    k_wavefront<Lane, COMPACT><<<grid, block, smem, st>>>(f, n, smem_nodes, cnt_nodes, (uint32_t)h->use_kd_grid, (uint32_t)h->splat_aggregate);
+    k_wavefront<Lane, COMPACT, TILE_MUL><<<grid, block, smem, st>>>(f, n, smem_nodes, cnt_nodes, (uint32_t)h->use_kd_grid, (uint32_t)h->splat_aggregate);
     ++h->launches;
     h->last_stream = st;
     return sdt_post_launch(h, "k_wavefront");
@@ -173,7 +176,16 @@ static int launch_wavefront_c(sdt_handle h, cudaStream_t st, uint32_t n, const L
 // compact = the wavefront may contain idle lanes / several kinds of lanes
 template <class Lane>
 static int launch_wavefront(sdt_handle h, cudaStream_t st, uint32_t n, const Lane& f, int block, int ctas_per_sm, bool compact) {
-    if (compact && h->use_compaction) return launch_wavefront_c<Lane, true>(h, st, n, f, block, ctas_per_sm);
+    if (compact && h->use_compaction) {
+        // A 256-lane tile sorts the lanes of several rounds into dense warps, but a thread then owns 8 lanes one after the
+        // other.  A wavefront that cannot give every resident thread two lanes anyway (a 256 x 256 or 512 x 512 pass: 65 k /
+        // 262 k lanes on 227 k thread slots) pays latency, not issue slots: 64-lane tiles put its lanes side by side -- the
+        // first bounces of such a pass take 2 rounds of descents per warp instead of up to 8.
+        const uint64_t slots = (uint64_t)h->num_sms * (uint64_t)(ctas_per_sm > 0 ? ctas_per_sm : 1) *
+                               (uint64_t)((block > 0 && block <= Lane::kMaxThreads) ? block : Lane::kMaxThreads);
+        if ((uint64_t)n <= 2u * slots) return launch_wavefront_c<Lane, true, SDT_TILE_MUL_SMALL>(h, st, n, f, block, ctas_per_sm);
+        return launch_wavefront_c<Lane, true>(h, st, n, f, block, ctas_per_sm);
+    }
     return launch_wavefront_c<Lane, false>(h, st, n, f, block, ctas_per_sm);
 }
 #else

@@ -154,3 +154,30 @@ def test_two_handles_on_two_devices():
     d1, p1 = trees[1].sample(torch.from_numpy(pos).to("cuda:1"), seed=9)
     d0, p0 = trees[0].sample(torch.from_numpy(pos).to("cuda:0"), seed=9)
     assert cases.beq(d0.cpu().numpy(), d1.cpu().numpy()) and cases.beq(p0.cpu().numpy(), p1.cpu().numpy())
+
+
+def test_tile_sizes_agree():
+    """The compacting kernel sorts 256-lane tiles per warp on large wavefronts and 64-lane tiles on wavefronts too small
+    to give every resident thread two lanes (launch_wavefront): the same masked bounce / masked sample evaluated as ONE
+    large launch and as small launches over slices of it (lane_offset keeps the generator keys) gives the same bits --
+    the small-tile path is the one the oracle-checked cases run."""
+    import torch
+    c = _ctx("device")
+    t, cur, prev = cases.train(c, iters=3)
+    n, chunk = 1 << 20, 1 << 16
+    g = torch.Generator(device="cuda").manual_seed(17)
+    pos = torch.rand(n, 3, device="cuda", generator=g)
+    mode = (torch.rand(n, device="cuda", generator=g) * 3).to(torch.uint8).clamp_(max=2)
+    wo = torch.nn.functional.normalize(torch.randn(n, 3, device="cuda", generator=g), dim=1)
+    bp = torch.rand(n, device="cuda", generator=g) * 2
+    bv = torch.rand(n, 3, device="cuda", generator=g)
+    act = (torch.rand(n, device="cuda", generator=g) < 0.4).to(torch.uint8)
+    big = t.guided(pos, mode, wo=wo, seed=11, bsdf_pdf=bp, bsdf_value=bv, em_dir=wo, em_active=act)
+    sd, sp = t.sample(pos, active=act, seed=5)
+    for a in range(0, n, chunk):
+        s = slice(a, a + chunk)
+        small = t.guided(pos[s], mode[s], wo=wo[s], seed=11, lane_offset=a, bsdf_pdf=bp[s], bsdf_value=bv[s], em_dir=wo[s], em_active=act[s])
+        for x, y in zip(big, small):
+            assert torch.equal(x[s], y), a
+        d2, p2 = t.sample(pos[s], active=act[s], seed=5, lane_offset=a)
+        assert torch.equal(sd[s], d2) and torch.equal(sp[s], p2), a
