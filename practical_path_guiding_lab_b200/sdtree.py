@@ -31,6 +31,17 @@ def _is_torch(x):
     return type(x).__module__.startswith("torch")
 
 
+_TORCH_DTYPES = None       # numpy dtype -> torch dtype of a device buffer, filled on first use (torch is imported lazily)
+
+
+def _torch_dtypes():
+    global _TORCH_DTYPES
+    if _TORCH_DTYPES is None:
+        import torch
+        _TORCH_DTYPES = (torch, {np.float32: torch.float32, np.uint32: torch.int32, np.uint8: torch.uint8})
+    return _TORCH_DTYPES
+
+
 class _Buf:
     """Resolves numpy / torch buffers to raw pointers; remembers whether the call is a
     host-pointer call and keeps temporaries alive."""
@@ -42,7 +53,7 @@ class _Buf:
 
     def _kind(self, x):
         host = not _is_torch(x)
-        if not host and x.device.type != "cuda":
+        if not host and not x.is_cuda:
             raise TypeError("torch tensors passed to SDTree must live on a CUDA device (use numpy for host data)")
         if self.host is None:
             self.host = host
@@ -62,9 +73,12 @@ class _Buf:
                 a = a.reshape(shape)
             self.keep.append(a)
             return a.ctypes.data
-        import torch
-        td = {np.float32: torch.float32, np.uint32: torch.int32, np.uint8: torch.uint8}[dtype]
+        torch, tds = _torch_dtypes()
+        td = tds[dtype]
         t = x
+        if t.dtype is td and t.is_contiguous():              # the common case: nothing to convert (a wavefront loop makes
+            self.keep.append(t)                              # a dozen of these per call)
+            return t.data_ptr()
         if dtype is np.uint8 and t.dtype == torch.bool:
             t = t.view(torch.uint8) if t.is_contiguous() else t.contiguous().view(torch.uint8)
         if dtype is np.uint32 and t.dtype == torch.uint32:
